@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s of closest-hit queries (BVH + triangle) on BASELINE config C4.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c3|c2|c5]
+
+One "step" = one frame of the hot path: per-pixel ray generation, BVH traversal, Möller–Trumbore
+closest hit, HW2 direct shading with one shadow ray per lit hit, 8-bit resolve (and, for N > 1, the
+NCCL tile gather to rank 0).  Default workload (config.workload = "c4"): synthetic 1,000,000-triangle
+terrain, 3840x2160, 1 spp with the reference jitter pair, primary + shadow rays.
+
+value   = rays (primary + shadow) per second, scene/BVH resident in HBM, L2 flushed between steps,
+          device time from CUDA events on the library's stream, max over ranks.
+e2e     = the same metric through the public C ABI with host buffers: rt_render (frame description,
+          lights and jitter copied host->device) + rt_download_image of the 8-bit frame into pinned
+          host memory, every step, wall clock.  This is what the reference's own "GPU Render Time"
+          brackets (render + D2H copy, GPUandCPU/src/main.cu:370-378).
+--impl reference: the reference's own CPU implementation of the path (oracle/_ref/libref_hw2.so,
+          compiled in place from the reference sources; falls back to the oracle port) on all host
+          cores, each step a bounded row sample of the same frame.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nx, ny, W, H, spp)
+    "c4": (1000, 500, 3840, 2160, 1),
+    "c5": (2500, 2000, 7680, 4320, 16),
+    "c4small": (200, 100, 960, 540, 1),
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------- reference arm ----
+def reference_lib():
+    p = os.path.join(ROOT, "oracle", "_ref", "libref_hw2.so")
+    if os.path.exists(p):
+        lib = C.CDLL(p)
+        lib.ref_hw2_world.restype = C.c_void_p
+        lib.ref_hw2_build.restype = C.c_double
+        return lib
+    return None
+
+
+class CpuReference:
+    """The reference CPU renderer of the path on host threads: kind 'reference' when the in-place
+    build of the reference sources is present, else the oracle port."""
+
+    def __init__(self, scene, frame):
+        from raytracinginonesemester_b200 import _abi as A
+        self.A, self.scene, self.frame = A, scene, frame
+        self.cores = os.cpu_count() or 1
+        self.lib = reference_lib()
+        self.kind = "reference" if self.lib else "port"
+        t0 = time.perf_counter()
+        if self.lib:
+            f32p, u32p, i32p = A.f32p, A.u32p, A.i32p
+            self.h = self.lib.ref_hw2_world(scene.positions.ctypes.data_as(f32p), None, C.c_uint64(scene.positions.shape[0]),
+                                            scene.indices.ctypes.data_as(u32p), C.c_uint64(scene.indices.shape[0]),
+                                            scene.tri_obj_ids.ctypes.data_as(i32p))
+            self.lib.ref_hw2_build(C.c_void_p(self.h))
+        else:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import orclib
+            self.orclib = orclib
+            self.h = orclib.oracle_bvh(scene)
+        self.build_s = time.perf_counter() - t0
+
+    def rays_in_rows(self, row_begin, row_step):
+        """Times one row-strided pass; returns (rays, seconds).  Shadow rays are counted with the
+        oracle's counter-free rule: one per lit hit — measured by the port, estimated as
+        primary * shadow_ratio for the in-place reference (which has no counters)."""
+        fr, A = self.frame, self.A
+        W, H = fr.width, fr.height
+        rows = len(range(row_begin, H, row_step))
+        t0 = time.perf_counter()
+        if self.lib:
+            cp = np.array([0, 0, 1], np.float32); lk = np.zeros(3, np.float32); up = np.array([0, 1, 0], np.float32)
+            ms = np.array(fr.miss_color, np.float32)
+            rgb = np.zeros((H, W, 3), np.float32)
+            marr = (A.rt_material * len(self.scene.materials))(*self.scene.materials)
+            larr = (A.rt_light * len(fr.lights))(*fr.lights)
+            self.lib.ref_hw2_render_rows(C.c_void_p(self.h), cp.ctypes.data_as(A.f32p), lk.ctypes.data_as(A.f32p), up.ctypes.data_as(A.f32p),
+                                         C.c_double(24.0), C.c_double(24.0), W, H, ms.ctypes.data_as(A.f32p), 1, fr.spp,
+                                         marr, len(self.scene.materials), larr, len(fr.lights), 1, row_begin, row_step, self.cores,
+                                         rgb.ctypes.data_as(A.f32p), None, None)
+        else:
+            self.orclib.oracle_render(self.scene, fr, bvh=self.h, threads=self.cores, row_begin=row_begin, row_step=row_step, want=("rgb",))
+        dt = time.perf_counter() - t0
+        return rows * W * fr.spp, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from raytracinginonesemester_b200 import _abi as A, scenes
+    nx, ny, W, H, spp = WORKLOADS[args.workload]
+    scene = scenes.terrain_scene(nx, ny)
+    frame = scenes.terrain_frame(W, H, spp=spp, outputs=A.RT_OUT_RGB8)
+    ref = CpuReference(scene, frame)
+    shadow_ratio = args.shadow_ratio
+    # size a step for ~6 s of CPU work: calibrate on a thin sample first
+    cal_step = max(1, H // 8)
+    rays, dt = ref.rays_in_rows(3, cal_step)
+    rate = rays / dt
+    target_rows = max(1, int(rate * 6.0 / (W * spp)))
+    step = max(1, H // target_rows)
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        ref.rays_in_rows(1, step)
+    tot_rays, tot_s = 0, 0.0
+    for k in range(args.steps):
+        rays, dt = ref.rays_in_rows(k % step, step)
+        tot_rays += rays
+        tot_s += dt
+    mrays = tot_rays * (1.0 + shadow_ratio) / tot_s / 1e6
+    line = {
+        "impl": "reference", "metric": "Mrays/s closest-hit (BVH+tri)", "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "triangles": nx * ny * 2, "width": W, "height": H, "spp": spp, "rays": "primary+shadow"},
+        "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": ref.cores, "kind": ref.kind,
+                         "sample": "every %d-th row of the %dx%d frame per step (%d rows), full-frame rate extrapolated; shadow rays = primary x %.4f" % (step, W, H, len(range(0, H, step)), shadow_ratio),
+                         "lbvh_build_s": ref.build_s},
+        "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------ our arm ----
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from raytracinginonesemester_b200 import _abi as A, api, scenes
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    nccl_id = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(api.Renderer.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
+    r = api.Renderer(local_rank, rank, world, nccl_id)
+    nx, ny, W, H, spp = WORKLOADS[args.workload]
+    scene = scenes.terrain_scene(nx, ny, build_flags=A.RT_BUILD_LEAF_MAX(args.leaf_max)) if rank == 0 else None
+    t0 = time.perf_counter()
+    info = r.upload_scene(scene)
+    upload_wall = time.perf_counter() - t0
+    frame = scenes.terrain_frame(W, H, spp=spp, outputs=A.RT_OUT_RGB8, kernel_variant=args.variant)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    pinned = torch.empty((H, W, 3), dtype=torch.uint8, pin_memory=True).numpy() if rank == 0 else None
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(do_flush=True):
+        if do_flush:
+            flush.zero_()
+        barrier()
+        r.render(frame)
+        return r.sync()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    # traversal statistics (untimed): bytes per ray for the roofline
+    frame.kernel_variant = A.RT_VARIANT_STATS
+    r.render(frame)
+    st = r.download(into={"rgb8": pinned} if rank == 0 else None)
+    nv, nt = r.frame_stats()
+    frame.kernel_variant = args.variant
+    rays_local = st["rays_primary"] + st["rays_shadow"]
+    cnt = torch.tensor([st["rays_primary"], st["rays_shadow"], nv, nt], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(cnt)
+    rays_primary, rays_shadow, nv_all, nt_all = [float(x) for x in cnt.cpu()]
+    rays = rays_primary + rays_shadow
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    step_ms = []
+    for _ in range(args.steps):
+        step_ms.append(step_device())
+    warm_ms = []
+    for _ in range(min(args.steps, 5)):
+        warm_ms.append(step_device(do_flush=False))
+    barrier()
+    # end to end through the C ABI with host buffers (render + blocking download), wall clock
+    e2e_s = []
+    for _ in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        r.render(frame)
+        r.download(into={"rgb8": pinned} if rank == 0 else None)
+        if dist is not None:
+            dist.barrier()
+        e2e_s.append(time.perf_counter() - t0)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([step_ms, e2e_s + [0.0] * (len(step_ms) - len(e2e_s))], dtype=torch.float64, device="cuda")
+    tw = torch.tensor(warm_ms, dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    step_ms = t[0].cpu().numpy()
+    e2e_s = t[1].cpu().numpy()
+    ms = float(step_ms.mean())
+    value = rays / (ms * 1e-3) / 1e6
+    e2e_value = rays / float(e2e_s.mean()) / 1e6
+
+    if rank == 0:
+        peak, peak_kind = measured_peaks()
+        b_ray = (64.0 * nv_all + 48.0 * nt_all) / rays + 16.0
+        achieved = rays / (ms * 1e-3) * b_ray / 1e9
+        line = {
+            "metric": "Mrays/s closest-hit (BVH+tri)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "triangles": nx * ny * 2, "width": W, "height": H, "spp": spp,
+                       "rays": "primary+shadow", "rays_primary": rays_primary, "rays_shadow": rays_shadow,
+                       "l2": "flushed between timed steps (256 MiB memset); warm-L2 figure in value_warm_l2",
+                       "tile_sharding": "16x8 tiles, tile k -> rank k %% %d" % world, "leaf_max": args.leaf_max, "variant": args.variant},
+            "primary_mrays_s": rays_primary / (ms * 1e-3) / 1e6,
+            "value_warm_l2": rays / (float(tw.mean()) * 1e-3) / 1e6,
+            "bvh_nodes": int(info.num_nodes), "bvh_build_ms": float(info.build_ms), "scene_upload_ms": float(info.upload_ms),
+            "scene_upload_wall_s": upload_wall,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": 1e3 * float(e2e_s.mean()),
+                    "h2d_bytes_per_step": int(C.sizeof(A.rt_frame) + 28 * len(frame.lights) + 8 * spp),
+                    "d2h_bytes_per_step": int(3 * W * H + 32)},
+            "gpu_launches": int(args.steps * (1 if world == 1 else 1 + world)),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_kind": peak_kind, "bytes_per_ray": b_ray, "nodes_per_ray": nv_all / rays, "tris_per_ray": nt_all / rays},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            ref = CpuReference(scenes.terrain_scene(nx, ny), frame)
+            cal_rays, cal_dt = ref.rays_in_rows(5, max(1, H // 8))
+            rows = max(1, int(cal_rays / cal_dt * 12.0 / (W * spp)))
+            stp = max(1, H // rows)
+            n, dt = ref.rays_in_rows(2, stp)
+            ratio = rays_shadow / max(rays_primary, 1.0)
+            line["cpu_baseline"] = {"value": n * (1 + ratio) / dt / 1e6, "unit": "Mrays/s", "cores": ref.cores, "kind": ref.kind,
+                                    "sample": "every %d-th row of the %dx%d frame (%d rows, %.1f s); shadow rays = primary x %.4f (device count)" % (stp, W, H, len(range(2, H, stp)), dt, ratio)}
+        print(json.dumps(line))
+    r.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--leaf-max", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shadow-ratio", type=float, default=0.8144, help="shadow rays per primary ray on c4 (device count), used by --impl reference")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

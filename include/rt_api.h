@@ -1,0 +1,216 @@
+/* rt_api.h — C ABI of the B200 ray-casting hot path.
+ *
+ * This is the drop-in boundary for the HW1 / HW2 renderers of the reference
+ * class repository.  The reference has no FFI layer of its own; its de-facto
+ * operator interface is
+ *
+ *     render(numTriangles, W, H, cam, missColor, max_depth, spp, nodes, aabbs,
+ *            triangles, triObjectIds, objectMaterials, numObjectMaterials,
+ *            lights, numLights, diffuse_bounce, output)
+ *                         HW2/HW2/GPUandCPU/include/query.h:13-29
+ *     AccStruct::BVH::calculateAABBs / buildBVH
+ *                         HW2/HW2/GPUandCPU/include/bvh.h:412-433
+ *     the pixel loop inlined in main()
+ *                         HW1/src/render.cpp:60-124
+ *
+ * Every export below replaces a slice of that interface (file:line cited per
+ * function).  Conventions: extern "C"; plain pointers and sizes; caller-owned
+ * host buffers are copied on upload and filled on download; int status
+ * (0 = ok, <0 = error, text via rt_last_error); one host thread per context;
+ * all device work runs on the context's own non-default stream; rt_render is
+ * asynchronous, rt_download_image blocks.  There is no CPU fallback: every
+ * entry point fails with RT_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef RT_API_H
+#define RT_API_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_API_VERSION 1
+
+/* status codes */
+#define RT_OK            0
+#define RT_ERR_ARG      -1   /* bad argument / NULL / out of range                */
+#define RT_ERR_CUDA     -2   /* CUDA runtime failure (message has the CUDA text) */
+#define RT_ERR_STATE    -3   /* call order: render before upload, etc.           */
+#define RT_ERR_NCCL     -4   /* NCCL failure                                      */
+#define RT_ERR_NOMEM    -5
+
+/* rt_frame.mode — which reference renderer's contract the frame follows
+ * (SURVEY §8a "mode parameters"). */
+#define RT_MODE_HW1      0   /* HW1/src/render.cpp + HW1/include/{ray,raytracer}.h        */
+#define RT_MODE_HW2_BVH  1   /* HW2/HW2/GPUandCPU/include/{query,shader,brdf}.h           */
+#define RT_MODE_HW2_CPU  2   /* HW2/HW2/CPUOnly/include/{ray,raytracer,brdf}.h (direct)  */
+
+/* rt_frame.accel */
+#define RT_ACCEL_BRUTE   0   /* test every triangle (HW1/src/render.cpp:89-107)   */
+#define RT_ACCEL_BVH     1   /* BVH traversal (query.h:224-311)                    */
+
+/* rt_frame.outputs / rt_image: which planes are produced */
+#define RT_OUT_RGB_F32   1u  /* float rgb[3*W*H], the reference's Vec3 image       */
+#define RT_OUT_RGB8      2u  /* uint8 rgb8[3*W*H], quantised on device             */
+#define RT_OUT_TRI_ID    4u  /* int32 tri_id[W*H]: closest-hit triangle of sample 0, -1 = miss */
+#define RT_OUT_T         8u  /* float t[W*H]: hit distance of sample 0, -1 = miss  */
+
+/* rt_frame.quantiser: float -> u8 rule used for RT_OUT_RGB8 */
+#define RT_QUANT_PPM_LROUND   0  /* ppm_p6.cpp:137-155  lround(clamp01(x)*255), gamma off */
+#define RT_QUANT_PPM_GAMMA2   1  /* same with sqrt() first (ppm_p6 default gamma2=true)    */
+#define RT_QUANT_HW1_TRUNC    2  /* HW1/src/render.cpp:121-123   (uchar)(255.99f*c)        */
+#define RT_QUANT_HW2_TRUNC    3  /* GPUandCPU/src/main.cu:428-430 (uchar)(255*min(c,1))    */
+
+/* rt_frame.kernel_variant */
+#define RT_VARIANT_DEFAULT    0
+#define RT_VARIANT_STATS    100  /* same results, also counts BVH node visits / triangle tests */
+
+/* rt_scene.build_flags */
+#define RT_BUILD_DEFAULT      0u
+#define RT_BUILD_NO_BVH       1u  /* brute-force frames only; skip the BVH build  */
+#define RT_BUILD_LEAF_MAX(n)  (((uint32_t)(n) & 0xFu) << 8)  /* max triangles per BVH leaf, 1..8 (0 = default 4) */
+
+typedef struct rt_ctx rt_ctx;
+
+/* 13 floats, 52 bytes, field order of HW2/HW2/GPUandCPU/include/material.h:6-20 */
+typedef struct rt_material {
+    float albedo[3];
+    float kd;
+    float specular_color[3];
+    float ks;
+    float shininess;
+    float kr;
+    float emission[3];
+} rt_material;
+
+/* 28 bytes, HW2/HW2/GPUandCPU/include/scene.h:21-25 (intensity is an int there).
+ * RT_MODE_HW1 uses position+color only (HW1/include/raytracer.h:8-11). */
+typedef struct rt_light {
+    float   position[3];
+    float   color[3];
+    int32_t intensity;
+} rt_light;
+
+/* Indexed triangle mesh exactly as the reference loaders hand it to render():
+ * MeshView (GPUandCPU/include/MeshOBJ.h:24-40) + objectMaterials (main.cu:165-190). */
+typedef struct rt_scene {
+    const float*       positions;      /* [3*num_vertices]                         */
+    const float*       normals;        /* [3*num_vertices] or NULL (zero normals)  */
+    uint64_t           num_vertices;
+    const uint32_t*    indices;        /* [3*num_triangles]                        */
+    uint64_t           num_triangles;
+    const int32_t*     tri_obj_ids;    /* [num_triangles] or NULL                  */
+    const rt_material* materials;      /* [num_materials] or NULL                  */
+    int32_t            num_materials;
+    uint32_t           build_flags;
+} rt_scene;
+
+/* The four vectors Camera::initialize leaves behind
+ * (GPUandCPU/include/camera.h:72-94, HW1/include/camera.h:55-92). */
+typedef struct rt_camera {
+    float center[3];
+    float pixel00_loc[3];
+    float pixel_delta_u[3];
+    float pixel_delta_v[3];
+} rt_camera;
+
+typedef struct rt_frame {
+    int32_t         mode;          /* RT_MODE_*                                    */
+    int32_t         accel;         /* RT_ACCEL_*                                   */
+    int32_t         width, height;
+    rt_camera       cam;
+    const rt_light* lights;
+    int32_t         num_lights;
+    float           miss_color[3]; /* HW2 constant miss colour (query.h:181-184)   */
+    int32_t         spp;           /* samples per pixel (>=1)                      */
+    const float*    jitter;        /* [2*spp] sub-pixel offsets; NULL = pixel centre */
+    int32_t         max_depth;     /* 1 = primary + direct light (+ shadow ray)    */
+    int32_t         shadows;       /* HW2 modes: trace the IsInShadow ray (shader.h:44-62) */
+    uint32_t        outputs;       /* RT_OUT_* mask                                */
+    int32_t         quantiser;     /* RT_QUANT_*                                   */
+    int32_t         kernel_variant;/* 0 = default; >0 selects an experimental traversal kernel */
+} rt_frame;
+
+typedef struct rt_image {
+    float*    rgb;        /* [3*W*H] or NULL */
+    uint8_t*  rgb8;       /* [3*W*H] or NULL */
+    int32_t*  tri_id;     /* [W*H]   or NULL */
+    float*    t;          /* [W*H]   or NULL */
+    int32_t   width, height;       /* filled */
+    uint64_t  rays_primary;        /* filled: closest-hit queries traced (this rank) */
+    uint64_t  rays_shadow;         /* filled: shadow queries traced (this rank)      */
+    float     gpu_ms;              /* filled: device time of the last rt_render     */
+} rt_image;
+
+typedef struct rt_build_info {
+    uint64_t num_triangles;
+    uint64_t num_nodes;        /* flattened 64-byte BVH2 nodes                      */
+    uint64_t num_leaves;
+    uint64_t arena_bytes;      /* nodes + triangle blocks + shading attributes      */
+    float    build_ms;         /* device time of the BVH build                      */
+    float    upload_ms;        /* host->device copies                               */
+    float    scene_min[3], scene_max[3];
+} rt_build_info;
+
+/* -- lifetime ------------------------------------------------------------ */
+int  rt_api_version(void);
+/* Context bound to CUDA device `device` (replaces the cudaMalloc block of
+ * GPUandCPU/src/main.cu:199-252). */
+int  rt_create(rt_ctx** out, int device);
+int  rt_destroy(rt_ctx* ctx);
+/* Message of the last failing call on this thread (ctx may be NULL). */
+const char* rt_last_error(const rt_ctx* ctx);
+
+/* -- multi-GPU (one process per GPU; screen-space tile sharding) --------- */
+/* 128-byte NCCL unique id produced on rank 0 and handed to every rank by the host. */
+int  rt_comm_unique_id(void* id128);
+int  rt_comm_init(rt_ctx* ctx, int rank, int world, const void* id128);
+int  rt_comm_rank(const rt_ctx* ctx, int* rank, int* world);
+
+/* -- scene --------------------------------------------------------------- */
+/* Pack triangles, build the BVH on the device and (world>1) broadcast the arena
+ * from rank 0; ranks != 0 may pass scene == NULL to receive.  Replaces
+ * calculateAABBs + buildBVH + buildTrianglesKernel
+ * (bvh.cu:60-90, 93-206; main.cu:19-41, 254-293, 347-358). */
+int  rt_upload_scene(rt_ctx* ctx, const rt_scene* scene);
+int  rt_build_info_get(const rt_ctx* ctx, rt_build_info* info);
+
+/* -- frame --------------------------------------------------------------- */
+/* Asynchronous: ray generation + closest hit + shading (+ tile gather to rank 0).
+ * Replaces render() (query.cu:79-167) and the HW1 pixel loop (render.cpp:72-116). */
+int  rt_render(rt_ctx* ctx, const rt_frame* frame);
+/* Blocking: waits for the frame and fills the requested planes (rank 0 holds
+ * the gathered image).  Replaces the D2H copy + 8-bit conversion of
+ * main.cu:374, 426-431 / render.cpp:119-124. */
+int  rt_download_image(rt_ctx* ctx, rt_image* img);
+/* Blocks until the last rt_render finished; returns its device time. */
+int  rt_sync(rt_ctx* ctx, float* gpu_ms);
+
+/* Traversal work of the last frame rendered with RT_VARIANT_STATS: BVH nodes visited and
+ * triangles tested, summed over primary and shadow queries of this rank (the per-ray byte figure
+ * of the roofline is 64*nodes + 48*tris + 16 per ray).  Blocks like rt_sync. */
+int  rt_frame_stats(rt_ctx* ctx, uint64_t* node_visits, uint64_t* tri_tests);
+
+/* -- host helpers (pure host arithmetic, no device work) ------------------ */
+/* Camera::initialize restated with the reference's mixed fp64/fp32 rounding
+ * (GPUandCPU/include/camera.h:72-94; HW1/include/camera.h:55-92 is identical
+ * for valid sizes).  Returns RT_ERR_ARG when width/height < 1 (HW1 throws). */
+int  rt_camera_init(rt_camera* out, const float pos[3], const float look_at[3],
+                    const float up[3], double focal_length_mm,
+                    double sensor_height_mm, int width, int height);
+/* jittered_samples(spp, seed) of GPUandCPU/include/antialias.h:12-27:
+ * std::mt19937 + uniform_real_distribution<float>(0,1) - 0.5.  out[2*spp]. */
+int  rt_jitter_table(float* out, int spp, uint32_t seed, int centered);
+
+/* -- introspection for tests / profiling ---------------------------------- */
+/* Copies the flattened BVH back to the host (nodes: 64 B each; tri blocks: 48 B
+ * each, leaf order; tri_ids: original triangle id per block). Any pointer may be
+ * NULL; counts come from rt_build_info_get. */
+int  rt_debug_download_bvh(rt_ctx* ctx, void* nodes64, void* tri_blocks48, int32_t* tri_ids);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_API_H */

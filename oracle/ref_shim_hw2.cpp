@@ -1,0 +1,209 @@
+// ref_shim_hw2.cpp — C-ABI doorway into the UNMODIFIED HW2/GPUandCPU reference sources
+// (CPU build of the one tree that also compiles as CUDA).
+//
+// TEST INFRASTRUCTURE ONLY (see oracle/rt_oracle.c header).  No renderer arithmetic is
+// restated here: the reference headers are #included where they lie
+// (/root/reference/HW2/HW2/GPUandCPU/include, -I from oracle/build.py), include/bvh.cu and
+// include/query.cu are compiled next to this file with `-x c++ -D__device__=`
+// (antialias.h:30 has an unguarded __device__), and the exports call the reference's
+// calculateAABBs / buildBVH / render / SearchBVH / TraceRayIterative / Camera.
+// Output: oracle/_ref/libref_hw2.so (git-ignored).
+#define private public   // Camera keeps pixel00_loc / pixel_delta_* private
+#include "camera.h"
+#undef private
+#include "MeshOBJ.h"
+#include "buffers.h"
+#include "bvh.h"
+#include "scene.h"
+#include "query.h"
+
+#include <cfloat>
+#include <cstring>
+#include <numeric>
+#include <thread>
+#include <vector>
+
+// BVHState::fromChunk is defined in the reference's main.cu (src/main.cu:45-51), which
+// also holds main(); the two obtain() calls are repeated here to carve the same arena.
+RayTracer::BVHState RayTracer::BVHState::fromChunk(char*& chunk, size_t P) {
+    BVHState state;
+    obtain(chunk, state.Nodes, 2 * P - 1, 128);
+    obtain(chunk, state.AABBs, 2 * P - 1, 128);
+    return state;
+}
+
+struct ref_world {
+    Mesh mesh;
+    std::vector<Triangle> tris;
+    std::vector<char> chunk;
+    RayTracer::BVHState st;
+    size_t P = 0;
+    double build_ms = 0;
+};
+
+extern "C" {
+
+// LoadOBJ_ToMesh (MeshOBJ.h:260-427) --------------------------------------------------
+void* ref_hw2_load_obj(const char* path, int* next_object_id) {
+    ref_world* w = new ref_world;
+    int nid = *next_object_id;
+    if (!LoadOBJ_ToMesh(path, w->mesh, nid)) { delete w; return nullptr; }
+    *next_object_id = nid;
+    return w;
+}
+void ref_hw2_mesh_counts(void* h, uint64_t* nv, uint64_t* nn, uint64_t* nt) {
+    ref_world* w = (ref_world*)h;
+    *nv = w->mesh.positions.size(); *nn = w->mesh.normals.size(); *nt = w->mesh.indices.size() / 3;
+}
+void ref_hw2_mesh_copy(void* h, float* pos, float* nrm, uint32_t* idx, int32_t* obj) {
+    ref_world* w = (ref_world*)h;
+    if (pos) std::memcpy(pos, w->mesh.positions.data(), w->mesh.positions.size() * sizeof(Vec3));
+    if (nrm) std::memcpy(nrm, w->mesh.normals.data(), w->mesh.normals.size() * sizeof(Vec3));
+    if (idx) std::memcpy(idx, w->mesh.indices.data(), w->mesh.indices.size() * sizeof(uint32_t));
+    if (obj) std::memcpy(obj, w->mesh.triangleObjIds.data(), w->mesh.triangleObjIds.size() * sizeof(int32_t));
+}
+
+// World from raw arrays (synthetic meshes) ---------------------------------------------
+void* ref_hw2_world(const float* pos, const float* nrm, uint64_t nv, const uint32_t* idx,
+                    uint64_t nt, const int32_t* obj) {
+    ref_world* w = new ref_world;
+    w->mesh.positions.assign((const Vec3*)pos, (const Vec3*)pos + nv);
+    if (nrm) w->mesh.normals.assign((const Vec3*)nrm, (const Vec3*)nrm + nv);
+    w->mesh.indices.assign(idx, idx + 3 * nt);
+    if (obj) w->mesh.triangleObjIds.assign(obj, obj + nt);
+    else w->mesh.triangleObjIds.assign(nt, 0);
+    return w;
+}
+void ref_hw2_free(void* h) { delete (ref_world*)h; }
+
+// calculateAABBs + scene bounds + buildBVH + triangle gather, as main.cu:199-211,254-317,387-403
+double ref_hw2_build(void* h) {
+    ref_world* w = (ref_world*)h;
+    size_t P = w->mesh.indices.size() / 3;
+    w->P = P;
+    w->chunk.assign(required<RayTracer::BVHState>(P), 0);
+    char* c = w->chunk.data();
+    w->st = RayTracer::BVHState::fromChunk(c, P);
+    AccStruct::BVH bvh;
+    MeshView mv = w->mesh.getView();
+    bvh.calculateAABBs(mv, w->st.AABBs);
+    AABB scene = std::accumulate(w->st.AABBs + (P - 1), w->st.AABBs + (2 * P - 1), AABB(),
+                                 [](const AABB& l, const AABB& r) { return AABB::merge(l, r); });
+    std::vector<unsigned int> tri_idx(P);
+    std::iota(tri_idx.begin(), tri_idx.end(), 0);
+    auto t0 = std::chrono::high_resolution_clock::now();
+    bvh.buildBVH(w->st.Nodes, w->st.AABBs, scene, tri_idx, (int)P);
+    auto t1 = std::chrono::high_resolution_clock::now();
+    w->build_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    w->tris.resize(P);
+    for (size_t i = 0; i < P; ++i) {
+        const uint32_t i0 = w->mesh.indices[i * 3 + 0], i1 = w->mesh.indices[i * 3 + 1], i2 = w->mesh.indices[i * 3 + 2];
+        Vec3 n0 = make_vec3(0, 0, 0), n1 = n0, n2 = n0;
+        if (!w->mesh.normals.empty()) { n0 = w->mesh.normals[i0]; n1 = w->mesh.normals[i1]; n2 = w->mesh.normals[i2]; }
+        w->tris[i] = Triangle(w->mesh.positions[i0], w->mesh.positions[i1], w->mesh.positions[i2], n0, n1, n2);
+    }
+    return w->build_ms;
+}
+void ref_hw2_bvh_export(void* h, uint32_t* nodes, float* aabbs) {
+    ref_world* w = (ref_world*)h;
+    size_t total = 2 * w->P - 1;
+    if (nodes) std::memcpy(nodes, w->st.Nodes, total * sizeof(BVHNode));
+    if (aabbs) std::memcpy(aabbs, w->st.AABBs, total * sizeof(AABB));
+}
+
+int ref_hw2_camera(const float* pos, const float* look, const float* up, double focal_mm,
+                   double sensor_mm, int W, int H, float* out12) {
+    Camera cam(make_vec3(pos[0], pos[1], pos[2]), make_vec3(look[0], look[1], look[2]),
+               make_vec3(up[0], up[1], up[2]), focal_mm, sensor_mm, W, H);
+    Vec3 v[4] = {cam.center, cam.pixel00_loc, cam.pixel_delta_u, cam.pixel_delta_v};
+    std::memcpy(out12, v, sizeof v);
+    return 0;
+}
+void ref_hw2_jitter(int spp, unsigned seed, float* out) {
+    auto o = jittered_samples(spp, seed);
+    for (int i = 0; i < spp; ++i) { out[2 * i] = o[i].first; out[2 * i + 1] = o[i].second; }
+}
+
+struct ref_lightc { float position[3]; float color[3]; int32_t intensity; };
+
+// Whole frame through the reference's own render() (query.cu:79-167, CPU branch).
+void ref_hw2_render(void* h, const float* cpos, const float* look, const float* up, double focal_mm,
+                    double sensor_mm, int W, int H, const float* miss, int max_depth, int spp,
+                    const void* materials52, int num_materials, const ref_lightc* lights, int num_lights,
+                    int diffuse_bounce, float* rgb)
+{
+    ref_world* w = (ref_world*)h;
+    Camera cam(make_vec3(cpos[0], cpos[1], cpos[2]), make_vec3(look[0], look[1], look[2]),
+               make_vec3(up[0], up[1], up[2]), focal_mm, sensor_mm, W, H);
+    static_assert(sizeof(Material) == 52, "Material layout");
+    static_assert(sizeof(Light) == sizeof(ref_lightc), "Light layout");
+    render(w->P, W, H, cam, make_vec3(miss[0], miss[1], miss[2]), max_depth, spp, w->st.Nodes, w->st.AABBs,
+           w->tris.data(), w->mesh.triangleObjIds.data(), (const Material*)materials52, num_materials,
+           (const Light*)lights, num_lights, diffuse_bounce != 0, (Vec3*)rgb);
+}
+
+// Row-strided / threaded driver of the same per-pixel body (query.cu:136-165) calling the
+// reference's Camera::get_ray, SearchBVH and TraceRayIterative; additionally reports the
+// closest-hit triangle id and t of sample 0.  Any output may be NULL.
+void ref_hw2_render_rows(void* h, const float* cpos, const float* look, const float* up, double focal_mm,
+                         double sensor_mm, int W, int H, const float* miss, int max_depth, int spp,
+                         const void* materials52, int num_materials, const ref_lightc* lights, int num_lights,
+                         int diffuse_bounce, int row_begin, int row_step, int nthreads,
+                         float* rgb, int32_t* tri_id, float* tout)
+{
+    ref_world* w = (ref_world*)h;
+    Camera cam(make_vec3(cpos[0], cpos[1], cpos[2]), make_vec3(look[0], look[1], look[2]),
+               make_vec3(up[0], up[1], up[2]), focal_mm, sensor_mm, W, H);
+    const Vec3 missColor = make_vec3(miss[0], miss[1], miss[2]);
+    const int triCount = (int)w->P;
+    if (nthreads < 1) nthreads = 1;
+    if (row_step < 1) row_step = 1;
+    auto body = [&](int tid) {
+        int kk = 0;
+        for (int y = row_begin; y < H; y += row_step, ++kk) {
+            if (kk % nthreads != tid) continue;
+            for (int x = 0; x < W; ++x) {
+                const size_t pix = (size_t)W * y + x;
+                Vec3 col{0, 0, 0};
+                auto offsets = jittered_samples(spp, 42u);
+                for (int si = 0; si < (int)offsets.size(); ++si) {
+                    float px = float(x) + offsets[si].first;
+                    float py = float(y) + offsets[si].second;
+                    const Ray ray = cam.get_ray(px, py);
+                    if (si == 0 && (tri_id || tout)) {
+                        HitRecord rec;
+                        SearchBVH(triCount, ray, w->st.Nodes, w->st.AABBs, w->tris.data(), rec);
+                        if (tri_id) tri_id[pix] = rec.hit ? rec.triangleIdx : -1;
+                        if (tout) tout[pix] = rec.hit ? (float)rec.t : -1.0f;
+                    }
+                    if (rgb) {
+                        unsigned int rng = make_rng_seed(x, y, si);
+                        col = col + TraceRayIterative(ray, max_depth, missColor, triCount, w->st.Nodes, w->st.AABBs,
+                                                      w->tris.data(), w->mesh.triangleObjIds.data(),
+                                                      (const Material*)materials52, num_materials,
+                                                      (const Light*)lights, num_lights, rng, diffuse_bounce != 0);
+                    }
+                }
+                if (rgb) { Vec3 o = col / float(spp); rgb[3 * pix] = o.x; rgb[3 * pix + 1] = o.y; rgb[3 * pix + 2] = o.z; }
+            }
+        }
+    };
+    if (nthreads == 1) body(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; ++t) th.emplace_back(body, t);
+        for (auto& t : th) t.join();
+    }
+}
+
+// Single-triangle probe: intersectTriangle (query.h:72-132), tmin 1e-4, tmax FLT_MAX.
+int ref_hw2_ray_triangle(const float* orig, const float* dir, const float* v0, const float* v1,
+                         const float* v2, float* t_out) {
+    Ray r(make_vec3(orig[0], orig[1], orig[2]), make_vec3(dir[0], dir[1], dir[2]));
+    Triangle tri(make_vec3(v0[0], v0[1], v0[2]), make_vec3(v1[0], v1[1], v1[2]), make_vec3(v2[0], v2[1], v2[2]));
+    HitRecord rec = intersectTriangle(r, tri, 1e-4f, FLT_MAX);
+    if (t_out) *t_out = rec.hit ? (float)rec.t : -1.0f;
+    return rec.hit ? 1 : 0;
+}
+
+} // extern "C"

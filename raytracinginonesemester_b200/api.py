@@ -1,0 +1,256 @@
+"""Host-side mirror of the reference's operator interface over the C ABI (include/rt_api.h).
+
+The reference's seam is `render(numTriangles, W, H, cam, missColor, max_depth, spp, nodes, aabbs,
+triangles, triObjectIds, objectMaterials, ..., lights, ..., output)` plus
+`BVH::calculateAABBs / buildBVH` (HW2/HW2/GPUandCPU/include/query.h:13-29, bvh.h:412-433) and the
+pixel loop inlined in HW1/src/render.cpp:60-124.  `Renderer.upload_scene` / `render` / `download`
+wrap rt_upload_scene / rt_render / rt_download_image with the same argument meaning; errors raise
+RtError carrying rt_last_error() (the reference throws std::runtime_error, imports.h:40-47).
+
+There is no CPU path: importing works anywhere, but creating a Renderer needs the CUDA library
+(librt_b200.so, built in-tree by build.py) and an sm_100 device, and fails loudly otherwise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi as A
+
+_LIB = None
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "librt_b200.so")
+
+
+class RtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("rt error %d: %s" % (code, msg))
+        self.code = code
+
+
+def load_library():
+    """Loads librt_b200.so (raises if it has not been built: there is no fallback)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s is missing: run `python -m raytracinginonesemester_b200.build` "
+                               "(the CUDA extension is the product; there is no CPU fallback)" % LIB_PATH)
+        _LIB = A.bind(C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL))
+    return _LIB
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a, typ):
+    return a.ctypes.data_as(typ) if a is not None else typ()
+
+
+def camera_init(pos, look_at, up, focal_length_mm, sensor_height_mm, width, height):
+    """Camera::initialize (GPUandCPU/include/camera.h:72-94) -> rt_camera.  Raises on W/H < 1 like
+    HW1's camera (HW1/include/camera.h:57-62)."""
+    lib = load_library()
+    cam = A.rt_camera()
+    p, l, u = _f32(pos), _f32(look_at), _f32(up)
+    rc = lib.rt_camera_init(C.byref(cam), _ptr(p, A.f32p), _ptr(l, A.f32p), _ptr(u, A.f32p),
+                            float(focal_length_mm), float(sensor_height_mm), int(width), int(height))
+    if rc != A.RT_OK:
+        raise RtError(rc, "pixel_width and pixel_height must be >= 1")
+    return cam
+
+
+def jitter_table(spp, seed=42, centered=True):
+    """jittered_samples(spp, seed) of GPUandCPU/include/antialias.h:12-27 (centered) or HW1's."""
+    lib = load_library()
+    out = np.zeros((spp, 2), np.float32)
+    rc = lib.rt_jitter_table(_ptr(out, A.f32p), int(spp), int(seed), 1 if centered else 0)
+    if rc != A.RT_OK:
+        raise RtError(rc, "rt_jitter_table")
+    return out
+
+
+def make_material(albedo=(0.8, 0.8, 0.8), kd=1.0, specular_color=(0.04, 0.04, 0.04), ks=0.0, shininess=32.0,
+                  kr=0.0, emission=(0.0, 0.0, 0.0)):
+    """Material with the defaults of GPUandCPU/include/material.h:6-20."""
+    m = A.rt_material()
+    m.albedo[:] = albedo
+    m.kd = kd
+    m.specular_color[:] = specular_color
+    m.ks = ks
+    m.shininess = shininess
+    m.kr = kr
+    m.emission[:] = emission
+    return m
+
+
+def make_light(position, color=(1.0, 1.0, 1.0), intensity=1):
+    l = A.rt_light()
+    l.position[:] = position
+    l.color[:] = color
+    l.intensity = int(intensity)
+    return l
+
+
+class Scene:
+    """Indexed triangle mesh + per-object materials, as the reference loaders produce them."""
+
+    def __init__(self, positions, indices, normals=None, tri_obj_ids=None, materials=None, build_flags=0):
+        self.positions = _f32(positions).reshape(-1, 3)
+        self.indices = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1, 3)
+        self.normals = _f32(normals).reshape(-1, 3) if normals is not None and len(normals) else None
+        self.tri_obj_ids = np.ascontiguousarray(tri_obj_ids, dtype=np.int32) if tri_obj_ids is not None else None
+        self.materials = list(materials) if materials else []
+        self.build_flags = build_flags
+        self._mat_arr = (A.rt_material * max(1, len(self.materials)))(*self.materials)
+
+    def c_struct(self):
+        s = A.rt_scene()
+        s.positions = _ptr(self.positions, A.f32p)
+        s.normals = _ptr(self.normals, A.f32p)
+        s.num_vertices = self.positions.shape[0]
+        s.indices = _ptr(self.indices, A.u32p)
+        s.num_triangles = self.indices.shape[0]
+        s.tri_obj_ids = _ptr(self.tri_obj_ids, A.i32p)
+        s.materials = C.cast(self._mat_arr, C.POINTER(A.rt_material)) if self.materials else C.POINTER(A.rt_material)()
+        s.num_materials = len(self.materials)
+        s.build_flags = self.build_flags
+        return s
+
+
+class Frame:
+    """Per-frame arguments of render() (query.h:13-29): camera, lights, miss colour, spp, depth."""
+
+    def __init__(self, cam, width, height, mode=A.RT_MODE_HW2_BVH, accel=A.RT_ACCEL_BVH, lights=(), miss_color=(0, 0, 0),
+                 spp=1, jitter=None, max_depth=1, shadows=True, outputs=A.RT_OUT_RGB_F32, quantiser=A.RT_QUANT_PPM_LROUND,
+                 kernel_variant=0):
+        self.cam, self.width, self.height, self.mode, self.accel = cam, int(width), int(height), mode, accel
+        self.lights = list(lights)
+        self._light_arr = (A.rt_light * max(1, len(self.lights)))(*self.lights)
+        self.miss_color = tuple(miss_color)
+        self.spp = int(spp)
+        self.jitter = _f32(jitter).reshape(-1, 2) if jitter is not None else None
+        self.max_depth, self.shadows, self.outputs, self.quantiser = int(max_depth), bool(shadows), int(outputs), int(quantiser)
+        self.kernel_variant = int(kernel_variant)
+
+    def c_struct(self):
+        f = A.rt_frame()
+        f.mode, f.accel, f.width, f.height = self.mode, self.accel, self.width, self.height
+        f.cam = self.cam
+        f.lights = C.cast(self._light_arr, C.POINTER(A.rt_light)) if self.lights else C.POINTER(A.rt_light)()
+        f.num_lights = len(self.lights)
+        f.miss_color[:] = self.miss_color
+        f.spp = self.spp
+        f.jitter = _ptr(self.jitter, A.f32p)
+        f.max_depth, f.shadows, f.outputs, f.quantiser = self.max_depth, int(self.shadows), self.outputs, self.quantiser
+        f.kernel_variant = self.kernel_variant
+        return f
+
+
+class Renderer:
+    """One context per GPU (one process per GPU; screen-space tiles are sharded across ranks)."""
+
+    def __init__(self, device=0, rank=0, world=1, nccl_id=None):
+        self.lib = load_library()
+        self.ctx = C.c_void_p()
+        rc = self.lib.rt_create(C.byref(self.ctx), int(device))
+        if rc != A.RT_OK:
+            raise RtError(rc, (self.lib.rt_last_error(None) or b"").decode())
+        self.rank, self.world = rank, world
+        if world > 1:
+            assert nccl_id is not None and len(nccl_id) == 128
+            buf = (C.c_char * 128).from_buffer_copy(bytes(nccl_id))
+            self._check(self.lib.rt_comm_init(self.ctx, rank, world, buf))
+        self._frame = None
+        self._scene = None
+
+    @staticmethod
+    def nccl_unique_id():
+        lib = load_library()
+        buf = (C.c_char * 128)()
+        rc = lib.rt_comm_unique_id(buf)
+        if rc != A.RT_OK:
+            raise RtError(rc, (lib.rt_last_error(None) or b"").decode())
+        return bytes(buf)
+
+    def _check(self, rc):
+        if rc != A.RT_OK:
+            raise RtError(rc, (self.lib.rt_last_error(self.ctx) or b"").decode())
+
+    def close(self):
+        if self.ctx:
+            self.lib.rt_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload_scene(self, scene):
+        """calculateAABBs + buildBVH + triangle packing on the device; returns rt_build_info."""
+        self._scene = scene
+        if scene is None:
+            self._check(self.lib.rt_upload_scene(self.ctx, None))
+        else:
+            s = scene.c_struct()
+            self._check(self.lib.rt_upload_scene(self.ctx, C.byref(s)))
+        info = A.rt_build_info()
+        self._check(self.lib.rt_build_info_get(self.ctx, C.byref(info)))
+        return info
+
+    def render(self, frame):
+        """Asynchronous launch of the fused ray-gen / traversal / shading kernel."""
+        self._frame = frame
+        f = frame.c_struct()
+        self._check(self.lib.rt_render(self.ctx, C.byref(f)))
+
+    def sync(self):
+        ms = C.c_float()
+        self._check(self.lib.rt_sync(self.ctx, C.byref(ms)))
+        return ms.value
+
+    def download(self, into=None):
+        """Blocking read-back of the planes requested in Frame.outputs -> dict of numpy arrays.
+        `into` may map plane name -> preallocated (e.g. pinned) array."""
+        fr = self._frame
+        W, H = fr.width, fr.height
+        img = A.rt_image()
+        out = {}
+        into = into or {}
+        root = self.world == 1 or self.rank == 0
+
+        def buf(name, shape, dt):
+            a = into.get(name)
+            if a is None:
+                a = np.empty(shape, dt)
+            out[name] = a
+            return a
+
+        if root:
+            if fr.outputs & A.RT_OUT_RGB_F32:
+                img.rgb = _ptr(buf("rgb", (H, W, 3), np.float32), A.f32p)
+            if fr.outputs & A.RT_OUT_RGB8:
+                img.rgb8 = _ptr(buf("rgb8", (H, W, 3), np.uint8), A.u8p)
+            if fr.outputs & A.RT_OUT_TRI_ID:
+                img.tri_id = _ptr(buf("tri_id", (H, W), np.int32), A.i32p)
+            if fr.outputs & A.RT_OUT_T:
+                img.t = _ptr(buf("t", (H, W), np.float32), A.f32p)
+        self._check(self.lib.rt_download_image(self.ctx, C.byref(img)))
+        out["rays_primary"], out["rays_shadow"], out["gpu_ms"] = int(img.rays_primary), int(img.rays_shadow), float(img.gpu_ms)
+        return out
+
+    def frame_stats(self):
+        """(node_visits, tri_tests) of the last frame rendered with kernel_variant=RT_VARIANT_STATS."""
+        n, t = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.rt_frame_stats(self.ctx, C.byref(n), C.byref(t)))
+        return int(n.value), int(t.value)
+
+    def download_bvh(self):
+        info = A.rt_build_info()
+        self._check(self.lib.rt_build_info_get(self.ctx, C.byref(info)))
+        nodes = np.zeros((int(info.num_nodes), 16), np.uint32)
+        geom = np.zeros((int(info.num_triangles), 12), np.float32)
+        ids = np.zeros(int(info.num_triangles), np.int32)
+        self._check(self.lib.rt_debug_download_bvh(self.ctx, nodes.ctypes.data, geom.ctypes.data, _ptr(ids, A.i32p)))
+        return nodes, geom, ids

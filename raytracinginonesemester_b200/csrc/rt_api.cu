@@ -1,0 +1,443 @@
+// rt_api.cu — host side of the C ABI declared in include/rt_api.h.
+//
+// Owns the context (device, stream, events), the scene arena (64-byte nodes, 48-byte triangle
+// geometry/shading blocks, materials), the per-frame output planes and the NCCL communicator.
+// There is no CPU rendering path here: without a usable CUDA device every entry point returns
+// RT_ERR_CUDA.
+#include "rt_kernels.h"
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+thread_local std::string g_last_error;
+
+struct Plane {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+} // namespace
+
+struct rt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    // scene
+    BvhNode* nodes = nullptr; TriBlock* geom = nullptr; TriBlock* shade = nullptr; rt_material* materials = nullptr;
+    uint32_t num_tris = 0, num_nodes = 0; int num_materials = 0; bool has_scene = false, has_bvh = false;
+    rt_build_info info{};
+    // frame
+    Plane lights, jitter, counters;
+    Plane loc_rgb, loc_rgb8, loc_id, loc_t;       // this rank's planes (row-major if world==1, tile-packed otherwise)
+    Plane img_rgb, img_rgb8, img_id, img_t;       // rank 0, world>1: gathered row-major image
+    Plane stage_rgb, stage_rgb8, stage_id, stage_t; // rank 0, world>1: receive staging for ranks 1..world-1
+    FrameParams fp{};
+    uint32_t outputs = 0;
+    bool frame_valid = false;
+    int launches = 0;
+    // comm
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+};
+
+namespace {
+
+int fail(rt_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_last_error = buf;
+    if (c) c->err = buf;
+    return code;
+}
+#define CU(c, x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail((c), RT_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } while (0)
+#define NC(c, x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) return fail((c), RT_ERR_NCCL, "%s: %s", #x, ncclGetErrorString(r_)); } while (0)
+
+void free_scene(rt_ctx* c) {
+    if (c->nodes) cudaFree(c->nodes);
+    if (c->geom) cudaFree(c->geom);
+    if (c->shade) cudaFree(c->shade);
+    if (c->materials) cudaFree(c->materials);
+    c->nodes = nullptr; c->geom = nullptr; c->shade = nullptr; c->materials = nullptr;
+    c->num_tris = c->num_nodes = 0; c->num_materials = 0; c->has_scene = c->has_bvh = false;
+}
+
+int tiles_of_rank(int total, int rank, int world) { return rt_tiles_of_rank(total, rank, world); }
+
+struct SceneHeader { uint32_t num_tris, num_nodes, num_materials, has_bvh; float smin[3], smax[3]; };
+
+// Broadcast of the built arena from rank 0 (scene + BVH travel once per scene over NVLink).
+int broadcast_scene(rt_ctx* c) {
+    SceneHeader h{};
+    if (c->rank == 0) {
+        h.num_tris = c->num_tris; h.num_nodes = c->num_nodes; h.num_materials = (uint32_t)c->num_materials; h.has_bvh = c->has_bvh;
+        memcpy(h.smin, c->info.scene_min, sizeof h.smin); memcpy(h.smax, c->info.scene_max, sizeof h.smax);
+    }
+    SceneHeader* dh = nullptr;
+    CU(c, cudaMalloc(&dh, sizeof h));
+    if (c->rank == 0) CU(c, cudaMemcpyAsync(dh, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+    NC(c, ncclBroadcast(dh, dh, sizeof h, ncclUint8, 0, c->comm, c->stream));
+    CU(c, cudaMemcpyAsync(&h, dh, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(dh);
+    if (c->rank != 0) {
+        free_scene(c);
+        c->num_tris = h.num_tris; c->num_nodes = h.num_nodes; c->num_materials = (int)h.num_materials; c->has_bvh = h.has_bvh != 0;
+        if (c->num_nodes) CU(c, cudaMalloc(&c->nodes, sizeof(BvhNode) * (size_t)c->num_nodes));
+        CU(c, cudaMalloc(&c->geom, sizeof(TriBlock) * (size_t)c->num_tris));
+        CU(c, cudaMalloc(&c->shade, sizeof(TriBlock) * (size_t)c->num_tris));
+        if (c->num_materials) CU(c, cudaMalloc(&c->materials, sizeof(rt_material) * (size_t)c->num_materials));
+        memset(&c->info, 0, sizeof c->info);
+        c->info.num_triangles = h.num_tris; c->info.num_nodes = h.num_nodes;
+        memcpy(c->info.scene_min, h.smin, sizeof h.smin); memcpy(c->info.scene_max, h.smax, sizeof h.smax);
+    }
+    NC(c, ncclGroupStart());
+    if (c->num_nodes) NC(c, ncclBroadcast(c->nodes, c->nodes, sizeof(BvhNode) * (size_t)c->num_nodes, ncclUint8, 0, c->comm, c->stream));
+    NC(c, ncclBroadcast(c->geom, c->geom, sizeof(TriBlock) * (size_t)c->num_tris, ncclUint8, 0, c->comm, c->stream));
+    NC(c, ncclBroadcast(c->shade, c->shade, sizeof(TriBlock) * (size_t)c->num_tris, ncclUint8, 0, c->comm, c->stream));
+    if (c->num_materials) NC(c, ncclBroadcast(c->materials, c->materials, sizeof(rt_material) * (size_t)c->num_materials, ncclUint8, 0, c->comm, c->stream));
+    NC(c, ncclGroupEnd());
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->has_scene = true;
+    c->info.arena_bytes = sizeof(BvhNode) * (uint64_t)c->num_nodes + 2 * sizeof(TriBlock) * (uint64_t)c->num_tris +
+                          sizeof(rt_material) * (uint64_t)c->num_materials;
+    return RT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int rt_api_version(void) { return RT_API_VERSION; }
+
+const char* rt_last_error(const rt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int rt_create(rt_ctx** out, int device) {
+    if (!out) return fail(nullptr, RT_ERR_ARG, "rt_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    CU(nullptr, cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(nullptr, RT_ERR_ARG, "rt_create: device %d out of range (%d visible)", device, count);
+    CU(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(nullptr, RT_ERR_CUDA, "rt_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    rt_ctx* c = new (std::nothrow) rt_ctx;
+    if (!c) return fail(nullptr, RT_ERR_NOMEM, "rt_create: out of host memory");
+    c->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = c->counters.reserve(4 * sizeof(unsigned long long));
+    if (e != cudaSuccess) { int r = fail(nullptr, RT_ERR_CUDA, "rt_create: %s", cudaGetErrorString(e)); delete c; return r; }
+    *out = c;
+    return RT_OK;
+}
+
+int rt_destroy(rt_ctx* c) {
+    if (!c) return RT_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm) ncclCommDestroy(c->comm);
+    free_scene(c);
+    Plane* planes[] = {&c->lights, &c->jitter, &c->counters, &c->loc_rgb, &c->loc_rgb8, &c->loc_id, &c->loc_t,
+                       &c->img_rgb, &c->img_rgb8, &c->img_id, &c->img_t, &c->stage_rgb, &c->stage_rgb8, &c->stage_id, &c->stage_t};
+    for (Plane* p : planes) p->release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return RT_OK;
+}
+
+int rt_comm_unique_id(void* id128) {
+    if (!id128) return fail(nullptr, RT_ERR_ARG, "rt_comm_unique_id: NULL");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NC(nullptr, ncclGetUniqueId(&id));
+    memcpy(id128, &id, sizeof id);
+    return RT_OK;
+}
+
+int rt_comm_init(rt_ctx* c, int rank, int world, const void* id128) {
+    if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(c, RT_ERR_ARG, "rt_comm_init: bad arguments");
+    CU(c, cudaSetDevice(c->device));
+    if (c->comm) { ncclCommDestroy(c->comm); c->comm = nullptr; }
+    c->rank = rank; c->world = world;
+    if (world > 1) {
+        ncclUniqueId id;
+        memcpy(&id, id128, sizeof id);
+        NC(c, ncclCommInitRank(&c->comm, world, id, rank));
+    }
+    c->frame_valid = false;
+    return RT_OK;
+}
+
+int rt_comm_rank(const rt_ctx* c, int* rank, int* world) {
+    if (!c) return fail(nullptr, RT_ERR_ARG, "rt_comm_rank: NULL ctx");
+    if (rank) *rank = c->rank;
+    if (world) *world = c->world;
+    return RT_OK;
+}
+
+int rt_upload_scene(rt_ctx* c, const rt_scene* sc) {
+    if (!c) return fail(nullptr, RT_ERR_ARG, "rt_upload_scene: NULL ctx");
+    CU(c, cudaSetDevice(c->device));
+    c->frame_valid = false;
+    if (!sc) {
+        if (c->world > 1 && c->rank != 0) return broadcast_scene(c);
+        return fail(c, RT_ERR_ARG, "rt_upload_scene: scene is NULL (only ranks != 0 of a multi-GPU context may receive)");
+    }
+    if (c->world > 1 && c->rank != 0) return broadcast_scene(c);   // rank 0's scene wins
+    if (!sc->positions || !sc->indices || sc->num_triangles == 0 || sc->num_vertices == 0)
+        return fail(c, RT_ERR_ARG, "rt_upload_scene: empty mesh (positions/indices NULL or zero counts)");
+    if (sc->num_triangles >= (1ull << 28)) return fail(c, RT_ERR_ARG, "rt_upload_scene: more than 2^28 triangles");
+    if (sc->num_materials < 0 || (sc->num_materials > 0 && !sc->materials)) return fail(c, RT_ERR_ARG, "rt_upload_scene: materials");
+    for (uint64_t i = 0; i < 3 * sc->num_triangles; ++i)
+        if (sc->indices[i] >= sc->num_vertices) return fail(c, RT_ERR_ARG, "rt_upload_scene: index %llu out of range", (unsigned long long)i);
+    free_scene(c);
+
+    const size_t nv = (size_t)sc->num_vertices, nt = (size_t)sc->num_triangles;
+    float *d_pos = nullptr, *d_nrm = nullptr; uint32_t* d_idx = nullptr; int32_t* d_obj = nullptr;
+    cudaEvent_t e0, e1, e2;
+    CU(c, cudaEventCreate(&e0)); CU(c, cudaEventCreate(&e1)); CU(c, cudaEventCreate(&e2));
+    int rc = RT_OK;
+    auto cleanup = [&]() {
+        if (d_pos) cudaFree(d_pos); if (d_nrm) cudaFree(d_nrm); if (d_idx) cudaFree(d_idx); if (d_obj) cudaFree(d_obj);
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    };
+#define CUS(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = fail(c, RT_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); cleanup(); free_scene(c); return rc; } } while (0)
+    CUS(cudaMalloc(&d_pos, sizeof(float) * 3 * nv));
+    CUS(cudaMalloc(&d_idx, sizeof(uint32_t) * 3 * nt));
+    if (sc->normals) CUS(cudaMalloc(&d_nrm, sizeof(float) * 3 * nv));
+    if (sc->tri_obj_ids) CUS(cudaMalloc(&d_obj, sizeof(int32_t) * nt));
+    CUS(cudaMalloc(&c->geom, sizeof(TriBlock) * nt));
+    CUS(cudaMalloc(&c->shade, sizeof(TriBlock) * nt));
+    if (sc->num_materials) CUS(cudaMalloc(&c->materials, sizeof(rt_material) * (size_t)sc->num_materials));
+    CUS(cudaEventRecord(e0, c->stream));
+    CUS(cudaMemcpyAsync(d_pos, sc->positions, sizeof(float) * 3 * nv, cudaMemcpyHostToDevice, c->stream));
+    CUS(cudaMemcpyAsync(d_idx, sc->indices, sizeof(uint32_t) * 3 * nt, cudaMemcpyHostToDevice, c->stream));
+    if (d_nrm) CUS(cudaMemcpyAsync(d_nrm, sc->normals, sizeof(float) * 3 * nv, cudaMemcpyHostToDevice, c->stream));
+    if (d_obj) CUS(cudaMemcpyAsync(d_obj, sc->tri_obj_ids, sizeof(int32_t) * nt, cudaMemcpyHostToDevice, c->stream));
+    if (sc->num_materials) CUS(cudaMemcpyAsync(c->materials, sc->materials, sizeof(rt_material) * (size_t)sc->num_materials, cudaMemcpyHostToDevice, c->stream));
+    CUS(cudaEventRecord(e1, c->stream));
+
+    BuildParams bp{};
+    bp.positions = d_pos; bp.normals = d_nrm; bp.indices = d_idx; bp.obj_ids = d_obj;
+    bp.num_tris = (uint32_t)nt;
+    uint32_t leaf_max = (sc->build_flags >> 8) & 0xFu;     // bits 8..11: leaf size override (0 = default)
+    bp.leaf_max = leaf_max ? leaf_max : 4u;
+    BuildResult br{};
+    memset(&c->info, 0, sizeof c->info);
+    if (sc->build_flags & RT_BUILD_NO_BVH) {
+        CUS(rt_pack_triangles(bp, c->geom, c->shade, c->stream));
+        c->has_bvh = false; c->num_nodes = 0;
+    } else {
+        CUS(rt_build_bvh(bp, &c->nodes, c->geom, c->shade, &br, c->stream));
+        c->has_bvh = true; c->num_nodes = br.num_nodes;
+        memcpy(c->info.scene_min, br.scene_min, sizeof br.scene_min);
+        memcpy(c->info.scene_max, br.scene_max, sizeof br.scene_max);
+    }
+    CUS(cudaEventRecord(e2, c->stream));
+    CUS(cudaStreamSynchronize(c->stream));
+    float up_ms = 0.f, b_ms = 0.f;
+    cudaEventElapsedTime(&up_ms, e0, e1);
+    cudaEventElapsedTime(&b_ms, e1, e2);
+    cleanup();
+#undef CUS
+    c->num_tris = (uint32_t)nt; c->num_materials = sc->num_materials; c->has_scene = true;
+    c->info.num_triangles = nt; c->info.num_nodes = c->num_nodes; c->info.build_ms = b_ms; c->info.upload_ms = up_ms;
+    c->info.arena_bytes = sizeof(BvhNode) * (uint64_t)c->num_nodes + 2 * sizeof(TriBlock) * (uint64_t)nt +
+                          sizeof(rt_material) * (uint64_t)sc->num_materials;
+    if (c->world > 1) return broadcast_scene(c);
+    return RT_OK;
+}
+
+int rt_build_info_get(const rt_ctx* c, rt_build_info* info) {
+    if (!c || !info) return fail(nullptr, RT_ERR_ARG, "rt_build_info_get: NULL");
+    if (!c->has_scene) return fail(const_cast<rt_ctx*>(c), RT_ERR_STATE, "rt_build_info_get: no scene uploaded");
+    *info = c->info;
+    return RT_OK;
+}
+
+int rt_render(rt_ctx* c, const rt_frame* fr) {
+    if (!c || !fr) return fail(c, RT_ERR_ARG, "rt_render: NULL argument");
+    CU(c, cudaSetDevice(c->device));
+    if (!c->has_scene) return fail(c, RT_ERR_STATE, "rt_render: no scene uploaded");
+    if (fr->width < 1 || fr->height < 1) return fail(c, RT_ERR_ARG, "rt_render: pixel_width/pixel_height must be >= 1");
+    if ((uint64_t)fr->width * (uint64_t)fr->height > (1ull << 31)) return fail(c, RT_ERR_ARG, "rt_render: image too large");
+    if (fr->spp < 1) return fail(c, RT_ERR_ARG, "rt_render: spp must be >= 1");
+    if (fr->mode != RT_MODE_HW1 && fr->mode != RT_MODE_HW2_BVH) return fail(c, RT_ERR_ARG, "rt_render: unsupported mode %d", fr->mode);
+    if (fr->accel != RT_ACCEL_BRUTE && fr->accel != RT_ACCEL_BVH) return fail(c, RT_ERR_ARG, "rt_render: unsupported accel %d", fr->accel);
+    if (fr->accel == RT_ACCEL_BVH && !c->has_bvh) return fail(c, RT_ERR_STATE, "rt_render: scene was uploaded with RT_BUILD_NO_BVH");
+    if (fr->num_lights < 0 || (fr->num_lights > 0 && !fr->lights)) return fail(c, RT_ERR_ARG, "rt_render: lights");
+    if (fr->mode == RT_MODE_HW1 && fr->num_lights < 1) return fail(c, RT_ERR_ARG, "rt_render: HW1 mode needs one light");
+    if (fr->quantiser < RT_QUANT_PPM_LROUND || fr->quantiser > RT_QUANT_HW2_TRUNC) return fail(c, RT_ERR_ARG, "rt_render: quantiser");
+    const uint32_t outputs = fr->outputs ? fr->outputs : RT_OUT_RGB_F32;
+
+    FrameParams& P = c->fp;
+    memset(&P, 0, sizeof P);
+    P.cam = fr->cam; P.mode = fr->mode; P.accel = fr->accel; P.W = fr->width; P.H = fr->height; P.spp = fr->spp;
+    P.max_depth = fr->max_depth; P.shadows = fr->shadows; P.quantiser = fr->quantiser; P.num_lights = fr->num_lights;
+    P.num_materials = c->num_materials;
+    memcpy(P.miss, fr->miss_color, sizeof P.miss);
+    P.nodes = c->nodes; P.geom = c->geom; P.shade = c->shade; P.num_tris = c->num_tris; P.materials = c->materials;
+    P.tiles_x = (P.W + RT_TILE_W - 1) / RT_TILE_W; P.tiles_y = (P.H + RT_TILE_H - 1) / RT_TILE_H;
+    P.rank = c->rank; P.world = c->world;
+    const int total_tiles = P.tiles_x * P.tiles_y;
+    P.local_tiles = tiles_of_rank(total_tiles, c->rank, c->world);
+
+    if (fr->num_lights) {
+        CU(c, c->lights.reserve(sizeof(rt_light) * (size_t)fr->num_lights));
+        CU(c, cudaMemcpyAsync(c->lights.p, fr->lights, sizeof(rt_light) * (size_t)fr->num_lights, cudaMemcpyHostToDevice, c->stream));
+    }
+    P.lights = (const rt_light*)c->lights.p;
+    if (fr->jitter) {
+        CU(c, c->jitter.reserve(sizeof(float) * 2 * (size_t)fr->spp));
+        CU(c, cudaMemcpyAsync(c->jitter.p, fr->jitter, sizeof(float) * 2 * (size_t)fr->spp, cudaMemcpyHostToDevice, c->stream));
+        P.jitter = (const float*)c->jitter.p;
+    }
+    const size_t npix_full = (size_t)P.W * P.H;
+    const size_t npix_loc = c->world == 1 ? npix_full : (size_t)P.local_tiles * RT_BLOCK_THREADS;
+    if (outputs & RT_OUT_RGB_F32) { CU(c, c->loc_rgb.reserve(12 * npix_loc + 16)); P.rgb = (float*)c->loc_rgb.p; }
+    if (outputs & RT_OUT_RGB8) { CU(c, c->loc_rgb8.reserve(3 * npix_loc + 16)); P.rgb8 = (uint8_t*)c->loc_rgb8.p; }
+    if (outputs & RT_OUT_TRI_ID) { CU(c, c->loc_id.reserve(4 * npix_loc + 16)); P.tri_id = (int32_t*)c->loc_id.p; }
+    if (outputs & RT_OUT_T) { CU(c, c->loc_t.reserve(4 * npix_loc + 16)); P.t = (float*)c->loc_t.p; }
+    P.counters = (unsigned long long*)c->counters.p;
+    CU(c, cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(unsigned long long), c->stream));
+
+    CU(c, cudaEventRecord(c->ev0, c->stream));
+    int launches = 0;
+    CU(c, rt_launch_render(P, fr->kernel_variant, c->stream, &launches));
+
+    if (c->world > 1) {
+        // Tile gather to rank 0: one grouped send/recv per requested plane, then an unpack kernel per source rank.
+        const size_t other_pix = ((size_t)total_tiles - (size_t)tiles_of_rank(total_tiles, 0, c->world)) * RT_BLOCK_THREADS;
+        if (c->rank == 0) {
+            if (outputs & RT_OUT_RGB_F32) { CU(c, c->img_rgb.reserve(12 * npix_full)); CU(c, c->stage_rgb.reserve(12 * other_pix + 16)); }
+            if (outputs & RT_OUT_RGB8) { CU(c, c->img_rgb8.reserve(3 * npix_full)); CU(c, c->stage_rgb8.reserve(3 * other_pix + 16)); }
+            if (outputs & RT_OUT_TRI_ID) { CU(c, c->img_id.reserve(4 * npix_full)); CU(c, c->stage_id.reserve(4 * other_pix + 16)); }
+            if (outputs & RT_OUT_T) { CU(c, c->img_t.reserve(4 * npix_full)); CU(c, c->stage_t.reserve(4 * other_pix + 16)); }
+        }
+        struct PlaneIo { uint32_t bit; size_t bpp; Plane* loc; Plane* stage; };
+        PlaneIo io[4] = {{RT_OUT_RGB_F32, 12, &c->loc_rgb, &c->stage_rgb}, {RT_OUT_RGB8, 3, &c->loc_rgb8, &c->stage_rgb8},
+                         {RT_OUT_TRI_ID, 4, &c->loc_id, &c->stage_id}, {RT_OUT_T, 4, &c->loc_t, &c->stage_t}};
+        NC(c, ncclGroupStart());
+        for (const PlaneIo& q : io) {
+            if (!(outputs & q.bit)) continue;
+            if (c->rank == 0) {
+                size_t off = 0;
+                for (int r = 1; r < c->world; ++r) {
+                    size_t bytes = (size_t)tiles_of_rank(total_tiles, r, c->world) * RT_BLOCK_THREADS * q.bpp;
+                    if (bytes) NC(c, ncclRecv((char*)q.stage->p + off, bytes, ncclUint8, r, c->comm, c->stream));
+                    off += bytes;
+                }
+            } else {
+                size_t bytes = npix_loc * q.bpp;
+                if (bytes) NC(c, ncclSend(q.loc->p, bytes, ncclUint8, 0, c->comm, c->stream));
+            }
+        }
+        NC(c, ncclGroupEnd());
+        if (c->rank == 0) {
+            size_t off_pix = 0;
+            for (int r = 0; r < c->world; ++r) {
+                const bool self = r == 0;
+                const float* s_rgb = (outputs & RT_OUT_RGB_F32) ? (self ? (const float*)c->loc_rgb.p : (const float*)((char*)c->stage_rgb.p + 12 * off_pix)) : nullptr;
+                const uint8_t* s_rgb8 = (outputs & RT_OUT_RGB8) ? (self ? (const uint8_t*)c->loc_rgb8.p : (const uint8_t*)c->stage_rgb8.p + 3 * off_pix) : nullptr;
+                const int32_t* s_id = (outputs & RT_OUT_TRI_ID) ? (self ? (const int32_t*)c->loc_id.p : (const int32_t*)c->stage_id.p + off_pix) : nullptr;
+                const float* s_t = (outputs & RT_OUT_T) ? (self ? (const float*)c->loc_t.p : (const float*)c->stage_t.p + off_pix) : nullptr;
+                CU(c, rt_launch_unpack(P, r, s_rgb, s_rgb8, s_id, s_t, (float*)c->img_rgb.p, (uint8_t*)c->img_rgb8.p,
+                                       (int32_t*)c->img_id.p, (float*)c->img_t.p, c->stream));
+                ++launches;
+                if (!self) off_pix += (size_t)tiles_of_rank(total_tiles, r, c->world) * RT_BLOCK_THREADS;
+            }
+        }
+    }
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    c->outputs = outputs;
+    c->launches = launches;
+    c->frame_valid = true;
+    return RT_OK;
+}
+
+int rt_sync(rt_ctx* c, float* gpu_ms) {
+    if (!c) return fail(nullptr, RT_ERR_ARG, "rt_sync: NULL ctx");
+    CU(c, cudaSetDevice(c->device));
+    if (!c->frame_valid) return fail(c, RT_ERR_STATE, "rt_sync: no frame rendered");
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (gpu_ms) CU(c, cudaEventElapsedTime(gpu_ms, c->ev0, c->ev1));
+    return RT_OK;
+}
+
+int rt_frame_stats(rt_ctx* c, uint64_t* node_visits, uint64_t* tri_tests) {
+    if (!c) return fail(nullptr, RT_ERR_ARG, "rt_frame_stats: NULL ctx");
+    CU(c, cudaSetDevice(c->device));
+    if (!c->frame_valid) return fail(c, RT_ERR_STATE, "rt_frame_stats: no frame rendered");
+    unsigned long long cnt[4] = {0, 0, 0, 0};
+    CU(c, cudaMemcpyAsync(cnt, c->counters.p, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (node_visits) *node_visits = cnt[2];
+    if (tri_tests) *tri_tests = cnt[3];
+    return RT_OK;
+}
+
+int rt_download_image(rt_ctx* c, rt_image* img) {
+    if (!c || !img) return fail(c, RT_ERR_ARG, "rt_download_image: NULL argument");
+    CU(c, cudaSetDevice(c->device));
+    if (!c->frame_valid) return fail(c, RT_ERR_STATE, "rt_download_image: no frame rendered");
+    const FrameParams& P = c->fp;
+    const size_t npix = (size_t)P.W * P.H;
+    const bool gathered = c->world > 1;
+    if (!gathered || c->rank == 0) {
+        struct Out { void* host; uint32_t bit; size_t bpp; const Plane* single; const Plane* multi; const char* name; };
+        Out outs[4] = {{img->rgb, RT_OUT_RGB_F32, 12, &c->loc_rgb, &c->img_rgb, "rgb"}, {img->rgb8, RT_OUT_RGB8, 3, &c->loc_rgb8, &c->img_rgb8, "rgb8"},
+                       {img->tri_id, RT_OUT_TRI_ID, 4, &c->loc_id, &c->img_id, "tri_id"}, {img->t, RT_OUT_T, 4, &c->loc_t, &c->img_t, "t"}};
+        for (const Out& o : outs) {
+            if (!o.host) continue;
+            if (!(c->outputs & o.bit)) return fail(c, RT_ERR_STATE, "rt_download_image: plane '%s' was not requested in rt_frame.outputs", o.name);
+            const Plane* src = gathered ? o.multi : o.single;
+            CU(c, cudaMemcpyAsync(o.host, src->p, o.bpp * npix, cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
+    unsigned long long cnt[2] = {0, 0};
+    CU(c, cudaMemcpyAsync(cnt, c->counters.p, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    img->width = P.W; img->height = P.H;
+    img->rays_primary = cnt[0]; img->rays_shadow = cnt[1];
+    float ms = 0.f;
+    CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    img->gpu_ms = ms;
+    return RT_OK;
+}
+
+int rt_debug_download_bvh(rt_ctx* c, void* nodes64, void* tri_blocks48, int32_t* tri_ids) {
+    if (!c) return fail(nullptr, RT_ERR_ARG, "rt_debug_download_bvh: NULL ctx");
+    CU(c, cudaSetDevice(c->device));
+    if (!c->has_scene) return fail(c, RT_ERR_STATE, "rt_debug_download_bvh: no scene uploaded");
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (nodes64 && c->num_nodes) CU(c, cudaMemcpy(nodes64, c->nodes, sizeof(BvhNode) * (size_t)c->num_nodes, cudaMemcpyDeviceToHost));
+    if (tri_blocks48) CU(c, cudaMemcpy(tri_blocks48, c->geom, sizeof(TriBlock) * (size_t)c->num_tris, cudaMemcpyDeviceToHost));
+    if (tri_ids) {
+        std::vector<TriBlock> tmp(c->num_tris);
+        CU(c, cudaMemcpy(tmp.data(), c->geom, sizeof(TriBlock) * (size_t)c->num_tris, cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < c->num_tris; ++i) memcpy(&tri_ids[i], &tmp[i].g[3], 4);
+    }
+    return RT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,239 @@
+// rt_build.cu — device BVH construction: triangle bounds + 63-bit Morton keys, radix sort,
+// Karras-2012 hierarchy, atomic bottom-up refit, subtree collapse into multi-triangle leaves
+// and emission of the flattened 64-byte-node / 48-byte-triangle-block arena.
+//
+// Replaces calculateAABBs + buildBVH + buildTrianglesKernel of the reference
+// (HW2/HW2/GPUandCPU/include/bvh.cu:7-206, bvh.h:131-289, src/main.cu:19-41).  Not a port:
+// the reference keeps a 2P-1 array of 16-byte topology nodes next to a 2P-1 array of AABBs,
+// 30-bit codes (1024^3 cells, saturating at ~1M triangles — SURVEY §7 H5) and one triangle
+// per leaf; this build uses 63-bit codes, collapses subtrees of <= leaf_max triangles into
+// contiguous leaf ranges (Karras ranges are contiguous in sorted order, so no extra
+// permutation is needed), compacts the surviving internal nodes with a prefix sum and writes
+// each node once as a single line holding both children's padded boxes.  Closest-hit results
+// do not depend on the topology (canonical min-t / min-id rule), only speed does.
+#include "rt_kernels.h"
+#include "rt_build_core.h"
+
+#include <cub/cub.cuh>
+
+namespace {
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+
+__device__ __forceinline__ void atomic_min_f(float* a, float v) {
+    if (v >= 0.f) atomicMin(reinterpret_cast<int*>(a), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* a, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(a), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
+}
+
+__global__ void k_init_bounds(Bounds* b) {
+    for (int a = 0; a < 3; ++a) { b->lo[a] = INFINITY; b->hi[a] = -INFINITY; }
+}
+
+// Scene bounds (thrust::reduce of main.cu:264-270): warp shuffle reduction + one float atomic per warp.
+__global__ void k_scene_bounds(BuildParams bp, Bounds* scene) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (i < bp.num_tris) {
+        f3 a, b, c; uint32_t ia, ib, ic;
+        rt_tri_verts(bp, i, a, b, c, ia, ib, ic);
+        rt_tri_box(a, b, c, lo, hi);
+    }
+    for (int o = 16; o > 0; o >>= 1)
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 3; ++k) {
+            if (lo[k] <= hi[k]) { atomic_min_f(&scene->lo[k], lo[k]); atomic_max_f(&scene->hi[k], hi[k]); }
+        }
+}
+
+// Replaces ComputeMortonCodes (bvh.cu:34-55).
+__global__ void k_morton(BuildParams bp, const Bounds* scene, uint64_t* keys, uint32_t* vals) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= bp.num_tris) return;
+    f3 a, b, c; uint32_t ia, ib, ic;
+    rt_tri_verts(bp, i, a, b, c, ia, ib, ic);
+    keys[i] = rt_morton63(a, b, c, *scene);
+    vals[i] = i;
+}
+
+__global__ void k_karras(const uint64_t* __restrict__ keys, int n, Topo* topo, uint32_t* parent) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const Topo tp = rt_karras_node(keys, n, i);
+    topo[i] = tp;
+    parent[tp.left] = (uint32_t)i;
+    parent[tp.right] = (uint32_t)i;
+    if (i == 0) parent[0] = 0xFFFFFFFFu;
+}
+
+// Padded leaf boxes + bottom-up merge: the second thread to reach a node merges its children
+// (replaces the atomicCAS refit of bvh.cu:172-203).
+__global__ void k_refit(BuildParams bp, const uint32_t* __restrict__ vals, int n, const Topo* __restrict__ topo,
+                        const uint32_t* __restrict__ parent, const Bounds* scene, float4* blo, float4* bhi, int* flags) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    f3 a, b, c; uint32_t ia, ib, ic;
+    rt_tri_verts(bp, vals[k], a, b, c, ia, ib, ic);
+    float lo[3], hi[3];
+    rt_padded_leaf_box(a, b, c, *scene, lo, hi);
+    uint32_t node = (uint32_t)(n - 1 + k);
+    blo[node] = make_float4(lo[0], lo[1], lo[2], 0.f);
+    bhi[node] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    if (n == 1) return;
+    __threadfence();
+    uint32_t p = parent[node];
+    while (p != 0xFFFFFFFFu) {
+        if (atomicAdd(&flags[p], 1) == 0) return;      // first arrival: the sibling subtree is not done yet
+        __threadfence();
+        const Topo tp = topo[p];
+        float4 l0 = __ldcg(&blo[tp.left]), h0 = __ldcg(&bhi[tp.left]);
+        float4 l1 = __ldcg(&blo[tp.right]), h1 = __ldcg(&bhi[tp.right]);
+        blo[p] = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.f);
+        bhi[p] = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f);
+        __threadfence();
+        p = parent[p];
+    }
+}
+
+__global__ void k_keep_flags(const Topo* __restrict__ topo, int n, uint32_t leaf_max, uint32_t* keep) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    keep[i] = (topo[i].last - topo[i].first + 1u) > leaf_max ? 1u : 0u;
+}
+
+__global__ void k_emit_nodes(const Topo* __restrict__ topo, int n, const uint32_t* __restrict__ keep,
+                             const uint32_t* __restrict__ newidx, const float4* __restrict__ blo,
+                             const float4* __restrict__ bhi, BvhNode* nodes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1 || !keep[i]) return;
+    const Topo tp = topo[i];
+    const BvhNode nd = rt_make_node(blo[tp.left], bhi[tp.left], blo[tp.right], bhi[tp.right],
+                                    rt_child_ref(tp.left, n, topo, keep, newidx), rt_child_ref(tp.right, n, topo, keep, newidx),
+                                    tp.first, tp.last - tp.first + 1u);
+    float4* dst = reinterpret_cast<float4*>(nodes + newidx[i]);
+    const float4* src = reinterpret_cast<const float4*>(&nd);
+    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+}
+
+// Root for scenes with <= leaf_max triangles: one node, child 0 = everything, child 1 = absent.
+__global__ void k_emit_single(int n, const float4* __restrict__ blo, const float4* __restrict__ bhi, BvhNode* nodes) {
+    if (blockIdx.x || threadIdx.x) return;
+    float4 lo = make_float4(INFINITY, INFINITY, INFINITY, 0.f), hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
+    for (int k = 0; k < n; ++k) {
+        float4 l = blo[n - 1 + k], h = bhi[n - 1 + k];
+        lo.x = fminf(lo.x, l.x); lo.y = fminf(lo.y, l.y); lo.z = fminf(lo.z, l.z);
+        hi.x = fmaxf(hi.x, h.x); hi.y = fmaxf(hi.y, h.y); hi.z = fmaxf(hi.z, h.z);
+    }
+    const float4 elo = make_float4(INFINITY, INFINITY, INFINITY, 0.f), ehi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
+    nodes[0] = rt_make_node(lo, hi, elo, ehi, rt_leaf_ref(0u, (uint32_t)n), rt_leaf_ref(0u, 1u), 0u, (uint32_t)n);
+}
+
+// Triangle blocks in slot order (vals == NULL: identity order).
+__global__ void k_pack_tris(BuildParams bp, const uint32_t* __restrict__ vals, TriBlock* geom, TriBlock* shade) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= bp.num_tris) return;
+    rt_pack_tri(bp, vals ? vals[k] : k, geom + k, shade + k);
+}
+
+inline unsigned blocks_for(size_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+
+} // namespace
+
+cudaError_t rt_pack_triangles(const BuildParams& bp, TriBlock* geom, TriBlock* shade, cudaStream_t stream) {
+    if (bp.num_tris == 0) return cudaSuccess;
+    k_pack_tris<<<blocks_for(bp.num_tris, 256), 256, 0, stream>>>(bp, nullptr, geom, shade);
+    return cudaGetLastError();
+}
+
+cudaError_t rt_build_bvh(const BuildParams& bp, BvhNode** nodes_out, TriBlock* geom, TriBlock* shade,
+                         BuildResult* res, cudaStream_t stream) {
+    const int n = (int)bp.num_tris;
+    if (n <= 0) return cudaErrorInvalidValue;
+    const unsigned T = 256;
+    const uint32_t leaf_max = bp.leaf_max < 1 ? 1 : (bp.leaf_max > 8 ? 8 : bp.leaf_max);
+
+    Bounds* d_scene = nullptr;
+    uint64_t *d_keys = nullptr, *d_keys2 = nullptr;
+    uint32_t *d_vals = nullptr, *d_vals2 = nullptr, *d_parent = nullptr, *d_keep = nullptr, *d_newidx = nullptr;
+    Topo* d_topo = nullptr;
+    float4 *d_blo = nullptr, *d_bhi = nullptr;
+    int* d_flags = nullptr;
+    void* d_tmp = nullptr;
+    size_t tmp_bytes = 0, tmp2 = 0;
+    const size_t nn = 2 * (size_t)n - 1;
+    cudaError_t err = cudaSuccess;
+    BvhNode* nodes = nullptr;
+    uint32_t num_nodes = 0;
+
+#define CKG(x) do { err = (x); if (err != cudaSuccess) goto done; } while (0)
+    CKG(cudaMallocAsync(&d_scene, sizeof(Bounds), stream));
+    CKG(cudaMallocAsync(&d_keys, sizeof(uint64_t) * n, stream));
+    CKG(cudaMallocAsync(&d_keys2, sizeof(uint64_t) * n, stream));
+    CKG(cudaMallocAsync(&d_vals, sizeof(uint32_t) * n, stream));
+    CKG(cudaMallocAsync(&d_vals2, sizeof(uint32_t) * n, stream));
+    CKG(cudaMallocAsync(&d_parent, sizeof(uint32_t) * nn, stream));
+    CKG(cudaMallocAsync(&d_topo, sizeof(Topo) * (size_t)(n > 1 ? n - 1 : 1), stream));
+    CKG(cudaMallocAsync(&d_keep, sizeof(uint32_t) * (size_t)n, stream));
+    CKG(cudaMallocAsync(&d_newidx, sizeof(uint32_t) * (size_t)n, stream));
+    CKG(cudaMallocAsync(&d_blo, sizeof(float4) * nn, stream));
+    CKG(cudaMallocAsync(&d_bhi, sizeof(float4) * nn, stream));
+    CKG(cudaMallocAsync(&d_flags, sizeof(int) * (size_t)n, stream));
+    CKG(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, n, 0, 63, stream));
+    CKG(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, d_keep, d_newidx, n, stream));
+    if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
+    CKG(cudaMallocAsync(&d_tmp, tmp_bytes ? tmp_bytes : 16, stream));
+
+    k_init_bounds<<<1, 1, 0, stream>>>(d_scene);
+    k_scene_bounds<<<blocks_for(n, T), T, 0, stream>>>(bp, d_scene);
+    k_morton<<<blocks_for(n, T), T, 0, stream>>>(bp, d_scene, d_keys, d_vals);
+    CKG(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, n, 0, 63, stream));
+    CKG(cudaMemsetAsync(d_flags, 0, sizeof(int) * (size_t)n, stream));
+    if (n > 1) k_karras<<<blocks_for(n - 1, T), T, 0, stream>>>(d_keys2, n, d_topo, d_parent);
+    k_refit<<<blocks_for(n, T), T, 0, stream>>>(bp, d_vals2, n, d_topo, d_parent, d_scene, d_blo, d_bhi, d_flags);
+    k_pack_tris<<<blocks_for(n, T), T, 0, stream>>>(bp, d_vals2, geom, shade);
+
+    if ((uint32_t)n > leaf_max) {
+        CKG(cudaMemsetAsync(d_keep, 0, sizeof(uint32_t) * (size_t)n, stream));
+        k_keep_flags<<<blocks_for(n - 1, T), T, 0, stream>>>(d_topo, n, leaf_max, d_keep);
+        CKG(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_keep, d_newidx, n, stream));
+        uint32_t last_idx = 0;   // d_keep[n-1] == 0, so newidx[n-1] is the number of kept nodes
+        CKG(cudaMemcpyAsync(&last_idx, d_newidx + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        CKG(cudaStreamSynchronize(stream));
+        num_nodes = last_idx;
+        CKG(cudaMalloc(&nodes, sizeof(BvhNode) * (size_t)num_nodes));
+        k_emit_nodes<<<blocks_for(n - 1, T), T, 0, stream>>>(d_topo, n, d_keep, d_newidx, d_blo, d_bhi, nodes);
+    } else {
+        num_nodes = 1;
+        CKG(cudaMalloc(&nodes, sizeof(BvhNode)));
+        k_emit_single<<<1, 32, 0, stream>>>(n, d_blo, d_bhi, nodes);
+    }
+    CKG(cudaGetLastError());
+    {
+        Bounds hb;
+        CKG(cudaMemcpyAsync(&hb, d_scene, sizeof(Bounds), cudaMemcpyDeviceToHost, stream));
+        CKG(cudaStreamSynchronize(stream));
+        if (res) {
+            res->num_nodes = num_nodes;
+            res->num_leaves = 0;
+            for (int k = 0; k < 3; ++k) { res->scene_min[k] = hb.lo[k]; res->scene_max[k] = hb.hi[k]; }
+        }
+    }
+    *nodes_out = nodes;
+    nodes = nullptr;
+done:
+    if (nodes) cudaFree(nodes);
+    cudaFreeAsync(d_scene, stream); cudaFreeAsync(d_keys, stream); cudaFreeAsync(d_keys2, stream);
+    cudaFreeAsync(d_vals, stream); cudaFreeAsync(d_vals2, stream); cudaFreeAsync(d_parent, stream);
+    cudaFreeAsync(d_topo, stream); cudaFreeAsync(d_keep, stream); cudaFreeAsync(d_newidx, stream);
+    cudaFreeAsync(d_blo, stream); cudaFreeAsync(d_bhi, stream); cudaFreeAsync(d_flags, stream);
+    cudaFreeAsync(d_tmp, stream);
+    return err;
+#undef CKG
+}

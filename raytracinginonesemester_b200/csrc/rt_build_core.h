@@ -1,0 +1,125 @@
+// rt_build_core.h — per-element steps of the BVH build, host/device compilable: 63-bit
+// Morton keys, Karras-2012 hierarchy emission, leaf padding, subtree collapse, node packing.
+#pragma once
+
+#include "rt_params.h"
+
+struct Bounds { float lo[3]; float hi[3]; };
+// Karras numbering: internal k -> k, leaf k -> (n-1)+k.  [first,last] = sorted-order range.
+struct Topo { uint32_t left, right, first, last; };
+
+RT_HD void rt_tri_verts(const BuildParams& bp, uint32_t i, f3& a, f3& b, f3& c, uint32_t& ia, uint32_t& ib, uint32_t& ic) {
+    ia = RT_LDG(bp.indices + 3 * (size_t)i); ib = RT_LDG(bp.indices + 3 * (size_t)i + 1); ic = RT_LDG(bp.indices + 3 * (size_t)i + 2);
+    a = ld3(bp.positions + 3 * (size_t)ia); b = ld3(bp.positions + 3 * (size_t)ib); c = ld3(bp.positions + 3 * (size_t)ic);
+}
+RT_HD void rt_tri_box(f3 a, f3 b, f3 c, float lo[3], float hi[3]) {
+    lo[0] = fminf(a.x, fminf(b.x, c.x)); lo[1] = fminf(a.y, fminf(b.y, c.y)); lo[2] = fminf(a.z, fminf(b.z, c.z));
+    hi[0] = fmaxf(a.x, fmaxf(b.x, c.x)); hi[1] = fmaxf(a.y, fmaxf(b.y, c.y)); hi[2] = fmaxf(a.z, fmaxf(b.z, c.z));
+}
+
+RT_HD uint64_t rt_expand21(uint64_t v) {
+    v &= 0x1fffffull;
+    v = (v | v << 32) & 0x1f00000000ffffull;
+    v = (v | v << 16) & 0x1f0000ff0000ffull;
+    v = (v | v << 8) & 0x100f00f00f00f00full;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+}
+
+// Morton key of the box centroid, 21 bits per axis (the reference uses 10: bvh.h:142-151).
+RT_HD uint64_t rt_morton63(f3 a, f3 b, f3 c, const Bounds& scene) {
+    float lo[3], hi[3];
+    rt_tri_box(a, b, c, lo, hi);
+    const float R = 2097152.0f;
+    uint64_t q[3];
+    for (int k = 0; k < 3; ++k) {
+        const float ce = 0.5f * (lo[k] + hi[k]);
+        const float e = scene.hi[k] - scene.lo[k];
+        const float nrm = e > 0.f ? (ce - scene.lo[k]) / e : 0.f;
+        q[k] = (uint64_t)fminf(fmaxf(nrm * R, 0.f), R - 1.f);
+    }
+    return (rt_expand21(q[0]) << 2) | (rt_expand21(q[1]) << 1) | rt_expand21(q[2]);
+}
+
+// Common-prefix length with index tie-break (Karras 2012, section 4).
+RT_HD int rt_delta(const uint64_t* __restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const uint64_t a = keys[i], b = keys[j];
+    if (a == b) return 64 + RT_CLZ32((uint32_t)(i ^ j));
+    return RT_CLZ64(a ^ b);
+}
+
+// Internal node i of the radix tree over n sorted keys (replaces determine_range + find_split,
+// GPUandCPU/include/bvh.h:163-257).
+RT_HD Topo rt_karras_node(const uint64_t* __restrict__ keys, int n, int i) {
+    int d = (rt_delta(keys, n, i, i + 1) - rt_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    if (i == 0) d = 1;
+    const int dmin = rt_delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (rt_delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (rt_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = rt_delta(keys, n, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (rt_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + (d < 0 ? d : 0);
+    const int first = i < j ? i : j, last = i < j ? j : i;
+    Topo tp;
+    tp.left = (first == gamma) ? (uint32_t)(n - 1 + gamma) : (uint32_t)gamma;
+    tp.right = (last == gamma + 1) ? (uint32_t)(n - 1 + gamma + 1) : (uint32_t)(gamma + 1);
+    tp.first = (uint32_t)first; tp.last = (uint32_t)last;
+    return tp;
+}
+
+// Leaf box, padded outward by 2^-18 of the local/scene scale so the fp32 slab test stays a
+// superset of what the fp32 Möller–Trumbore test accepts (rt_core.h, rt_slab).
+RT_HD void rt_padded_leaf_box(f3 a, f3 b, f3 c, const Bounds& scene, float lo[3], float hi[3]) {
+    rt_tri_box(a, b, c, lo, hi);
+    const float ext = fmaxf(scene.hi[0] - scene.lo[0], fmaxf(scene.hi[1] - scene.lo[1], scene.hi[2] - scene.lo[2]));
+    for (int q = 0; q < 3; ++q) {
+        const float pad = fmaxf(ext, fmaxf(fabsf(lo[q]), fabsf(hi[q]))) * 3.8146973e-06f + 1e-30f;
+        lo[q] -= pad; hi[q] += pad;
+    }
+}
+
+RT_HD int32_t rt_child_ref(uint32_t c, int n, const Topo* __restrict__ topo, const uint32_t* __restrict__ keep,
+                           const uint32_t* __restrict__ newidx) {
+    if (c >= (uint32_t)(n - 1)) return rt_leaf_ref(c - (uint32_t)(n - 1), 1u);     // original leaf
+    if (keep[c]) return (int32_t)newidx[c];
+    return rt_leaf_ref(topo[c].first, topo[c].last - topo[c].first + 1u);          // collapsed subtree
+}
+
+RT_HD BvhNode rt_make_node(float4 l0, float4 h0, float4 l1, float4 h1, int32_t r0, int32_t r1, uint32_t first, uint32_t count) {
+    BvhNode nd;
+    nd.q[0] = l0.x; nd.q[1] = l0.y; nd.q[2] = l0.z; nd.q[3] = h0.x; nd.q[4] = h0.y; nd.q[5] = h0.z;
+    nd.q[6] = l1.x; nd.q[7] = l1.y; nd.q[8] = l1.z; nd.q[9] = h1.x; nd.q[10] = h1.y; nd.q[11] = h1.z;
+    nd.ref0 = r0; nd.ref1 = r1; nd.first_slot = first; nd.slot_count = count;
+    return nd;
+}
+
+// Triangle blocks of slot k (triangle `tri`).  e1/e2 are the same rounded differences the
+// reference forms inside every test (query.h:80-81, HW1 ray.h:72-73).
+RT_HD void rt_pack_tri(const BuildParams& bp, uint32_t tri, TriBlock* geom_k, TriBlock* shade_k) {
+    f3 a, b, c; uint32_t ia, ib, ic;
+    rt_tri_verts(bp, tri, a, b, c, ia, ib, ic);
+    const f3 e1 = xsub3(b, a), e2 = xsub3(c, a);
+    float4* g = reinterpret_cast<float4*>(geom_k);
+    g[0] = make_float4(a.x, a.y, a.z, RT_I2F((int)tri));
+    g[1] = make_float4(e1.x, e1.y, e1.z, 0.f);
+    g[2] = make_float4(e2.x, e2.y, e2.z, 0.f);
+    f3 n0 = mk3(0.f, 0.f, 0.f), n1 = n0, n2 = n0;
+    if (bp.normals) {
+        n0 = ld3(bp.normals + 3 * (size_t)ia); n1 = ld3(bp.normals + 3 * (size_t)ib); n2 = ld3(bp.normals + 3 * (size_t)ic);
+    }
+    const int obj = bp.obj_ids ? bp.obj_ids[tri] : -1;
+    float4* s = reinterpret_cast<float4*>(shade_k);
+    s[0] = make_float4(n0.x, n0.y, n0.z, RT_I2F(obj));
+    s[1] = make_float4(n1.x, n1.y, n1.z, 0.f);
+    s[2] = make_float4(n2.x, n2.y, n2.z, 0.f);
+}

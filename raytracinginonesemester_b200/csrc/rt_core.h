@@ -1,0 +1,200 @@
+// rt_core.h — data layout in HBM and the per-ray device functions (ray generation,
+// Möller–Trumbore under the three reference contracts, slab test, shading, quantisers).
+// Host-compilable (RT_HD) so the same code can be exercised by tests without a GPU;
+// kernels live in rt_trace.cu / rt_build.cu.
+#pragma once
+
+#include <float.h>
+#include "rt_math.h"
+#include "../../include/rt_api.h"
+
+// ----------------------------------------------------------------- layout ----
+// One BVH2 node = one 64-byte line: both children's boxes + both child references, so a
+// node visit is four 16-byte loads from a single aligned line (ld.global.nc.v4).
+//   q0 = (lo0.x, lo0.y, lo0.z, hi0.x)   q1 = (hi0.y, hi0.z, lo1.x, lo1.y)
+//   q2 = (lo1.z, hi1.x, hi1.y, hi1.z)   q3 = (ref0, ref1, first_slot, slot_count) as ints
+// Child reference: >= 0 -> index of another node; < 0 -> leaf, ~ref = (first_slot << 3) | (count-1).
+// An absent child has an inverted box (+inf/-inf) that no ray can hit.
+struct alignas(64) BvhNode {
+    float q[12];
+    int32_t ref0, ref1;
+    uint32_t first_slot, slot_count;   // triangle slots spanned by this subtree (debug / stats)
+};
+static_assert(sizeof(BvhNode) == 64, "BvhNode must be one 64-byte line");
+
+#define RT_LEAF_MAX_LOG2 3
+RT_HD int32_t rt_leaf_ref(uint32_t first, uint32_t count) { return ~(int32_t)((first << RT_LEAF_MAX_LOG2) | (count - 1u)); }
+RT_HD uint32_t rt_leaf_first(int32_t ref) { return ((uint32_t)~ref) >> RT_LEAF_MAX_LOG2; }
+RT_HD uint32_t rt_leaf_count(int32_t ref) { return (((uint32_t)~ref) & ((1u << RT_LEAF_MAX_LOG2) - 1u)) + 1u; }
+
+// Triangle "geometry block", 48 bytes, stored in BVH leaf order (slot index):
+//   g0 = (v0.x, v0.y, v0.z, bits(original triangle id))
+//   g1 = (e1.x, e1.y, e1.z, 0)   e1 = fl(v1 - v0)   (the reference recomputes the same
+//   g2 = (e2.x, e2.y, e2.z, 0)   e2 = fl(v2 - v0)    rounded differences per test)
+// Triangle "shading block", 48 bytes, same slot: (n0, bits(object id)), (n1, 0), (n2, 0).
+struct alignas(16) TriBlock { float g[12]; };
+static_assert(sizeof(TriBlock) == 48, "TriBlock must be 48 bytes");
+
+struct Ray { f3 o, d; };
+
+struct Hit {
+    float t, u, v;
+    int32_t slot;     // leaf-order slot of the closest triangle, -1 = miss
+    int32_t id;       // original triangle id
+};
+
+// -------------------------------------------------------- ray generation ----
+// HW2: Camera::get_ray(float,float), GPUandCPU/include/camera.h:49-53.
+// HW1: get_pixel_position(int,int) + Ray ctor, HW1/include/camera.h:33-35, ray.h:25 — the
+//      float pixel coordinate is truncated to int by overload resolution (quirk Q1).
+RT_HD Ray rt_make_ray(const rt_camera& cam, int mode, int x, int y, float jx, float jy) {
+    float px = XADD((float)x, jx), py = XADD((float)y, jy);
+    f3 c = ld3(cam.center), p00 = ld3(cam.pixel00_loc), du = ld3(cam.pixel_delta_u), dv = ld3(cam.pixel_delta_v);
+    Ray r; r.o = c;
+    if (mode == RT_MODE_HW1) {
+        px = (float)(int)px; py = (float)(int)py;
+        f3 pp = xadd3(xadd3(p00, xmuls(du, px)), xmuls(dv, py));
+        r.d = xunit(xsub3(pp, c));
+    } else {
+        f3 pp = xadd3(xadd3(p00, xmuls(du, px)), xmuls(dv, py));
+        r.d = xunit_cam(xsub3(pp, c));
+    }
+    return r;
+}
+
+// ------------------------------------------------------- Möller–Trumbore ----
+// One routine, three contracts (SURVEY §8a "mode parameters"):
+//   HW1      HW1/include/ray.h:67-117           |det| < FLT_EPSILON rejects, t >= 0
+//   HW2_BVH  GPUandCPU/include/query.h:72-132    |det| < 1e-8 rejects, tmin <= t <= tmax
+//   HW2_CPU  CPUOnly/include/ray.h:48-97         as HW1 (1.0f/det)
+// Operation order and rounding are the reference's; e1/e2 come pre-rounded from the block.
+// Returns true when the triangle test accepts; the caller applies the closest-hit rule.
+RT_HD bool rt_moller_trumbore(const Ray& r, f3 v0, f3 e1, f3 e2, float det_eps, float tmin, float tmax,
+                              float& t_out, float& u_out, float& v_out) {
+    f3 pvec = xcross(r.d, e2);
+    float det = xdot(e1, pvec);
+    if (fabsf(det) < det_eps) return false;
+    float invDet = XDIV(1.0f, det);
+    f3 tvec = xsub3(r.o, v0);
+    float u = XMUL(xdot(tvec, pvec), invDet);
+    if (u < 0.0f || u > 1.0f) return false;
+    f3 qvec = xcross(tvec, e1);
+    float v = XMUL(xdot(r.d, qvec), invDet);
+    if (v < 0.0f || XADD(u, v) > 1.0f) return false;
+    float t = XMUL(xdot(e2, qvec), invDet);
+    if (t < tmin || t > tmax) return false;
+    t_out = t; u_out = u; v_out = v;
+    return true;
+}
+
+RT_HD float rt_det_eps(int mode) { return mode == RT_MODE_HW2_BVH ? 1e-8f : FLT_EPSILON; }
+RT_HD float rt_tmin(int mode) { return mode == RT_MODE_HW1 ? 0.0f : 1e-4f; }
+
+// ------------------------------------------------------------- slab test ----
+// Conservative fp32 slab test.  The reference tests boxes in fp64 (GPUandCPU/include/bvh.h:81-129);
+// ours only has to accept a superset: boxes are padded outward at build time
+// and the far bound is widened by a few ulps here, so every triangle the fp32 Möller–Trumbore
+// test would accept is reached.  A zero direction component gives +-inf / NaN plane distances;
+// fminf/fmaxf drop NaNs, which reproduces the reference's origin-in-slab branch (bvh.h:90-91).
+struct RayInv { f3 o, inv; };
+RT_HD RayInv rt_ray_inv(const Ray& r) {
+    RayInv k; k.o = r.o;
+    k.inv = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+    return k;
+}
+RT_HD bool rt_slab(const RayInv& k, float lox, float loy, float loz, float hix, float hiy, float hiz,
+                   float tmin, float tmax, float& tnear) {
+    float ax = (lox - k.o.x) * k.inv.x, bx = (hix - k.o.x) * k.inv.x;
+    float ay = (loy - k.o.y) * k.inv.y, by = (hiy - k.o.y) * k.inv.y;
+    float az = (loz - k.o.z) * k.inv.z, bz = (hiz - k.o.z) * k.inv.z;
+    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
+    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+    tnear = tn;
+    return tn <= tf * 1.0000005f + 1e-30f;
+}
+
+// ---------------------------------------------------------------- shading ----
+// shade(), HW1/include/raytracer.h:21-48, constant METAL material of HW1/include/ray.h:111-114.
+RT_HD f3 rt_shade_hw1_miss(const Ray& r) {
+    f3 ud = xunit(r.d);
+    float t = XMUL(0.5f, XADD(ud.z, 1.0f));
+    return xadd3(xmuls(mk3(1.0f, 1.0f, 1.0f), XSUB(1.0f, t)), xmuls(mk3(0.5f, 0.7f, 1.0f), t));
+}
+RT_HD f3 rt_shade_hw1_hit(const Ray& r, f3 p, f3 normal, const rt_light& light) {
+    const f3 albedo = mk3(0.8f, 0.2f, 0.2f);
+    f3 lpos = ld3(light.position), lcol = ld3(light.color);
+    f3 ambient = xmuls(albedo, 0.1f);
+    f3 lightDir = xunit(xsub3(lpos, p));
+    float diff = fmaxf(xdot(normal, lightDir), 0.0f);
+    f3 diffuse = xmuls(xmulv(albedo, lcol), diff);
+    f3 viewDir = xunit(xsub3(r.o, p));
+    f3 halfDir = xunit(xadd3(lightDir, viewDir));
+    float spec = XPOW(fmaxf(xdot(normal, halfDir), 0.0f), 64.0f);
+    f3 specular = xmuls(lcol, spec);
+    f3 c = xadd3(xadd3(ambient, diffuse), specular);
+    if (c.x > 1.0f) c.x = 1.0f;
+    if (c.y > 1.0f) c.y = 1.0f;
+    if (c.z > 1.0f) c.z = 1.0f;
+    return c;
+}
+
+// Hit attributes of intersectTriangle, GPUandCPU/include/query.h:110-129.
+RT_HD void rt_hit_frame_hw2(const Ray& r, f3 e1, f3 e2, f3 n0, f3 n1, f3 n2, float t, float u, float v,
+                            f3& p, f3& normal) {
+    p = xadd3(r.o, xmuls(r.d, t));
+    f3 geomN = xunit(xcross(e1, e2));
+    bool front = xdot(r.d, geomN) < 0.0f;
+    if (!front) geomN = xneg3(geomN);
+    f3 sn = xadd3(xadd3(xmuls(n0, XSUB(XSUB(1.0f, u), v)), xmuls(n1, u)), xmuls(n2, v));
+    if (xdot(sn, sn) < 1e-12f) {
+        sn = geomN;
+    } else {
+        sn = xunit(sn);
+        if (xdot(sn, geomN) < 0.0f) sn = xneg3(sn);
+    }
+    normal = sn;
+}
+
+// EvaluateBRDF, GPUandCPU/include/brdf.h:12-39.
+RT_HD f3 rt_brdf_hw2(const rt_material& m, f3 N, f3 V, f3 L) {
+    float NdotL = fmaxf(xdot(N, L), 0.0f);
+    float NdotV = fmaxf(xdot(N, V), 0.0f);
+    if (NdotL <= 0.f || NdotV <= 0.f) return mk3(0.f, 0.f, 0.f);
+    const float invPi = 0.31830988618f;
+    f3 fd = xmuls(ld3(m.albedo), XMUL(m.kd, invPi));
+    f3 H = xunit(xadd3(L, V));
+    float NdotH = fmaxf(xdot(N, H), 0.0f);
+    const float inv2Pi = 0.15915494309f;
+    float specNorm = XMUL(XADD(m.shininess, 2.0f), inv2Pi);
+    float specLobe = XMUL(specNorm, XPOW(NdotH, m.shininess));
+    f3 fs = xmuls(xmuls(ld3(m.specular_color), m.ks), specLobe);
+    return xadd3(fd, fs);
+}
+
+RT_HD f3 rt_clamp01(f3 c) {   // clamp(), GPUandCPU/include/shader.h:24-32
+    if (c.x > 1.0f) c.x = 1.0f; if (c.y > 1.0f) c.y = 1.0f; if (c.z > 1.0f) c.z = 1.0f;
+    if (c.x < 0.0f) c.x = 0.0f; if (c.y < 0.0f) c.y = 0.0f; if (c.z < 0.0f) c.z = 0.0f;
+    return c;
+}
+
+RT_HD rt_material rt_default_material() {   // Material(), GPUandCPU/include/material.h:6-20
+    rt_material m;
+    m.albedo[0] = m.albedo[1] = m.albedo[2] = 0.8f; m.kd = 1.0f;
+    m.specular_color[0] = m.specular_color[1] = m.specular_color[2] = 0.04f; m.ks = 0.0f;
+    m.shininess = 32.0f; m.kr = 0.0f; m.emission[0] = m.emission[1] = m.emission[2] = 0.0f;
+    return m;
+}
+
+// -------------------------------------------------------------- quantiser ----
+RT_HD uint8_t rt_quantise(float c, int q) {
+    if (q == RT_QUANT_HW1_TRUNC) return (uint8_t)(XMUL(255.99f, c));                 // HW1/src/render.cpp:121-123
+    if (q == RT_QUANT_HW2_TRUNC) return (uint8_t)(XMUL(255.0f, (c < 1.0f ? c : 1.0f))); // GPUandCPU/src/main.cu:428-430
+    double x = (double)c;                                                            // ppm_p6.cpp:137-155
+    if (q == RT_QUANT_PPM_GAMMA2) { if (x < 0.0) x = 0.0; x = sqrt(x); }
+    if (x < 0.0) x = 0.0;
+    if (x > 1.0) x = 1.0;
+    long long r = llround(x * 255.0);   // std::lround: half away from zero
+    if (r < 0) r = 0;
+    if (r > 255) r = 255;
+    return (uint8_t)r;
+}

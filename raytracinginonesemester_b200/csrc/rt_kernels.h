@@ -1,0 +1,22 @@
+// rt_kernels.h — launch interface between the C-ABI host layer (rt_api.cu) and the
+// device code (rt_build.cu, rt_trace.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include "rt_params.h"
+
+// rt_build.cu --------------------------------------------------------------------------
+// Device LBVH build.  On return (stream-ordered) nodes/geom/shade hold the flattened BVH;
+// *num_nodes_out (host) is valid after the call (it synchronises once to size the node array).
+struct BuildResult { uint32_t num_nodes; uint32_t num_leaves; float scene_min[3], scene_max[3]; };
+cudaError_t rt_build_bvh(const BuildParams& bp, BvhNode** nodes_out, TriBlock* geom, TriBlock* shade,
+                         BuildResult* res, cudaStream_t stream);
+// Pack triangles in input order without a BVH (brute-force-only scenes).
+cudaError_t rt_pack_triangles(const BuildParams& bp, TriBlock* geom, TriBlock* shade, cudaStream_t stream);
+
+// rt_trace.cu --------------------------------------------------------------------------
+cudaError_t rt_launch_render(const FrameParams& fp, int kernel_variant, cudaStream_t stream, int* launches);
+// Scatter tile-packed planes of rank `src_rank` into the row-major image (rank 0, world > 1).
+cudaError_t rt_launch_unpack(const FrameParams& fp, int src_rank, const float* rgb, const uint8_t* rgb8,
+                             const int32_t* tri_id, const float* t, float* o_rgb, uint8_t* o_rgb8,
+                             int32_t* o_tri_id, float* o_t, cudaStream_t stream);

@@ -1,0 +1,66 @@
+// rt_params.h — parameter blocks shared by the host layer, the kernels and the host-side
+// emulation used by the CPU tests (no CUDA runtime types here).
+#pragma once
+
+#include "rt_core.h"
+
+// Screen-space tile: the unit of rank ownership (tile k belongs to rank k % world) and of
+// one thread block (4 warps, each an 8x4 pixel sub-tile).
+#define RT_TILE_W 16
+#define RT_TILE_H 8
+#define RT_BLOCK_THREADS (RT_TILE_W * RT_TILE_H)
+#define RT_STACK_DEPTH 32
+
+struct FrameParams {
+    rt_camera cam;
+    int mode, accel, W, H, spp, max_depth, shadows, quantiser, num_lights, num_materials;
+    float miss[3];
+    // scene arena
+    const BvhNode* nodes;
+    const TriBlock* geom;
+    const TriBlock* shade;
+    uint32_t num_tris;
+    const rt_material* materials;   // may be NULL
+    const rt_light* lights;
+    const float* jitter;            // [2*spp] or NULL
+    // tile sharding
+    int tiles_x, tiles_y, rank, world;
+    int local_tiles;                // tiles owned by this rank
+    // output planes: row-major image when world == 1, tile-packed when world > 1
+    float* rgb; uint8_t* rgb8; int32_t* tri_id; float* t;
+    unsigned long long* counters;   // [0] primary rays, [1] shadow rays
+};
+
+struct BuildParams {
+    const float* positions; const float* normals; const uint32_t* indices; const int32_t* obj_ids;
+    uint32_t num_tris;
+    uint32_t leaf_max;              // max triangles per leaf (<= 8)
+};
+
+// Pixel owned by thread `tid` of the block working on rank-local tile `ltile`.
+// Tile k of the frame (row-major tile order) belongs to rank k % world; within a tile each warp
+// covers an 8x4 pixel patch.  `out` is the index into the output planes: row-major pixel index
+// when world == 1, tile-packed (ltile*128 + ly*16 + lx) when the frame is sharded.
+struct Pixel { int x, y; bool inside; size_t out; };
+RT_HD Pixel rt_map_pixel(const FrameParams& P, int ltile, int tid) {
+    const int gtile = ltile * P.world + P.rank;
+    const int tx = gtile % P.tiles_x, ty = gtile / P.tiles_x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
+    Pixel px;
+    px.x = tx * RT_TILE_W + lx; px.y = ty * RT_TILE_H + ly;
+    px.inside = (px.x < P.W) && (px.y < P.H) && (ty < P.tiles_y);
+    px.out = (P.world == 1) ? ((size_t)px.y * P.W + px.x)
+                            : ((size_t)ltile * RT_BLOCK_THREADS + (size_t)ly * RT_TILE_W + lx);
+    return px;
+}
+RT_HD int rt_tiles_of_rank(int total, int rank, int world) { return total > rank ? (total - rank + world - 1) / world : 0; }
+// Unpack: element `e` (= ly*16 + lx) of packed tile `ltile` of rank `src_rank` -> row-major pixel
+// index, or -1 when the element is padding outside the frame.
+RT_HD long long rt_unpack_index(const FrameParams& P, int src_rank, int ltile, int e) {
+    const int gtile = ltile * P.world + src_rank;
+    const int tx = gtile % P.tiles_x, ty = gtile / P.tiles_x;
+    const int x = tx * RT_TILE_W + e % RT_TILE_W, y = ty * RT_TILE_H + e / RT_TILE_W;
+    if (x >= P.W || y >= P.H) return -1;
+    return (long long)y * P.W + x;
+}

@@ -1,0 +1,249 @@
+// rt_trace_core.h — per-ray traversal and shading glue, host/device compilable.
+// The kernels in rt_trace.cu call these with a shared-memory stack column per thread
+// (stride RT_BLOCK_THREADS); the host-side emulation in tests/ calls them with stride 1.
+#pragma once
+
+#include "rt_params.h"
+
+struct Tri { f3 v0, e1, e2; int id; };
+
+RT_HD Tri rt_load_tri(const TriBlock* __restrict__ geom, uint32_t slot) {
+    const float4* p = reinterpret_cast<const float4*>(geom + slot);
+    const float4 a = RT_LDG(p), b = RT_LDG(p + 1), c = RT_LDG(p + 2);
+    Tri t;
+    t.v0 = mk3(a.x, a.y, a.z); t.id = RT_F2I(a.w);
+    t.e1 = mk3(b.x, b.y, b.z);
+    t.e2 = mk3(c.x, c.y, c.z);
+    return t;
+}
+
+// Canonical closest-hit rule: min t, then min original triangle id.
+// rt_moller_trumbore is called with tmax = best.t, so an accepted t is <= best.t.
+RT_HD void rt_consider(const Ray& ray, const Tri& tr, uint32_t slot, float det_eps, float tmin, Hit& best) {
+    float t, u, v;
+    if (rt_moller_trumbore(ray, tr.v0, tr.e1, tr.e2, det_eps, tmin, best.t, t, u, v)) {
+        if (t < best.t || tr.id < best.id) { best.t = t; best.u = u; best.v = v; best.slot = (int)slot; best.id = tr.id; }
+    }
+}
+
+RT_HD void rt_hit_reset(Hit& h) { h.t = FLT_MAX; h.u = 0.f; h.v = 0.f; h.slot = -1; h.id = 0x7fffffff; }
+
+struct NodeQ { float4 q0, q1, q2; int4 q3; };
+RT_HD NodeQ rt_load_node(const BvhNode* __restrict__ nodes, int idx) {
+    const float4* n = reinterpret_cast<const float4*>(nodes + idx);
+    NodeQ q;
+    q.q0 = RT_LDG(n); q.q1 = RT_LDG(n + 1); q.q2 = RT_LDG(n + 2);
+    q.q3 = RT_LDG(reinterpret_cast<const int4*>(n + 3));
+    return q;
+}
+
+struct TraceStats { uint32_t nodes, tris, max_sp; };
+
+// Stack-based BVH2 closest hit (replaces SearchBVH, GPUandCPU/include/query.h:224-311):
+// one 64-byte node visit tests both children, descends into the nearer one and pushes the
+// farther; leaves are contiguous runs of triangle blocks.  STRIDE is the distance between
+// consecutive stack entries of one thread (shared-memory column layout on the device).
+template <int MODE, int STRIDE, bool STATS>
+RT_HD void rt_trace_closest(const FrameParams& P, const Ray& ray, uint32_t* stk, Hit& best, TraceStats* st) {
+    const float det_eps = rt_det_eps(MODE), tmin = rt_tmin(MODE);
+    rt_hit_reset(best);
+    const RayInv k = rt_ray_inv(ray);
+    int sp = 0, cur = 0;
+    bool overflow = false;
+    while (true) {
+        if (cur >= 0) {
+            const NodeQ q = rt_load_node(P.nodes, cur);
+            if (STATS) st->nodes++;
+            float tn0, tn1;
+            const bool h0 = rt_slab(k, q.q0.x, q.q0.y, q.q0.z, q.q0.w, q.q1.x, q.q1.y, tmin, best.t, tn0);
+            const bool h1 = rt_slab(k, q.q1.z, q.q1.w, q.q2.x, q.q2.y, q.q2.z, q.q2.w, tmin, best.t, tn1);
+            if (h0 & h1) {
+                int nearc = q.q3.x, farc = q.q3.y;
+                if (tn1 < tn0) { nearc = q.q3.y; farc = q.q3.x; }
+                if (sp < RT_STACK_DEPTH) { stk[sp * STRIDE] = (uint32_t)farc; ++sp; } else overflow = true;
+                if (STATS && (uint32_t)sp > st->max_sp) st->max_sp = (uint32_t)sp;
+                cur = nearc;
+                continue;
+            }
+            if (h0) { cur = q.q3.x; continue; }
+            if (h1) { cur = q.q3.y; continue; }
+        } else {
+            const uint32_t first = rt_leaf_first(cur), cnt = rt_leaf_count(cur);
+            for (uint32_t s = first; s < first + cnt; ++s) {
+                const Tri tr = rt_load_tri(P.geom, s);
+                if (STATS) st->tris++;
+                rt_consider(ray, tr, s, det_eps, tmin, best);
+            }
+        }
+        if (sp == 0) break;
+        --sp;
+        cur = (int)stk[sp * STRIDE];
+    }
+    if (overflow) {   // same safety net as the reference (query.h:297-308): finish by brute force
+        for (uint32_t s = 0; s < P.num_tris; ++s) {
+            const Tri tr = rt_load_tri(P.geom, s);
+            rt_consider(ray, tr, s, det_eps, tmin, best);
+        }
+    }
+}
+
+// Any-hit query for IsInShadow (GPUandCPU/include/shader.h:44-62): blocked iff some triangle is
+// accepted by intersectTriangle(tmin, FLT_MAX) with t < dist — the same boolean as the
+// reference's "closest hit exists and its t < dist".
+template <int MODE, int STRIDE, bool STATS>
+RT_HD bool rt_trace_any(const FrameParams& P, const Ray& ray, float tmax_excl, uint32_t* stk, TraceStats* st) {
+    const float det_eps = rt_det_eps(MODE), tmin = rt_tmin(MODE);
+    const RayInv k = rt_ray_inv(ray);
+    int sp = 0, cur = 0;
+    bool overflow = false;
+    while (true) {
+        if (cur >= 0) {
+            const NodeQ q = rt_load_node(P.nodes, cur);
+            if (STATS) st->nodes++;
+            float tn0, tn1;
+            const bool h0 = rt_slab(k, q.q0.x, q.q0.y, q.q0.z, q.q0.w, q.q1.x, q.q1.y, tmin, tmax_excl, tn0);
+            const bool h1 = rt_slab(k, q.q1.z, q.q1.w, q.q2.x, q.q2.y, q.q2.z, q.q2.w, tmin, tmax_excl, tn1);
+            if (h0 & h1) {
+                int nearc = q.q3.x, farc = q.q3.y;
+                if (tn1 < tn0) { nearc = q.q3.y; farc = q.q3.x; }
+                if (sp < RT_STACK_DEPTH) { stk[sp * STRIDE] = (uint32_t)farc; ++sp; } else overflow = true;
+                cur = nearc;
+                continue;
+            }
+            if (h0) { cur = q.q3.x; continue; }
+            if (h1) { cur = q.q3.y; continue; }
+        } else {
+            const uint32_t first = rt_leaf_first(cur), cnt = rt_leaf_count(cur);
+            for (uint32_t s = first; s < first + cnt; ++s) {
+                const Tri tr = rt_load_tri(P.geom, s);
+                if (STATS) st->tris++;
+                float t, u, v;
+                if (rt_moller_trumbore(ray, tr.v0, tr.e1, tr.e2, det_eps, tmin, FLT_MAX, t, u, v) && t < tmax_excl) return true;
+            }
+        }
+        if (sp == 0) break;
+        --sp;
+        cur = (int)stk[sp * STRIDE];
+    }
+    if (overflow) {
+        for (uint32_t s = 0; s < P.num_tris; ++s) {
+            const Tri tr = rt_load_tri(P.geom, s);
+            float t, u, v;
+            if (rt_moller_trumbore(ray, tr.v0, tr.e1, tr.e2, det_eps, tmin, FLT_MAX, t, u, v) && t < tmax_excl) return true;
+        }
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------ shading glue ----
+struct Surface {       // hit-point state shared by the per-light steps
+    f3 p, normal, N, V, Lo;
+    rt_material mat;
+};
+
+RT_HD void rt_load_normals(const FrameParams& P, int slot, f3& n0, f3& n1, f3& n2, int& obj) {
+    const float4* p = reinterpret_cast<const float4*>(P.shade + slot);
+    const float4 a = RT_LDG(p), b = RT_LDG(p + 1), c = RT_LDG(p + 2);
+    n0 = mk3(a.x, a.y, a.z); obj = RT_F2I(a.w);
+    n1 = mk3(b.x, b.y, b.z);
+    n2 = mk3(c.x, c.y, c.z);
+}
+
+// ShadeDirect prologue, GPUandCPU/include/shader.h:75-85 (+ assignMaterialToHit, query.h:134-153)
+RT_HD void rt_surface_hw2(const FrameParams& P, const Ray& ray, const Hit& h, Surface& s) {
+    const Tri tr = rt_load_tri(P.geom, (uint32_t)h.slot);
+    f3 n0, n1, n2; int obj;
+    rt_load_normals(P, h.slot, n0, n1, n2, obj);
+    rt_hit_frame_hw2(ray, tr.e1, tr.e2, n0, n1, n2, h.t, h.u, h.v, s.p, s.normal);
+    s.mat = rt_default_material();
+    if (P.materials != nullptr && obj >= 0 && obj < P.num_materials) s.mat = P.materials[obj];
+    s.N = xunit(s.normal);
+    s.V = xunit(xsub3(ray.o, s.p));
+    s.Lo = mk3(0.f, 0.f, 0.f);
+    s.Lo = xadd3(s.Lo, xmuls(ld3(s.mat.albedo), 0.05f));
+    s.Lo = xadd3(s.Lo, ld3(s.mat.emission));
+}
+
+// Per-light setup: false when the light contributes nothing (N.L <= 0).  need_shadow is set and
+// (sray, dist) describe the IsInShadow query (shader.h:44-58, RT_EPS = 1e-3, shader.h:22).
+RT_HD bool rt_light_setup_hw2(const Surface& s, const rt_light& light, f3& L, float& NdotL,
+                              bool& need_shadow, Ray& sray, float& dist) {
+    const f3 lpos = ld3(light.position);
+    L = xunit(xsub3(lpos, s.p));
+    NdotL = fmaxf(xdot(s.N, L), 0.0f);
+    need_shadow = false;
+    if (NdotL <= 0.0f) return false;
+    const f3 toL = xsub3(lpos, s.p);
+    dist = xlen3(toL);
+    if (!(dist <= 0.0f)) {
+        need_shadow = true;
+        sray.d = xdivs(toL, dist);
+        sray.o = xadd3(s.p, xmuls(s.N, 1e-3f));
+    }
+    return true;
+}
+RT_HD void rt_light_finish_hw2(Surface& s, const rt_light& light, f3 L, float NdotL) {
+    const f3 f = rt_brdf_hw2(s.mat, s.normal, s.V, L);
+    const f3 radiance = xmuls(ld3(light.color), (float)light.intensity);
+    const f3 direct = xmuls(xmulv(radiance, f), NdotL);
+    s.Lo = xadd3(s.Lo, direct);
+}
+// TraceRayIterative epilogue at depth 1 (query.h:186-191, 219)
+RT_HD f3 rt_radiance_hw2(f3 direct) {
+    f3 radiance = mk3(0.f, 0.f, 0.f);
+    const f3 throughput = mk3(1.f, 1.f, 1.f);
+    radiance = xadd3(radiance, xmulv(throughput, direct));
+    return rt_clamp01(radiance);
+}
+
+RT_HD f3 rt_shade_hw1(const FrameParams& P, const Ray& ray, const Hit& h) {
+    if (h.slot < 0) return rt_shade_hw1_miss(ray);
+    f3 n0, n1, n2; int obj;
+    rt_load_normals(P, h.slot, n0, n1, n2, obj);
+    const f3 p = xadd3(ray.o, xmuls(ray.d, h.t));
+    const f3 normal = xadd3(xadd3(xmuls(n0, XSUB(XSUB(1.0f, h.u), h.v)), xmuls(n1, h.u)), xmuls(n2, h.v));
+    return rt_shade_hw1_hit(ray, p, normal, P.lights[0]);
+}
+
+// One sample of one pixel through the BVH path: primary closest hit, shading, shadow rays.
+template <int MODE, int STRIDE, bool STATS>
+RT_HD f3 rt_sample_bvh(const FrameParams& P, int x, int y, int s, uint32_t* stk, Hit& h,
+                       unsigned& nprim, unsigned& nshadow, TraceStats* st) {
+    const float jx = P.jitter ? RT_LDG(P.jitter + 2 * s) : 0.0f;
+    const float jy = P.jitter ? RT_LDG(P.jitter + 2 * s + 1) : 0.0f;
+    const Ray ray = rt_make_ray(P.cam, MODE, x, y, jx, jy);
+    if (MODE != RT_MODE_HW1 && P.max_depth <= 0) {   // TraceRayIterative: maxDepth <= 0 -> black
+        rt_hit_reset(h);
+        return mk3(0.f, 0.f, 0.f);
+    }
+    rt_trace_closest<MODE, STRIDE, STATS>(P, ray, stk, h, st);
+    ++nprim;
+    if (MODE == RT_MODE_HW1) return rt_shade_hw1(P, ray, h);
+    if (h.slot < 0) return rt_radiance_hw2(ld3(P.miss));
+    Surface sf;
+    rt_surface_hw2(P, ray, h, sf);
+    for (int l = 0; l < P.num_lights; ++l) {
+        const rt_light light = P.lights[l];
+        f3 L; float NdotL, dist; bool need; Ray sray;
+        if (!rt_light_setup_hw2(sf, light, L, NdotL, need, sray, dist)) continue;
+        if (need && P.shadows) {
+            ++nshadow;
+            if (rt_trace_any<MODE, STRIDE, STATS>(P, sray, dist, stk, st)) continue;
+        }
+        rt_light_finish_hw2(sf, light, L, NdotL);
+    }
+    return rt_radiance_hw2(sf.Lo);
+}
+
+// Resolve: col / float(spp) (query.cu:163, render.cpp:110) + requested planes.
+RT_HD void rt_write_pixel(const FrameParams& P, size_t out, f3 accum, const Hit& first) {
+    const f3 fin = xdivs(accum, (float)P.spp);
+    if (P.rgb) { P.rgb[3 * out] = fin.x; P.rgb[3 * out + 1] = fin.y; P.rgb[3 * out + 2] = fin.z; }
+    if (P.rgb8) {
+        P.rgb8[3 * out] = rt_quantise(fin.x, P.quantiser);
+        P.rgb8[3 * out + 1] = rt_quantise(fin.y, P.quantiser);
+        P.rgb8[3 * out + 2] = rt_quantise(fin.z, P.quantiser);
+    }
+    if (P.tri_id) P.tri_id[out] = first.slot >= 0 ? first.id : -1;
+    if (P.t) P.t[out] = first.slot >= 0 ? first.t : -1.0f;
+}

@@ -1,0 +1,236 @@
+// emul_host.cpp — TEST INFRASTRUCTURE: runs the product's host/device-compilable per-element
+// functions (csrc/rt_build_core.h, rt_trace_core.h) sequentially on the CPU so the BVH build,
+// the flattened layout and the traversal/shading logic can be checked against the oracle in a
+// container without a GPU (pytest -m "not gpu").  Nothing in the product links this file; the
+// product itself has no CPU path.  Built by tests/emul/build_emul.py with
+// g++ -O2 -ffp-contract=off (so the X* macros round like the device intrinsics).
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "../../raytracinginonesemester_b200/csrc/rt_build_core.h"
+#include "../../raytracinginonesemester_b200/csrc/rt_trace_core.h"
+
+struct EmuScene {
+    std::vector<BvhNode> nodes;
+    std::vector<TriBlock> geom, shade;
+    std::vector<rt_material> materials;
+    uint32_t num_tris = 0;
+};
+
+extern "C" {
+
+// Mirrors rt_build_bvh (csrc/rt_build.cu) step for step with the same per-element functions.
+void* emu_build(const rt_scene* sc, uint32_t leaf_max) {
+    const int n = (int)sc->num_triangles;
+    if (n <= 0) return nullptr;
+    if (leaf_max < 1) leaf_max = 1;
+    if (leaf_max > 8) leaf_max = 8;
+    EmuScene* es = new EmuScene;
+    es->num_tris = (uint32_t)n;
+    BuildParams bp{};
+    bp.positions = sc->positions; bp.normals = sc->normals; bp.indices = sc->indices; bp.obj_ids = sc->tri_obj_ids;
+    bp.num_tris = (uint32_t)n; bp.leaf_max = leaf_max;
+    if (sc->num_materials > 0) es->materials.assign(sc->materials, sc->materials + sc->num_materials);
+
+    Bounds scene;
+    for (int k = 0; k < 3; ++k) { scene.lo[k] = INFINITY; scene.hi[k] = -INFINITY; }
+    for (int i = 0; i < n; ++i) {
+        f3 a, b, c; uint32_t ia, ib, ic; float lo[3], hi[3];
+        rt_tri_verts(bp, (uint32_t)i, a, b, c, ia, ib, ic);
+        rt_tri_box(a, b, c, lo, hi);
+        for (int k = 0; k < 3; ++k) { scene.lo[k] = fminf(scene.lo[k], lo[k]); scene.hi[k] = fmaxf(scene.hi[k], hi[k]); }
+    }
+    std::vector<uint64_t> keys(n);
+    std::vector<uint32_t> vals(n);
+    for (int i = 0; i < n; ++i) {
+        f3 a, b, c; uint32_t ia, ib, ic;
+        rt_tri_verts(bp, (uint32_t)i, a, b, c, ia, ib, ic);
+        keys[i] = rt_morton63(a, b, c, scene);
+    }
+    std::iota(vals.begin(), vals.end(), 0u);
+    std::stable_sort(vals.begin(), vals.end(), [&](uint32_t x, uint32_t y) { return keys[x] < keys[y]; });  // radix sort is stable
+    std::vector<uint64_t> skeys(n);
+    for (int i = 0; i < n; ++i) skeys[i] = keys[vals[i]];
+
+    const size_t nn = 2 * (size_t)n - 1;
+    std::vector<Topo> topo(n > 1 ? n - 1 : 1);
+    std::vector<uint32_t> parent(nn, 0xFFFFFFFFu);
+    for (int i = 0; i + 1 < n; ++i) {
+        topo[i] = rt_karras_node(skeys.data(), n, i);
+        parent[topo[i].left] = (uint32_t)i; parent[topo[i].right] = (uint32_t)i;
+    }
+    std::vector<float4> blo(nn), bhi(nn);
+    std::vector<int> flags(n, 0);
+    for (int k = 0; k < n; ++k) {
+        f3 a, b, c; uint32_t ia, ib, ic; float lo[3], hi[3];
+        rt_tri_verts(bp, vals[k], a, b, c, ia, ib, ic);
+        rt_padded_leaf_box(a, b, c, scene, lo, hi);
+        blo[n - 1 + k] = make_float4(lo[0], lo[1], lo[2], 0.f);
+        bhi[n - 1 + k] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    }
+    for (int k = 0; k < n && n > 1; ++k) {        // same second-arrival walk as k_refit
+        uint32_t p = parent[n - 1 + k];
+        while (p != 0xFFFFFFFFu) {
+            if (flags[p]++ == 0) break;
+            const Topo tp = topo[p];
+            blo[p] = make_float4(fminf(blo[tp.left].x, blo[tp.right].x), fminf(blo[tp.left].y, blo[tp.right].y), fminf(blo[tp.left].z, blo[tp.right].z), 0.f);
+            bhi[p] = make_float4(fmaxf(bhi[tp.left].x, bhi[tp.right].x), fmaxf(bhi[tp.left].y, bhi[tp.right].y), fmaxf(bhi[tp.left].z, bhi[tp.right].z), 0.f);
+            p = parent[p];
+        }
+    }
+    es->geom.resize(n); es->shade.resize(n);
+    for (int k = 0; k < n; ++k) rt_pack_tri(bp, vals[k], &es->geom[k], &es->shade[k]);
+
+    if ((uint32_t)n > leaf_max) {
+        std::vector<uint32_t> keep(n, 0), newidx(n, 0);
+        for (int i = 0; i + 1 < n; ++i) keep[i] = (topo[i].last - topo[i].first + 1u) > leaf_max ? 1u : 0u;
+        uint32_t run = 0;
+        for (int i = 0; i < n; ++i) { newidx[i] = run; run += keep[i]; }
+        es->nodes.resize(run);
+        for (int i = 0; i + 1 < n; ++i) {
+            if (!keep[i]) continue;
+            const Topo tp = topo[i];
+            es->nodes[newidx[i]] = rt_make_node(blo[tp.left], bhi[tp.left], blo[tp.right], bhi[tp.right],
+                                                rt_child_ref(tp.left, n, topo.data(), keep.data(), newidx.data()),
+                                                rt_child_ref(tp.right, n, topo.data(), keep.data(), newidx.data()),
+                                                tp.first, tp.last - tp.first + 1u);
+        }
+    } else {
+        float4 lo = make_float4(INFINITY, INFINITY, INFINITY, 0.f), hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
+        for (int k = 0; k < n; ++k) {
+            lo.x = fminf(lo.x, blo[n - 1 + k].x); lo.y = fminf(lo.y, blo[n - 1 + k].y); lo.z = fminf(lo.z, blo[n - 1 + k].z);
+            hi.x = fmaxf(hi.x, bhi[n - 1 + k].x); hi.y = fmaxf(hi.y, bhi[n - 1 + k].y); hi.z = fmaxf(hi.z, bhi[n - 1 + k].z);
+        }
+        const float4 elo = make_float4(INFINITY, INFINITY, INFINITY, 0.f), ehi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
+        es->nodes.push_back(rt_make_node(lo, hi, elo, ehi, rt_leaf_ref(0u, (uint32_t)n), rt_leaf_ref(0u, 1u), 0u, (uint32_t)n));
+    }
+    return es;
+}
+
+// Adopt a BVH downloaded from the device (rt_debug_download_bvh) + shading data rebuilt on the host.
+void* emu_adopt(const void* nodes64, uint32_t num_nodes, const void* geom48, uint32_t num_tris, const rt_scene* sc) {
+    EmuScene* es = new EmuScene;
+    es->num_tris = num_tris;
+    es->nodes.resize(num_nodes); es->geom.resize(num_tris); es->shade.resize(num_tris);
+    memcpy(es->nodes.data(), nodes64, sizeof(BvhNode) * (size_t)num_nodes);
+    memcpy(es->geom.data(), geom48, sizeof(TriBlock) * (size_t)num_tris);
+    BuildParams bp{};
+    bp.positions = sc->positions; bp.normals = sc->normals; bp.indices = sc->indices; bp.obj_ids = sc->tri_obj_ids;
+    bp.num_tris = num_tris;
+    std::vector<TriBlock> scratch(1);
+    for (uint32_t k = 0; k < num_tris; ++k) {
+        int tri = RT_F2I(es->geom[k].g[3]);
+        rt_pack_tri(bp, (uint32_t)tri, &scratch[0], &es->shade[k]);
+    }
+    if (sc->num_materials > 0) es->materials.assign(sc->materials, sc->materials + sc->num_materials);
+    return es;
+}
+
+void emu_free(void* h) { delete (EmuScene*)h; }
+uint32_t emu_num_nodes(void* h) { return (uint32_t)((EmuScene*)h)->nodes.size(); }
+void emu_export(void* h, void* nodes64, void* geom48) {
+    EmuScene* es = (EmuScene*)h;
+    if (nodes64) memcpy(nodes64, es->nodes.data(), sizeof(BvhNode) * es->nodes.size());
+    if (geom48) memcpy(geom48, es->geom.data(), sizeof(TriBlock) * es->geom.size());
+}
+
+// Structural check of a flattened BVH: every slot reachable exactly once, child boxes contain
+// their triangles, refs in range.  Returns 0 when sound, else a negative code.
+int emu_validate(void* h) {
+    EmuScene* es = (EmuScene*)h;
+    std::vector<int> seen(es->num_tris, 0);
+    std::vector<int> stack{0};
+    std::vector<int> visited(es->nodes.size(), 0);
+    while (!stack.empty()) {
+        int ni = stack.back(); stack.pop_back();
+        if (ni < 0 || (size_t)ni >= es->nodes.size()) return -1;
+        if (visited[ni]++) return -2;
+        const BvhNode& nd = es->nodes[ni];
+        for (int c = 0; c < 2; ++c) {
+            const float* lo = nd.q + 6 * c; const float* hi = lo + 3;
+            int32_t ref = c ? nd.ref1 : nd.ref0;
+            if (lo[0] > hi[0]) continue;   // absent child
+            if (ref >= 0) { stack.push_back(ref); continue; }
+            uint32_t first = rt_leaf_first(ref), cnt = rt_leaf_count(ref);
+            if (first + cnt > es->num_tris) return -3;
+            for (uint32_t s = first; s < first + cnt; ++s) {
+                if (seen[s]++) return -4;
+                const float* g = es->geom[s].g;
+                for (int k = 0; k < 3; ++k) {
+                    float v0 = g[k], v1 = g[k] + g[4 + k], v2 = g[k] + g[8 + k];
+                    float mn = fminf(v0, fminf(v1, v2)), mx = fmaxf(v0, fmaxf(v1, v2));
+                    if (mn < lo[k] - 1e-6f * (1.f + fabsf(mn)) || mx > hi[k] + 1e-6f * (1.f + fabsf(mx))) return -5;
+                }
+            }
+        }
+    }
+    for (uint32_t s = 0; s < es->num_tris; ++s) if (seen[s] != 1) return -6;
+    return 0;
+}
+
+// Renders through rt_sample_bvh exactly as k_render_bvh does (stack stride 1), tile by tile with
+// the kernel's own pixel mapping.  world > 1: the planes in img are this rank's tile-packed buffers
+// (local_tiles*128 elements).  stats[0..3] = primary rays, shadow rays, node visits, triangle
+// tests; stats[4] = deepest stack use.
+int emu_render_rank(void* h, const rt_frame* fr, rt_image* img, uint64_t* stats, int rank, int world) {
+    EmuScene* es = (EmuScene*)h;
+    FrameParams P{};
+    P.cam = fr->cam; P.mode = fr->mode; P.accel = fr->accel; P.W = fr->width; P.H = fr->height; P.spp = fr->spp;
+    P.max_depth = fr->max_depth; P.shadows = fr->shadows; P.quantiser = fr->quantiser; P.num_lights = fr->num_lights;
+    P.num_materials = (int)es->materials.size();
+    memcpy(P.miss, fr->miss_color, sizeof P.miss);
+    P.nodes = es->nodes.data(); P.geom = es->geom.data(); P.shade = es->shade.data(); P.num_tris = es->num_tris;
+    P.materials = es->materials.empty() ? nullptr : es->materials.data();
+    P.lights = fr->lights; P.jitter = fr->jitter;
+    P.tiles_x = (P.W + RT_TILE_W - 1) / RT_TILE_W; P.tiles_y = (P.H + RT_TILE_H - 1) / RT_TILE_H;
+    P.rank = rank; P.world = world;
+    P.local_tiles = rt_tiles_of_rank(P.tiles_x * P.tiles_y, rank, world);
+    P.rgb = img->rgb; P.rgb8 = img->rgb8; P.tri_id = img->tri_id; P.t = img->t;
+    unsigned long long tot[5] = {0, 0, 0, 0, 0};
+    uint32_t stk[RT_STACK_DEPTH];
+    for (int lt = 0; lt < P.local_tiles; ++lt)
+        for (int tid = 0; tid < RT_BLOCK_THREADS; ++tid) {
+            const Pixel px = rt_map_pixel(P, lt, tid);
+            if (!px.inside) continue;
+            f3 accum = mk3(0.f, 0.f, 0.f);
+            Hit first; rt_hit_reset(first);
+            unsigned np = 0, ns = 0;
+            TraceStats st{0, 0, 0};
+            for (int s = 0; s < P.spp; ++s) {
+                Hit hh;
+                f3 color = fr->mode == RT_MODE_HW1
+                    ? rt_sample_bvh<RT_MODE_HW1, 1, true>(P, px.x, px.y, s, stk, hh, np, ns, &st)
+                    : rt_sample_bvh<RT_MODE_HW2_BVH, 1, true>(P, px.x, px.y, s, stk, hh, np, ns, &st);
+                if (s == 0) first = hh;
+                accum = xadd3(accum, color);
+            }
+            rt_write_pixel(P, px.out, accum, first);
+            tot[0] += np; tot[1] += ns; tot[2] += st.nodes; tot[3] += st.tris;
+            if (st.max_sp > tot[4]) tot[4] = st.max_sp;
+        }
+    img->width = P.W; img->height = P.H; img->rays_primary = tot[0]; img->rays_shadow = tot[1];
+    if (stats) for (int k = 0; k < 5; ++k) stats[k] = tot[k];
+    return P.local_tiles;
+}
+int emu_render(void* h, const rt_frame* fr, rt_image* img, uint64_t* stats) {
+    emu_render_rank(h, fr, img, stats, 0, 1);
+    return 0;
+}
+// Host mirror of k_unpack for one packed u8 rgb plane of rank src_rank.
+void emu_unpack_rgb8(int W, int H, int world, int src_rank, const uint8_t* packed, uint8_t* image) {
+    FrameParams P{};
+    P.W = W; P.H = H; P.world = world;
+    P.tiles_x = (W + RT_TILE_W - 1) / RT_TILE_W; P.tiles_y = (H + RT_TILE_H - 1) / RT_TILE_H;
+    const int n = rt_tiles_of_rank(P.tiles_x * P.tiles_y, src_rank, world);
+    for (int lt = 0; lt < n; ++lt)
+        for (int e = 0; e < RT_BLOCK_THREADS; ++e) {
+            long long di = rt_unpack_index(P, src_rank, lt, e);
+            if (di < 0) continue;
+            for (int c = 0; c < 3; ++c) image[3 * di + c] = packed[3 * ((size_t)lt * RT_BLOCK_THREADS + e) + c];
+        }
+}
+
+} // extern "C"

@@ -1,0 +1,121 @@
+"""ctypes bindings of the TEST oracle (oracle/), the in-place reference shims (oracle/_ref/) and
+the host emulation of the device functions (tests/emul/).  Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+from raytracinginonesemester_b200 import _abi as A  # noqa: E402
+
+import build as oracle_build  # noqa: E402  (oracle/build.py)
+
+
+class orc_counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("rays_primary", "rays_shadow", "node_pops", "box_tests", "tri_tests", "max_stack")]
+
+
+_cache = {}
+
+
+def oracle():
+    if "orc" not in _cache:
+        lib = C.CDLL(oracle_build.build_oracle())
+        lib.orc_camera_init.argtypes = [C.POINTER(A.rt_camera), A.f32p, A.f32p, A.f32p, C.c_double, C.c_double, C.c_int, C.c_int]
+        lib.orc_jitter_table.argtypes = [A.f32p, C.c_int, C.c_uint32, C.c_int]
+        lib.orc_bvh_build.restype = C.c_void_p
+        lib.orc_bvh_build.argtypes = [C.POINTER(A.rt_scene)]
+        lib.orc_bvh_free.argtypes = [C.c_void_p]
+        lib.orc_bvh_export.argtypes = [C.c_void_p, A.u32p, A.f32p]
+        lib.orc_render.argtypes = [C.POINTER(A.rt_scene), C.POINTER(A.rt_frame), C.c_void_p, C.POINTER(A.rt_image),
+                                   C.c_int, C.c_int, C.c_int, C.POINTER(orc_counters)]
+        lib.orc_ray_triangle.argtypes = [C.c_int, A.f32p, A.f32p, C.c_int, A.f32p, A.f32p, A.f32p, A.f32p]
+        lib.orc_quantise.restype = C.c_uint8
+        lib.orc_quantise.argtypes = [C.c_float, C.c_int]
+        _cache["orc"] = lib
+    return _cache["orc"]
+
+
+def ref_libs():
+    """dict name -> CDLL for the reference shims that exist (built here when /root/reference is present)."""
+    if "ref" not in _cache:
+        paths = oracle_build.build_ref()
+        _cache["ref"] = {k: C.CDLL(v) for k, v in paths.items()}
+    return _cache["ref"]
+
+
+def emul():
+    if "emu" not in _cache:
+        here = os.path.join(ROOT, "tests", "emul")
+        out = os.path.join(here, "libemul_host.so")
+        src = os.path.join(here, "emul_host.cpp")
+        csrc = os.path.join(ROOT, "raytracinginonesemester_b200", "csrc")
+        deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".h")]
+        if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+            subprocess.run(["g++", "-x", "c++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", out, src], check=True)
+        lib = C.CDLL(out)
+        lib.emu_build.restype = C.c_void_p
+        lib.emu_build.argtypes = [C.POINTER(A.rt_scene), C.c_uint32]
+        lib.emu_adopt.restype = C.c_void_p
+        lib.emu_adopt.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(A.rt_scene)]
+        lib.emu_free.argtypes = [C.c_void_p]
+        lib.emu_num_nodes.restype = C.c_uint32
+        lib.emu_num_nodes.argtypes = [C.c_void_p]
+        lib.emu_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.emu_validate.argtypes = [C.c_void_p]
+        lib.emu_render.argtypes = [C.c_void_p, C.POINTER(A.rt_frame), C.POINTER(A.rt_image), C.POINTER(C.c_uint64)]
+        _cache["emu"] = lib
+    return _cache["emu"]
+
+
+def _planes(fr, want):
+    H, W = fr.height, fr.width
+    img = A.rt_image()
+    out = {}
+    if "rgb" in want:
+        out["rgb"] = np.zeros((H, W, 3), np.float32); img.rgb = out["rgb"].ctypes.data_as(A.f32p)
+    if "rgb8" in want:
+        out["rgb8"] = np.zeros((H, W, 3), np.uint8); img.rgb8 = out["rgb8"].ctypes.data_as(A.u8p)
+    if "tri_id" in want:
+        out["tri_id"] = np.full((H, W), -2, np.int32); img.tri_id = out["tri_id"].ctypes.data_as(A.i32p)
+    if "t" in want:
+        out["t"] = np.full((H, W), -2, np.float32); img.t = out["t"].ctypes.data_as(A.f32p)
+    return img, out
+
+
+def oracle_render(scene, frame, bvh=None, threads=8, row_begin=0, row_step=1, want=("rgb", "rgb8", "tri_id", "t")):
+    """scene/frame: raytracinginonesemester_b200.api.Scene / Frame.  bvh: handle from oracle_bvh()
+    (reference-exact LBVH + SearchBVH) or None (canonical brute force)."""
+    lib = oracle()
+    s, f = scene.c_struct(), frame.c_struct()
+    img, out = _planes(frame, want)
+    cnt = orc_counters()
+    rc = lib.orc_render(C.byref(s), C.byref(f), bvh, C.byref(img), threads, row_begin, row_step, C.byref(cnt))
+    assert rc == 0, rc
+    out["counters"] = {n: getattr(cnt, n) for n, _ in orc_counters._fields_}
+    return out
+
+
+def oracle_bvh(scene):
+    s = scene.c_struct()
+    return oracle().orc_bvh_build(C.byref(s))
+
+
+def emul_build(scene, leaf_max=4):
+    s = scene.c_struct()
+    return emul().emu_build(C.byref(s), leaf_max)
+
+
+def emul_render(handle, frame, want=("rgb", "rgb8", "tri_id", "t")):
+    f = frame.c_struct()
+    img, out = _planes(frame, want)
+    stats = (C.c_uint64 * 5)()
+    rc = emul().emu_render(handle, C.byref(f), C.byref(img), stats)
+    assert rc == 0
+    out["stats"] = dict(rays_primary=stats[0], rays_shadow=stats[1], nodes=stats[2], tris=stats[3], max_stack=stats[4])
+    return out

@@ -1,0 +1,296 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle (oracle/), the
+committed reference fixtures (tests/golden/) and size-independent properties at full size.
+
+Bars (BASELINE.json north_star): closest-hit triangle id bit-exact on >= 99.99 % of pixels against
+the reference CPU path (mismatches only at exact-t ties), hit t within 1e-5 relative, 8-bit image
+within 1 LSB.  Against the canonical oracle (min t, then min id over the reference's
+intersectTriangle on every triangle) the bar is bit-exact ids, t and float rgb."""
+import numpy as np
+import pytest
+
+import orclib
+from raytracinginonesemester_b200 import _abi as A, api, scenes
+
+pytestmark = pytest.mark.gpu
+ALL = A.RT_OUT_RGB_F32 | A.RT_OUT_RGB8 | A.RT_OUT_TRI_ID | A.RT_OUT_T
+
+
+def run(renderer, frame):
+    renderer.render(frame)
+    return renderer.download()
+
+
+def assert_reference_bar(got, ref_id, ref_t, ref_rgb=None, quant=A.RT_QUANT_HW2_TRUNC, what=""):
+    n = ref_id.size
+    mism = got["tri_id"] != ref_id
+    assert mism.sum() <= 1e-4 * n, "%s: %d of %d ids differ" % (what, mism.sum(), n)
+    # every id mismatch must be an exact-t tie (both hit, same t) — the "stated epsilon ties"
+    if mism.any():
+        assert np.all((got["tri_id"][mism] >= 0) & (ref_id[mism] >= 0)), what + ": hit/miss flip"
+        assert np.array_equal(got["t"][mism], ref_t[mism]), what + ": id mismatch that is not an exact-t tie"
+    hit = (ref_id >= 0) & ~mism
+    rel = np.abs(got["t"][hit] - ref_t[hit]) / np.maximum(np.abs(ref_t[hit]), 1e-30)
+    assert rel.size == 0 or rel.max() <= 1e-5, "%s: t rel err %g" % (what, rel.max())
+    if ref_rgb is not None:
+        q = np.vectorize(lambda c: orclib.oracle().orc_quantise(float(c), quant), otypes=[np.uint8])
+        ref8 = q(ref_rgb)
+        d = np.abs(got["rgb8"].astype(int) - ref8.astype(int))
+        ok = ~np.repeat(mism[..., None], 3, -1)
+        assert d[ok].max() <= 1, "%s: 8-bit image differs by %d LSB" % (what, d[ok].max())
+
+
+# ------------------------------------------------------------------------------ HW1 ----
+def test_hw1_frog_brute_matches_reference_fixture(renderer, frog_scene, golden):
+    renderer.upload_scene(frog_scene)
+    for name, col in (("white", (1, 1, 1)), ("magenta", (1, 0, 1))):
+        ref = golden("ref_hw1_frog_96x54_%s.npz" % name)
+        got = run(renderer, scenes.hw1_frame(96, 54, light_color=col, outputs=ALL))
+        assert np.array_equal(got["tri_id"], ref["tri_id"])
+        assert np.array_equal(got["t"], ref["t"])
+        assert np.array_equal(got["rgb8"], ref["rgb8"])
+        d = np.abs(got["rgb"] - ref["rgb"])
+        assert d.max() <= 2e-7, d.max()      # powf: fp64 pow narrowed vs glibc powf
+
+
+def test_hw1_frog_golden_png_bit_exact(renderer, frog_scene, golden):
+    """HW1/frog_output.png, the reference's committed golden (rendered with a white light)."""
+    renderer.upload_scene(frog_scene)
+    got = run(renderer, scenes.hw1_frame(320, 180, light_color=(1, 1, 1), outputs=ALL))
+    ref = golden("hw1_frog_output.npz")["rgb8"]
+    assert np.array_equal(got["rgb8"], ref), "%d px differ" % (got["rgb8"] != ref).any(-1).sum()
+    assert (got["tri_id"] >= 0).sum() == 3795           # hit mask of 3 795 px
+
+
+def test_hw1_bvh_accel_equals_brute(renderer, frog_scene):
+    renderer.upload_scene(frog_scene)
+    a = run(renderer, scenes.hw1_frame(160, 90, light_color=(1, 1, 1), outputs=ALL, accel=A.RT_ACCEL_BRUTE))
+    b = run(renderer, scenes.hw1_frame(160, 90, light_color=(1, 1, 1), outputs=ALL, accel=A.RT_ACCEL_BVH))
+    for k in ("tri_id", "t", "rgb", "rgb8"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_hw1_sphere_as_the_repo_runs_it(renderer, golden):
+    """C1: sphere.obj under the frog camera — every pixel is (20,5,5)."""
+    d = golden("sphere_mesh.npz")
+    renderer.upload_scene(api.Scene(d["positions"], d["indices"], normals=d["normals"], build_flags=A.RT_BUILD_NO_BVH))
+    ref = golden("ref_hw1_sphere_64x36.npz")
+    got = run(renderer, scenes.hw1_frame(64, 36, outputs=ALL))
+    assert np.array_equal(got["rgb8"], ref["rgb8"]) and np.array_equal(got["tri_id"], ref["tri_id"])
+    assert np.all(got["rgb8"] == np.array([20, 5, 5], np.uint8))
+
+
+# ---------------------------------------------------------------------------- HW2 BVH ----
+@pytest.mark.parametrize("name,filling", [("frog", False), ("frogfill", True)])
+def test_hw2_frog_vs_reference_and_oracle(renderer, frog_scene, golden, name, filling):
+    renderer.upload_scene(frog_scene)
+    fr = scenes.frog_frame(160, 90, filling=filling, outputs=ALL)
+    got = run(renderer, fr)
+    ref = golden("ref_hw2_%s_160x90.npz" % name)
+    assert_reference_bar(got, ref["tri_id"], ref["t"], ref["rgb"], what=name)
+    fr.accel = A.RT_ACCEL_BRUTE
+    orc = orclib.oracle_render(frog_scene, fr)        # canonical brute force on the CPU
+    assert np.array_equal(got["tri_id"], orc["tri_id"]) and np.array_equal(got["t"], orc["t"])
+    assert np.abs(got["rgb"] - orc["rgb"]).max() <= 2e-7
+    assert np.abs(got["rgb8"].astype(int) - orc["rgb8"].astype(int)).max() <= 1
+
+
+def test_hw2_terrain_vs_reference(renderer, golden):
+    sc = scenes.terrain_scene(60, 30)
+    renderer.upload_scene(sc)
+    ref = golden("ref_hw2_terrain_128x72.npz")
+    got = run(renderer, scenes.terrain_frame(128, 72, outputs=ALL, quantiser=A.RT_QUANT_HW2_TRUNC))
+    assert_reference_bar(got, ref["tri_id"], ref["t"], ref["rgb"], what="terrain")
+    assert got["rays_primary"] == 128 * 72 and got["rays_shadow"] > 0
+    ref4 = golden("ref_hw2_terrain_64x36_spp4.npz")
+    got4 = run(renderer, scenes.terrain_frame(64, 36, spp=4, outputs=ALL, quantiser=A.RT_QUANT_HW2_TRUNC))
+    assert_reference_bar(got4, ref4["tri_id"], ref4["t"], ref4["rgb"], what="terrain spp4")
+    assert np.abs(got4["rgb"] - ref4["rgb"]).max() <= 1e-6
+
+
+def test_hw2_brute_accel_equals_bvh(renderer):
+    sc = scenes.terrain_scene(24, 12)
+    renderer.upload_scene(sc)
+    a = run(renderer, scenes.terrain_frame(80, 45, spp=2, outputs=ALL, accel=A.RT_ACCEL_BVH))
+    b = run(renderer, scenes.terrain_frame(80, 45, spp=2, outputs=ALL, accel=A.RT_ACCEL_BRUTE))
+    for k in ("tri_id", "t", "rgb", "rgb8"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["rays_shadow"] == b["rays_shadow"]
+
+
+def test_hw2_cornell_multi_material(renderer, golden):
+    d = golden("cornell_mesh.npz")
+    mats = [api.make_material(albedo=(0.7, 0.7, 0.7)), api.make_material(albedo=(0.8, 0.1, 0.1), ks=0.4, shininess=16.0),
+            api.make_material(albedo=(0.1, 0.8, 0.1), kd=0.5, ks=0.5, specular_color=(0.9, 0.9, 0.9), shininess=64.0, emission=(0.05, 0.0, 0.0))]
+    nobj = int(d["tri_obj_ids"].max()) + 2
+    sc = api.Scene(d["positions"], d["indices"], normals=None, tri_obj_ids=d["tri_obj_ids"], materials=[mats[i % 3] for i in range(nobj)])
+    renderer.upload_scene(sc)
+    ref = golden("ref_hw2_cornell_96x96.npz")
+    cam = ref["cam"]
+    c = api.camera_init(cam[:3], cam[3:6], (0, 0, 1), 35.0, 24.0, 96, 96)
+    lp = ref["lights"]
+    fr = api.Frame(c, 96, 96, lights=[api.make_light(lp[0], (1, 1, 1), 2), api.make_light(lp[1], (0.4, 0.4, 1.0), 1)],
+                   miss_color=(0.1, 0.2, 0.3), jitter=api.jitter_table(1, 42, True), outputs=ALL, quantiser=A.RT_QUANT_HW2_TRUNC)
+    got = run(renderer, fr)
+    assert_reference_bar(got, ref["tri_id"], ref["t"], ref["rgb"], what="cornell")
+
+
+@pytest.mark.parametrize("leaf_max", [1, 2, 8])
+def test_leaf_size_does_not_change_results(renderer, frog_scene, leaf_max):
+    renderer.upload_scene(frog_scene)
+    base = run(renderer, scenes.frog_frame(128, 72, filling=True, outputs=ALL))
+    sc = api.Scene(frog_scene.positions, frog_scene.indices, normals=frog_scene.normals, tri_obj_ids=frog_scene.tri_obj_ids,
+                   materials=frog_scene.materials, build_flags=A.RT_BUILD_LEAF_MAX(leaf_max))
+    renderer.upload_scene(sc)
+    got = run(renderer, scenes.frog_frame(128, 72, filling=True, outputs=ALL))
+    for k in ("tri_id", "t", "rgb"):
+        assert np.array_equal(base[k], got[k]), k
+
+
+def test_device_bvh_is_sound_and_host_walk_agrees(renderer):
+    """Download the BVH the device built, check it structurally and walk it on the host with the same
+    per-ray functions: ids/t must equal what the kernel produced."""
+    sc = scenes.terrain_scene(50, 25)
+    info = renderer.upload_scene(sc)
+    nodes, geom, ids = renderer.download_bvh()
+    assert sorted(ids.tolist()) == list(range(sc.indices.shape[0]))
+    s = sc.c_struct()
+    import ctypes as C
+    h = orclib.emul().emu_adopt(nodes.ctypes.data, int(info.num_nodes), geom.ctypes.data, int(info.num_triangles), C.byref(s))
+    assert orclib.emul().emu_validate(h) == 0
+    fr = scenes.terrain_frame(96, 54, outputs=ALL)
+    got = run(renderer, fr)
+    emu = orclib.emul_render(h, fr)
+    for k in ("tri_id", "t", "rgb8"):
+        assert np.array_equal(got[k], emu[k]), k
+    fr.kernel_variant = A.RT_VARIANT_STATS
+    st = run(renderer, fr)
+    nv, nt = renderer.frame_stats()
+    assert (nv, nt) == (emu["stats"]["nodes"], emu["stats"]["tris"])
+    assert np.array_equal(st["tri_id"], got["tri_id"])
+
+
+def test_tiny_and_degenerate_scenes(renderer):
+    # one triangle, two triangles, a degenerate (zero-area) triangle and duplicated triangles (exact ties)
+    pos = np.array([[-1, -1, 0], [1, -1, 0], [0, 1, 0], [0, 0, 0.5], [0, 0, 0.5], [0, 0, 0.5]], np.float32)
+    for idx in ([[0, 1, 2]], [[0, 1, 2], [0, 2, 1]], [[0, 1, 2], [3, 4, 5]], [[0, 1, 2]] * 7 + [[3, 4, 5]] * 3):
+        sc = api.Scene(pos, np.array(idx, np.uint32))
+        renderer.upload_scene(sc)
+        cam = api.camera_init((0.1, 0.05, 3), (0, 0, 0), (0, 1, 0), 50.0, 24.0, 40, 30)
+        fr = api.Frame(cam, 40, 30, lights=[api.make_light((1, 1, 2), (1, 1, 1), 3)], miss_color=(0.2, 0.3, 0.4), outputs=ALL)
+        got = run(renderer, fr)
+        fr.accel = A.RT_ACCEL_BRUTE
+        orc = orclib.oracle_render(sc, fr)
+        assert np.array_equal(got["tri_id"], orc["tri_id"]) and np.array_equal(got["t"], orc["t"])
+        assert np.abs(got["rgb"] - orc["rgb"]).max() <= 2e-7
+        assert (got["tri_id"] >= 0).any() and (got["tri_id"] < 0).any()
+        assert got["tri_id"].max() == 0                  # ties resolve to the lowest triangle id
+
+
+def test_axis_parallel_rays_and_flat_boxes(renderer):
+    """Camera looking straight down an axis at an axis-aligned plane: direction components that are
+    exactly zero and zero-thickness boxes (the reference's origin-in-slab branch, bvh.h:90-91)."""
+    g = np.linspace(-1, 1, 9, dtype=np.float32)
+    xx, yy = np.meshgrid(g, g)
+    pos = np.stack([xx.ravel(), yy.ravel(), np.zeros(81, np.float32)], 1)
+    idx = []
+    for j in range(8):
+        for i in range(8):
+            a = j * 9 + i
+            idx += [[a, a + 1, a + 10], [a, a + 10, a + 9]]
+    sc = api.Scene(pos, np.array(idx, np.uint32))
+    renderer.upload_scene(sc)
+    cam = api.camera_init((0, 0, 2), (0, 0, 0), (0, 1, 0), 30.0, 24.0, 33, 33)   # centre pixel ray = (0,0,-1) exactly
+    fr = api.Frame(cam, 33, 33, lights=[api.make_light((0, 0, 5), (1, 1, 1), 2)], outputs=ALL)
+    got = run(renderer, fr)
+    fr.accel = A.RT_ACCEL_BRUTE
+    orc = orclib.oracle_render(sc, fr)
+    assert np.array_equal(got["tri_id"], orc["tri_id"]) and np.array_equal(got["t"], orc["t"])
+    assert got["tri_id"][16, 16] >= 0
+
+
+# --------------------------------------------------------------- full-size properties ----
+def test_c4_full_size_properties(renderer):
+    """BASELINE config C4 (1M-triangle terrain, 3840x2160, primary + shadow): properties that do not
+    need a full CPU render + a strided comparison with the reference-exact oracle."""
+    sc = scenes.terrain_scene(1000, 500)
+    info = renderer.upload_scene(sc)
+    assert info.num_triangles == 1000000
+    W, H = 3840, 2160
+    fr = scenes.terrain_frame(W, H, outputs=A.RT_OUT_RGB8 | A.RT_OUT_TRI_ID | A.RT_OUT_T)
+    a = run(renderer, fr)
+    assert a["rays_primary"] == W * H
+    assert (a["tri_id"] >= 0).mean() > 0.9999          # straight-down camera: every ray hits (bar cracks)
+    b = run(renderer, fr)
+    for k in ("tri_id", "t", "rgb8"):                   # idempotence / determinism
+        assert np.array_equal(a[k], b[k]), k
+    # triangles of one grid cell are 2c, 2c+1: hit ids must walk the grid monotonically along a row
+    cell = a["tri_id"][H // 2] // 2
+    assert np.all(np.diff(cell[cell >= 0] % 1000) >= 0)
+    # strided rows against the reference-exact CPU oracle (reference LBVH + SearchBVH restated)
+    bvh = orclib.oracle_bvh(sc)
+    step = 135
+    orc = orclib.oracle_render(sc, scenes.terrain_frame(W, H, outputs=ALL), bvh=bvh, row_begin=7, row_step=step, want=("rgb8", "tri_id", "t"))
+    rows = slice(7, H, step)
+    n = orc["tri_id"][rows].size
+    mism = a["tri_id"][rows] != orc["tri_id"][rows]
+    assert mism.sum() <= 1e-4 * n, mism.sum()
+    hit = (orc["tri_id"][rows] >= 0) & ~mism
+    rel = np.abs(a["t"][rows][hit] - orc["t"][rows][hit]) / orc["t"][rows][hit]
+    assert rel.max() <= 1e-5
+    assert np.abs(a["rgb8"][rows].astype(int) - orc["rgb8"][rows].astype(int))[~mism].max() <= 1
+    # brute force on the device at a size it finishes quickly: BVH result == every-triangle result
+    small = scenes.terrain_frame(240, 135, outputs=ALL)
+    x = run(renderer, small)
+    small.accel = A.RT_ACCEL_BRUTE
+    y = run(renderer, small)
+    for k in ("tri_id", "t", "rgb8"):
+        assert np.array_equal(x[k], y[k]), k
+
+
+# ----------------------------------------------------------------------- error behaviour ----
+def test_error_behaviour():
+    r = api.Renderer(0)
+    cam = api.camera_init((0, 0, 1), (0, 0, 0), (0, 1, 0), 24, 24, 8, 8)
+    with pytest.raises(api.RtError) as e:
+        r.render(api.Frame(cam, 8, 8))
+    assert e.value.code == A.RT_ERR_STATE
+    with pytest.raises(api.RtError):
+        r.upload_scene(api.Scene(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32)))
+    with pytest.raises(api.RtError):
+        r.upload_scene(api.Scene(np.zeros((3, 3), np.float32), np.array([[0, 1, 7]], np.uint32)))   # index out of range
+    r.upload_scene(scenes.terrain_scene(4, 4, build_flags=A.RT_BUILD_NO_BVH))
+    with pytest.raises(api.RtError) as e:
+        r.render(api.Frame(cam, 8, 8, accel=A.RT_ACCEL_BVH))
+    assert e.value.code == A.RT_ERR_STATE
+    with pytest.raises(api.RtError) as e:
+        r.render(api.Frame(cam, 0, 8, accel=A.RT_ACCEL_BRUTE))
+    assert e.value.code == A.RT_ERR_ARG
+    with pytest.raises(api.RtError):
+        r.render(api.Frame(cam, 8, 8, mode=A.RT_MODE_HW1, accel=A.RT_ACCEL_BRUTE))   # HW1 needs a light
+    with pytest.raises(api.RtError):
+        api.camera_init((0, 0, 1), (0, 0, 0), (0, 1, 0), 24, 24, 0, 8)              # HW1 camera throws on W < 1
+    fr = api.Frame(cam, 8, 8, accel=A.RT_ACCEL_BRUTE, outputs=A.RT_OUT_RGB8)
+    r.render(fr)
+    fr.outputs = A.RT_OUT_RGB_F32
+    with pytest.raises(api.RtError):
+        r.download()                                                                 # plane not requested
+    r.close()
+
+
+def test_ppm_bytes_match_reference_writer(renderer, frog_scene, tmp_path):
+    """The u8 plane quantised on the device equals the bytes the reference's ppm_p6 writer emits for
+    the float image (ppm_p6.cpp:137-155, 257-301)."""
+    libs = orclib.ref_libs()
+    if "ref_ppm" not in libs:
+        pytest.skip("oracle/_ref/libref_ppm.so not built (needs /root/reference at build time)")
+    import ctypes as C
+    renderer.upload_scene(frog_scene)
+    for quant, gamma in ((A.RT_QUANT_PPM_LROUND, 0), (A.RT_QUANT_PPM_GAMMA2, 1)):
+        got = run(renderer, scenes.frog_frame(160, 90, filling=True, outputs=ALL, quantiser=quant))
+        path = str(tmp_path / ("q%d.ppm" % quant))
+        rc = libs["ref_ppm"].ref_ppm_write_rgbf(path.encode(), 160, 90, got["rgb"].ctypes.data_as(A.f32p), 255, 1, gamma, 0, None, 0)
+        assert rc == 0
+        data = open(path, "rb").read()
+        head = b"P6\n160 90\n255\n"
+        assert data[:len(head)] == head
+        assert data[len(head):] == got["rgb8"].tobytes()
