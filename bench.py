@@ -217,10 +217,10 @@ def run_ours(args, rank, world, local_rank):
         r.render(frame)
         return r.sync()
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(args.warmup if args.profile else max(args.warmup, 3)):
         step_device()
     # traversal statistics (untimed): bytes per ray for the roofline
-    frame.kernel_variant = A.RT_VARIANT_STATS
+    frame.kernel_variant = A.RT_VARIANT_PER_RAY_STATS if args.variant >= 10 else A.RT_VARIANT_STATS
     r.render(frame)
     st = r.download(into={"rgb8": pinned} if rank == 0 else None)
     nv, nt = r.frame_stats()
@@ -287,15 +287,18 @@ def run_ours(args, rank, world, local_rank):
                          "peak_kind": peak_kind, "bytes_per_ray": b_ray, "nodes_per_ray": nv_all / rays, "tris_per_ray": nt_all / rays},
             "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not args.profile:
             ref = CpuReference(scenes.terrain_scene(nx, ny), frame)
             cal_rays, cal_dt = ref.rays_in_rows(5, max(1, H // 8))
             rows = max(1, int(cal_rays / cal_dt * 12.0 / (W * spp)))
             stp = max(1, H // rows)
-            n, dt = ref.rays_in_rows(2, stp)
+            n, dt, passes = 0, 0.0, 0
+            while dt < 10.0 and passes < 64:                  # bounded sample: ~10 s of CPU work
+                a, b = ref.rays_in_rows(passes % stp, stp)
+                n += a; dt += b; passes += 1
             ratio = rays_shadow / max(rays_primary, 1.0)
             line["cpu_baseline"] = {"value": n * (1 + ratio) / dt / 1e6, "unit": "Mrays/s", "cores": ref.cores, "kind": ref.kind,
-                                    "sample": "every %d-th row of the %dx%d frame (%d rows, %.1f s); shadow rays = primary x %.4f (device count)" % (stp, W, H, len(range(2, H, stp)), dt, ratio)}
+                                    "sample": "%d pass(es) over every %d-th row of the %dx%d frame, %.1f s of CPU work; shadow rays = primary x %.4f (device count)" % (passes, stp, W, H, dt, ratio)}
         print(json.dumps(line))
     r.close()
     if dist is not None:
@@ -310,8 +313,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--variant", type=int, default=0)
-    ap.add_argument("--leaf-max", type=int, default=4)
+    ap.add_argument("--leaf-max", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="short run for ncu: honour --warmup < 3, skip the CPU baseline")
     ap.add_argument("--shadow-ratio", type=float, default=0.8144, help="shadow rays per primary ray on c4 (device count), used by --impl reference")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

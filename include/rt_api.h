@@ -64,13 +64,18 @@ extern "C" {
 #define RT_QUANT_HW2_TRUNC    3  /* GPUandCPU/src/main.cu:428-430 (uchar)(255*min(c,1))    */
 
 /* rt_frame.kernel_variant */
-#define RT_VARIANT_DEFAULT    0
-#define RT_VARIANT_STATS    100  /* same results, also counts BVH node visits / triangle tests */
+#define RT_VARIANT_DEFAULT          0  /* warp-packet traversal (one 8x4 tile per warp), 8 blocks/SM    */
+#define RT_VARIANT_PACKET_OCC6      1  /* same, compiled for >= 6 resident blocks per SM               */
+#define RT_VARIANT_PACKET_OCC10     2  /* same, >= 10 resident blocks per SM                           */
+#define RT_VARIANT_PACKET_EXACT_SLAB 3 /* same as default with the unfused (b-o)*inv slab test         */
+#define RT_VARIANT_PER_RAY         10  /* independent per-thread stack traversal (shared-memory stack) */
+#define RT_VARIANT_STATS          100  /* default kernel, also counts BVH node visits / triangle tests per ray */
+#define RT_VARIANT_PER_RAY_STATS  110  /* per-ray kernel with the same counters                        */
 
 /* rt_scene.build_flags */
 #define RT_BUILD_DEFAULT      0u
 #define RT_BUILD_NO_BVH       1u  /* brute-force frames only; skip the BVH build  */
-#define RT_BUILD_LEAF_MAX(n)  (((uint32_t)(n) & 0xFu) << 8)  /* max triangles per BVH leaf, 1..8 (0 = default 4) */
+#define RT_BUILD_LEAF_MAX(n)  (((uint32_t)(n) & 0xFu) << 8)  /* max triangles per BVH leaf, 1..8 (0 = default 2) */
 
 typedef struct rt_ctx rt_ctx;
 

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <nccl.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -241,7 +242,7 @@ int rt_upload_scene(rt_ctx* c, const rt_scene* sc) {
     bp.positions = d_pos; bp.normals = d_nrm; bp.indices = d_idx; bp.obj_ids = d_obj;
     bp.num_tris = (uint32_t)nt;
     uint32_t leaf_max = (sc->build_flags >> 8) & 0xFu;     // bits 8..11: leaf size override (0 = default)
-    bp.leaf_max = leaf_max ? leaf_max : 4u;
+    bp.leaf_max = leaf_max ? leaf_max : 2u;
     BuildResult br{};
     memset(&c->info, 0, sizeof c->info);
     if (sc->build_flags & RT_BUILD_NO_BVH) {
@@ -301,6 +302,15 @@ int rt_render(rt_ctx* c, const rt_frame* fr) {
     P.rank = c->rank; P.world = c->world;
     const int total_tiles = P.tiles_x * P.tiles_y;
     P.local_tiles = tiles_of_rank(total_tiles, c->rank, c->world);
+    {   // fused slab test only when the camera is within 8 scene extents of the scene (rt_core.h, rt_slab_fma)
+        float ext = 0.f, far = 0.f;
+        for (int k = 0; k < 3; ++k) {
+            ext = fmaxf(ext, c->info.scene_max[k] - c->info.scene_min[k]);
+            ext = fmaxf(ext, fmaxf(fabsf(c->info.scene_max[k]), fabsf(c->info.scene_min[k])));
+            far = fmaxf(far, fabsf(fr->cam.center[k]));
+        }
+        P.fast_slab = (c->has_bvh && far <= 8.0f * ext) ? 1 : 0;
+    }
 
     if (fr->num_lights) {
         CU(c, c->lights.reserve(sizeof(rt_light) * (size_t)fr->num_lights));

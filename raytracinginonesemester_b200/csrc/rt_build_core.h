@@ -32,10 +32,13 @@ RT_HD uint64_t rt_morton63(f3 a, f3 b, f3 c, const Bounds& scene) {
     float lo[3], hi[3];
     rt_tri_box(a, b, c, lo, hi);
     const float R = 2097152.0f;
+    // One scale for all three axes (the scene's longest extent): a thin axis (a terrain's height)
+    // then keeps its top bits constant instead of slicing the mesh into interleaved layers, which is
+    // what per-axis normalisation (the reference's, bvh.cu:44-47) does.
+    const float e = fmaxf(scene.hi[0] - scene.lo[0], fmaxf(scene.hi[1] - scene.lo[1], scene.hi[2] - scene.lo[2]));
     uint64_t q[3];
     for (int k = 0; k < 3; ++k) {
         const float ce = 0.5f * (lo[k] + hi[k]);
-        const float e = scene.hi[k] - scene.lo[k];
         const float nrm = e > 0.f ? (ce - scene.lo[k]) / e : 0.f;
         q[k] = (uint64_t)fminf(fmaxf(nrm * R, 0.f), R - 1.f);
     }

@@ -113,6 +113,29 @@ RT_HD bool rt_slab(const RayInv& k, float lox, float loy, float loz, float hix, 
     return tn <= tf * 1.0000005f + 1e-30f;
 }
 
+// Fused form: plane distance = fma(b, inv, -(o*inv)), half the arithmetic of rt_slab.  Its extra
+// rounding error is a few ulps of |o| + |b| in space, which the 2^-18 build-time padding of the
+// boxes absorbs as long as the ray origin is within ~8 scene extents of the scene (the host
+// checks this per frame and otherwise selects the exact form; shadow-ray origins lie on the
+// surface and always qualify).
+struct RayFma { f3 inv, oi; };
+RT_HD RayFma rt_ray_fma(const Ray& r) {
+    RayFma k;
+    k.inv = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+    k.oi = mk3(r.o.x * k.inv.x, r.o.y * k.inv.y, r.o.z * k.inv.z);
+    return k;
+}
+RT_HD bool rt_slab_fma(const RayFma& k, float lox, float loy, float loz, float hix, float hiy, float hiz,
+                       float tmin, float tmax, float& tnear) {
+    const float ax = fmaf(lox, k.inv.x, -k.oi.x), bx = fmaf(hix, k.inv.x, -k.oi.x);
+    const float ay = fmaf(loy, k.inv.y, -k.oi.y), by = fmaf(hiy, k.inv.y, -k.oi.y);
+    const float az = fmaf(loz, k.inv.z, -k.oi.z), bz = fmaf(hiz, k.inv.z, -k.oi.z);
+    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
+    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+    tnear = tn;
+    return tn <= tf * 1.0000005f + 1e-30f;
+}
+
 // ---------------------------------------------------------------- shading ----
 // shade(), HW1/include/raytracer.h:21-48, constant METAL material of HW1/include/ray.h:111-114.
 RT_HD f3 rt_shade_hw1_miss(const Ray& r) {

@@ -28,7 +28,8 @@ struct FrameParams {
     int local_tiles;                // tiles owned by this rank
     // output planes: row-major image when world == 1, tile-packed when world > 1
     float* rgb; uint8_t* rgb8; int32_t* tri_id; float* t;
-    unsigned long long* counters;   // [0] primary rays, [1] shadow rays
+    unsigned long long* counters;   // [0] primary rays, [1] shadow rays, [2] node visits, [3] triangle tests (stats variants)
+    int fast_slab;                  // 1: ray origins are close enough to the scene for rt_slab_fma (host decides)
 };
 
 struct BuildParams {

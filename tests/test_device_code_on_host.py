@@ -1,0 +1,128 @@
+"""The product's per-element device functions (csrc/rt_build_core.h, rt_trace_core.h), compiled for
+the host by tests/emul/, against the oracle: BVH build + flattening + traversal + shading logic is
+checked here without a GPU; the -m gpu tests then check the kernels that wrap the same functions."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import orclib
+from raytracinginonesemester_b200 import _abi as A, api, scenes
+
+ALL = A.RT_OUT_RGB_F32 | A.RT_OUT_RGB8 | A.RT_OUT_TRI_ID | A.RT_OUT_T
+
+
+def check(scene, frame, leaf_max=4, exact_rgb=True):
+    h = orclib.emul_build(scene, leaf_max)
+    assert h
+    assert orclib.emul().emu_validate(h) == 0
+    e = orclib.emul_render(h, frame)
+    frame.accel = A.RT_ACCEL_BRUTE
+    o = orclib.oracle_render(scene, frame)
+    frame.accel = A.RT_ACCEL_BVH
+    assert np.array_equal(e["tri_id"], o["tri_id"])
+    assert np.array_equal(e["t"], o["t"])
+    if exact_rgb:
+        assert np.array_equal(e["rgb"], o["rgb"]) and np.array_equal(e["rgb8"], o["rgb8"])
+    assert e["stats"]["max_stack"] < 32
+    orclib.emul().emu_free(h)
+    return e, o
+
+
+@pytest.mark.parametrize("leaf_max", [1, 2, 4, 8])
+def test_terrain_all_leaf_sizes(leaf_max):
+    e, o = check(scenes.terrain_scene(48, 24), scenes.terrain_frame(128, 72, spp=2, outputs=ALL), leaf_max)
+    assert e["stats"]["rays_shadow"] == o["counters"]["rays_shadow"] > 0
+
+
+def test_frog_hw2_and_hw1(frog_scene):
+    check(frog_scene, scenes.frog_frame(96, 54, filling=True, outputs=ALL))
+    check(frog_scene, scenes.hw1_frame(96, 54, light_color=(1, 1, 1), outputs=ALL, accel=A.RT_ACCEL_BVH))
+
+
+def test_matches_reference_fixture_bar(frog_scene, golden):
+    """Emulated device code vs the reference BVH path: the north-star bar (99.99 % ids, t 1e-5)."""
+    ref = golden("ref_hw2_frogfill_160x90.npz")
+    h = orclib.emul_build(frog_scene, 4)
+    e = orclib.emul_render(h, scenes.frog_frame(160, 90, filling=True, outputs=ALL))
+    mism = e["tri_id"] != ref["tri_id"]
+    assert mism.sum() <= 1e-4 * mism.size
+    assert np.array_equal(e["t"][mism], ref["t"][mism])
+    hit = (ref["tri_id"] >= 0) & ~mism
+    assert np.array_equal(e["t"][hit], ref["t"][hit])
+    assert np.array_equal(e["rgb"][~mism], ref["rgb"][~mism])
+
+
+def test_tiny_degenerate_and_tied_scenes():
+    pos = np.array([[-1, -1, 0], [1, -1, 0], [0, 1, 0], [0, 0, 0.5], [0, 0, 0.5], [0, 0, 0.5]], np.float32)
+    for idx in ([[0, 1, 2]], [[0, 1, 2], [0, 2, 1]], [[0, 1, 2], [3, 4, 5]], [[0, 1, 2]] * 7 + [[3, 4, 5]] * 3):
+        sc = api.Scene(pos, np.array(idx, np.uint32))
+        cam = api.camera_init((0.1, 0.05, 3), (0, 0, 0), (0, 1, 0), 50.0, 24.0, 40, 30)
+        fr = api.Frame(cam, 40, 30, lights=[api.make_light((1, 1, 2), (1, 1, 1), 3)], miss_color=(0.2, 0.3, 0.4), outputs=ALL)
+        for lm in (1, 4):
+            e, o = check(sc, fr, lm)
+            assert e["tri_id"].max() == 0 and (e["tri_id"] < 0).any()
+
+
+def test_axis_parallel_rays_and_flat_boxes():
+    g = np.linspace(-1, 1, 9, dtype=np.float32)
+    xx, yy = np.meshgrid(g, g)
+    pos = np.stack([xx.ravel(), yy.ravel(), np.zeros(81, np.float32)], 1)
+    idx = []
+    for j in range(8):
+        for i in range(8):
+            a = j * 9 + i
+            idx += [[a, a + 1, a + 10], [a, a + 10, a + 9]]
+    sc = api.Scene(pos, np.array(idx, np.uint32))
+    cam = api.camera_init((0, 0, 2), (0, 0, 0), (0, 1, 0), 30.0, 24.0, 33, 33)
+    fr = api.Frame(cam, 33, 33, lights=[api.make_light((0, 0, 5), (1, 1, 1), 2)], outputs=ALL)
+    e, o = check(sc, fr, 2)
+    assert e["tri_id"][16, 16] >= 0
+
+
+def test_random_soup_with_materials_and_two_lights():
+    rng = np.random.default_rng(11)
+    pos = rng.uniform(-1, 1, (300, 3)).astype(np.float32)
+    idx = rng.integers(0, 300, (700, 3)).astype(np.uint32)
+    nrm = rng.normal(size=(300, 3)).astype(np.float32)
+    obj = rng.integers(-1, 4, 700).astype(np.int32)          # includes out-of-range ids -> default material
+    mats = [api.make_material(albedo=(0.9, 0.3, 0.2), ks=0.2), api.make_material(albedo=(0.2, 0.9, 0.2), kd=0.7, ks=0.6, shininess=8.0),
+            api.make_material(emission=(0.1, 0.1, 0.2))]
+    sc = api.Scene(pos, idx, normals=nrm, tri_obj_ids=obj, materials=mats)
+    cam = api.camera_init((0.2, -3, 0.4), (0, 0, 0), (0, 0, 1), 30.0, 24.0, 80, 60)
+    fr = api.Frame(cam, 80, 60, lights=[api.make_light((2, -2, 3), (1, 0.9, 0.8), 3), api.make_light((-2, -1, -2), (0.3, 0.3, 1), 2)],
+                   miss_color=(0.1, 0.1, 0.1), spp=3, jitter=api.jitter_table(3, 42, True), outputs=ALL)
+    check(sc, fr, 4)
+    fr.shadows = False
+    check(sc, fr, 4)
+    fr.max_depth = 0                                           # TraceRayIterative returns black
+    e, o = check(sc, fr, 4)
+    assert not e["rgb"].any()
+
+
+def test_tile_sharding_covers_the_frame_once():
+    """rt_map_pixel / rt_unpack_index (used by the kernels): every pixel is owned by exactly one rank and
+    pack -> unpack is the identity, for sizes that are not multiples of the 16x8 tile."""
+    sc = scenes.terrain_scene(16, 8)
+    h = orclib.emul_build(sc, 4)
+    lib = orclib.emul()
+    lib.emu_render_rank.argtypes = [C.c_void_p, C.POINTER(A.rt_frame), C.POINTER(A.rt_image), C.POINTER(C.c_uint64), C.c_int, C.c_int]
+    lib.emu_unpack_rgb8.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, A.u8p, A.u8p]
+    for (W, H) in ((50, 21), (64, 32), (7, 3)):
+        fr = scenes.terrain_frame(W, H, outputs=A.RT_OUT_RGB8)
+        full = orclib.emul_render(h, fr, want=("rgb8",))["rgb8"]
+        for world in (2, 3, 8):
+            img = np.full((H, W, 3), 255, np.uint8)
+            total_prim = 0
+            for rank in range(world):
+                tiles = ((W + 15) // 16) * ((H + 7) // 8)
+                ntl = (tiles - rank + world - 1) // world if tiles > rank else 0
+                packed = np.zeros((max(ntl, 1) * 128, 3), np.uint8)
+                im = A.rt_image(); im.rgb8 = packed.ctypes.data_as(A.u8p)
+                f = fr.c_struct()
+                got = lib.emu_render_rank(h, C.byref(f), C.byref(im), None, rank, world)
+                assert got == ntl
+                total_prim += im.rays_primary
+                lib.emu_unpack_rgb8(W, H, world, rank, packed.ctypes.data_as(A.u8p), img.ctypes.data_as(A.u8p))
+            assert total_prim == W * H
+            assert np.array_equal(img, full)

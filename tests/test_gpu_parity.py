@@ -20,14 +20,21 @@ def run(renderer, frame):
     return renderer.download()
 
 
-def assert_reference_bar(got, ref_id, ref_t, ref_rgb=None, quant=A.RT_QUANT_HW2_TRUNC, what=""):
+def assert_reference_bar(got, ref_id, ref_t, ref_rgb=None, quant=A.RT_QUANT_HW2_TRUNC, what="", coplanar_overlaps=False):
+    """coplanar_overlaps: the scene stacks distinct triangles in one plane (cornellbox.obj: block
+    footprints on the floor), so whole regions are t-ties decided by traversal order in the reference
+    (last visited wins, query.h:105) and by min id here; the id bar then applies to non-tied pixels."""
     n = ref_id.size
     mism = got["tri_id"] != ref_id
-    assert mism.sum() <= 1e-4 * n, "%s: %d of %d ids differ" % (what, mism.sum(), n)
-    # every id mismatch must be an exact-t tie (both hit, same t) — the "stated epsilon ties"
+    if not coplanar_overlaps:
+        assert mism.sum() <= 1e-4 * n, "%s: %d of %d ids differ" % (what, mism.sum(), n)
+    # every id mismatch must be a t-tie (both hit, same t to 1e-6 relative) — the "stated epsilon ties"
     if mism.any():
         assert np.all((got["tri_id"][mism] >= 0) & (ref_id[mism] >= 0)), what + ": hit/miss flip"
-        assert np.array_equal(got["t"][mism], ref_t[mism]), what + ": id mismatch that is not an exact-t tie"
+        tie = np.abs(got["t"][mism] - ref_t[mism]) <= 1e-6 * np.abs(ref_t[mism])
+        assert tie.all(), what + ": id mismatch that is not a t-tie"
+        if not coplanar_overlaps:
+            assert np.array_equal(got["t"][mism], ref_t[mism]), what + ": id mismatch that is not an exact-t tie"
     hit = (ref_id >= 0) & ~mism
     rel = np.abs(got["t"][hit] - ref_t[hit]) / np.maximum(np.abs(ref_t[hit]), 1e-30)
     assert rel.size == 0 or rel.max() <= 1e-5, "%s: t rel err %g" % (what, rel.max())
@@ -131,7 +138,8 @@ def test_hw2_cornell_multi_material(renderer, golden):
     fr = api.Frame(c, 96, 96, lights=[api.make_light(lp[0], (1, 1, 1), 2), api.make_light(lp[1], (0.4, 0.4, 1.0), 1)],
                    miss_color=(0.1, 0.2, 0.3), jitter=api.jitter_table(1, 42, True), outputs=ALL, quantiser=A.RT_QUANT_HW2_TRUNC)
     got = run(renderer, fr)
-    assert_reference_bar(got, ref["tri_id"], ref["t"], ref["rgb"], what="cornell")
+    assert_reference_bar(got, ref["tri_id"], ref["t"], ref["rgb"], what="cornell", coplanar_overlaps=True)
+    assert (got["tri_id"] != ref["tri_id"]).mean() < 0.08
 
 
 @pytest.mark.parametrize("leaf_max", [1, 2, 8])
@@ -162,11 +170,29 @@ def test_device_bvh_is_sound_and_host_walk_agrees(renderer):
     emu = orclib.emul_render(h, fr)
     for k in ("tri_id", "t", "rgb8"):
         assert np.array_equal(got[k], emu[k]), k
-    fr.kernel_variant = A.RT_VARIANT_STATS
+    fr.kernel_variant = A.RT_VARIANT_PER_RAY_STATS          # per-ray kernel: the same walk as the host emulation
     st = run(renderer, fr)
     nv, nt = renderer.frame_stats()
     assert (nv, nt) == (emu["stats"]["nodes"], emu["stats"]["tris"])
     assert np.array_equal(st["tri_id"], got["tri_id"])
+    fr.kernel_variant = A.RT_VARIANT_STATS                  # packet kernel: a lane tests a superset, results identical
+    pk = run(renderer, fr)
+    nvp, ntp = renderer.frame_stats()
+    assert nvp >= nv and ntp >= nt
+    for k in ("tri_id", "t", "rgb8"):
+        assert np.array_equal(pk[k], got[k]), k
+
+
+@pytest.mark.parametrize("variant", [A.RT_VARIANT_DEFAULT, A.RT_VARIANT_PACKET_OCC6, A.RT_VARIANT_PACKET_OCC10, A.RT_VARIANT_PACKET_EXACT_SLAB, A.RT_VARIANT_PER_RAY])
+def test_all_kernel_variants_agree(renderer, frog_scene, variant):
+    renderer.upload_scene(frog_scene)
+    base = run(renderer, scenes.frog_frame(200, 120, filling=True, outputs=ALL, accel=A.RT_ACCEL_BRUTE))
+    fr = scenes.frog_frame(200, 120, filling=True, outputs=ALL)
+    fr.kernel_variant = variant
+    got = run(renderer, fr)
+    for k in ("tri_id", "t", "rgb", "rgb8"):
+        assert np.array_equal(base[k], got[k]), k
+    assert got["rays_shadow"] == base["rays_shadow"]
 
 
 def test_tiny_and_degenerate_scenes(renderer):
