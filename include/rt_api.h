@@ -193,10 +193,12 @@ int  rt_download_image(rt_ctx* ctx, rt_image* img);
 /* Blocks until the last rt_render finished; returns its device time. */
 int  rt_sync(rt_ctx* ctx, float* gpu_ms);
 
-/* Traversal work of the last frame rendered with RT_VARIANT_STATS: BVH nodes visited and
- * triangles tested, summed over primary and shadow queries of this rank (the per-ray byte figure
- * of the roofline is 64*nodes + 48*tris + 16 per ray).  Blocks like rt_sync. */
-int  rt_frame_stats(rt_ctx* ctx, uint64_t* node_visits, uint64_t* tri_tests);
+/* Traversal work of the last frame rendered with a *_STATS variant, summed over primary and shadow
+ * queries of this rank: per-ray BVH node visits and triangle tests, and the memory requests behind
+ * them — 64-byte node lines and 48-byte triangle blocks fetched (one per warp visit in the packet
+ * kernel, one per lane in the per-ray kernel).  The roofline's algorithmic bytes per launch are
+ * 64*node_lines + 48*tri_blocks + output bytes.  Blocks like rt_sync. */
+int  rt_frame_stats(rt_ctx* ctx, uint64_t* node_visits, uint64_t* tri_tests, uint64_t* node_lines, uint64_t* tri_blocks);
 
 /* -- host helpers (pure host arithmetic, no device work) ------------------ */
 /* Camera::initialize restated with the reference's mixed fp64/fp32 rounding

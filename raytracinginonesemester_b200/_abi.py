@@ -77,7 +77,7 @@ EXPORTS = {
     "rt_render": (C.c_int, [C.c_void_p, C.POINTER(rt_frame)]),
     "rt_download_image": (C.c_int, [C.c_void_p, C.POINTER(rt_image)]),
     "rt_sync": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
-    "rt_frame_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "rt_frame_stats": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_uint64)] * 4),
     "rt_camera_init": (C.c_int, [C.POINTER(rt_camera), f32p, f32p, f32p, C.c_double, C.c_double, C.c_int, C.c_int]),
     "rt_jitter_table": (C.c_int, [f32p, C.c_int, C.c_uint32, C.c_int]),
     "rt_debug_download_bvh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, i32p]),

@@ -34,7 +34,7 @@ def load_library():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError("%s is missing: run `python -m raytracinginonesemester_b200.build` "
                                "(the CUDA extension is the product; there is no CPU fallback)" % LIB_PATH)
-        _LIB = A.bind(C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL))
+        _LIB = A.bind(C.CDLL(LIB_PATH))
     return _LIB
 
 
@@ -241,10 +241,10 @@ class Renderer:
         return out
 
     def frame_stats(self):
-        """(node_visits, tri_tests) of the last frame rendered with kernel_variant=RT_VARIANT_STATS."""
-        n, t = C.c_uint64(), C.c_uint64()
-        self._check(self.lib.rt_frame_stats(self.ctx, C.byref(n), C.byref(t)))
-        return int(n.value), int(t.value)
+        """(node_visits, tri_tests, node_lines, tri_blocks) of the last frame rendered with a *_STATS variant."""
+        v = [C.c_uint64() for _ in range(4)]
+        self._check(self.lib.rt_frame_stats(self.ctx, *[C.byref(x) for x in v]))
+        return tuple(int(x.value) for x in v)
 
     def download_bvh(self):
         info = A.rt_build_info()

@@ -7,7 +7,8 @@
 #include "rt_kernels.h"
 
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the library is resolved at run time, see NcclApi below
 
 #include <cmath>
 #include <cstdarg>
@@ -19,6 +20,35 @@
 
 namespace {
 thread_local std::string g_last_error;
+
+// NCCL is bound lazily, on the first multi-GPU call, and to whichever libnccl.so.2 the process
+// already has (a host that also runs torch.distributed has torch's bundled NCCL loaded; linking a
+// second copy at load time makes the two fight over one SONAME).  Single-GPU contexts never load it.
+struct NcclApi {
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclBroadcast) Broadcast = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    bool ok = false;
+    std::string why;
+    NcclApi() {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { why = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
+#define RT_SYM(f) f = reinterpret_cast<decltype(f)>(dlsym(h, "nccl" #f)); if (!f) { why = "libnccl.so.2 lacks nccl" #f; return; }
+        RT_SYM(GetUniqueId) RT_SYM(CommInitRank) RT_SYM(CommDestroy) RT_SYM(Broadcast) RT_SYM(Send) RT_SYM(Recv)
+        RT_SYM(GroupStart) RT_SYM(GroupEnd) RT_SYM(GetErrorString)
+#undef RT_SYM
+        ok = true;
+    }
+};
+NcclApi& nccl() { static NcclApi api; return api; }
 
 struct Plane {
     void* p = nullptr; size_t cap = 0;
@@ -67,7 +97,7 @@ int fail(rt_ctx* c, int code, const char* fmt, ...) {
     return code;
 }
 #define CU(c, x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail((c), RT_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } while (0)
-#define NC(c, x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) return fail((c), RT_ERR_NCCL, "%s: %s", #x, ncclGetErrorString(r_)); } while (0)
+#define NC(c, x) do { if (!nccl().ok) return fail((c), RT_ERR_NCCL, "%s", nccl().why.c_str()); ncclResult_t r_ = nccl().x; if (r_ != ncclSuccess) return fail((c), RT_ERR_NCCL, "nccl%s: %s", #x, nccl().GetErrorString(r_)); } while (0)
 
 void free_scene(rt_ctx* c) {
     if (c->nodes) cudaFree(c->nodes);
@@ -92,7 +122,7 @@ int broadcast_scene(rt_ctx* c) {
     SceneHeader* dh = nullptr;
     CU(c, cudaMalloc(&dh, sizeof h));
     if (c->rank == 0) CU(c, cudaMemcpyAsync(dh, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
-    NC(c, ncclBroadcast(dh, dh, sizeof h, ncclUint8, 0, c->comm, c->stream));
+    NC(c, Broadcast(dh, dh, sizeof h, ncclUint8, 0, c->comm, c->stream));
     CU(c, cudaMemcpyAsync(&h, dh, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     cudaFree(dh);
@@ -107,12 +137,12 @@ int broadcast_scene(rt_ctx* c) {
         c->info.num_triangles = h.num_tris; c->info.num_nodes = h.num_nodes;
         memcpy(c->info.scene_min, h.smin, sizeof h.smin); memcpy(c->info.scene_max, h.smax, sizeof h.smax);
     }
-    NC(c, ncclGroupStart());
-    if (c->num_nodes) NC(c, ncclBroadcast(c->nodes, c->nodes, sizeof(BvhNode) * (size_t)c->num_nodes, ncclUint8, 0, c->comm, c->stream));
-    NC(c, ncclBroadcast(c->geom, c->geom, sizeof(TriBlock) * (size_t)c->num_tris, ncclUint8, 0, c->comm, c->stream));
-    NC(c, ncclBroadcast(c->shade, c->shade, sizeof(TriBlock) * (size_t)c->num_tris, ncclUint8, 0, c->comm, c->stream));
-    if (c->num_materials) NC(c, ncclBroadcast(c->materials, c->materials, sizeof(rt_material) * (size_t)c->num_materials, ncclUint8, 0, c->comm, c->stream));
-    NC(c, ncclGroupEnd());
+    NC(c, GroupStart());
+    if (c->num_nodes) NC(c, Broadcast(c->nodes, c->nodes, sizeof(BvhNode) * (size_t)c->num_nodes, ncclUint8, 0, c->comm, c->stream));
+    NC(c, Broadcast(c->geom, c->geom, sizeof(TriBlock) * (size_t)c->num_tris, ncclUint8, 0, c->comm, c->stream));
+    NC(c, Broadcast(c->shade, c->shade, sizeof(TriBlock) * (size_t)c->num_tris, ncclUint8, 0, c->comm, c->stream));
+    if (c->num_materials) NC(c, Broadcast(c->materials, c->materials, sizeof(rt_material) * (size_t)c->num_materials, ncclUint8, 0, c->comm, c->stream));
+    NC(c, GroupEnd());
     CU(c, cudaStreamSynchronize(c->stream));
     c->has_scene = true;
     c->info.arena_bytes = sizeof(BvhNode) * (uint64_t)c->num_nodes + 2 * sizeof(TriBlock) * (uint64_t)c->num_tris +
@@ -144,7 +174,7 @@ int rt_create(rt_ctx** out, int device) {
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
-    if (e == cudaSuccess) e = c->counters.reserve(4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = c->counters.reserve(8 * sizeof(unsigned long long));
     if (e != cudaSuccess) { int r = fail(nullptr, RT_ERR_CUDA, "rt_create: %s", cudaGetErrorString(e)); delete c; return r; }
     *out = c;
     return RT_OK;
@@ -154,7 +184,7 @@ int rt_destroy(rt_ctx* c) {
     if (!c) return RT_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    if (c->comm) ncclCommDestroy(c->comm);
+    if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
     free_scene(c);
     Plane* planes[] = {&c->lights, &c->jitter, &c->counters, &c->loc_rgb, &c->loc_rgb8, &c->loc_id, &c->loc_t,
                        &c->img_rgb, &c->img_rgb8, &c->img_id, &c->img_t, &c->stage_rgb, &c->stage_rgb8, &c->stage_id, &c->stage_t};
@@ -170,7 +200,7 @@ int rt_comm_unique_id(void* id128) {
     if (!id128) return fail(nullptr, RT_ERR_ARG, "rt_comm_unique_id: NULL");
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
     ncclUniqueId id;
-    NC(nullptr, ncclGetUniqueId(&id));
+    NC(nullptr, GetUniqueId(&id));
     memcpy(id128, &id, sizeof id);
     return RT_OK;
 }
@@ -178,12 +208,12 @@ int rt_comm_unique_id(void* id128) {
 int rt_comm_init(rt_ctx* c, int rank, int world, const void* id128) {
     if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(c, RT_ERR_ARG, "rt_comm_init: bad arguments");
     CU(c, cudaSetDevice(c->device));
-    if (c->comm) { ncclCommDestroy(c->comm); c->comm = nullptr; }
+    if (c->comm && nccl().ok) { nccl().CommDestroy(c->comm); c->comm = nullptr; }
     c->rank = rank; c->world = world;
     if (world > 1) {
         ncclUniqueId id;
         memcpy(&id, id128, sizeof id);
-        NC(c, ncclCommInitRank(&c->comm, world, id, rank));
+        NC(c, CommInitRank(&c->comm, world, id, rank));
     }
     c->frame_valid = false;
     return RT_OK;
@@ -329,7 +359,7 @@ int rt_render(rt_ctx* c, const rt_frame* fr) {
     if (outputs & RT_OUT_TRI_ID) { CU(c, c->loc_id.reserve(4 * npix_loc + 16)); P.tri_id = (int32_t*)c->loc_id.p; }
     if (outputs & RT_OUT_T) { CU(c, c->loc_t.reserve(4 * npix_loc + 16)); P.t = (float*)c->loc_t.p; }
     P.counters = (unsigned long long*)c->counters.p;
-    CU(c, cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(unsigned long long), c->stream));
+    CU(c, cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
 
     CU(c, cudaEventRecord(c->ev0, c->stream));
     int launches = 0;
@@ -347,22 +377,22 @@ int rt_render(rt_ctx* c, const rt_frame* fr) {
         struct PlaneIo { uint32_t bit; size_t bpp; Plane* loc; Plane* stage; };
         PlaneIo io[4] = {{RT_OUT_RGB_F32, 12, &c->loc_rgb, &c->stage_rgb}, {RT_OUT_RGB8, 3, &c->loc_rgb8, &c->stage_rgb8},
                          {RT_OUT_TRI_ID, 4, &c->loc_id, &c->stage_id}, {RT_OUT_T, 4, &c->loc_t, &c->stage_t}};
-        NC(c, ncclGroupStart());
+        NC(c, GroupStart());
         for (const PlaneIo& q : io) {
             if (!(outputs & q.bit)) continue;
             if (c->rank == 0) {
                 size_t off = 0;
                 for (int r = 1; r < c->world; ++r) {
                     size_t bytes = (size_t)tiles_of_rank(total_tiles, r, c->world) * RT_BLOCK_THREADS * q.bpp;
-                    if (bytes) NC(c, ncclRecv((char*)q.stage->p + off, bytes, ncclUint8, r, c->comm, c->stream));
+                    if (bytes) NC(c, Recv((char*)q.stage->p + off, bytes, ncclUint8, r, c->comm, c->stream));
                     off += bytes;
                 }
             } else {
                 size_t bytes = npix_loc * q.bpp;
-                if (bytes) NC(c, ncclSend(q.loc->p, bytes, ncclUint8, 0, c->comm, c->stream));
+                if (bytes) NC(c, Send(q.loc->p, bytes, ncclUint8, 0, c->comm, c->stream));
             }
         }
-        NC(c, ncclGroupEnd());
+        NC(c, GroupEnd());
         if (c->rank == 0) {
             size_t off_pix = 0;
             for (int r = 0; r < c->world; ++r) {
@@ -394,15 +424,17 @@ int rt_sync(rt_ctx* c, float* gpu_ms) {
     return RT_OK;
 }
 
-int rt_frame_stats(rt_ctx* c, uint64_t* node_visits, uint64_t* tri_tests) {
+int rt_frame_stats(rt_ctx* c, uint64_t* node_visits, uint64_t* tri_tests, uint64_t* node_lines, uint64_t* tri_blocks) {
     if (!c) return fail(nullptr, RT_ERR_ARG, "rt_frame_stats: NULL ctx");
     CU(c, cudaSetDevice(c->device));
     if (!c->frame_valid) return fail(c, RT_ERR_STATE, "rt_frame_stats: no frame rendered");
-    unsigned long long cnt[4] = {0, 0, 0, 0};
+    unsigned long long cnt[6] = {0, 0, 0, 0, 0, 0};
     CU(c, cudaMemcpyAsync(cnt, c->counters.p, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     if (node_visits) *node_visits = cnt[2];
     if (tri_tests) *tri_tests = cnt[3];
+    if (node_lines) *node_lines = cnt[4];
+    if (tri_blocks) *tri_blocks = cnt[5];
     return RT_OK;
 }
 

@@ -105,7 +105,7 @@ __global__ void k_refit(BuildParams bp, const uint32_t* __restrict__ vals, int n
 __global__ void k_keep_flags(const Topo* __restrict__ topo, int n, uint32_t leaf_max, uint32_t* keep) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
-    keep[i] = (topo[i].last - topo[i].first + 1u) > leaf_max ? 1u : 0u;
+    keep[i] = (RT_TOPO_LAST(topo[i]) - topo[i].first + 1u) > leaf_max ? 1u : 0u;
 }
 
 __global__ void k_emit_nodes(const Topo* __restrict__ topo, int n, const uint32_t* __restrict__ keep,
@@ -116,7 +116,7 @@ __global__ void k_emit_nodes(const Topo* __restrict__ topo, int n, const uint32_
     const Topo tp = topo[i];
     const BvhNode nd = rt_make_node(blo[tp.left], bhi[tp.left], blo[tp.right], bhi[tp.right],
                                     rt_child_ref(tp.left, n, topo, keep, newidx), rt_child_ref(tp.right, n, topo, keep, newidx),
-                                    tp.first, tp.last - tp.first + 1u);
+                                    tp.first, (RT_TOPO_LAST(tp) - tp.first + 1u) | (RT_TOPO_AXIS(tp) << 30));
     float4* dst = reinterpret_cast<float4*>(nodes + newidx[i]);
     const float4* src = reinterpret_cast<const float4*>(&nd);
     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];

@@ -6,7 +6,9 @@
 
 struct Bounds { float lo[3]; float hi[3]; };
 // Karras numbering: internal k -> k, leaf k -> (n-1)+k.  [first,last] = sorted-order range.
-struct Topo { uint32_t left, right, first, last; };
+struct Topo { uint32_t left, right, first, last; };   // last: bits 0..29 = index, bits 30..31 = split axis (0 z, 1 y, 2 x, 3 none)
+#define RT_TOPO_LAST(tp) ((tp).last & 0x3fffffffu)
+#define RT_TOPO_AXIS(tp) ((tp).last >> 30)
 
 RT_HD void rt_tri_verts(const BuildParams& bp, uint32_t i, f3& a, f3& b, f3& c, uint32_t& ia, uint32_t& ib, uint32_t& ic) {
     ia = RT_LDG(bp.indices + 3 * (size_t)i); ib = RT_LDG(bp.indices + 3 * (size_t)i + 1); ic = RT_LDG(bp.indices + 3 * (size_t)i + 2);
@@ -76,17 +78,22 @@ RT_HD Topo rt_karras_node(const uint64_t* __restrict__ keys, int n, int i) {
     Topo tp;
     tp.left = (first == gamma) ? (uint32_t)(n - 1 + gamma) : (uint32_t)gamma;
     tp.right = (last == gamma + 1) ? (uint32_t)(n - 1 + gamma + 1) : (uint32_t)(gamma + 1);
-    tp.first = (uint32_t)first; tp.last = (uint32_t)last;
+    // Split axis: the highest key bit in which the two children's ranges differ (key bit p belongs to
+    // axis p % 3: 2 = x, 1 = y, 0 = z).  The right child holds the larger coordinates along it, so a
+    // ray travelling in the negative direction of that axis meets the right child first.
+    const uint64_t ka = keys[gamma], kb = keys[gamma + 1];
+    const uint32_t axis = (ka == kb) ? 3u : (uint32_t)((63 - RT_CLZ64(ka ^ kb)) % 3);
+    tp.first = (uint32_t)first; tp.last = (uint32_t)last | (axis << 30);
     return tp;
 }
 
-// Leaf box, padded outward by 2^-18 of the local/scene scale so the fp32 slab test stays a
+// Leaf box, padded outward by 2^-17 of the local/scene scale so the fp32 slab test stays a
 // superset of what the fp32 Möller–Trumbore test accepts (rt_core.h, rt_slab).
 RT_HD void rt_padded_leaf_box(f3 a, f3 b, f3 c, const Bounds& scene, float lo[3], float hi[3]) {
     rt_tri_box(a, b, c, lo, hi);
     const float ext = fmaxf(scene.hi[0] - scene.lo[0], fmaxf(scene.hi[1] - scene.lo[1], scene.hi[2] - scene.lo[2]));
     for (int q = 0; q < 3; ++q) {
-        const float pad = fmaxf(ext, fmaxf(fabsf(lo[q]), fabsf(hi[q]))) * 3.8146973e-06f + 1e-30f;
+        const float pad = fmaxf(ext, fmaxf(fabsf(lo[q]), fabsf(hi[q]))) * 7.6293945e-06f + 1e-30f;   // 2^-17
         lo[q] -= pad; hi[q] += pad;
     }
 }
@@ -95,14 +102,21 @@ RT_HD int32_t rt_child_ref(uint32_t c, int n, const Topo* __restrict__ topo, con
                            const uint32_t* __restrict__ newidx) {
     if (c >= (uint32_t)(n - 1)) return rt_leaf_ref(c - (uint32_t)(n - 1), 1u);     // original leaf
     if (keep[c]) return (int32_t)newidx[c];
-    return rt_leaf_ref(topo[c].first, topo[c].last - topo[c].first + 1u);          // collapsed subtree
+    return rt_leaf_ref(topo[c].first, RT_TOPO_LAST(topo[c]) - topo[c].first + 1u);   // collapsed subtree
 }
 
+// lo/hi -> centre + half-extent, half-extent rounded up so that [c-h, c+h] contains [lo, hi].
+RT_HD void rt_box_to_ch(float lo, float hi, float& c, float& h) {
+    if (!(lo <= hi)) { c = 0.f; h = -1.f; return; }           // absent child
+    c = 0.5f * lo + 0.5f * hi;
+    const float e = fmaxf(hi - c, c - lo);
+    h = e * 1.000001f + 1e-30f + fabsf(c) * 1.2e-7f;
+}
 RT_HD BvhNode rt_make_node(float4 l0, float4 h0, float4 l1, float4 h1, int32_t r0, int32_t r1, uint32_t first, uint32_t count) {
     BvhNode nd;
-    nd.q[0] = l0.x; nd.q[1] = l0.y; nd.q[2] = l0.z; nd.q[3] = h0.x; nd.q[4] = h0.y; nd.q[5] = h0.z;
-    nd.q[6] = l1.x; nd.q[7] = l1.y; nd.q[8] = l1.z; nd.q[9] = h1.x; nd.q[10] = h1.y; nd.q[11] = h1.z;
-    nd.ref0 = r0; nd.ref1 = r1; nd.first_slot = first; nd.slot_count = count;
+    rt_box_to_ch(l0.x, h0.x, nd.q[0], nd.q[3]); rt_box_to_ch(l0.y, h0.y, nd.q[1], nd.q[4]); rt_box_to_ch(l0.z, h0.z, nd.q[2], nd.q[5]);
+    rt_box_to_ch(l1.x, h1.x, nd.q[6], nd.q[9]); rt_box_to_ch(l1.y, h1.y, nd.q[7], nd.q[10]); rt_box_to_ch(l1.z, h1.z, nd.q[8], nd.q[11]);
+    nd.ref0 = r0; nd.ref1 = r1; nd.first_slot = first; nd.slot_count = count;   // count: bits 30..31 carry the split axis
     return nd;
 }
 

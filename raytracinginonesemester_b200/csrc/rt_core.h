@@ -11,10 +11,15 @@
 // ----------------------------------------------------------------- layout ----
 // One BVH2 node = one 64-byte line: both children's boxes + both child references, so a
 // node visit is four 16-byte loads from a single aligned line (ld.global.nc.v4).
-//   q0 = (lo0.x, lo0.y, lo0.z, hi0.x)   q1 = (hi0.y, hi0.z, lo1.x, lo1.y)
-//   q2 = (lo1.z, hi1.x, hi1.y, hi1.z)   q3 = (ref0, ref1, first_slot, slot_count) as ints
+// Boxes are stored as centre + half-extent: the slab distances are then m -+ h*|1/d| with
+// m = (c - o)/d, i.e. nine FMAs per box and no per-axis min/max (those run on the half-rate
+// ALU pipe, which ncu showed to be the busiest pipe of the first packet kernel).
+//   q0 = (c0.x, c0.y, c0.z, h0.x)   q1 = (h0.y, h0.z, c1.x, c1.y)
+//   q2 = (c1.z, h1.x, h1.y, h1.z)   q3 = (ref0, ref1, first_slot, slot_count) as ints
 // Child reference: >= 0 -> index of another node; < 0 -> leaf, ~ref = (first_slot << 3) | (count-1).
-// An absent child has an inverted box (+inf/-inf) that no ray can hit.
+// An absent child has negative half-extents (never hit; if NaNs from a zero direction component
+// make it pass, its reference is a valid one-triangle leaf, and testing an extra triangle cannot
+// change a closest-hit result).
 struct alignas(64) BvhNode {
     float q[12];
     int32_t ref0, ref1;
@@ -93,47 +98,56 @@ RT_HD float rt_tmin(int mode) { return mode == RT_MODE_HW1 ? 0.0f : 1e-4f; }
 // ------------------------------------------------------------- slab test ----
 // Conservative fp32 slab test.  The reference tests boxes in fp64 (GPUandCPU/include/bvh.h:81-129);
 // ours only has to accept a superset: boxes are padded outward at build time
-// and the far bound is widened by a few ulps here, so every triangle the fp32 Möller–Trumbore
-// test would accept is reached.  A zero direction component gives +-inf / NaN plane distances;
-// fminf/fmaxf drop NaNs, which reproduces the reference's origin-in-slab branch (bvh.h:90-91).
-struct RayInv { f3 o, inv; };
+// (2^-17 of the scene scale, half-extents rounded up) and the far bound is widened by a few ulps
+// here, so every triangle the fp32 Möller–Trumbore test would accept is reached.  A zero
+// direction component gives +-inf / NaN plane distances; fminf/fmaxf drop NaNs, which makes that
+// axis accept — a superset of the reference's origin-in-slab branch (bvh.h:90-91).
+struct RayInv { f3 o, inv, ainv; };
 RT_HD RayInv rt_ray_inv(const Ray& r) {
     RayInv k; k.o = r.o;
     k.inv = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+    k.ainv = mk3(fabsf(k.inv.x), fabsf(k.inv.y), fabsf(k.inv.z));
     return k;
 }
-RT_HD bool rt_slab(const RayInv& k, float lox, float loy, float loz, float hix, float hiy, float hiz,
-                   float tmin, float tmax, float& tnear) {
-    float ax = (lox - k.o.x) * k.inv.x, bx = (hix - k.o.x) * k.inv.x;
-    float ay = (loy - k.o.y) * k.inv.y, by = (hiy - k.o.y) * k.inv.y;
-    float az = (loz - k.o.z) * k.inv.z, bz = (hiz - k.o.z) * k.inv.z;
-    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
-    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+RT_HD bool rt_slab_combine(float mx, float my, float mz, const f3& ainv, float hx, float hy, float hz,
+                           float tmin, float tmax, float& tnear) {
+    const float nx = fmaf(-hx, ainv.x, mx), fx = fmaf(hx, ainv.x, mx);
+    const float ny = fmaf(-hy, ainv.y, my), fy = fmaf(hy, ainv.y, my);
+    const float nz = fmaf(-hz, ainv.z, mz), fz = fmaf(hz, ainv.z, mz);
+    const float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, tmin));
+    const float tf = fminf(fminf(fx, fy), fminf(fz, tmax));
     tnear = tn;
     return tn <= tf * 1.0000005f + 1e-30f;
 }
-
-// Fused form: plane distance = fma(b, inv, -(o*inv)), half the arithmetic of rt_slab.  Its extra
-// rounding error is a few ulps of |o| + |b| in space, which the 2^-18 build-time padding of the
-// boxes absorbs as long as the ray origin is within ~8 scene extents of the scene (the host
-// checks this per frame and otherwise selects the exact form; shadow-ray origins lie on the
-// surface and always qualify).
-struct RayFma { f3 inv, oi; };
+// exact-difference form: m = (c - o) * inv (no cancellation error however far the origin is)
+RT_HD bool rt_slab(const RayInv& k, float cx, float cy, float cz, float hx, float hy, float hz,
+                   float tmin, float tmax, float& tnear) {
+    return rt_slab_combine((cx - k.o.x) * k.inv.x, (cy - k.o.y) * k.inv.y, (cz - k.o.z) * k.inv.z, k.ainv, hx, hy, hz, tmin, tmax, tnear);
+}
+// Fused form: m = fma(c, inv, -(o*inv)).  Its extra rounding error is a few ulps of |o| + |c| in
+// space, which the build-time padding absorbs as long as the ray origin is within ~8 scene
+// extents of the scene (the host checks this per frame and otherwise selects rt_slab; shadow-ray
+// origins lie on the surface and always qualify).
+struct RayFma { f3 inv, ainv, oi; };
 RT_HD RayFma rt_ray_fma(const Ray& r) {
     RayFma k;
     k.inv = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+    k.ainv = mk3(fabsf(k.inv.x), fabsf(k.inv.y), fabsf(k.inv.z));
     k.oi = mk3(r.o.x * k.inv.x, r.o.y * k.inv.y, r.o.z * k.inv.z);
     return k;
 }
-RT_HD bool rt_slab_fma(const RayFma& k, float lox, float loy, float loz, float hix, float hiy, float hiz,
+RT_HD bool rt_slab_fma(const RayFma& k, float cx, float cy, float cz, float hx, float hy, float hz,
                        float tmin, float tmax, float& tnear) {
-    const float ax = fmaf(lox, k.inv.x, -k.oi.x), bx = fmaf(hix, k.inv.x, -k.oi.x);
-    const float ay = fmaf(loy, k.inv.y, -k.oi.y), by = fmaf(hiy, k.inv.y, -k.oi.y);
-    const float az = fmaf(loz, k.inv.z, -k.oi.z), bz = fmaf(hiz, k.inv.z, -k.oi.z);
-    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
-    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
-    tnear = tn;
-    return tn <= tf * 1.0000005f + 1e-30f;
+    return rt_slab_combine(fmaf(cx, k.inv.x, -k.oi.x), fmaf(cy, k.inv.y, -k.oi.y), fmaf(cz, k.inv.z, -k.oi.z), k.ainv, hx, hy, hz, tmin, tmax, tnear);
+}
+// Same without the final widening of the far bound: with the origin within 8 scene extents the
+// accumulated rounding error of the nine FMAs is below scale*2^-18 in space, half of the 2^-17
+// padding every box carries, so the plain comparison is already conservative.
+RT_HD bool rt_slab_fma_tight(const RayFma& k, float cx, float cy, float cz, float hx, float hy, float hz, float tmin, float tmax) {
+    const float mx = fmaf(cx, k.inv.x, -k.oi.x), my = fmaf(cy, k.inv.y, -k.oi.y), mz = fmaf(cz, k.inv.z, -k.oi.z);
+    const float tn = fmaxf(fmaxf(fmaf(-hx, k.ainv.x, mx), fmaf(-hy, k.ainv.y, my)), fmaxf(fmaf(-hz, k.ainv.z, mz), tmin));
+    const float tf = fminf(fminf(fmaf(hx, k.ainv.x, mx), fmaf(hy, k.ainv.y, my)), fminf(fmaf(hz, k.ainv.z, mz), tmax));
+    return tn <= tf;
 }
 
 // ---------------------------------------------------------------- shading ----

@@ -39,7 +39,7 @@ k_render_bvh(const __grid_constant__ FrameParams P) {
     uint32_t* stk = s_stack + threadIdx.x;
     const Pixel px = map_pixel(P);
     unsigned nprim = 0, nshadow = 0;
-    TraceStats st{0, 0, 0};
+    TraceStats st{0, 0, 0, 0, 0};
     if (px.inside) {
         f3 accum = mk3(0.f, 0.f, 0.f);
         Hit first; rt_hit_reset(first);
@@ -58,6 +58,8 @@ k_render_bvh(const __grid_constant__ FrameParams P) {
         if ((threadIdx.x & 31) == 0 && P.counters) {
             atomicAdd(&P.counters[2], (unsigned long long)nn);
             atomicAdd(&P.counters[3], (unsigned long long)nt);
+            atomicAdd(&P.counters[4], (unsigned long long)nn);          // per-ray kernel: every lane fetches its own lines
+            atomicAdd(&P.counters[5], (unsigned long long)nt);
         }
     }
 }
@@ -172,6 +174,8 @@ k_render_brute(const __grid_constant__ FrameParams P) {
 #define FULLMASK 0xffffffffu
 #define RT_PACKET_STACK 64
 
+struct TraceResult { Hit hit; bool blocked; };
+
 struct WarpStack {
     uint32_t s0, s1; int sp; bool overflow;
     __device__ __forceinline__ void reset() { sp = 0; overflow = false; s0 = s1 = 0u; }
@@ -187,75 +191,86 @@ struct WarpStack {
     }
 };
 
-// ANY = false: closest hit into `best` for lanes with live == true.
-// ANY = true : live lanes become blocked when a triangle is accepted with t < tlimit (IsInShadow).
+// any == false: closest hit into `best` for lanes with live == true.
+// any == true : live lanes become blocked when a triangle is accepted with t < tlimit (IsInShadow).
+// `any` is a run-time, warp-uniform flag so that primary and shadow queries share one copy of the
+// loop (the first packet kernel spent 15 % of its issue slots waiting on instruction fetch).
 // FAST selects the fused slab test (rt_slab_fma).
-template <int MODE, bool ANY, bool STATS, bool FAST>
-__device__ __forceinline__ void packet_trace(const FrameParams& P, const Ray& ray, bool live, float tlimit, Hit& best, bool& blocked,
-                                             TraceStats* st) {
+template <int MODE, bool STATS, bool FAST>
+__device__ __noinline__ TraceResult packet_trace(const BvhNode* __restrict__ nodes, const TriBlock* __restrict__ geom, const uint32_t num_tris,
+                                                 const Ray ray, bool live, const bool any, float tlimit, TraceStats* st) {
+    Hit best; rt_hit_reset(best);
+    bool blocked = false;
     const float det_eps = rt_det_eps(MODE), tmin = rt_tmin(MODE);
     const int lane = threadIdx.x & 31;
     RayInv k; RayFma kf;
     if (FAST) kf = rt_ray_fma(ray); else k = rt_ray_inv(ray);
     WarpStack stk; stk.reset();
     int cur = 0;
-    if (!__any_sync(FULLMASK, live)) return;
+    const unsigned mlive = __ballot_sync(FULLMASK, live);
+    if (!mlive) return TraceResult{best, blocked};
+    // Descent order without a per-node vote: LBVH children are split along a known axis with the
+    // right child on the high side, so the packet visits the right child first iff most of its rays
+    // travel in the negative direction of that axis (bit a of dirneg; axis 3 = no spatial split).
+    const int half = __popc(mlive);
+    const unsigned dirneg = (2 * __popc(__ballot_sync(FULLMASK, live && ray.d.z < 0.f)) > half ? 1u : 0u) |
+                            (2 * __popc(__ballot_sync(FULLMASK, live && ray.d.y < 0.f)) > half ? 2u : 0u) |
+                            (2 * __popc(__ballot_sync(FULLMASK, live && ray.d.x < 0.f)) > half ? 4u : 0u);
+    if (!any) tlimit = FLT_MAX;                 // closest: the far bound is the lane's best t so far
     while (true) {
         if (cur >= 0) {
-            const NodeQ q = rt_load_node(P.nodes, cur);
-            if (STATS && live) st->nodes++;
-            const float far = ANY ? tlimit : best.t;
-            float tn0, tn1;
+            const NodeQ q = rt_load_node(nodes, cur);
+            if (STATS) { if (live) st->nodes++; if (lane == 0) st->wnodes++; }
             bool h0, h1;
             if (FAST) {
-                h0 = rt_slab_fma(kf, q.q0.x, q.q0.y, q.q0.z, q.q0.w, q.q1.x, q.q1.y, tmin, far, tn0);
-                h1 = rt_slab_fma(kf, q.q1.z, q.q1.w, q.q2.x, q.q2.y, q.q2.z, q.q2.w, tmin, far, tn1);
+                h0 = rt_slab_fma_tight(kf, q.q0.x, q.q0.y, q.q0.z, q.q0.w, q.q1.x, q.q1.y, tmin, tlimit);
+                h1 = rt_slab_fma_tight(kf, q.q1.z, q.q1.w, q.q2.x, q.q2.y, q.q2.z, q.q2.w, tmin, tlimit);
             } else {
-                h0 = rt_slab(k, q.q0.x, q.q0.y, q.q0.z, q.q0.w, q.q1.x, q.q1.y, tmin, far, tn0);
-                h1 = rt_slab(k, q.q1.z, q.q1.w, q.q2.x, q.q2.y, q.q2.z, q.q2.w, tmin, far, tn1);
+                float tn0, tn1;
+                h0 = rt_slab(k, q.q0.x, q.q0.y, q.q0.z, q.q0.w, q.q1.x, q.q1.y, tmin, tlimit, tn0);
+                h1 = rt_slab(k, q.q1.z, q.q1.w, q.q2.x, q.q2.y, q.q2.z, q.q2.w, tmin, tlimit, tn1);
             }
-            h0 = h0 && live; h1 = h1 && live;
-            const unsigned m0 = __ballot_sync(FULLMASK, h0), m1 = __ballot_sync(FULLMASK, h1);
-            if (m0 && m1) {
-                const unsigned v1 = __ballot_sync(FULLMASK, h1 && (!h0 || tn1 < tn0));   // lanes that want child 1 first
-                const bool c1first = 2 * __popc(v1) > __popc(m0 | m1);
+            const bool a0 = __any_sync(FULLMASK, h0 && live), a1 = __any_sync(FULLMASK, h1 && live);
+            if (a0 && a1) {
+                const bool c1first = (dirneg >> ((unsigned)q.q3.w >> 30)) & 1u;
                 stk.push((uint32_t)(c1first ? q.q3.x : q.q3.y), lane);
                 cur = c1first ? q.q3.y : q.q3.x;
                 continue;
             }
-            if (m0) { cur = q.q3.x; continue; }
-            if (m1) { cur = q.q3.y; continue; }
+            if (a0) { cur = q.q3.x; continue; }
+            if (a1) { cur = q.q3.y; continue; }
         } else {
             const uint32_t first = rt_leaf_first(cur), cnt = rt_leaf_count(cur);
             for (uint32_t s = first; s < first + cnt; ++s) {
-                const Tri tr = rt_load_tri(P.geom, s);
+                const Tri tr = rt_load_tri(geom, s);
+                if (STATS && lane == 0) st->wtris++;
                 if (live) {
                     if (STATS) st->tris++;
-                    if (ANY) {
-                        float t, u, v;
-                        if (rt_moller_trumbore(ray, tr.v0, tr.e1, tr.e2, det_eps, tmin, FLT_MAX, t, u, v) && t < tlimit) { blocked = true; live = false; }
-                    } else {
-                        rt_consider(ray, tr, s, det_eps, tmin, best);
+                    float t, u, v;
+                    // closest: accepted t <= best.t (== tlimit); canonical rule min t, then min id
+                    if (rt_moller_trumbore(ray, tr.v0, tr.e1, tr.e2, det_eps, tmin, any ? FLT_MAX : tlimit, t, u, v)) {
+                        if (any) { if (t < tlimit) { blocked = true; live = false; } }
+                        else if (t < tlimit || tr.id < best.id) { best.t = t; best.u = u; best.v = v; best.slot = (int)s; best.id = tr.id; tlimit = t; }
                     }
                 }
             }
-            if (ANY && !__any_sync(FULLMASK, live)) return;
+            if (any && !__any_sync(FULLMASK, live)) return TraceResult{best, blocked};
         }
         if (stk.sp == 0) break;
         cur = (int)stk.pop();
     }
     if (stk.overflow) {        // deeper than 64 levels: finish by brute force, like the reference (query.h:297-308)
-        for (uint32_t s = 0; s < P.num_tris; ++s) {
-            const Tri tr = rt_load_tri(P.geom, s);
+        for (uint32_t s = 0; s < num_tris; ++s) {
+            const Tri tr = rt_load_tri(geom, s);
             if (!live) continue;
-            if (ANY) {
-                float t, u, v;
-                if (rt_moller_trumbore(ray, tr.v0, tr.e1, tr.e2, det_eps, tmin, FLT_MAX, t, u, v) && t < tlimit) { blocked = true; live = false; }
-            } else {
-                rt_consider(ray, tr, s, det_eps, tmin, best);
+            float t, u, v;
+            if (rt_moller_trumbore(ray, tr.v0, tr.e1, tr.e2, det_eps, tmin, any ? FLT_MAX : tlimit, t, u, v)) {
+                if (any) { if (t < tlimit) { blocked = true; live = false; } }
+                else if (t < tlimit || tr.id < best.id) { best.t = t; best.u = u; best.v = v; best.slot = (int)s; best.id = tr.id; tlimit = t; }
             }
         }
     }
+    return TraceResult{best, blocked};
 }
 
 // Values that are cheap to recompute are deliberately NOT kept in registers across a shadow
@@ -272,7 +287,7 @@ k_render_packet(const __grid_constant__ FrameParams P) {
     const Pixel px = map_pixel(P);
     int x = px.inside ? px.x : 0, y = px.inside ? px.y : 0;
     unsigned nprim = 0, nshadow = 0;
-    TraceStats st{0, 0, 0};
+    TraceStats st{0, 0, 0, 0, 0};
     f3 accum = mk3(0.f, 0.f, 0.f);
     for (int s = 0; s < P.spp; ++s) {
         const float jx = P.jitter ? __ldg(P.jitter + 2 * s) : 0.0f;
@@ -281,8 +296,7 @@ k_render_packet(const __grid_constant__ FrameParams P) {
         Hit h; rt_hit_reset(h);
         {
             const Ray ray = rt_make_ray(P.cam, MODE, x, y, jx, jy);
-            bool dummy = false;
-            packet_trace<MODE, false, STATS, FAST>(P, ray, live, 0.f, h, dummy, &st);
+            h = packet_trace<MODE, STATS, FAST>(P.nodes, P.geom, P.num_tris, ray, live, false, 0.f, &st).hit;
         }
         if (live) ++nprim;
         if (s == 0 && px.inside) {                     // id / t planes describe sample 0
@@ -313,8 +327,7 @@ k_render_packet(const __grid_constant__ FrameParams P) {
                         lit = rt_light_setup_hw2(sf, P.lights[l], L, NdotL, need, sray, dist);
                         need = need && lit && P.shadows;
                     }
-                    Hit unused;
-                    packet_trace<MODE, true, STATS, FAST>(P, sray, need, dist, unused, blocked, &st);
+                    blocked = packet_trace<MODE, STATS, FAST>(P.nodes, P.geom, P.num_tris, sray, need, true, dist, &st).blocked;
                 }
                 if (need) ++nshadow;
                 if (lit && !blocked) {
@@ -347,6 +360,8 @@ k_render_packet(const __grid_constant__ FrameParams P) {
         if ((threadIdx.x & 31) == 0 && P.counters) {
             atomicAdd(&P.counters[2], (unsigned long long)nn);
             atomicAdd(&P.counters[3], (unsigned long long)nt);
+            atomicAdd(&P.counters[4], (unsigned long long)st.wnodes);   // one 64-byte node line per warp visit
+            atomicAdd(&P.counters[5], (unsigned long long)st.wtris);    // one 48-byte triangle block per warp test
         }
     }
 }

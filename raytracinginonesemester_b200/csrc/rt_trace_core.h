@@ -37,7 +37,7 @@ RT_HD NodeQ rt_load_node(const BvhNode* __restrict__ nodes, int idx) {
     return q;
 }
 
-struct TraceStats { uint32_t nodes, tris, max_sp; };
+struct TraceStats { uint32_t nodes, tris, max_sp, wnodes, wtris; };
 
 // Stack-based BVH2 closest hit (replaces SearchBVH, GPUandCPU/include/query.h:224-311):
 // one 64-byte node visit tests both children, descends into the nearer one and pushes the

@@ -86,7 +86,7 @@ void* emu_build(const rt_scene* sc, uint32_t leaf_max) {
 
     if ((uint32_t)n > leaf_max) {
         std::vector<uint32_t> keep(n, 0), newidx(n, 0);
-        for (int i = 0; i + 1 < n; ++i) keep[i] = (topo[i].last - topo[i].first + 1u) > leaf_max ? 1u : 0u;
+        for (int i = 0; i + 1 < n; ++i) keep[i] = (RT_TOPO_LAST(topo[i]) - topo[i].first + 1u) > leaf_max ? 1u : 0u;
         uint32_t run = 0;
         for (int i = 0; i < n; ++i) { newidx[i] = run; run += keep[i]; }
         es->nodes.resize(run);
@@ -96,7 +96,7 @@ void* emu_build(const rt_scene* sc, uint32_t leaf_max) {
             es->nodes[newidx[i]] = rt_make_node(blo[tp.left], bhi[tp.left], blo[tp.right], bhi[tp.right],
                                                 rt_child_ref(tp.left, n, topo.data(), keep.data(), newidx.data()),
                                                 rt_child_ref(tp.right, n, topo.data(), keep.data(), newidx.data()),
-                                                tp.first, tp.last - tp.first + 1u);
+                                                tp.first, (RT_TOPO_LAST(tp) - tp.first + 1u) | (RT_TOPO_AXIS(tp) << 30));
         }
     } else {
         float4 lo = make_float4(INFINITY, INFINITY, INFINITY, 0.f), hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
@@ -150,9 +150,10 @@ int emu_validate(void* h) {
         if (visited[ni]++) return -2;
         const BvhNode& nd = es->nodes[ni];
         for (int c = 0; c < 2; ++c) {
-            const float* lo = nd.q + 6 * c; const float* hi = lo + 3;
+            const float* cc = nd.q + 6 * c; const float* hh = cc + 3;     // centre, half-extent
             int32_t ref = c ? nd.ref1 : nd.ref0;
-            if (lo[0] > hi[0]) continue;   // absent child
+            if (hh[0] < 0.f) continue;   // absent child
+            const float lo[3] = {cc[0] - hh[0], cc[1] - hh[1], cc[2] - hh[2]}, hi[3] = {cc[0] + hh[0], cc[1] + hh[1], cc[2] + hh[2]};
             if (ref >= 0) { stack.push_back(ref); continue; }
             uint32_t first = rt_leaf_first(ref), cnt = rt_leaf_count(ref);
             if (first + cnt > es->num_tris) return -3;
@@ -198,7 +199,7 @@ int emu_render_rank(void* h, const rt_frame* fr, rt_image* img, uint64_t* stats,
             f3 accum = mk3(0.f, 0.f, 0.f);
             Hit first; rt_hit_reset(first);
             unsigned np = 0, ns = 0;
-            TraceStats st{0, 0, 0};
+            TraceStats st{0, 0, 0, 0, 0};
             for (int s = 0; s < P.spp; ++s) {
                 Hit hh;
                 f3 color = fr->mode == RT_MODE_HW1

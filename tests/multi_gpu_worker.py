@@ -1,0 +1,52 @@
+"""Worker for tests/test_multi_gpu.py (launched with torch.distributed.run, one rank per GPU):
+renders tile-sharded frames through the C ABI (scene + BVH broadcast from rank 0 over NCCL, tile
+gather to rank 0) and compares the gathered image with a single-GPU render of the same frame."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from raytracinginonesemester_b200 import _abi as A, api, parallel, scenes  # noqa: E402
+
+ALL = A.RT_OUT_RGB_F32 | A.RT_OUT_RGB8 | A.RT_OUT_TRI_ID | A.RT_OUT_T
+
+
+def main():
+    dist, rank, world, local_rank = parallel.init_process_group("nccl")
+    r = parallel.make_renderer(dist, rank, world, local_rank)
+    sc = scenes.terrain_scene(120, 60)
+    info = r.upload_scene(sc if rank == 0 else None)          # ranks != 0 receive the arena by broadcast
+    assert info.num_triangles == 120 * 60 * 2 and info.num_nodes > 0
+    ok = True
+    for (W, H, spp) in ((333, 201, 1), (256, 128, 2), (40, 9, 1)):
+        fr = scenes.terrain_frame(W, H, spp=spp, outputs=ALL)
+        r.render(fr)
+        got = r.download()
+        import torch
+        cnt = torch.tensor([float(got["rays_primary"]), float(got["rays_shadow"])], device="cuda")
+        dist.all_reduce(cnt)
+        assert int(cnt[0].item()) == W * H * spp
+        assert got["rays_primary"] == int((parallel.tile_owner_map(W, H, world) == rank).sum()) * spp
+        if rank == 0:
+            solo = api.Renderer(local_rank)
+            solo.upload_scene(sc)
+            solo.render(fr)
+            ref = solo.download()
+            solo.close()
+            for k in ("tri_id", "t", "rgb", "rgb8"):
+                if not np.array_equal(got[k], ref[k]):
+                    print("MISMATCH", W, H, spp, k, int((got[k] != ref[k]).sum()))
+                    ok = False
+            assert int(cnt[1].item()) == ref["rays_shadow"]
+    dist.barrier()
+    r.close()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTI_GPU_OK" if ok else "MULTI_GPU_FAILED")
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

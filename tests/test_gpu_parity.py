@@ -172,13 +172,14 @@ def test_device_bvh_is_sound_and_host_walk_agrees(renderer):
         assert np.array_equal(got[k], emu[k]), k
     fr.kernel_variant = A.RT_VARIANT_PER_RAY_STATS          # per-ray kernel: the same walk as the host emulation
     st = run(renderer, fr)
-    nv, nt = renderer.frame_stats()
-    assert (nv, nt) == (emu["stats"]["nodes"], emu["stats"]["tris"])
+    nv, nt, nl, nb = renderer.frame_stats()
+    assert (nv, nt) == (emu["stats"]["nodes"], emu["stats"]["tris"]) and (nl, nb) == (nv, nt)
     assert np.array_equal(st["tri_id"], got["tri_id"])
     fr.kernel_variant = A.RT_VARIANT_STATS                  # packet kernel: a lane tests a superset, results identical
     pk = run(renderer, fr)
-    nvp, ntp = renderer.frame_stats()
+    nvp, ntp, nlp, nbp = renderer.frame_stats()
     assert nvp >= nv and ntp >= nt
+    assert nlp * 32 >= nvp and nbp * 32 >= ntp and nlp < nvp          # one line per warp visit, shared by its lanes
     for k in ("tri_id", "t", "rgb8"):
         assert np.array_equal(pk[k], got[k]), k
 
