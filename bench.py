@@ -193,7 +193,7 @@ def run_ours(args, rank, world, local_rank):
     t0 = time.perf_counter()
     info = r.upload_scene(scene)
     upload_wall = time.perf_counter() - t0
-    frame = scenes.terrain_frame(W, H, spp=spp, outputs=A.RT_OUT_RGB8, kernel_variant=args.variant)
+    frame = scenes.terrain_frame(W, H, spp=spp, outputs=A.RT_OUT_RGB8, kernel_variant=args.variant, shadows=not args.no_shadows)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     pinned = torch.empty((H, W, 3), dtype=torch.uint8, pin_memory=True).numpy() if rank == 0 else None
 
@@ -313,6 +313,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--leaf-max", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-shadows", action="store_true", help="primary rays only (diagnostic; not the headline workload)")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: honour --warmup < 3, skip the CPU baseline")
     ap.add_argument("--shadow-ratio", type=float, default=0.8144, help="shadow rays per primary ray on c4 (device count), used by --impl reference")
     args = ap.parse_args()

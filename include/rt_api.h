@@ -211,6 +211,21 @@ int  rt_camera_init(rt_camera* out, const float pos[3], const float look_at[3],
  * std::mt19937 + uniform_real_distribution<float>(0,1) - 0.5.  out[2*spp]. */
 int  rt_jitter_table(float* out, int spp, uint32_t seed, int centered);
 
+/* -- host mesh ingest (pure host code) ------------------------------------------ */
+/* The reference loaders' output format for callers that do not link C++: OBJ -> unified indexed mesh
+ * (vertices de-duplicated by their v/vt/vn reference in order of first use, quads split (0,1,2),(0,2,3),
+ * one object id per o/g tag: GPUandCPU/include/MeshOBJ.h:260-427, HW1/src/MeshOBJ.cpp:143-281), the
+ * per-object transform of GPUandCPU/src/main.cu:57-96 and AppendMesh (MeshOBJ.h:429-466). */
+typedef struct rt_mesh rt_mesh;
+int  rt_mesh_load_obj(const char* path, int32_t* next_object_id, rt_mesh** out);
+int  rt_mesh_create(rt_mesh** out);                 /* empty mesh, target of rt_mesh_append */
+void rt_mesh_free(rt_mesh* mesh);
+int  rt_mesh_counts(const rt_mesh* mesh, uint64_t* num_vertices, uint64_t* num_normals, uint64_t* num_triangles);
+int  rt_mesh_copy(const rt_mesh* mesh, float* positions, float* normals, uint32_t* indices, int32_t* tri_obj_ids);
+int  rt_mesh_transform(rt_mesh* mesh, const float position[3], const float rotation_deg[3], const float scale[3]);
+int  rt_mesh_append(rt_mesh* dst, const rt_mesh* src);
+const char* rt_mesh_last_error(void);
+
 /* -- introspection for tests / profiling ---------------------------------- */
 /* Copies the flattened BVH back to the host (nodes: 64 B each; tri blocks: 48 B
  * each, leaf order; tri_ids: original triangle id per block). Any pointer may be

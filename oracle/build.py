@@ -5,6 +5,7 @@ TEST INFRASTRUCTURE ONLY.  Produces
   oracle/_ref/libref_hw1.so       reference HW1 sources compiled where they lie
   oracle/_ref/libref_hw2.so       reference HW2/GPUandCPU sources (CPU build) compiled where they lie
   oracle/_ref/libref_ppm.so       reference ppm_p6_lib compiled where it lies
+  oracle/_ref/libref_hw2_main.so  the reference's whole bvh_viz program (main renamed), for end-to-end fixtures
 The _ref outputs need /root/reference (present in the authoring container only); on the GPU
 box the prebuilt files travel with the snapshot.  No reference source is copied into the repo.
 Flags: -O2 -ffp-contract=off, no -march=native (hit ids depend on no-FMA rounding).
@@ -46,7 +47,7 @@ def have_reference():
 
 def build_ref(force=False):
     """Compile the reference's own sources in place.  Returns dict name -> path (existing files)."""
-    outs = {n: os.path.join(REF_OUT, "lib%s.so" % n) for n in ("ref_hw1", "ref_hw2", "ref_ppm")}
+    outs = {n: os.path.join(REF_OUT, "lib%s.so" % n) for n in ("ref_hw1", "ref_hw2", "ref_ppm", "ref_hw2_main")}
     if have_reference():
         os.makedirs(REF_OUT, exist_ok=True)
         hw1, g = os.path.join(REF, "HW1"), os.path.join(REF, "HW2", "HW2", "GPUandCPU")
@@ -58,6 +59,11 @@ def build_ref(force=False):
         if force or _stale(outs["ref_hw2"], [s]):
             inc = ["-I", os.path.join(g, "third_party", "glm"), "-I", os.path.join(g, "include"), "-I", os.path.join(g, "src")]
             _run(["g++", "-x", "c++", "-std=c++14", "-w", "-D__device__="] + FP + inc + ["-o", outs["ref_hw2"],
+                  s, os.path.join(g, "include", "bvh.cu"), os.path.join(g, "include", "query.cu")])
+        s = os.path.join(HERE, "ref_shim_hw2_main.cpp")
+        if force or _stale(outs["ref_hw2_main"], [s]):
+            inc = ["-I", os.path.join(g, "third_party", "glm"), "-I", os.path.join(g, "include"), "-I", os.path.join(g, "src")]
+            _run(["g++", "-x", "c++", "-std=c++14", "-w", "-D__device__="] + FP + inc + ["-o", outs["ref_hw2_main"],
                   s, os.path.join(g, "include", "bvh.cu"), os.path.join(g, "include", "query.cu")])
         s = os.path.join(HERE, "ref_shim_ppm.cpp")
         if force or _stale(outs["ref_ppm"], [s]):

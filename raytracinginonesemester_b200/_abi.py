@@ -80,6 +80,14 @@ EXPORTS = {
     "rt_frame_stats": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_uint64)] * 4),
     "rt_camera_init": (C.c_int, [C.POINTER(rt_camera), f32p, f32p, f32p, C.c_double, C.c_double, C.c_int, C.c_int]),
     "rt_jitter_table": (C.c_int, [f32p, C.c_int, C.c_uint32, C.c_int]),
+    "rt_mesh_load_obj": (C.c_int, [C.c_char_p, i32p, C.POINTER(C.c_void_p)]),
+    "rt_mesh_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "rt_mesh_free": (None, [C.c_void_p]),
+    "rt_mesh_counts": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_uint64)] * 3),
+    "rt_mesh_copy": (C.c_int, [C.c_void_p, f32p, f32p, u32p, i32p]),
+    "rt_mesh_transform": (C.c_int, [C.c_void_p, f32p, f32p, f32p]),
+    "rt_mesh_append": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rt_mesh_last_error": (C.c_char_p, []),
     "rt_debug_download_bvh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, i32p]),
 }
 

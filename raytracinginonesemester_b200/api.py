@@ -91,6 +91,31 @@ def make_light(position, color=(1.0, 1.0, 1.0), intensity=1):
     return l
 
 
+def load_obj(path, next_object_id=0, position=None, rotation=None, scale=None):
+    """LoadOBJ_ToMesh (+ applyObjectTransform when a transform is given) -> (positions, normals | None,
+    indices, tri_obj_ids, next_object_id).  Pure host code in the C library (rt_mesh_*)."""
+    lib = load_library()
+    h = C.c_void_p()
+    nid = C.c_int32(next_object_id)
+    rc = lib.rt_mesh_load_obj(os.fsencode(path), C.byref(nid), C.byref(h))
+    if rc != A.RT_OK:
+        raise RtError(rc, (lib.rt_mesh_last_error() or b"").decode())
+    try:
+        if position is not None or rotation is not None or scale is not None:
+            p, r, s = _f32(position or (0, 0, 0)), _f32(rotation or (0, 0, 0)), _f32(scale or (1, 1, 1))
+            lib.rt_mesh_transform(h, _ptr(p, A.f32p), _ptr(r, A.f32p), _ptr(s, A.f32p))
+        nv, nn, nt = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib.rt_mesh_counts(h, C.byref(nv), C.byref(nn), C.byref(nt))
+        pos = np.zeros((nv.value, 3), np.float32)
+        nrm = np.zeros((nn.value, 3), np.float32)
+        idx = np.zeros((nt.value, 3), np.uint32)
+        obj = np.zeros(nt.value, np.int32)
+        lib.rt_mesh_copy(h, _ptr(pos, A.f32p), _ptr(nrm, A.f32p) if nn.value else A.f32p(), _ptr(idx, A.u32p), _ptr(obj, A.i32p))
+    finally:
+        lib.rt_mesh_free(h)
+    return pos, (nrm if nn.value else None), idx, obj, int(nid.value)
+
+
 class Scene:
     """Indexed triangle mesh + per-object materials, as the reference loaders produce them."""
 
