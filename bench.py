@@ -51,26 +51,62 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in a thread every 5 ms
+    (nvidia_ml_py), falling back to a streaming nvidia-smi query when NVML cannot be loaded."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
-        self.rows, self.proc = [], None
+        self.sm, self.max_mhz, self.reasons, self.proc, self.nvml = [], None, set(), None, None
+        self._stop = threading.Event()
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.nvml = None
+            try:
+                self.rows = []
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.t = threading.Thread(target=self._read, daemon=True)
+                self.t.start()
+            except Exception:
+                self.proc = None
+
+    def _poll(self):
+        n = self.nvml
+        bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown if hasattr(n, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                r = int(get_reasons(self.h))
+                for k, b in bits.items():
+                    if r & b:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml:
+            self._stop.set()
+            self.t.join(timeout=1)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -80,7 +116,8 @@ class ClockSampler:
         mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------- reference arm ----
@@ -168,7 +205,7 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": "Mrays/s closest-hit (BVH+tri)", "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "triangles": nx * ny * 2, "width": W, "height": H, "spp": spp, "rays": "primary+shadow"},
         "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": ref.cores, "kind": ref.kind,
                          "sample": "every %d-th row of the %dx%d frame per step (%d rows), full-frame rate extrapolated; shadow rays = primary x %.4f" % (step, W, H, len(range(0, H, step)), shadow_ratio),
@@ -188,11 +225,15 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dist, rank, world, local_rank = parallel.init_process_group("nccl")
     r = parallel.make_renderer(dist, rank, world, local_rank)
+    if world > 1:
+        r.set_gather({"auto": A.RT_GATHER_AUTO, "nccl": A.RT_GATHER_NCCL, "peer": A.RT_GATHER_PEER}[args.gather])
     nx, ny, W, H, spp = WORKLOADS[args.workload]
     scene = scenes.terrain_scene(nx, ny, build_flags=A.RT_BUILD_LEAF_MAX(args.leaf_max)) if rank == 0 else None
+    first = r.upload_scene(scene)          # first call in the process: pays CUDA module loading and CUB temp sizing
     t0 = time.perf_counter()
-    info = r.upload_scene(scene)
+    info = r.upload_scene(scene)           # steady state (what a second scene or a re-upload costs)
     upload_wall = time.perf_counter() - t0
+    gather = {A.RT_GATHER_NCCL: "nccl send/recv + unpack", A.RT_GATHER_PEER: "peer stores into rank 0's image over NVLink + flag words"}[r.gather_mode()] if world > 1 else "none"
     frame = scenes.terrain_frame(W, H, spp=spp, outputs=A.RT_OUT_RGB8, kernel_variant=args.variant, shadows=not args.no_shadows)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     pinned = torch.empty((H, W, 3), dtype=torch.uint8, pin_memory=True).numpy() if rank == 0 else None
@@ -224,6 +265,7 @@ def run_ours(args, rank, world, local_rank):
     rays_primary, rays_shadow, nv_all, nt_all, nl_all, nb_all = [float(x) for x in cnt.cpu()]
     rays = rays_primary + rays_shadow
 
+    launches_per_step = 1 if world == 1 else (3 if r.gather_mode() == A.RT_GATHER_PEER else 1 + world)   # rank 0: frame kernel + flag set/wait, or + unpack per rank
     sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     step_ms = []
@@ -270,15 +312,16 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": args.workload, "triangles": nx * ny * 2, "width": W, "height": H, "spp": spp,
                        "rays": "primary+shadow", "rays_primary": rays_primary, "rays_shadow": rays_shadow,
                        "l2": "flushed between timed steps (256 MiB memset); warm-L2 figure in value_warm_l2",
-                       "tile_sharding": "16x8 tiles, tile k -> rank k %% %d" % world, "leaf_max": args.leaf_max, "variant": args.variant},
+                       "tile_sharding": "16x8 tiles, tile k -> rank k %% %d" % world, "gather": gather, "leaf_max": args.leaf_max, "variant": args.variant},
             "primary_mrays_s": rays_primary / (ms * 1e-3) / 1e6,
             "value_warm_l2": rays / (float(tw.mean()) * 1e-3) / 1e6,
-            "bvh_nodes": int(info.num_nodes), "bvh_build_ms": float(info.build_ms), "scene_upload_ms": float(info.upload_ms),
+            "bvh_nodes": int(info.num_nodes), "bvh_build_ms": float(info.build_ms), "bvh_build_first_call_ms": float(first.build_ms),
+            "scene_upload_ms": float(info.upload_ms),
             "scene_upload_wall_s": upload_wall,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": 1e3 * float(e2e_s.mean()),
                     "h2d_bytes_per_step": int(C.sizeof(A.rt_frame) + 28 * len(frame.lights) + 8 * spp),
                     "d2h_bytes_per_step": int(3 * W * H + 32)},
-            "gpu_launches": int(args.steps * (1 if world == 1 else 1 + world)),
+            "gpu_launches": int(args.steps * launches_per_step),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_kind": peak_kind + (" x %d GPUs" % world if world > 1 else ""), "bytes_per_ray": b_ray, "bytes_per_launch": bytes_launch,
                          "nodes_per_ray": nv_all / rays, "tris_per_ray": nt_all / rays, "node_lines_per_ray": nl_all / rays, "tri_blocks_per_ray": nb_all / rays,
@@ -313,6 +356,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--leaf-max", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "peer"], help="multi-GPU tile delivery to rank 0")
     ap.add_argument("--no-shadows", action="store_true", help="primary rays only (diagnostic; not the headline workload)")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: honour --warmup < 3, skip the CPU baseline")
     ap.add_argument("--shadow-ratio", type=float, default=0.8144, help="shadow rays per primary ray on c4 (device count), used by --impl reference")

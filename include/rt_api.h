@@ -173,6 +173,14 @@ const char* rt_last_error(const rt_ctx* ctx);
 int  rt_comm_unique_id(void* id128);
 int  rt_comm_init(rt_ctx* ctx, int rank, int world, const void* id128);
 int  rt_comm_rank(const rt_ctx* ctx, int* rank, int* world);
+/* How the ranks' tiles reach rank 0 every frame.  Collective: every rank calls rt_comm_set_gather
+ * with the same mode after rt_comm_init (which selects RT_GATHER_AUTO). */
+#define RT_GATHER_AUTO  0   /* peer stores when every rank can map rank 0's image (CUDA IPC over NVLink), else NCCL */
+#define RT_GATHER_NCCL  1   /* tile-packed planes, one grouped ncclSend/ncclRecv per plane, unpack kernel on rank 0 */
+#define RT_GATHER_PEER  2   /* fused: the frame kernel stores its pixels straight into rank 0's row-major image
+                               over NVLink; a per-rank flag word in rank 0's memory signals completion */
+int  rt_comm_set_gather(rt_ctx* ctx, int mode);
+int  rt_comm_gather_mode(const rt_ctx* ctx, int* mode);   /* mode in effect: RT_GATHER_NCCL or RT_GATHER_PEER */
 
 /* -- scene --------------------------------------------------------------- */
 /* Pack triangles, build the BVH on the device and (world>1) broadcast the arena

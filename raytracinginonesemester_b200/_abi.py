@@ -9,6 +9,7 @@ RT_QUANT_PPM_LROUND, RT_QUANT_PPM_GAMMA2, RT_QUANT_HW1_TRUNC, RT_QUANT_HW2_TRUNC
 RT_BUILD_DEFAULT, RT_BUILD_NO_BVH = 0, 1
 RT_VARIANT_DEFAULT, RT_VARIANT_PACKET_OCC6, RT_VARIANT_PACKET_OCC10, RT_VARIANT_PACKET_EXACT_SLAB, RT_VARIANT_PER_RAY = 0, 1, 2, 3, 10
 RT_VARIANT_STATS, RT_VARIANT_PER_RAY_STATS = 100, 110
+RT_GATHER_AUTO, RT_GATHER_NCCL, RT_GATHER_PEER = 0, 1, 2
 
 
 def RT_BUILD_LEAF_MAX(n):
@@ -72,6 +73,8 @@ EXPORTS = {
     "rt_comm_unique_id": (C.c_int, [C.c_void_p]),
     "rt_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "rt_comm_rank": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "rt_comm_set_gather": (C.c_int, [C.c_void_p, C.c_int]),
+    "rt_comm_gather_mode": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "rt_upload_scene": (C.c_int, [C.c_void_p, C.POINTER(rt_scene)]),
     "rt_build_info_get": (C.c_int, [C.c_void_p, C.POINTER(rt_build_info)]),
     "rt_render": (C.c_int, [C.c_void_p, C.POINTER(rt_frame)]),

@@ -212,6 +212,16 @@ class Renderer:
         except Exception:
             pass
 
+    def set_gather(self, mode):
+        """Collective: how tiles reach rank 0 (A.RT_GATHER_AUTO / _NCCL / _PEER); returns the mode in effect."""
+        self._check(self.lib.rt_comm_set_gather(self.ctx, int(mode)))
+        return self.gather_mode()
+
+    def gather_mode(self):
+        m = C.c_int()
+        self._check(self.lib.rt_comm_gather_mode(self.ctx, C.byref(m)))
+        return int(m.value)
+
     def upload_scene(self, scene):
         """calculateAABBs + buildBVH + triangle packing on the device; returns rt_build_info."""
         self._scene = scene

@@ -29,6 +29,7 @@ struct NcclApi {
     decltype(&ncclCommInitRank) CommInitRank = nullptr;
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclBroadcast) Broadcast = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
     decltype(&ncclSend) Send = nullptr;
     decltype(&ncclRecv) Recv = nullptr;
     decltype(&ncclGroupStart) GroupStart = nullptr;
@@ -42,7 +43,7 @@ struct NcclApi {
         if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
         if (!h) { why = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
 #define RT_SYM(f) f = reinterpret_cast<decltype(f)>(dlsym(h, "nccl" #f)); if (!f) { why = "libnccl.so.2 lacks nccl" #f; return; }
-        RT_SYM(GetUniqueId) RT_SYM(CommInitRank) RT_SYM(CommDestroy) RT_SYM(Broadcast) RT_SYM(Send) RT_SYM(Recv)
+        RT_SYM(GetUniqueId) RT_SYM(CommInitRank) RT_SYM(CommDestroy) RT_SYM(Broadcast) RT_SYM(AllReduce) RT_SYM(Send) RT_SYM(Recv)
         RT_SYM(GroupStart) RT_SYM(GroupEnd) RT_SYM(GetErrorString)
 #undef RT_SYM
         ok = true;
@@ -85,6 +86,16 @@ struct rt_ctx {
     // comm
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
+    Plane xfer;                                   // small device staging buffer for host<->NCCL messages
+    // peer-store gather (RT_GATHER_PEER): rank 0 exports its image planes and a flag block through CUDA IPC;
+    // the other ranks map them and their frame kernels write rank 0's image in place over NVLink.
+    bool peer = false;                            // mode in effect
+    unsigned* flags = nullptr;                    // rank 0: own allocation; others: IPC mapping of rank 0's
+    unsigned* peer_err = nullptr;                 // local: set by a flag wait that timed out
+    void* peer_img[4] = {nullptr, nullptr, nullptr, nullptr};   // ranks != 0: mapped rank-0 planes (rgb, rgb8, id, t)
+    size_t gather_cap[4] = {0, 0, 0, 0};          // every rank tracks rank 0's plane capacities identically
+    std::vector<void*> retired;                   // rank 0: outgrown exported planes, freed at teardown
+    unsigned seq = 0;                             // frame sequence number of the peer protocol
 };
 
 namespace {
@@ -150,6 +161,132 @@ int broadcast_scene(rt_ctx* c) {
     return RT_OK;
 }
 
+// ---- small host-side collectives over the library's communicator (setup paths only) ----
+int bcast_bytes(rt_ctx* c, void* host, size_t n) {           // rank 0's bytes -> every rank's `host`
+    CU(c, c->xfer.reserve(n < 256 ? 256 : n));
+    if (c->rank == 0) CU(c, cudaMemcpyAsync(c->xfer.p, host, n, cudaMemcpyHostToDevice, c->stream));
+    NC(c, Broadcast(c->xfer.p, c->xfer.p, n, ncclUint8, 0, c->comm, c->stream));
+    if (c->rank != 0) CU(c, cudaMemcpyAsync(host, c->xfer.p, n, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return RT_OK;
+}
+int all_min(rt_ctx* c, int v, int* out) {                     // also a true barrier
+    CU(c, c->xfer.reserve(256));
+    CU(c, cudaMemcpyAsync(c->xfer.p, &v, sizeof v, cudaMemcpyHostToDevice, c->stream));
+    NC(c, AllReduce(c->xfer.p, c->xfer.p, 1, ncclInt32, ncclMin, c->comm, c->stream));
+    CU(c, cudaMemcpyAsync(out, c->xfer.p, sizeof v, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return RT_OK;
+}
+
+const size_t kFlagBytes = sizeof(unsigned) * RT_PEER_FLAG_STRIDE * 16;   // [0]: ready, [r*STRIDE]: done by rank r
+const unsigned long long kPeerTimeoutNs = 20ull * 1000000000ull;
+
+// Drops every peer mapping / exported allocation.  `collective`: all ranks are here and the communicator is
+// healthy, so rank 0 can wait for the importers to unmap before it frees (otherwise the exported memory is
+// left to process teardown: freeing it under a live import is undefined).
+void peer_teardown(rt_ctx* c, bool collective) {
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->rank != 0) {
+        for (void*& p : c->peer_img) { if (p) cudaIpcCloseMemHandle(p); p = nullptr; }
+        if (c->flags) cudaIpcCloseMemHandle(c->flags);
+        c->flags = nullptr;
+    }
+    bool safe = c->world == 1;
+    if (c->world > 1 && collective && c->comm && nccl().ok) { int dummy = 0; safe = all_min(c, 1, &dummy) == RT_OK; }
+    if (c->rank == 0) {
+        Plane* planes[4] = {&c->img_rgb, &c->img_rgb8, &c->img_id, &c->img_t};
+        for (int i = 0; i < 4; ++i) {
+            if (!c->gather_cap[i]) continue;                    // exported plane
+            if (safe) planes[i]->release(); else { planes[i]->p = nullptr; planes[i]->cap = 0; }   // else leaked on purpose
+        }
+        if (safe) { for (void* p : c->retired) cudaFree(p); if (c->flags) cudaFree(c->flags); }
+        c->retired.clear();
+        c->flags = nullptr;
+    }
+    for (size_t& g : c->gather_cap) g = 0;
+    c->peer = false;
+}
+
+int peer_timeout(rt_ctx* c, unsigned code) {
+    cudaMemset(c->peer_err, 0, sizeof(unsigned));
+    c->frame_valid = false;
+    return fail(c, RT_ERR_STATE, "peer-store gather: rank %d waited more than %llu s for %s", c->rank, kPeerTimeoutNs / 1000000000ull,
+                c->rank == 0 ? "another rank's completion flag" : "rank 0 to start the frame");
+    (void)code;
+}
+
+// Collective.  Tries to put the peer-store gather in place: rank 0 exports the flag block, everybody maps it.
+int peer_setup(rt_ctx* c) {
+    c->peer = false;
+    if (c->world <= 1) return RT_OK;
+    if (!c->peer_err) { CU(c, cudaMalloc(&c->peer_err, sizeof(unsigned))); CU(c, cudaMemset(c->peer_err, 0, sizeof(unsigned))); }
+    cudaIpcMemHandle_t h; memset(&h, 0, sizeof h);
+    int ok = 1;
+    if (c->rank == 0) {
+        if (cudaMalloc(&c->flags, kFlagBytes) != cudaSuccess || cudaMemset(c->flags, 0, kFlagBytes) != cudaSuccess ||
+            cudaIpcGetMemHandle(&h, c->flags) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+    }
+    int rc = bcast_bytes(c, &h, sizeof h);
+    if (rc != RT_OK) return rc;
+    if (c->rank != 0) {
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+        c->flags = (unsigned*)p;
+    }
+    int all = 0;
+    rc = all_min(c, ok, &all);
+    if (rc != RT_OK) return rc;
+    c->seq = 0;
+    if (!all) {
+        if (c->rank != 0 && c->flags) cudaIpcCloseMemHandle(c->flags);
+        if (c->rank == 0 && c->flags) c->retired.push_back(c->flags);
+        c->flags = nullptr;
+        return RT_OK;                                           // stays on the NCCL gather
+    }
+    c->peer = true;
+    return RT_OK;
+}
+
+// Collective (every rank evaluates the same growth condition): rank 0 (re)allocates the image planes the
+// frame needs and exports them; the other ranks map them.  On any failure all ranks fall back to NCCL.
+int peer_planes(rt_ctx* c, uint32_t outputs, size_t npix) {
+    static const uint32_t bits[4] = {RT_OUT_RGB_F32, RT_OUT_RGB8, RT_OUT_TRI_ID, RT_OUT_T};
+    static const size_t bpp[4] = {12, 3, 4, 4};
+    Plane* planes[4] = {&c->img_rgb, &c->img_rgb8, &c->img_id, &c->img_t};
+    struct Msg { cudaIpcMemHandle_t h[4]; int ok; } m;
+    memset(&m, 0, sizeof m); m.ok = 1;
+    bool grow[4]; bool any = false;
+    for (int i = 0; i < 4; ++i) { grow[i] = (outputs & bits[i]) && bpp[i] * npix + 16 > c->gather_cap[i]; any = any || grow[i]; }
+    if (!any) return RT_OK;
+    CU(c, cudaStreamSynchronize(c->stream));                    // nobody is still writing the old planes
+    for (int i = 0; i < 4; ++i) {
+        if (!grow[i]) continue;
+        const size_t need = bpp[i] * npix + 16;
+        if (c->rank == 0) {
+            if (planes[i]->p) { c->retired.push_back(planes[i]->p); planes[i]->p = nullptr; planes[i]->cap = 0; }
+            if (cudaMalloc(&planes[i]->p, need) != cudaSuccess) { m.ok = 0; cudaGetLastError(); planes[i]->p = nullptr; continue; }
+            planes[i]->cap = need;
+            if (cudaIpcGetMemHandle(&m.h[i], planes[i]->p) != cudaSuccess) { m.ok = 0; cudaGetLastError(); }
+        } else if (c->peer_img[i]) { cudaIpcCloseMemHandle(c->peer_img[i]); c->peer_img[i] = nullptr; }
+    }
+    int rc = bcast_bytes(c, &m, sizeof m);
+    if (rc != RT_OK) return rc;
+    int ok = m.ok;
+    if (c->rank != 0 && ok) {
+        for (int i = 0; i < 4; ++i) {
+            if (!grow[i]) continue;
+            if (cudaIpcOpenMemHandle(&c->peer_img[i], m.h[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); c->peer_img[i] = nullptr; }
+        }
+    }
+    int all = 0;
+    rc = all_min(c, ok, &all);
+    if (rc != RT_OK) return rc;
+    if (!all) { peer_teardown(c, true); return RT_OK; }
+    for (int i = 0; i < 4; ++i) if (grow[i]) c->gather_cap[i] = bpp[i] * npix + 16;
+    return RT_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -184,8 +321,11 @@ int rt_destroy(rt_ctx* c) {
     if (!c) return RT_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    peer_teardown(c, true);
+    if (c->peer_err) cudaFree(c->peer_err);
     if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
     free_scene(c);
+    c->xfer.release();
     Plane* planes[] = {&c->lights, &c->jitter, &c->counters, &c->loc_rgb, &c->loc_rgb8, &c->loc_id, &c->loc_t,
                        &c->img_rgb, &c->img_rgb8, &c->img_id, &c->img_t, &c->stage_rgb, &c->stage_rgb8, &c->stage_id, &c->stage_t};
     for (Plane* p : planes) p->release();
@@ -208,14 +348,34 @@ int rt_comm_unique_id(void* id128) {
 int rt_comm_init(rt_ctx* c, int rank, int world, const void* id128) {
     if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(c, RT_ERR_ARG, "rt_comm_init: bad arguments");
     CU(c, cudaSetDevice(c->device));
+    if (world > 8) return fail(c, RT_ERR_ARG, "rt_comm_init: at most 8 ranks (one box)");
+    peer_teardown(c, true);
     if (c->comm && nccl().ok) { nccl().CommDestroy(c->comm); c->comm = nullptr; }
     c->rank = rank; c->world = world;
+    c->frame_valid = false;
     if (world > 1) {
         ncclUniqueId id;
         memcpy(&id, id128, sizeof id);
         NC(c, CommInitRank(&c->comm, world, id, rank));
+        return peer_setup(c);                                  // RT_GATHER_AUTO
     }
+    return RT_OK;
+}
+
+int rt_comm_set_gather(rt_ctx* c, int mode) {
+    if (!c || mode < RT_GATHER_AUTO || mode > RT_GATHER_PEER) return fail(c, RT_ERR_ARG, "rt_comm_set_gather: bad arguments");
+    CU(c, cudaSetDevice(c->device));
     c->frame_valid = false;
+    if (c->world <= 1) return RT_OK;
+    if (mode == RT_GATHER_NCCL) { peer_teardown(c, true); return RT_OK; }
+    if (!c->peer) { int rc = peer_setup(c); if (rc != RT_OK) return rc; }
+    if (mode == RT_GATHER_PEER && !c->peer) return fail(c, RT_ERR_CUDA, "rt_comm_set_gather: CUDA IPC peer mapping of rank 0's memory is not available on every rank");
+    return RT_OK;
+}
+
+int rt_comm_gather_mode(const rt_ctx* c, int* mode) {
+    if (!c || !mode) return fail(nullptr, RT_ERR_ARG, "rt_comm_gather_mode: NULL");
+    *mode = c->peer ? RT_GATHER_PEER : RT_GATHER_NCCL;
     return RT_OK;
 }
 
@@ -319,7 +479,6 @@ int rt_render(rt_ctx* c, const rt_frame* fr) {
     if (fr->num_lights < 0 || (fr->num_lights > 0 && !fr->lights)) return fail(c, RT_ERR_ARG, "rt_render: lights");
     if (fr->mode == RT_MODE_HW1 && fr->num_lights < 1) return fail(c, RT_ERR_ARG, "rt_render: HW1 mode needs one light");
     if (fr->quantiser < RT_QUANT_PPM_LROUND || fr->quantiser > RT_QUANT_HW2_TRUNC) return fail(c, RT_ERR_ARG, "rt_render: quantiser");
-    const uint32_t outputs = fr->outputs ? fr->outputs : RT_OUT_RGB_F32;
 
     FrameParams& P = c->fp;
     memset(&P, 0, sizeof P);
@@ -330,6 +489,13 @@ int rt_render(rt_ctx* c, const rt_frame* fr) {
     P.nodes = c->nodes; P.geom = c->geom; P.shade = c->shade; P.num_tris = c->num_tris; P.materials = c->materials;
     P.tiles_x = (P.W + RT_TILE_W - 1) / RT_TILE_W; P.tiles_y = (P.H + RT_TILE_H - 1) / RT_TILE_H;
     P.rank = c->rank; P.world = c->world;
+    const uint32_t outputs = fr->outputs ? fr->outputs : RT_OUT_RGB_F32;
+    if (c->world > 1 && c->peer) {                 // collective; may fall back to the NCCL gather
+        int rc = peer_planes(c, outputs, (size_t)fr->width * fr->height);
+        if (rc != RT_OK) return rc;
+    }
+    const bool peer = c->world > 1 && c->peer;
+    P.packed = (c->world > 1 && !peer) ? 1 : 0;
     const int total_tiles = P.tiles_x * P.tiles_y;
     P.local_tiles = tiles_of_rank(total_tiles, c->rank, c->world);
     {   // fused slab test only when the camera is within 8 scene extents of the scene (rt_core.h, rt_slab_fma)
@@ -354,18 +520,42 @@ int rt_render(rt_ctx* c, const rt_frame* fr) {
     }
     const size_t npix_full = (size_t)P.W * P.H;
     const size_t npix_loc = c->world == 1 ? npix_full : (size_t)P.local_tiles * RT_BLOCK_THREADS;
-    if (outputs & RT_OUT_RGB_F32) { CU(c, c->loc_rgb.reserve(12 * npix_loc + 16)); P.rgb = (float*)c->loc_rgb.p; }
-    if (outputs & RT_OUT_RGB8) { CU(c, c->loc_rgb8.reserve(3 * npix_loc + 16)); P.rgb8 = (uint8_t*)c->loc_rgb8.p; }
-    if (outputs & RT_OUT_TRI_ID) { CU(c, c->loc_id.reserve(4 * npix_loc + 16)); P.tri_id = (int32_t*)c->loc_id.p; }
-    if (outputs & RT_OUT_T) { CU(c, c->loc_t.reserve(4 * npix_loc + 16)); P.t = (float*)c->loc_t.p; }
+    if (peer) {                                    // every rank writes rank 0's row-major image in place
+        const bool root = c->rank == 0;
+        if (outputs & RT_OUT_RGB_F32) P.rgb = (float*)(root ? c->img_rgb.p : c->peer_img[0]);
+        if (outputs & RT_OUT_RGB8) P.rgb8 = (uint8_t*)(root ? c->img_rgb8.p : c->peer_img[1]);
+        if (outputs & RT_OUT_TRI_ID) P.tri_id = (int32_t*)(root ? c->img_id.p : c->peer_img[2]);
+        if (outputs & RT_OUT_T) P.t = (float*)(root ? c->img_t.p : c->peer_img[3]);
+    } else {
+        if (outputs & RT_OUT_RGB_F32) { CU(c, c->loc_rgb.reserve(12 * npix_loc + 16)); P.rgb = (float*)c->loc_rgb.p; }
+        if (outputs & RT_OUT_RGB8) { CU(c, c->loc_rgb8.reserve(3 * npix_loc + 16)); P.rgb8 = (uint8_t*)c->loc_rgb8.p; }
+        if (outputs & RT_OUT_TRI_ID) { CU(c, c->loc_id.reserve(4 * npix_loc + 16)); P.tri_id = (int32_t*)c->loc_id.p; }
+        if (outputs & RT_OUT_T) { CU(c, c->loc_t.reserve(4 * npix_loc + 16)); P.t = (float*)c->loc_t.p; }
+    }
     P.counters = (unsigned long long*)c->counters.p;
     CU(c, cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
 
     CU(c, cudaEventRecord(c->ev0, c->stream));
     int launches = 0;
-    CU(c, rt_launch_render(P, fr->kernel_variant, c->stream, &launches));
+    if (peer) {
+        // Frame k may overwrite rank 0's image only once rank 0 is done with frame k-1 (its downloads are
+        // stream-ordered before this point): rank 0 publishes `ready = k`, the others wait for it.
+        const unsigned seq = ++c->seq;
+        if (c->rank == 0) CU(c, rt_launch_flag_set(c->flags, seq, c->stream));
+        else CU(c, rt_launch_flag_wait(c->flags, RT_PEER_FLAG_STRIDE, 1, seq, kPeerTimeoutNs, c->peer_err, c->stream));
+        ++launches;
+        int l = 0;
+        CU(c, rt_launch_render(P, fr->kernel_variant, c->stream, &l));
+        launches += l;
+        // completion: one flag word per rank in rank 0's memory, written after the frame kernel
+        if (c->rank != 0) CU(c, rt_launch_flag_set(c->flags + (size_t)c->rank * RT_PEER_FLAG_STRIDE, seq, c->stream));
+        else CU(c, rt_launch_flag_wait(c->flags + RT_PEER_FLAG_STRIDE, RT_PEER_FLAG_STRIDE, c->world - 1, seq, kPeerTimeoutNs, c->peer_err, c->stream));
+        ++launches;
+    } else {
+        CU(c, rt_launch_render(P, fr->kernel_variant, c->stream, &launches));
+    }
 
-    if (c->world > 1) {
+    if (c->world > 1 && !peer) {
         // Tile gather to rank 0: one grouped send/recv per requested plane, then an unpack kernel per source rank.
         const size_t other_pix = ((size_t)total_tiles - (size_t)tiles_of_rank(total_tiles, 0, c->world)) * RT_BLOCK_THREADS;
         if (c->rank == 0) {
@@ -419,7 +609,10 @@ int rt_sync(rt_ctx* c, float* gpu_ms) {
     if (!c) return fail(nullptr, RT_ERR_ARG, "rt_sync: NULL ctx");
     CU(c, cudaSetDevice(c->device));
     if (!c->frame_valid) return fail(c, RT_ERR_STATE, "rt_sync: no frame rendered");
+    unsigned perr = 0;
+    if (c->peer && c->peer_err) CU(c, cudaMemcpyAsync(&perr, c->peer_err, sizeof perr, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    if (perr) return peer_timeout(c, perr);
     if (gpu_ms) CU(c, cudaEventElapsedTime(gpu_ms, c->ev0, c->ev1));
     return RT_OK;
 }
@@ -457,8 +650,11 @@ int rt_download_image(rt_ctx* c, rt_image* img) {
         }
     }
     unsigned long long cnt[2] = {0, 0};
+    unsigned perr = 0;
     CU(c, cudaMemcpyAsync(cnt, c->counters.p, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
+    if (c->peer && c->peer_err) CU(c, cudaMemcpyAsync(&perr, c->peer_err, sizeof perr, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    if (perr) return peer_timeout(c, perr);
     img->width = P.W; img->height = P.H;
     img->rays_primary = cnt[0]; img->rays_shadow = cnt[1];
     float ms = 0.f;

@@ -20,3 +20,8 @@ cudaError_t rt_launch_render(const FrameParams& fp, int kernel_variant, cudaStre
 cudaError_t rt_launch_unpack(const FrameParams& fp, int src_rank, const float* rgb, const uint8_t* rgb8,
                              const int32_t* tri_id, const float* t, float* o_rgb, uint8_t* o_rgb8,
                              int32_t* o_tri_id, float* o_t, cudaStream_t stream);
+// Completion flags of the peer-store gather (see k_flag_set / k_flag_wait in rt_trace.cu).
+#define RT_PEER_FLAG_STRIDE 16            // one 64-byte line per rank
+cudaError_t rt_launch_flag_set(unsigned* flag, unsigned seq, cudaStream_t stream);
+cudaError_t rt_launch_flag_wait(const unsigned* flags, int stride, int n, unsigned seq, unsigned long long timeout_ns,
+                                unsigned* err, cudaStream_t stream);

@@ -26,7 +26,9 @@ struct FrameParams {
     // tile sharding
     int tiles_x, tiles_y, rank, world;
     int local_tiles;                // tiles owned by this rank
-    // output planes: row-major image when world == 1, tile-packed when world > 1
+    int packed;                     // 1: planes are this rank's tile-packed buffers (NCCL gather); 0: row-major image
+                                    //    (single GPU, or rank 0's image written in place over NVLink peer memory)
+    // output planes
     float* rgb; uint8_t* rgb8; int32_t* tri_id; float* t;
     unsigned long long* counters;   // [0] primary rays, [1] shadow rays, [2] node visits, [3] triangle tests (stats variants)
     int fast_slab;                  // 1: ray origins are close enough to the scene for rt_slab_fma (host decides)
@@ -41,7 +43,7 @@ struct BuildParams {
 // Pixel owned by thread `tid` of the block working on rank-local tile `ltile`.
 // Tile k of the frame (row-major tile order) belongs to rank k % world; within a tile each warp
 // covers an 8x4 pixel patch.  `out` is the index into the output planes: row-major pixel index
-// when world == 1, tile-packed (ltile*128 + ly*16 + lx) when the frame is sharded.
+// when P.packed == 0, tile-packed (ltile*128 + ly*16 + lx) when P.packed == 1.
 struct Pixel { int x, y; bool inside; size_t out; };
 RT_HD Pixel rt_map_pixel(const FrameParams& P, int ltile, int tid) {
     const int gtile = ltile * P.world + P.rank;
@@ -51,7 +53,7 @@ RT_HD Pixel rt_map_pixel(const FrameParams& P, int ltile, int tid) {
     Pixel px;
     px.x = tx * RT_TILE_W + lx; px.y = ty * RT_TILE_H + ly;
     px.inside = (px.x < P.W) && (px.y < P.H) && (ty < P.tiles_y);
-    px.out = (P.world == 1) ? ((size_t)px.y * P.W + px.x)
+    px.out = (P.packed == 0) ? ((size_t)px.y * P.W + px.x)
                             : ((size_t)ltile * RT_BLOCK_THREADS + (size_t)ly * RT_TILE_W + lx);
     return px;
 }

@@ -381,7 +381,43 @@ __global__ void k_unpack(FrameParams P, int src_rank, const float* rgb, const ui
     if (o_t && t) o_t[dst] = t[src];
 }
 
+// ------------------------------------------------- peer flags (fused NVLink gather) ----
+// In the peer-store gather every rank's frame kernel writes its tiles straight into rank 0's
+// row-major image over NVLink (CUDA IPC mapping), so the "gather" is only a completion signal:
+// a flag word per rank in rank 0's memory.  k_flag_set publishes a frame sequence number after
+// everything the stream did before it (kernel boundary + system fence); k_flag_wait spins until
+// all `n` flags reached it, bounded by a wall-clock timeout so a dead peer cannot hang the GPU.
+__global__ void k_flag_set(volatile unsigned* flag, unsigned seq) {
+    __threadfence_system();
+    *flag = seq;
+    __threadfence_system();
+}
+__global__ void k_flag_wait(const volatile unsigned* flags, int stride, int n, unsigned seq, unsigned long long timeout_ns, unsigned* err) {
+    const int i = (int)threadIdx.x;
+    if (i < n) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while ((int)(flags[(size_t)i * stride] - seq) < 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) { atomicExch(err, 1u + (unsigned)i); break; }
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();
+}
+
 } // namespace
+
+cudaError_t rt_launch_flag_set(unsigned* flag, unsigned seq, cudaStream_t stream) {
+    k_flag_set<<<1, 1, 0, stream>>>(flag, seq);
+    return cudaGetLastError();
+}
+cudaError_t rt_launch_flag_wait(const unsigned* flags, int stride, int n, unsigned seq, unsigned long long timeout_ns, unsigned* err, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    k_flag_wait<<<1, 32, 0, stream>>>(flags, stride, n, seq, timeout_ns, err);
+    return cudaGetLastError();
+}
 
 template <int MODE>
 static cudaError_t launch_mode(const FrameParams& fp, int variant, cudaStream_t stream) {

@@ -187,7 +187,7 @@ int emu_render_rank(void* h, const rt_frame* fr, rt_image* img, uint64_t* stats,
     P.materials = es->materials.empty() ? nullptr : es->materials.data();
     P.lights = fr->lights; P.jitter = fr->jitter;
     P.tiles_x = (P.W + RT_TILE_W - 1) / RT_TILE_W; P.tiles_y = (P.H + RT_TILE_H - 1) / RT_TILE_H;
-    P.rank = rank; P.world = world;
+    P.rank = rank; P.world = world; P.packed = world > 1 ? 1 : 0;
     P.local_tiles = rt_tiles_of_rank(P.tiles_x * P.tiles_y, rank, world);
     P.rgb = img->rgb; P.rgb8 = img->rgb8; P.tri_id = img->tri_id; P.t = img->t;
     unsigned long long tot[5] = {0, 0, 0, 0, 0};

@@ -20,8 +20,16 @@ def main():
     info = r.upload_scene(sc if rank == 0 else None)          # ranks != 0 receive the arena by broadcast
     assert info.num_triangles == 120 * 60 * 2 and info.num_nodes > 0
     ok = True
-    for (W, H, spp) in ((333, 201, 1), (256, 128, 2), (40, 9, 1)):
-        fr = scenes.terrain_frame(W, H, spp=spp, outputs=ALL)
+    want_mode = {"auto": A.RT_GATHER_AUTO, "nccl": A.RT_GATHER_NCCL, "peer": A.RT_GATHER_PEER}
+    cases = [("auto", 333, 201, 1, ALL), ("nccl", 333, 201, 1, ALL), ("nccl", 256, 128, 2, ALL), ("nccl", 40, 9, 1, ALL),
+             ("peer", 333, 201, 1, ALL), ("peer", 64, 32, 1, A.RT_OUT_RGB8), ("peer", 256, 128, 2, ALL), ("peer", 40, 9, 1, ALL),
+             ("peer", 700, 400, 1, ALL), ("nccl", 700, 400, 1, ALL), ("peer", 333, 201, 1, ALL)]
+    for (gm, W, H, spp, outs) in cases:
+        mode = r.set_gather(want_mode[gm])
+        assert gm == "auto" or mode == want_mode[gm], (gm, mode)
+        if rank == 0:
+            print("gather", gm, "->", {A.RT_GATHER_NCCL: "nccl", A.RT_GATHER_PEER: "peer"}[mode], W, H, spp, flush=True)
+        fr = scenes.terrain_frame(W, H, spp=spp, outputs=outs)
         r.render(fr)
         got = r.download()
         import torch
@@ -36,10 +44,27 @@ def main():
             ref = solo.download()
             solo.close()
             for k in ("tri_id", "t", "rgb", "rgb8"):
+                if k not in got or got[k] is None:
+                    continue
                 if not np.array_equal(got[k], ref[k]):
                     print("MISMATCH", W, H, spp, k, int((got[k] != ref[k]).sum()))
                     ok = False
             assert int(cnt[1].item()) == ref["rays_shadow"]
+    # back-to-back frames without a download in between (what bench.py's timed loop does), then one download
+    r.set_gather(A.RT_GATHER_AUTO)
+    fr = scenes.terrain_frame(512, 256, outputs=A.RT_OUT_RGB8)
+    for _ in range(5):
+        r.render(fr)
+        r.sync()
+    got = r.download()
+    if rank == 0:
+        solo = api.Renderer(local_rank)
+        solo.upload_scene(sc)
+        solo.render(fr)
+        if not np.array_equal(got["rgb8"], solo.download()["rgb8"]):
+            print("MISMATCH back-to-back")
+            ok = False
+        solo.close()
     dist.barrier()
     r.close()
     dist.destroy_process_group()
