@@ -32,12 +32,37 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = {
-    # name: (nx, ny, W, H, spp)
-    "c4": (1000, 500, 3840, 2160, 1),
-    "c5": (2500, 2000, 7680, 4320, 16),
-    "c4small": (200, 100, 960, 540, 1),
-}
+WORKLOADS = ("c4", "c5", "c3", "c3fill", "c2", "c4small")
+FROG = os.path.join(ROOT, "tests", "golden", "frog_mesh.npz")
+
+
+def make_workload(name, leaf_max=2, variant=0, shadows=True):
+    """BASELINE.json configs (SURVEY §8d): scene + frame + description.  c4 is the headline (metric is quoted on it);
+    the others are parity/measurement cases selectable with --workload."""
+    from raytracinginonesemester_b200 import _abi as A, api, scenes
+    flags = A.RT_BUILD_LEAF_MAX(leaf_max)
+    terr = {"c4": (1000, 500, 3840, 2160, 1), "c5": (2500, 2000, 7680, 4320, 16), "c4small": (200, 100, 960, 540, 1)}
+    if name in terr:
+        nx, ny, W, H, spp = terr[name]
+        scene = lambda: scenes.terrain_scene(nx, ny, build_flags=flags)
+        frame = scenes.terrain_frame(W, H, spp=spp, outputs=A.RT_OUT_RGB8, kernel_variant=variant, shadows=shadows)
+        return dict(name=name, scene=scene, frame=frame, triangles=nx * ny * 2, mode="hw2",
+                    desc="synthetic terrain(%d,%d,seed 42), HW2 shading, primary + shadow rays, BVH" % (nx, ny))
+    d = np.load(FROG)
+
+    def frog(extra=0):
+        return api.Scene(d["positions"], d["indices"], normals=d["normals"], tri_obj_ids=d["tri_obj_ids"],
+                         materials=[api.make_material(**scenes.FROG_MATERIAL)], build_flags=flags | extra)
+    ntri = int(d["indices"].shape[0])
+    if name == "c2":      # HW1 frog, 1080p, brute force: every ray tests every triangle (HW1/src/render.cpp:89-107)
+        frame = scenes.hw1_frame(1920, 1080, accel=A.RT_ACCEL_BRUTE, outputs=A.RT_OUT_RGB8)
+        return dict(name=name, scene=lambda: frog(A.RT_BUILD_NO_BVH), frame=frame, triangles=ntri, mode="hw1",
+                    desc="HW1 frog.obj (19 858 triangles), 1920x1080, brute-force ray-triangle, HW1 shade()")
+    filling = name == "c3fill"
+    frame = scenes.frog_frame(3840, 2160, filling=filling, outputs=A.RT_OUT_RGB8, shadows=shadows, quantiser=A.RT_QUANT_PPM_LROUND)
+    frame.kernel_variant = variant
+    return dict(name=name, scene=frog, frame=frame, triangles=ntri, mode="hw2",
+                desc="HW2-BVH frog.obj at 3840x2160, depth 1, %s" % ("frame-filling view (focal 170 mm)" if filling else "stock frog.json view (3.2 % of pixels hit)"))
 
 
 def measured_peaks():
@@ -131,71 +156,108 @@ def reference_lib():
     return None
 
 
-class CpuReference:
-    """The reference CPU renderer of the path on host threads: kind 'reference' when the in-place
-    build of the reference sources is present, else the oracle port."""
+def hw1_lib():
+    p = os.path.join(ROOT, "oracle", "_ref", "libref_hw1.so")
+    if os.path.exists(p):
+        lib = C.CDLL(p)
+        lib.ref_hw1_render.restype = C.c_uint64
+        return lib
+    return None
 
-    def __init__(self, scene, frame):
+
+class CpuReference:
+    """The reference's CPU renderer of the path on host threads: kind 'reference' when the in-place build of the
+    reference sources is present (oracle/_ref), else the oracle port.  HW2 workloads run render()'s per-pixel body
+    (query.cu:136-165) over the reference LBVH; the HW1 workload runs the loop of HW1/src/render.cpp:72-116."""
+
+    def __init__(self, wl):
         from raytracinginonesemester_b200 import _abi as A
-        self.A, self.scene, self.frame = A, scene, frame
+        self.A, self.wl = A, wl
+        self.scene, self.frame = wl["scene"](), wl["frame"]
         self.cores = os.cpu_count() or 1
-        self.lib = reference_lib()
+        self.hw1 = wl["mode"] == "hw1"
+        self.lib = hw1_lib() if self.hw1 else reference_lib()
         self.kind = "reference" if self.lib else "port"
+        scene = self.scene
         t0 = time.perf_counter()
-        if self.lib:
+        if self.hw1:
+            self.h = None
+        elif self.lib:
             f32p, u32p, i32p = A.f32p, A.u32p, A.i32p
-            self.h = self.lib.ref_hw2_world(scene.positions.ctypes.data_as(f32p), None, C.c_uint64(scene.positions.shape[0]),
+            nrm = scene.normals.ctypes.data_as(f32p) if scene.normals is not None else None
+            self.h = self.lib.ref_hw2_world(scene.positions.ctypes.data_as(f32p), nrm, C.c_uint64(scene.positions.shape[0]),
                                             scene.indices.ctypes.data_as(u32p), C.c_uint64(scene.indices.shape[0]),
                                             scene.tri_obj_ids.ctypes.data_as(i32p))
             self.lib.ref_hw2_build(C.c_void_p(self.h))
-        else:
+        if not self.lib:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import orclib
             self.orclib = orclib
-            self.h = orclib.oracle_bvh(scene)
+            self.h = None if self.hw1 else orclib.oracle_bvh(scene)
         self.build_s = time.perf_counter() - t0
 
     def rays_in_rows(self, row_begin, row_step):
-        """Times one row-strided pass; returns (rays, seconds).  Shadow rays are counted with the
-        oracle's counter-free rule: one per lit hit — measured by the port, estimated as
-        primary * shadow_ratio for the in-place reference (which has no counters)."""
-        fr, A = self.frame, self.A
+        """Times one row-strided pass; returns (primary rays, seconds).  The in-place reference has no ray counters:
+        shadow rays are taken from the device count (one per lit hit — the same rule)."""
+        fr, A, scene = self.frame, self.A, self.scene
         W, H = fr.width, fr.height
         rows = len(range(row_begin, H, row_step))
+        cp = fr.cam.params
+        f3 = lambda v: np.array(v, np.float32)
+        cpos, look, up = f3(cp["pos"]), f3(cp["look_at"]), f3(cp["up"])
         t0 = time.perf_counter()
-        if self.lib:
-            cp = np.array([0, 0, 1], np.float32); lk = np.zeros(3, np.float32); up = np.array([0, 1, 0], np.float32)
-            ms = np.array(fr.miss_color, np.float32)
+        if self.lib and self.hw1:
+            l = fr.lights[0]
+            lp, lc = f3(list(l.position)), f3(list(l.color))
+            rgb8 = np.zeros((H, W, 3), np.uint8)
+            nrm = scene.normals if scene.normals is not None else np.zeros_like(scene.positions)
+            self.lib.ref_hw1_render(scene.positions.ctypes.data_as(A.f32p), nrm.ctypes.data_as(A.f32p), scene.indices.ctypes.data_as(A.u32p),
+                                    C.c_uint64(scene.indices.shape[0]), cpos.ctypes.data_as(A.f32p), look.ctypes.data_as(A.f32p),
+                                    up.ctypes.data_as(A.f32p), C.c_double(cp["focal_mm"]), C.c_double(cp["sensor_mm"]), W, H,
+                                    lp.ctypes.data_as(A.f32p), lc.ctypes.data_as(A.f32p), fr.spp, C.c_uint(42), row_begin, row_step, self.cores,
+                                    None, rgb8.ctypes.data_as(A.u8p), None, None)
+        elif self.lib:
+            ms = f3(fr.miss_color)
             rgb = np.zeros((H, W, 3), np.float32)
-            marr = (A.rt_material * len(self.scene.materials))(*self.scene.materials)
+            marr = (A.rt_material * len(scene.materials))(*scene.materials)
             larr = (A.rt_light * len(fr.lights))(*fr.lights)
-            self.lib.ref_hw2_render_rows(C.c_void_p(self.h), cp.ctypes.data_as(A.f32p), lk.ctypes.data_as(A.f32p), up.ctypes.data_as(A.f32p),
-                                         C.c_double(24.0), C.c_double(24.0), W, H, ms.ctypes.data_as(A.f32p), 1, fr.spp,
-                                         marr, len(self.scene.materials), larr, len(fr.lights), 1, row_begin, row_step, self.cores,
+            self.lib.ref_hw2_render_rows(C.c_void_p(self.h), cpos.ctypes.data_as(A.f32p), look.ctypes.data_as(A.f32p), up.ctypes.data_as(A.f32p),
+                                         C.c_double(cp["focal_mm"]), C.c_double(cp["sensor_mm"]), W, H, ms.ctypes.data_as(A.f32p), 1, fr.spp,
+                                         marr, len(scene.materials), larr, len(fr.lights), 1, row_begin, row_step, self.cores,
                                          rgb.ctypes.data_as(A.f32p), None, None)
         else:
-            self.orclib.oracle_render(self.scene, fr, bvh=self.h, threads=self.cores, row_begin=row_begin, row_step=row_step, want=("rgb",))
+            self.orclib.oracle_render(scene, fr, bvh=self.h, threads=self.cores, row_begin=row_begin, row_step=row_step, want=("rgb",))
         dt = time.perf_counter() - t0
         return rows * W * fr.spp, dt
+
+
+# shadow rays per primary ray, counted by the device on each workload (one shadow ray per lit hit; the in-place
+# reference has no counters, the rule is the same)
+SHADOW_RATIO = {"c4": 0.81550, "c5": 0.70824, "c4small": 0.8155, "c2": 0.0, "c3": 0.0, "c3fill": 0.0}
+METRIC = "Mrays/s closest-hit (BVH+tri)"
+
+
+def cpu_sample(ref, seconds, max_passes=64):
+    """Bounded CPU sample of the frame: row-strided passes sized from a thin calibration pass."""
+    fr = ref.frame
+    W, H, spp = fr.width, fr.height, fr.spp
+    cal_rays, cal_dt = ref.rays_in_rows(5, max(1, H // 8))
+    rows = max(1, int(cal_rays / cal_dt * seconds / (W * spp)))
+    stp = max(1, H // rows)
+    return stp
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    from raytracinginonesemester_b200 import _abi as A, scenes
-    nx, ny, W, H, spp = WORKLOADS[args.workload]
-    scene = scenes.terrain_scene(nx, ny)
-    frame = scenes.terrain_frame(W, H, spp=spp, outputs=A.RT_OUT_RGB8)
-    ref = CpuReference(scene, frame)
-    shadow_ratio = args.shadow_ratio
-    # size a step for ~6 s of CPU work: calibrate on a thin sample first
-    cal_step = max(1, H // 8)
-    rays, dt = ref.rays_in_rows(3, cal_step)
-    rate = rays / dt
-    target_rows = max(1, int(rate * 6.0 / (W * spp)))
-    step = max(1, H // target_rows)
+    wl = make_workload(args.workload)
+    ref = CpuReference(wl)
+    fr = wl["frame"]
+    W, H, spp = fr.width, fr.height, fr.spp
+    shadow_ratio = args.shadow_ratio if args.shadow_ratio >= 0 else SHADOW_RATIO.get(args.workload, 0.0)
+    step = cpu_sample(ref, 6.0)                    # a step = ~6 s of CPU work on a row sample of the same frame
     for _ in range(args.warmup if args.warmup < 2 else 1):
-        ref.rays_in_rows(1, step)
+        ref.rays_in_rows(1 % step, step)
     tot_rays, tot_s = 0, 0.0
     for k in range(args.steps):
         rays, dt = ref.rays_in_rows(k % step, step)
@@ -203,10 +265,11 @@ def run_reference(args, rank, world):
         tot_s += dt
     mrays = tot_rays * (1.0 + shadow_ratio) / tot_s / 1e6
     line = {
-        "impl": "reference", "metric": "Mrays/s closest-hit (BVH+tri)", "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC, "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "triangles": nx * ny * 2, "width": W, "height": H, "spp": spp, "rays": "primary+shadow"},
+        "config": {"workload": args.workload, "description": wl["desc"], "triangles": wl["triangles"], "width": W, "height": H, "spp": spp,
+                   "rays": "primary+shadow" if shadow_ratio else "primary"},
         "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": ref.cores, "kind": ref.kind,
                          "sample": "every %d-th row of the %dx%d frame per step (%d rows), full-frame rate extrapolated; shadow rays = primary x %.4f" % (step, W, H, len(range(0, H, step)), shadow_ratio),
                          "lbvh_build_s": ref.build_s},
@@ -226,15 +289,18 @@ def run_ours(args, rank, world, local_rank):
     dist, rank, world, local_rank = parallel.init_process_group("nccl")
     r = parallel.make_renderer(dist, rank, world, local_rank)
     if world > 1:
+        r.set_sharding(args.chunks)
         r.set_gather({"auto": A.RT_GATHER_AUTO, "nccl": A.RT_GATHER_NCCL, "peer": A.RT_GATHER_PEER}[args.gather])
-    nx, ny, W, H, spp = WORKLOADS[args.workload]
-    scene = scenes.terrain_scene(nx, ny, build_flags=A.RT_BUILD_LEAF_MAX(args.leaf_max)) if rank == 0 else None
+    wl = make_workload(args.workload, args.leaf_max, args.variant, not args.no_shadows)
+    frame = wl["frame"]
+    W, H, spp = frame.width, frame.height, frame.spp
+    brute = frame.accel == A.RT_ACCEL_BRUTE
+    scene = wl["scene"]() if rank == 0 else None
     first = r.upload_scene(scene)          # first call in the process: pays CUDA module loading and CUB temp sizing
     t0 = time.perf_counter()
     info = r.upload_scene(scene)           # steady state (what a second scene or a re-upload costs)
     upload_wall = time.perf_counter() - t0
     gather = {A.RT_GATHER_NCCL: "nccl send/recv + unpack", A.RT_GATHER_PEER: "peer stores into rank 0's image over NVLink + flag words"}[r.gather_mode()] if world > 1 else "none"
-    frame = scenes.terrain_frame(W, H, spp=spp, outputs=A.RT_OUT_RGB8, kernel_variant=args.variant, shadows=not args.no_shadows)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     pinned = torch.empty((H, W, 3), dtype=torch.uint8, pin_memory=True).numpy() if rank == 0 else None
 
@@ -243,22 +309,41 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device(do_flush=True):
-        if do_flush:
-            flush.zero_()
-        barrier()
-        r.render(frame)
-        return r.sync()
+    # All device work of a step is enqueued on the library's own stream (rt_stream_handle): the L2 flush, an event,
+    # rt_render (frame kernel + tile delivery to rank 0), an event.  The K timed steps are enqueued back to back
+    # and bracketed by barrier + synchronize on both sides; a step's time is the CUDA-event interval around its
+    # rt_render (the flush is outside it), max over ranks.
+    ext = torch.cuda.ExternalStream(r.stream_handle())
 
-    for _ in range(args.warmup if args.profile else max(args.warmup, 3)):
-        step_device()
+    def enqueue_step(do_flush=True):
+        with torch.cuda.stream(ext):
+            if do_flush:
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r.render(frame)
+            e1.record()
+        return e0, e1
+
+    def timed(n, do_flush=True):
+        barrier()
+        ev = [enqueue_step(do_flush) for _ in range(n)]
+        barrier()
+        return [a.elapsed_time(b) for a, b in ev]
+
+    timed(args.warmup if args.profile else max(args.warmup, 3))
     # traversal statistics (untimed): bytes per ray for the roofline
-    frame.kernel_variant = A.RT_VARIANT_PER_RAY_STATS if args.variant >= 10 else A.RT_VARIANT_STATS
+    if not brute:
+        frame.kernel_variant = A.RT_VARIANT_PER_RAY_STATS if args.variant >= 10 else A.RT_VARIANT_STATS
     r.render(frame)
     st = r.download(into={"rgb8": pinned} if rank == 0 else None)
     nv, nt, nl, nb = r.frame_stats()
+    if brute:      # every ray tests every triangle; a block of 128 rays streams the 48-byte blocks once through shared memory
+        ntri = wl["triangles"]
+        nv, nl = 0, 0
+        nt = st["rays_primary"] * ntri
+        nb = (st["rays_primary"] // 128) * ntri
     frame.kernel_variant = args.variant
-    rays_local = st["rays_primary"] + st["rays_shadow"]
     cnt = torch.tensor([st["rays_primary"], st["rays_shadow"], nv, nt, nl, nb], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(cnt)
@@ -267,14 +352,16 @@ def run_ours(args, rank, world, local_rank):
 
     launches_per_step = 1 if world == 1 else (3 if r.gather_mode() == A.RT_GATHER_PEER else 1 + world)   # rank 0: frame kernel + flag set/wait, or + unpack per rank
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    barrier()
-    step_ms = []
-    for _ in range(args.steps):
-        step_ms.append(step_device())
-    warm_ms = []
-    for _ in range(min(args.steps, 5)):
-        warm_ms.append(step_device(do_flush=False))
-    barrier()
+    step_ms = timed(args.steps)
+    warm_ms = timed(min(args.steps, 5), do_flush=False)
+    # frame kernel alone vs the whole rt_render, per rank (host-synchronised frames, untimed for the headline)
+    ktimes = []
+    for _ in range(3):
+        flush.zero_()
+        barrier()
+        r.render(frame)
+        ktimes.append(r.frame_times())
+    kern_ms = float(np.mean([k for _, k in ktimes]))
     # end to end through the C ABI with host buffers (render + blocking download), wall clock
     e2e_s = []
     for _ in range(args.steps):
@@ -287,7 +374,7 @@ def run_ours(args, rank, world, local_rank):
         e2e_s.append(time.perf_counter() - t0)
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([step_ms, e2e_s + [0.0] * (len(step_ms) - len(e2e_s))], dtype=torch.float64, device="cuda")
-    tw = torch.tensor(warm_ms, dtype=torch.float64, device="cuda")
+    tw = torch.tensor(warm_ms + [kern_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tw, op=dist.ReduceOp.MAX)
@@ -305,16 +392,29 @@ def run_ours(args, rank, world, local_rank):
         b_ray = bytes_launch / rays
         achieved = bytes_launch / (ms * 1e-3) / 1e9
         peak = peak * world
+        traffic, traffic_src = None, None          # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+            if tj and world == 1 and args.variant == 0:
+                traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj["source"]
+        except Exception:
+            pass
+        if brute:
+            note = "FP32-issue bound, not HBM-bound: triangles are streamed through shared memory once per 128 rays; see fp32_issue"
+        else:
+            note = ("instruction-issue/latency bound, not HBM-bound: the arena is L2/L1-resident (ncu: issue slots 76 % busy, DRAM < 1 % of peak); "
+                    "achieved = bytes the kernel REQUESTS (64 B per warp node visit, 48 B per warp triangle test), most served by L1/L2 - see traffic and profiles/")
         line = {
-            "metric": "Mrays/s closest-hit (BVH+tri)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "triangles": nx * ny * 2, "width": W, "height": H, "spp": spp,
-                       "rays": "primary+shadow", "rays_primary": rays_primary, "rays_shadow": rays_shadow,
+            "config": {"workload": args.workload, "description": wl["desc"], "triangles": wl["triangles"], "width": W, "height": H, "spp": spp,
+                       "rays": "primary+shadow" if rays_shadow else "primary", "rays_primary": rays_primary, "rays_shadow": rays_shadow,
                        "l2": "flushed between timed steps (256 MiB memset); warm-L2 figure in value_warm_l2",
-                       "tile_sharding": "16x8 tiles, tile k -> rank k %% %d" % world, "gather": gather, "leaf_max": args.leaf_max, "variant": args.variant},
+                       "tile_sharding": "16x8-px tiles in %d contiguous bands per rank, band c -> rank c %% %d" % (args.chunks or parallel.DEFAULT_CHUNKS_PER_RANK, world), "gather": gather, "leaf_max": args.leaf_max, "variant": args.variant},
             "primary_mrays_s": rays_primary / (ms * 1e-3) / 1e6,
-            "value_warm_l2": rays / (float(tw.mean()) * 1e-3) / 1e6,
+            "value_warm_l2": rays / (float(tw[:-1].mean()) * 1e-3) / 1e6,
+            "frame_kernel_ms_max_rank": float(tw[-1]), "gather_overhead_ms": ms - float(tw[-1]),
             "bvh_nodes": int(info.num_nodes), "bvh_build_ms": float(info.build_ms), "bvh_build_first_call_ms": float(first.build_ms),
             "scene_upload_ms": float(info.upload_ms),
             "scene_upload_wall_s": upload_wall,
@@ -322,17 +422,21 @@ def run_ours(args, rank, world, local_rank):
                     "h2d_bytes_per_step": int(C.sizeof(A.rt_frame) + 28 * len(frame.lights) + 8 * spp),
                     "d2h_bytes_per_step": int(3 * W * H + 32)},
             "gpu_launches": int(args.steps * launches_per_step),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_kind": peak_kind + (" x %d GPUs" % world if world > 1 else ""), "bytes_per_ray": b_ray, "bytes_per_launch": bytes_launch,
                          "nodes_per_ray": nv_all / rays, "tris_per_ray": nt_all / rays, "node_lines_per_ray": nl_all / rays, "tri_blocks_per_ray": nb_all / rays,
-                         "note": "latency/issue-bound, not HBM-bound: the 1M-triangle arena (~130 MB) sits in L2/L1; see profiles/"},
+                         "note": note},
             "clocks": clocks,
         }
+        if brute:   # 51 flop per ray-triangle test in the reference's unfused formulation (27 mul, 23 add/sub, 1 div)
+            tests_s = nt_all / (ms * 1e-3)
+            pk = 148 * 128 * 2 * 1.965e9 / 1e12 * world
+            line["fp32_issue"] = {"ray_triangle_tests_per_s": tests_s, "flop_per_test": 51, "achieved_tflops": tests_s * 51 / 1e12,
+                                  "peak_tflops": pk, "frac": tests_s * 51 / 1e12 / pk,
+                                  "note": "peak counts FMA as 2 flop; the exactly-rounded test cannot use FMA, so 0.5 is its ceiling"}
         if world == 1 and not args.no_cpu_baseline and not args.profile:
-            ref = CpuReference(scenes.terrain_scene(nx, ny), frame)
-            cal_rays, cal_dt = ref.rays_in_rows(5, max(1, H // 8))
-            rows = max(1, int(cal_rays / cal_dt * 12.0 / (W * spp)))
-            stp = max(1, H // rows)
+            ref = CpuReference(make_workload(args.workload))
+            stp = cpu_sample(ref, 12.0)
             n, dt, passes = 0, 0.0, 0
             while dt < 10.0 and passes < 64:                  # bounded sample: ~10 s of CPU work
                 a, b = ref.rays_in_rows(passes % stp, stp)
@@ -352,14 +456,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c4", choices=WORKLOADS)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--leaf-max", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunks", type=int, default=0, help="multi-GPU tile ownership bands per rank (0 = library default)")
     ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "peer"], help="multi-GPU tile delivery to rank 0")
     ap.add_argument("--no-shadows", action="store_true", help="primary rays only (diagnostic; not the headline workload)")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: honour --warmup < 3, skip the CPU baseline")
-    ap.add_argument("--shadow-ratio", type=float, default=0.8144, help="shadow rays per primary ray on c4 (device count), used by --impl reference")
+    ap.add_argument("--shadow-ratio", type=float, default=-1.0, help="--impl reference: shadow rays per primary ray (default: the device count of the workload)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

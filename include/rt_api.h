@@ -180,6 +180,10 @@ int  rt_comm_rank(const rt_ctx* ctx, int* rank, int* world);
 #define RT_GATHER_PEER  2   /* fused: the frame kernel stores its pixels straight into rank 0's row-major image
                                over NVLink; a per-rank flag word in rank 0's memory signals completion */
 int  rt_comm_set_gather(rt_ctx* ctx, int mode);
+/* Screen-space sharding: the frame's 16x8-pixel tiles (row-major) are cut into world*chunks_per_rank contiguous
+ * chunks — horizontal bands — and chunk c is rendered by rank c % world.  0 selects the default (4).  Every rank
+ * must use the same value. */
+int  rt_comm_set_sharding(rt_ctx* ctx, int chunks_per_rank);
 int  rt_comm_gather_mode(const rt_ctx* ctx, int* mode);   /* mode in effect: RT_GATHER_NCCL or RT_GATHER_PEER */
 
 /* -- scene --------------------------------------------------------------- */
@@ -200,6 +204,13 @@ int  rt_render(rt_ctx* ctx, const rt_frame* frame);
 int  rt_download_image(rt_ctx* ctx, rt_image* img);
 /* Blocks until the last rt_render finished; returns its device time. */
 int  rt_sync(rt_ctx* ctx, float* gpu_ms);
+/* Device times of the last frame on this rank: the whole rt_render (frame kernel + tile delivery to rank 0)
+ * and the frame kernel alone.  Blocks like rt_sync. */
+int  rt_frame_times(rt_ctx* ctx, float* total_ms, float* kernel_ms);
+/* The context's CUDA stream (a cudaStream_t), for hosts that order their own device work or events
+ * against rt_render / rt_download_image.  The reference serialises everything on the default stream
+ * (CHECK_CUDA, GPUandCPU/include/imports.h:40-47). */
+int  rt_stream_handle(const rt_ctx* ctx, void** cuda_stream);
 
 /* Traversal work of the last frame rendered with a *_STATS variant, summed over primary and shadow
  * queries of this rank: per-ray BVH node visits and triangle tests, and the memory requests behind
@@ -238,6 +249,10 @@ const char* rt_mesh_last_error(void);
 /* Copies the flattened BVH back to the host (nodes: 64 B each; tri blocks: 48 B
  * each, leaf order; tri_ids: original triangle id per block). Any pointer may be
  * NULL; counts come from rt_build_info_get. */
+/* Single-GPU contexts only: render just the tiles rank `rank` of a `world`-rank job would own (tile-packed
+ * planes, no delivery) so that per-rank load balance and kernel tails can be measured on one GPU.  Planes of
+ * such frames cannot be downloaded; ray counts and times can.  world = 0 switches it off. */
+int  rt_debug_set_shard(rt_ctx* ctx, int rank, int world);
 int  rt_debug_download_bvh(rt_ctx* ctx, void* nodes64, void* tri_blocks48, int32_t* tri_ids);
 
 #ifdef __cplusplus

@@ -74,7 +74,10 @@ EXPORTS = {
     "rt_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "rt_comm_rank": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rt_comm_set_gather": (C.c_int, [C.c_void_p, C.c_int]),
+    "rt_comm_set_sharding": (C.c_int, [C.c_void_p, C.c_int]),
     "rt_comm_gather_mode": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "rt_frame_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "rt_stream_handle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "rt_upload_scene": (C.c_int, [C.c_void_p, C.POINTER(rt_scene)]),
     "rt_build_info_get": (C.c_int, [C.c_void_p, C.POINTER(rt_build_info)]),
     "rt_render": (C.c_int, [C.c_void_p, C.POINTER(rt_frame)]),
@@ -91,6 +94,7 @@ EXPORTS = {
     "rt_mesh_transform": (C.c_int, [C.c_void_p, f32p, f32p, f32p]),
     "rt_mesh_append": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rt_mesh_last_error": (C.c_char_p, []),
+    "rt_debug_set_shard": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "rt_debug_download_bvh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, i32p]),
 }
 

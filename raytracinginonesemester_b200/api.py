@@ -56,6 +56,8 @@ def camera_init(pos, look_at, up, focal_length_mm, sensor_height_mm, width, heig
                             float(focal_length_mm), float(sensor_height_mm), int(width), int(height))
     if rc != A.RT_OK:
         raise RtError(rc, "pixel_width and pixel_height must be >= 1")
+    cam.params = dict(pos=tuple(float(x) for x in p), look_at=tuple(float(x) for x in l), up=tuple(float(x) for x in u),
+                      focal_mm=float(focal_length_mm), sensor_mm=float(sensor_height_mm))   # for callers that re-create it
     return cam
 
 
@@ -217,6 +219,10 @@ class Renderer:
         self._check(self.lib.rt_comm_set_gather(self.ctx, int(mode)))
         return self.gather_mode()
 
+    def set_sharding(self, chunks_per_rank):
+        """Tile ownership bands per rank (0 = default); every rank must use the same value."""
+        self._check(self.lib.rt_comm_set_sharding(self.ctx, int(chunks_per_rank)))
+
     def gather_mode(self):
         m = C.c_int()
         self._check(self.lib.rt_comm_gather_mode(self.ctx, C.byref(m)))
@@ -244,6 +250,17 @@ class Renderer:
         ms = C.c_float()
         self._check(self.lib.rt_sync(self.ctx, C.byref(ms)))
         return ms.value
+
+    def frame_times(self):
+        """(whole rt_render, frame kernel only) device ms of the last frame on this rank."""
+        a, b = C.c_float(), C.c_float()
+        self._check(self.lib.rt_frame_times(self.ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def stream_handle(self):
+        h = C.c_void_p()
+        self._check(self.lib.rt_stream_handle(self.ctx, C.byref(h)))
+        return int(h.value or 0)
 
     def download(self, into=None):
         """Blocking read-back of the planes requested in Frame.outputs -> dict of numpy arrays.

@@ -68,7 +68,7 @@ struct Plane {
 struct rt_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;   // whole frame / frame kernel only
     std::string err;
     // scene
     BvhNode* nodes = nullptr; TriBlock* geom = nullptr; TriBlock* shade = nullptr; rt_material* materials = nullptr;
@@ -96,6 +96,8 @@ struct rt_ctx {
     size_t gather_cap[4] = {0, 0, 0, 0};          // every rank tracks rank 0's plane capacities identically
     std::vector<void*> retired;                   // rank 0: outgrown exported planes, freed at teardown
     unsigned seq = 0;                             // frame sequence number of the peer protocol
+    int chunks_per_rank = 0;                      // tile ownership bands per rank (0 = RT_DEFAULT_CHUNKS_PER_RANK)
+    int dbg_rank = 0, dbg_world = 0;              // rt_debug_set_shard: render one rank's share on a single GPU (timing only)
 };
 
 namespace {
@@ -119,7 +121,6 @@ void free_scene(rt_ctx* c) {
     c->num_tris = c->num_nodes = 0; c->num_materials = 0; c->has_scene = c->has_bvh = false;
 }
 
-int tiles_of_rank(int total, int rank, int world) { return rt_tiles_of_rank(total, rank, world); }
 
 struct SceneHeader { uint32_t num_tris, num_nodes, num_materials, has_bvh; float smin[3], smax[3]; };
 
@@ -311,6 +312,8 @@ int rt_create(rt_ctx** out, int device) {
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->evk0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->evk1);
     if (e == cudaSuccess) e = c->counters.reserve(8 * sizeof(unsigned long long));
     if (e != cudaSuccess) { int r = fail(nullptr, RT_ERR_CUDA, "rt_create: %s", cudaGetErrorString(e)); delete c; return r; }
     *out = c;
@@ -331,6 +334,8 @@ int rt_destroy(rt_ctx* c) {
     for (Plane* p : planes) p->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->evk0) cudaEventDestroy(c->evk0);
+    if (c->evk1) cudaEventDestroy(c->evk1);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return RT_OK;
@@ -370,6 +375,13 @@ int rt_comm_set_gather(rt_ctx* c, int mode) {
     if (mode == RT_GATHER_NCCL) { peer_teardown(c, true); return RT_OK; }
     if (!c->peer) { int rc = peer_setup(c); if (rc != RT_OK) return rc; }
     if (mode == RT_GATHER_PEER && !c->peer) return fail(c, RT_ERR_CUDA, "rt_comm_set_gather: CUDA IPC peer mapping of rank 0's memory is not available on every rank");
+    return RT_OK;
+}
+
+int rt_comm_set_sharding(rt_ctx* c, int chunks_per_rank) {
+    if (!c || chunks_per_rank < 0 || chunks_per_rank > 4096) return fail(c, RT_ERR_ARG, "rt_comm_set_sharding: bad arguments");
+    c->chunks_per_rank = chunks_per_rank;
+    c->frame_valid = false;
     return RT_OK;
 }
 
@@ -489,15 +501,18 @@ int rt_render(rt_ctx* c, const rt_frame* fr) {
     P.nodes = c->nodes; P.geom = c->geom; P.shade = c->shade; P.num_tris = c->num_tris; P.materials = c->materials;
     P.tiles_x = (P.W + RT_TILE_W - 1) / RT_TILE_W; P.tiles_y = (P.H + RT_TILE_H - 1) / RT_TILE_H;
     P.rank = c->rank; P.world = c->world;
+    const bool dbg_shard = c->world == 1 && c->dbg_world > 1;
+    if (dbg_shard) { P.rank = c->dbg_rank; P.world = c->dbg_world; }
     const uint32_t outputs = fr->outputs ? fr->outputs : RT_OUT_RGB_F32;
     if (c->world > 1 && c->peer) {                 // collective; may fall back to the NCCL gather
         int rc = peer_planes(c, outputs, (size_t)fr->width * fr->height);
         if (rc != RT_OK) return rc;
     }
     const bool peer = c->world > 1 && c->peer;
-    P.packed = (c->world > 1 && !peer) ? 1 : 0;
+    P.packed = ((c->world > 1 && !peer) || dbg_shard) ? 1 : 0;
     const int total_tiles = P.tiles_x * P.tiles_y;
-    P.local_tiles = tiles_of_rank(total_tiles, c->rank, c->world);
+    P.chunk_tiles = rt_chunk_tiles(total_tiles, P.world, c->chunks_per_rank);
+    P.local_tiles = rt_tiles_of_rank(total_tiles, P.world, c->chunks_per_rank);
     {   // fused slab test only when the camera is within 8 scene extents of the scene (rt_core.h, rt_slab_fma)
         float ext = 0.f, far = 0.f;
         for (int k = 0; k < 3; ++k) {
@@ -519,7 +534,7 @@ int rt_render(rt_ctx* c, const rt_frame* fr) {
         P.jitter = (const float*)c->jitter.p;
     }
     const size_t npix_full = (size_t)P.W * P.H;
-    const size_t npix_loc = c->world == 1 ? npix_full : (size_t)P.local_tiles * RT_BLOCK_THREADS;
+    const size_t npix_loc = P.world == 1 ? npix_full : (size_t)P.local_tiles * RT_BLOCK_THREADS;
     if (peer) {                                    // every rank writes rank 0's row-major image in place
         const bool root = c->rank == 0;
         if (outputs & RT_OUT_RGB_F32) P.rgb = (float*)(root ? c->img_rgb.p : c->peer_img[0]);
@@ -545,19 +560,23 @@ int rt_render(rt_ctx* c, const rt_frame* fr) {
         else CU(c, rt_launch_flag_wait(c->flags, RT_PEER_FLAG_STRIDE, 1, seq, kPeerTimeoutNs, c->peer_err, c->stream));
         ++launches;
         int l = 0;
+        CU(c, cudaEventRecord(c->evk0, c->stream));
         CU(c, rt_launch_render(P, fr->kernel_variant, c->stream, &l));
+        CU(c, cudaEventRecord(c->evk1, c->stream));
         launches += l;
         // completion: one flag word per rank in rank 0's memory, written after the frame kernel
         if (c->rank != 0) CU(c, rt_launch_flag_set(c->flags + (size_t)c->rank * RT_PEER_FLAG_STRIDE, seq, c->stream));
         else CU(c, rt_launch_flag_wait(c->flags + RT_PEER_FLAG_STRIDE, RT_PEER_FLAG_STRIDE, c->world - 1, seq, kPeerTimeoutNs, c->peer_err, c->stream));
         ++launches;
     } else {
+        CU(c, cudaEventRecord(c->evk0, c->stream));
         CU(c, rt_launch_render(P, fr->kernel_variant, c->stream, &launches));
+        CU(c, cudaEventRecord(c->evk1, c->stream));
     }
 
     if (c->world > 1 && !peer) {
         // Tile gather to rank 0: one grouped send/recv per requested plane, then an unpack kernel per source rank.
-        const size_t other_pix = ((size_t)total_tiles - (size_t)tiles_of_rank(total_tiles, 0, c->world)) * RT_BLOCK_THREADS;
+        const size_t other_pix = (size_t)(c->world - 1) * npix_loc;   // every rank has the same number of tile slots
         if (c->rank == 0) {
             if (outputs & RT_OUT_RGB_F32) { CU(c, c->img_rgb.reserve(12 * npix_full)); CU(c, c->stage_rgb.reserve(12 * other_pix + 16)); }
             if (outputs & RT_OUT_RGB8) { CU(c, c->img_rgb8.reserve(3 * npix_full)); CU(c, c->stage_rgb8.reserve(3 * other_pix + 16)); }
@@ -573,7 +592,7 @@ int rt_render(rt_ctx* c, const rt_frame* fr) {
             if (c->rank == 0) {
                 size_t off = 0;
                 for (int r = 1; r < c->world; ++r) {
-                    size_t bytes = (size_t)tiles_of_rank(total_tiles, r, c->world) * RT_BLOCK_THREADS * q.bpp;
+                    size_t bytes = npix_loc * q.bpp;
                     if (bytes) NC(c, Recv((char*)q.stage->p + off, bytes, ncclUint8, r, c->comm, c->stream));
                     off += bytes;
                 }
@@ -594,7 +613,7 @@ int rt_render(rt_ctx* c, const rt_frame* fr) {
                 CU(c, rt_launch_unpack(P, r, s_rgb, s_rgb8, s_id, s_t, (float*)c->img_rgb.p, (uint8_t*)c->img_rgb8.p,
                                        (int32_t*)c->img_id.p, (float*)c->img_t.p, c->stream));
                 ++launches;
-                if (!self) off_pix += (size_t)tiles_of_rank(total_tiles, r, c->world) * RT_BLOCK_THREADS;
+                if (!self) off_pix += npix_loc;
             }
         }
     }
@@ -617,6 +636,19 @@ int rt_sync(rt_ctx* c, float* gpu_ms) {
     return RT_OK;
 }
 
+int rt_frame_times(rt_ctx* c, float* total_ms, float* kernel_ms) {
+    int rc = rt_sync(c, total_ms);
+    if (rc != RT_OK) return rc;
+    if (kernel_ms) CU(c, cudaEventElapsedTime(kernel_ms, c->evk0, c->evk1));
+    return RT_OK;
+}
+
+int rt_stream_handle(const rt_ctx* c, void** cuda_stream) {
+    if (!c || !cuda_stream) return fail(nullptr, RT_ERR_ARG, "rt_stream_handle: NULL");
+    *cuda_stream = (void*)c->stream;
+    return RT_OK;
+}
+
 int rt_frame_stats(rt_ctx* c, uint64_t* node_visits, uint64_t* tri_tests, uint64_t* node_lines, uint64_t* tri_blocks) {
     if (!c) return fail(nullptr, RT_ERR_ARG, "rt_frame_stats: NULL ctx");
     CU(c, cudaSetDevice(c->device));
@@ -635,6 +667,8 @@ int rt_download_image(rt_ctx* c, rt_image* img) {
     if (!c || !img) return fail(c, RT_ERR_ARG, "rt_download_image: NULL argument");
     CU(c, cudaSetDevice(c->device));
     if (!c->frame_valid) return fail(c, RT_ERR_STATE, "rt_download_image: no frame rendered");
+    if (c->world == 1 && c->dbg_world > 1 && (img->rgb || img->rgb8 || img->tri_id || img->t))
+        return fail(c, RT_ERR_STATE, "rt_download_image: rt_debug_set_shard frames are tile-packed and for timing only");
     const FrameParams& P = c->fp;
     const size_t npix = (size_t)P.W * P.H;
     const bool gathered = c->world > 1;
@@ -660,6 +694,13 @@ int rt_download_image(rt_ctx* c, rt_image* img) {
     float ms = 0.f;
     CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     img->gpu_ms = ms;
+    return RT_OK;
+}
+
+int rt_debug_set_shard(rt_ctx* c, int rank, int world) {
+    if (!c || world < 0 || (world > 0 && (rank < 0 || rank >= world))) return fail(c, RT_ERR_ARG, "rt_debug_set_shard: bad arguments");
+    c->dbg_rank = rank; c->dbg_world = world;
+    c->frame_valid = false;
     return RT_OK;
 }
 

@@ -4,7 +4,7 @@
 
 #include "rt_core.h"
 
-// Screen-space tile: the unit of rank ownership (tile k belongs to rank k % world) and of
+// Screen-space tile: the unit of rank ownership (contiguous chunks of tiles, see rt_global_tile) and of
 // one thread block (4 warps, each an 8x4 pixel sub-tile).
 #define RT_TILE_W 16
 #define RT_TILE_H 8
@@ -25,7 +25,8 @@ struct FrameParams {
     const float* jitter;            // [2*spp] or NULL
     // tile sharding
     int tiles_x, tiles_y, rank, world;
-    int local_tiles;                // tiles owned by this rank
+    int local_tiles;                // tile slots of this rank (= grid size)
+    int chunk_tiles;                // tiles per ownership chunk (see rt_global_tile)
     int packed;                     // 1: planes are this rank's tile-packed buffers (NCCL gather); 0: row-major image
                                     //    (single GPU, or rank 0's image written in place over NVLink peer memory)
     // output planes
@@ -40,28 +41,52 @@ struct BuildParams {
     uint32_t leaf_max;              // max triangles per leaf (<= 8)
 };
 
-// Pixel owned by thread `tid` of the block working on rank-local tile `ltile`.
-// Tile k of the frame (row-major tile order) belongs to rank k % world; within a tile each warp
+// Tile ownership.  The frame's tiles in row-major tile order are cut into world*chunks_per_rank contiguous
+// chunks of `chunk_tiles` tiles (horizontal bands of the image); chunk c belongs to rank c % world.  Contiguous
+// bands keep each GPU's working set to its share of the scene (the round-robin single-tile interleave made
+// every GPU walk the whole BVH); several bands per rank spread non-uniform images over the ranks.
+// A rank's local tile slots are its chunks back to back: slot = j*chunk_tiles + i  <->  global tile
+// (j*world + rank)*chunk_tiles + i; slots past the end of the frame are padding (rendered by nobody).
+#define RT_DEFAULT_CHUNKS_PER_RANK 4
+RT_HD int rt_chunk_tiles(int total, int world, int chunks_per_rank) {
+    const int c = world * (chunks_per_rank > 0 ? chunks_per_rank : RT_DEFAULT_CHUNKS_PER_RANK);
+    const int s = (total + c - 1) / c;
+    return s > 0 ? s : 1;
+}
+// number of local tile slots of every rank (padding included)
+RT_HD int rt_tiles_of_rank(int total, int world, int chunks_per_rank) {
+    if (world <= 1) return total;
+    return (chunks_per_rank > 0 ? chunks_per_rank : RT_DEFAULT_CHUNKS_PER_RANK) * rt_chunk_tiles(total, world, chunks_per_rank);
+}
+RT_HD int rt_global_tile(const FrameParams& P, int rank, int ltile) {
+    if (P.world <= 1) return ltile;
+    const int j = ltile / P.chunk_tiles, i = ltile - j * P.chunk_tiles;
+    const long long g = ((long long)j * P.world + rank) * P.chunk_tiles + i;
+    return g < (long long)P.tiles_x * P.tiles_y ? (int)g : -1;
+}
+
+// Pixel owned by thread `tid` of the block working on rank-local tile slot `ltile`.  Within a tile each warp
 // covers an 8x4 pixel patch.  `out` is the index into the output planes: row-major pixel index
 // when P.packed == 0, tile-packed (ltile*128 + ly*16 + lx) when P.packed == 1.
 struct Pixel { int x, y; bool inside; size_t out; };
 RT_HD Pixel rt_map_pixel(const FrameParams& P, int ltile, int tid) {
-    const int gtile = ltile * P.world + P.rank;
-    const int tx = gtile % P.tiles_x, ty = gtile / P.tiles_x;
+    const int gtile = rt_global_tile(P, P.rank, ltile);
+    const int g = gtile < 0 ? 0 : gtile;
+    const int tx = g % P.tiles_x, ty = g / P.tiles_x;
     const int warp = tid >> 5, lane = tid & 31;
     const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
     Pixel px;
     px.x = tx * RT_TILE_W + lx; px.y = ty * RT_TILE_H + ly;
-    px.inside = (px.x < P.W) && (px.y < P.H) && (ty < P.tiles_y);
+    px.inside = (gtile >= 0) && (px.x < P.W) && (px.y < P.H);
     px.out = (P.packed == 0) ? ((size_t)px.y * P.W + px.x)
                             : ((size_t)ltile * RT_BLOCK_THREADS + (size_t)ly * RT_TILE_W + lx);
     return px;
 }
-RT_HD int rt_tiles_of_rank(int total, int rank, int world) { return total > rank ? (total - rank + world - 1) / world : 0; }
-// Unpack: element `e` (= ly*16 + lx) of packed tile `ltile` of rank `src_rank` -> row-major pixel
+// Unpack: element `e` (= ly*16 + lx) of packed tile slot `ltile` of rank `src_rank` -> row-major pixel
 // index, or -1 when the element is padding outside the frame.
 RT_HD long long rt_unpack_index(const FrameParams& P, int src_rank, int ltile, int e) {
-    const int gtile = ltile * P.world + src_rank;
+    const int gtile = rt_global_tile(P, src_rank, ltile);
+    if (gtile < 0) return -1;
     const int tx = gtile % P.tiles_x, ty = gtile / P.tiles_x;
     const int x = tx * RT_TILE_W + e % RT_TILE_W, y = ty * RT_TILE_H + e / RT_TILE_W;
     if (x >= P.W || y >= P.H) return -1;

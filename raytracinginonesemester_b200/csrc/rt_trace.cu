@@ -456,8 +456,7 @@ cudaError_t rt_launch_render(const FrameParams& fp, int kernel_variant, cudaStre
 cudaError_t rt_launch_unpack(const FrameParams& fp, int src_rank, const float* rgb, const uint8_t* rgb8,
                              const int32_t* tri_id, const float* t, float* o_rgb, uint8_t* o_rgb8,
                              int32_t* o_tri_id, float* o_t, cudaStream_t stream) {
-    const int total = fp.tiles_x * fp.tiles_y;
-    const int src_tiles = (total - src_rank + fp.world - 1) / fp.world;
+    const int src_tiles = fp.local_tiles;        // every rank has the same number of tile slots
     if (src_tiles <= 0) return cudaSuccess;
     k_unpack<<<src_tiles, RT_BLOCK_THREADS, 0, stream>>>(fp, src_rank, rgb, rgb8, tri_id, t, o_rgb, o_rgb8, o_tri_id, o_t, src_tiles);
     return cudaGetLastError();

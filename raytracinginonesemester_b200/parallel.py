@@ -1,8 +1,9 @@
 """One process per GPU: torch.distributed is the plumbing (rendezvous, barriers, max-over-ranks
 timing, handing the NCCL unique id to every rank); the data path — scene/BVH broadcast from rank 0
 and the per-frame tile gather to rank 0 — runs inside the C library on its own NCCL communicator
-(rt_comm_init, rt_upload_scene, rt_render).  Screen-space tiles (16x8 px) are owned round-robin:
-tile k of the frame belongs to rank k % world (csrc/rt_params.h, rt_map_pixel)."""
+(rt_comm_init, rt_upload_scene, rt_render).  Screen-space tiles (16x8 px) are owned in contiguous chunks
+(horizontal bands, several per rank): chunk c of the row-major tile order belongs to rank c % world
+(csrc/rt_params.h, rt_global_tile)."""
 import os
 
 import numpy as np
@@ -50,13 +51,26 @@ def make_renderer(dist, rank, world, local_rank):
     return api.Renderer(local_rank, rank, world, nccl_id)
 
 
-def tiles_of_rank(width, height, rank, world, tile_w=16, tile_h=8):
+DEFAULT_CHUNKS_PER_RANK = 4
+
+
+def chunk_tiles(width, height, world, chunks_per_rank=0, tile_w=16, tile_h=8):
+    """Tiles per ownership chunk (csrc/rt_params.h, rt_chunk_tiles)."""
     total = ((width + tile_w - 1) // tile_w) * ((height + tile_h - 1) // tile_h)
-    return (total - rank + world - 1) // world if total > rank else 0
+    c = world * (chunks_per_rank or DEFAULT_CHUNKS_PER_RANK)
+    return max(1, (total + c - 1) // c)
 
 
-def tile_owner_map(width, height, world, tile_w=16, tile_h=8):
-    """(H, W) array: which rank renders each pixel."""
+def tiles_of_rank(width, height, rank, world, chunks_per_rank=0, tile_w=16, tile_h=8):
+    """Local tile slots of a rank (padding included; the same for every rank)."""
+    if world <= 1:
+        return ((width + tile_w - 1) // tile_w) * ((height + tile_h - 1) // tile_h)
+    return (chunks_per_rank or DEFAULT_CHUNKS_PER_RANK) * chunk_tiles(width, height, world, chunks_per_rank, tile_w, tile_h)
+
+
+def tile_owner_map(width, height, world, chunks_per_rank=0, tile_w=16, tile_h=8):
+    """(H, W) array: which rank renders each pixel (contiguous chunks of row-major tiles, chunk c -> rank c % world)."""
     tx = (width + tile_w - 1) // tile_w
     ys, xs = np.mgrid[0:height, 0:width]
-    return ((ys // tile_h) * tx + (xs // tile_w)) % world
+    g = (ys // tile_h) * tx + (xs // tile_w)
+    return (g // chunk_tiles(width, height, world, chunks_per_rank, tile_w, tile_h)) % world

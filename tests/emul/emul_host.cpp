@@ -176,7 +176,7 @@ int emu_validate(void* h) {
 // the kernel's own pixel mapping.  world > 1: the planes in img are this rank's tile-packed buffers
 // (local_tiles*128 elements).  stats[0..3] = primary rays, shadow rays, node visits, triangle
 // tests; stats[4] = deepest stack use.
-int emu_render_rank(void* h, const rt_frame* fr, rt_image* img, uint64_t* stats, int rank, int world) {
+int emu_render_rank(void* h, const rt_frame* fr, rt_image* img, uint64_t* stats, int rank, int world, int chunks_per_rank) {
     EmuScene* es = (EmuScene*)h;
     FrameParams P{};
     P.cam = fr->cam; P.mode = fr->mode; P.accel = fr->accel; P.W = fr->width; P.H = fr->height; P.spp = fr->spp;
@@ -188,7 +188,8 @@ int emu_render_rank(void* h, const rt_frame* fr, rt_image* img, uint64_t* stats,
     P.lights = fr->lights; P.jitter = fr->jitter;
     P.tiles_x = (P.W + RT_TILE_W - 1) / RT_TILE_W; P.tiles_y = (P.H + RT_TILE_H - 1) / RT_TILE_H;
     P.rank = rank; P.world = world; P.packed = world > 1 ? 1 : 0;
-    P.local_tiles = rt_tiles_of_rank(P.tiles_x * P.tiles_y, rank, world);
+    P.chunk_tiles = rt_chunk_tiles(P.tiles_x * P.tiles_y, world, chunks_per_rank);
+    P.local_tiles = rt_tiles_of_rank(P.tiles_x * P.tiles_y, world, chunks_per_rank);
     P.rgb = img->rgb; P.rgb8 = img->rgb8; P.tri_id = img->tri_id; P.t = img->t;
     unsigned long long tot[5] = {0, 0, 0, 0, 0};
     uint32_t stk[RT_STACK_DEPTH];
@@ -217,15 +218,16 @@ int emu_render_rank(void* h, const rt_frame* fr, rt_image* img, uint64_t* stats,
     return P.local_tiles;
 }
 int emu_render(void* h, const rt_frame* fr, rt_image* img, uint64_t* stats) {
-    emu_render_rank(h, fr, img, stats, 0, 1);
+    emu_render_rank(h, fr, img, stats, 0, 1, 0);
     return 0;
 }
 // Host mirror of k_unpack for one packed u8 rgb plane of rank src_rank.
-void emu_unpack_rgb8(int W, int H, int world, int src_rank, const uint8_t* packed, uint8_t* image) {
+void emu_unpack_rgb8(int W, int H, int world, int chunks_per_rank, int src_rank, const uint8_t* packed, uint8_t* image) {
     FrameParams P{};
     P.W = W; P.H = H; P.world = world;
     P.tiles_x = (W + RT_TILE_W - 1) / RT_TILE_W; P.tiles_y = (H + RT_TILE_H - 1) / RT_TILE_H;
-    const int n = rt_tiles_of_rank(P.tiles_x * P.tiles_y, src_rank, world);
+    P.chunk_tiles = rt_chunk_tiles(P.tiles_x * P.tiles_y, world, chunks_per_rank);
+    const int n = rt_tiles_of_rank(P.tiles_x * P.tiles_y, world, chunks_per_rank);
     for (int lt = 0; lt < n; ++lt)
         for (int e = 0; e < RT_BLOCK_THREADS; ++e) {
             long long di = rt_unpack_index(P, src_rank, lt, e);

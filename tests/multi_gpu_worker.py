@@ -24,7 +24,9 @@ def main():
     cases = [("auto", 333, 201, 1, ALL), ("nccl", 333, 201, 1, ALL), ("nccl", 256, 128, 2, ALL), ("nccl", 40, 9, 1, ALL),
              ("peer", 333, 201, 1, ALL), ("peer", 64, 32, 1, A.RT_OUT_RGB8), ("peer", 256, 128, 2, ALL), ("peer", 40, 9, 1, ALL),
              ("peer", 700, 400, 1, ALL), ("nccl", 700, 400, 1, ALL), ("peer", 333, 201, 1, ALL)]
-    for (gm, W, H, spp, outs) in cases:
+    for n, (gm, W, H, spp, outs) in enumerate(cases):
+        cpr = (0, 1, 3, 64)[n % 4]
+        r.set_sharding(cpr)
         mode = r.set_gather(want_mode[gm])
         assert gm == "auto" or mode == want_mode[gm], (gm, mode)
         if rank == 0:
@@ -36,7 +38,7 @@ def main():
         cnt = torch.tensor([float(got["rays_primary"]), float(got["rays_shadow"])], device="cuda")
         dist.all_reduce(cnt)
         assert int(cnt[0].item()) == W * H * spp
-        assert got["rays_primary"] == int((parallel.tile_owner_map(W, H, world) == rank).sum()) * spp
+        assert got["rays_primary"] == int((parallel.tile_owner_map(W, H, world, cpr) == rank).sum()) * spp
         if rank == 0:
             solo = api.Renderer(local_rank)
             solo.upload_scene(sc)
@@ -51,6 +53,7 @@ def main():
                     ok = False
             assert int(cnt[1].item()) == ref["rays_shadow"]
     # back-to-back frames without a download in between (what bench.py's timed loop does), then one download
+    r.set_sharding(0)
     r.set_gather(A.RT_GATHER_AUTO)
     fr = scenes.terrain_frame(512, 256, outputs=A.RT_OUT_RGB8)
     for _ in range(5):

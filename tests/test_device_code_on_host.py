@@ -106,23 +106,25 @@ def test_tile_sharding_covers_the_frame_once():
     sc = scenes.terrain_scene(16, 8)
     h = orclib.emul_build(sc, 4)
     lib = orclib.emul()
-    lib.emu_render_rank.argtypes = [C.c_void_p, C.POINTER(A.rt_frame), C.POINTER(A.rt_image), C.POINTER(C.c_uint64), C.c_int, C.c_int]
-    lib.emu_unpack_rgb8.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, A.u8p, A.u8p]
-    for (W, H) in ((50, 21), (64, 32), (7, 3)):
+    from raytracinginonesemester_b200 import parallel
+    lib.emu_render_rank.argtypes = [C.c_void_p, C.POINTER(A.rt_frame), C.POINTER(A.rt_image), C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_int]
+    lib.emu_unpack_rgb8.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, A.u8p, A.u8p]
+    for (W, H) in ((50, 21), (64, 32), (7, 3), (130, 70)):
         fr = scenes.terrain_frame(W, H, outputs=A.RT_OUT_RGB8)
         full = orclib.emul_render(h, fr, want=("rgb8",))["rgb8"]
-        for world in (2, 3, 8):
+        for world, cpr in ((2, 0), (3, 1), (8, 0), (2, 7), (8, 64)):
             img = np.full((H, W, 3), 255, np.uint8)
             total_prim = 0
+            owner = parallel.tile_owner_map(W, H, world, cpr)
             for rank in range(world):
-                tiles = ((W + 15) // 16) * ((H + 7) // 8)
-                ntl = (tiles - rank + world - 1) // world if tiles > rank else 0
+                ntl = parallel.tiles_of_rank(W, H, rank, world, cpr)
                 packed = np.zeros((max(ntl, 1) * 128, 3), np.uint8)
                 im = A.rt_image(); im.rgb8 = packed.ctypes.data_as(A.u8p)
                 f = fr.c_struct()
-                got = lib.emu_render_rank(h, C.byref(f), C.byref(im), None, rank, world)
+                got = lib.emu_render_rank(h, C.byref(f), C.byref(im), None, rank, world, cpr)
                 assert got == ntl
+                assert im.rays_primary == int((owner == rank).sum())        # python mirror of the ownership map
                 total_prim += im.rays_primary
-                lib.emu_unpack_rgb8(W, H, world, rank, packed.ctypes.data_as(A.u8p), img.ctypes.data_as(A.u8p))
+                lib.emu_unpack_rgb8(W, H, world, cpr, rank, packed.ctypes.data_as(A.u8p), img.ctypes.data_as(A.u8p))
             assert total_prim == W * H
             assert np.array_equal(img, full)

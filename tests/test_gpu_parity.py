@@ -274,6 +274,77 @@ def test_c4_full_size_properties(renderer):
         assert np.array_equal(x[k], y[k]), k
 
 
+def _strided_bar(a, orc, rows, what):
+    n = orc["tri_id"][rows].size
+    mism = a["tri_id"][rows] != orc["tri_id"][rows]
+    assert mism.sum() <= 1e-4 * n, "%s: %d of %d ids differ" % (what, mism.sum(), n)
+    hit = (orc["tri_id"][rows] >= 0) & ~mism
+    if hit.any():
+        rel = np.abs(a["t"][rows][hit] - orc["t"][rows][hit]) / orc["t"][rows][hit]
+        assert rel.max() <= 1e-5, what
+    assert np.abs(a["rgb8"][rows].astype(int) - orc["rgb8"][rows].astype(int))[~mism].max() <= 1, what
+
+
+def test_c2_full_size_hw1_brute_force(renderer, frog_scene):
+    """BASELINE config C2 (HW1 frog, 1920x1080, every ray against every triangle): determinism, the HW1 BVH
+    frame must be the same image, strided rows against the oracle's HW1 loop."""
+    renderer.upload_scene(frog_scene)
+    W, H = 1920, 1080
+    fr = scenes.hw1_frame(W, H, accel=A.RT_ACCEL_BRUTE, outputs=A.RT_OUT_RGB8 | A.RT_OUT_TRI_ID | A.RT_OUT_T)
+    a = run(renderer, fr)
+    assert a["rays_primary"] == W * H and a["rays_shadow"] == 0
+    assert 0.05 < (a["tri_id"] >= 0).mean() < 0.9
+    fr.accel = A.RT_ACCEL_BVH
+    b = run(renderer, fr)
+    for k in ("tri_id", "t", "rgb8"):
+        assert np.array_equal(a[k], b[k]), k
+    step = 90
+    fo = scenes.hw1_frame(W, H, accel=A.RT_ACCEL_BRUTE, outputs=ALL)
+    orc = orclib.oracle_render(frog_scene, fo, row_begin=11, row_step=step, want=("rgb8", "tri_id", "t"))
+    rows = slice(11, H, step)
+    for k in ("tri_id", "t", "rgb8"):                   # canonical oracle == HW1 loop: bit-exact
+        assert np.array_equal(a[k][rows], orc[k][rows]), k
+
+
+@pytest.mark.parametrize("filling", [False, True])
+def test_c3_full_size_hw2_frog_4k(renderer, frog_scene, filling):
+    """BASELINE config C3 (HW2-BVH frog at 3840x2160), stock frog.json view and the frame-filling view:
+    determinism, coverage, and strided rows against the reference-exact oracle (reference LBVH + SearchBVH)."""
+    renderer.upload_scene(frog_scene)
+    W, H = 3840, 2160
+    outs = A.RT_OUT_RGB8 | A.RT_OUT_TRI_ID | A.RT_OUT_T
+    fr = scenes.frog_frame(W, H, filling=filling, outputs=outs)
+    a = run(renderer, fr)
+    b = run(renderer, fr)
+    for k in ("tri_id", "t", "rgb8"):
+        assert np.array_equal(a[k], b[k]), k
+    cover = (a["tri_id"] >= 0).mean()
+    assert (cover > 0.4) if filling else (0.02 < cover < 0.05)      # SURVEY Q3: the stock view hits on ~3.2 % of pixels
+    assert a["rays_primary"] == W * H and 0 < a["rays_shadow"] <= (a["tri_id"] >= 0).sum()
+    bvh = orclib.oracle_bvh(frog_scene)
+    step = 180
+    orc = orclib.oracle_render(frog_scene, scenes.frog_frame(W, H, filling=filling, outputs=ALL), bvh=bvh, row_begin=3, row_step=step,
+                               want=("rgb8", "tri_id", "t"))
+    _strided_bar(a, orc, slice(3, H, step), "c3 filling=%s" % filling)
+
+
+def test_c5_scene_at_reduced_frame(renderer):
+    """BASELINE config C5's scene (10M-triangle terrain, 16 spp jitter table) at a frame the oracle can check:
+    device BVH over 10M triangles, 16-sample accumulation, strided rows against the reference-exact oracle."""
+    sc = scenes.terrain_scene(2500, 2000)
+    info = renderer.upload_scene(sc)
+    assert info.num_triangles == 10000000
+    W, H = 768, 432
+    fr = scenes.terrain_frame(W, H, spp=16, outputs=A.RT_OUT_RGB8 | A.RT_OUT_TRI_ID | A.RT_OUT_T)
+    a = run(renderer, fr)
+    assert a["rays_primary"] == W * H * 16
+    assert (a["tri_id"] >= 0).mean() > 0.9999
+    bvh = orclib.oracle_bvh(sc)
+    step = 54
+    orc = orclib.oracle_render(sc, scenes.terrain_frame(W, H, spp=16, outputs=ALL), bvh=bvh, row_begin=5, row_step=step, want=("rgb8", "tri_id", "t"))
+    _strided_bar(a, orc, slice(5, H, step), "c5 scene")
+
+
 # ----------------------------------------------------------------------- error behaviour ----
 def test_error_behaviour():
     r = api.Renderer(0)

@@ -34,15 +34,15 @@ def _worker(rank, world, port, W, H, out_path):
     sc = scenes.terrain_scene(24, 12)
     h = orclib.emul_build(sc, 2)
     lib = orclib.emul()
-    lib.emu_render_rank.argtypes = [C.c_void_p, C.POINTER(A.rt_frame), C.POINTER(A.rt_image), C.POINTER(C.c_uint64), C.c_int, C.c_int]
-    lib.emu_unpack_rgb8.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, A.u8p, A.u8p]
+    lib.emu_render_rank.argtypes = [C.c_void_p, C.POINTER(A.rt_frame), C.POINTER(A.rt_image), C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_int]
+    lib.emu_unpack_rgb8.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, A.u8p, A.u8p]
     fr = scenes.terrain_frame(W, H, outputs=A.RT_OUT_RGB8)
     ntl = parallel.tiles_of_rank(W, H, rank, world)
     cap = max(parallel.tiles_of_rank(W, H, q, world) for q in range(world))
     packed = np.zeros((cap * 128, 3), np.uint8)
     im = A.rt_image(); im.rgb8 = packed.ctypes.data_as(A.u8p)
     f = fr.c_struct()
-    assert lib.emu_render_rank(h, C.byref(f), C.byref(im), None, rank, world) == ntl
+    assert lib.emu_render_rank(h, C.byref(f), C.byref(im), None, rank, world, 0) == ntl
     owner = parallel.tile_owner_map(W, H, world)
     assert im.rays_primary == int((owner == rank).sum())    # each rank traced exactly the pixels it owns
     mine = torch.from_numpy(packed)
@@ -55,7 +55,7 @@ def _worker(rank, world, port, W, H, out_path):
         img = np.full((H, W, 3), 7, np.uint8)
         for q in range(world):
             b = np.ascontiguousarray(bufs[q].numpy())
-            lib.emu_unpack_rgb8(W, H, world, q, b.ctypes.data_as(A.u8p), img.ctypes.data_as(A.u8p))
+            lib.emu_unpack_rgb8(W, H, world, 0, q, b.ctypes.data_as(A.u8p), img.ctypes.data_as(A.u8p))
         np.save(out_path, img)
     dist.barrier()
     dist.destroy_process_group()
