@@ -233,7 +233,7 @@ class CpuReference:
 
 # shadow rays per primary ray, counted by the device on each workload (one shadow ray per lit hit; the in-place
 # reference has no counters, the rule is the same)
-SHADOW_RATIO = {"c4": 0.81550, "c5": 0.70824, "c4small": 0.8155, "c2": 0.0, "c3": 0.0, "c3fill": 0.0}
+SHADOW_RATIO = {"c4": 0.81550, "c5": 0.70824, "c4small": 0.8155, "c2": 0.0, "c3": 0.020735, "c3fill": 0.274944}
 METRIC = "Mrays/s closest-hit (BVH+tri)"
 
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RT_API_VERSION 1
+#define RT_API_VERSION 2
 
 /* status codes */
 #define RT_OK            0
@@ -131,11 +131,14 @@ typedef struct rt_frame {
     float           miss_color[3]; /* HW2 constant miss colour (query.h:181-184)   */
     int32_t         spp;           /* samples per pixel (>=1)                      */
     const float*    jitter;        /* [2*spp] sub-pixel offsets; NULL = pixel centre */
-    int32_t         max_depth;     /* 1 = primary + direct light (+ shadow ray)    */
+    int32_t         max_depth;     /* TraceRayIterative's maxDepth (query.h:156-220): 1 = primary + direct light
+                                      (+ shadow ray); > 1 adds mirror / hash-RNG diffuse bounces (HW2_BVH mode) */
     int32_t         shadows;       /* HW2 modes: trace the IsInShadow ray (shader.h:44-62) */
     uint32_t        outputs;       /* RT_OUT_* mask                                */
     int32_t         quantiser;     /* RT_QUANT_*                                   */
     int32_t         kernel_variant;/* 0 = default; >0 selects an experimental traversal kernel */
+    int32_t         diffuse_bounce;/* max_depth > 1: settings.diffuse_bounce (query.h:193-209): 1 = pick a diffuse or
+                                      a mirror bounce with the per-pixel hash RNG, 0 = mirror bounces only */
 } rt_frame;
 
 typedef struct rt_image {
@@ -144,7 +147,7 @@ typedef struct rt_image {
     int32_t*  tri_id;     /* [W*H]   or NULL */
     float*    t;          /* [W*H]   or NULL */
     int32_t   width, height;       /* filled */
-    uint64_t  rays_primary;        /* filled: closest-hit queries traced (this rank) */
+    uint64_t  rays_primary;        /* filled: closest-hit queries traced (this rank): primary rays + bounce rays */
     uint64_t  rays_shadow;         /* filled: shadow queries traced (this rank)      */
     float     gpu_ms;              /* filled: device time of the last rt_render     */
 } rt_image;

@@ -149,7 +149,8 @@ class Frame:
 
     def __init__(self, cam, width, height, mode=A.RT_MODE_HW2_BVH, accel=A.RT_ACCEL_BVH, lights=(), miss_color=(0, 0, 0),
                  spp=1, jitter=None, max_depth=1, shadows=True, outputs=A.RT_OUT_RGB_F32, quantiser=A.RT_QUANT_PPM_LROUND,
-                 kernel_variant=0):
+                 kernel_variant=0, diffuse_bounce=False):
+        self.diffuse_bounce = bool(diffuse_bounce)
         self.cam, self.width, self.height, self.mode, self.accel = cam, int(width), int(height), mode, accel
         self.lights = list(lights)
         self._light_arr = (A.rt_light * max(1, len(self.lights)))(*self.lights)
@@ -170,6 +171,7 @@ class Frame:
         f.jitter = _ptr(self.jitter, A.f32p)
         f.max_depth, f.shadows, f.outputs, f.quantiser = self.max_depth, int(self.shadows), self.outputs, self.quantiser
         f.kernel_variant = self.kernel_variant
+        f.diffuse_bounce = int(self.diffuse_bounce)
         return f
 
 

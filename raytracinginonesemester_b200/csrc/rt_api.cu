@@ -487,6 +487,8 @@ int rt_render(rt_ctx* c, const rt_frame* fr) {
     if (fr->spp < 1) return fail(c, RT_ERR_ARG, "rt_render: spp must be >= 1");
     if (fr->mode != RT_MODE_HW1 && fr->mode != RT_MODE_HW2_BVH) return fail(c, RT_ERR_ARG, "rt_render: unsupported mode %d", fr->mode);
     if (fr->accel != RT_ACCEL_BRUTE && fr->accel != RT_ACCEL_BVH) return fail(c, RT_ERR_ARG, "rt_render: unsupported accel %d", fr->accel);
+    if (fr->accel == RT_ACCEL_BRUTE && fr->mode != RT_MODE_HW1 && fr->max_depth > 1)
+        return fail(c, RT_ERR_ARG, "rt_render: bounces (max_depth > 1) need RT_ACCEL_BVH");
     if (fr->accel == RT_ACCEL_BVH && !c->has_bvh) return fail(c, RT_ERR_STATE, "rt_render: scene was uploaded with RT_BUILD_NO_BVH");
     if (fr->num_lights < 0 || (fr->num_lights > 0 && !fr->lights)) return fail(c, RT_ERR_ARG, "rt_render: lights");
     if (fr->mode == RT_MODE_HW1 && fr->num_lights < 1) return fail(c, RT_ERR_ARG, "rt_render: HW1 mode needs one light");
@@ -495,7 +497,7 @@ int rt_render(rt_ctx* c, const rt_frame* fr) {
     FrameParams& P = c->fp;
     memset(&P, 0, sizeof P);
     P.cam = fr->cam; P.mode = fr->mode; P.accel = fr->accel; P.W = fr->width; P.H = fr->height; P.spp = fr->spp;
-    P.max_depth = fr->max_depth; P.shadows = fr->shadows; P.quantiser = fr->quantiser; P.num_lights = fr->num_lights;
+    P.max_depth = fr->max_depth; P.diffuse_bounce = fr->diffuse_bounce ? 1 : 0; P.shadows = fr->shadows; P.quantiser = fr->quantiser; P.num_lights = fr->num_lights;
     P.num_materials = c->num_materials;
     memcpy(P.miss, fr->miss_color, sizeof P.miss);
     P.nodes = c->nodes; P.geom = c->geom; P.shade = c->shade; P.num_tris = c->num_tris; P.materials = c->materials;

@@ -42,6 +42,7 @@
 #define RT_I2F(i) __int_as_float(i)
 #define RT_CLZ32(x) __clz((int)(x))
 #define RT_CLZ64(x) __clzll((long long)(x))
+#define RT_U2F(u) __uint2float_rn(u)
 #else
 #include <string.h>
 #define RT_LDG(p) (*(p))
@@ -51,6 +52,7 @@ static inline float rt_i2f_host(int i) { float f; memcpy(&f, &i, 4); return f; }
 #define RT_I2F(i) rt_i2f_host(i)
 #define RT_CLZ32(x) ((x) == 0 ? 32 : __builtin_clz((unsigned)(x)))
 #define RT_CLZ64(x) ((x) == 0 ? 64 : __builtin_clzll((unsigned long long)(x)))
+#define RT_U2F(u) ((float)(u))
 #endif
 
 struct f3 { float x, y, z; };

@@ -13,7 +13,7 @@
 
 struct FrameParams {
     rt_camera cam;
-    int mode, accel, W, H, spp, max_depth, shadows, quantiser, num_lights, num_materials;
+    int mode, accel, W, H, spp, max_depth, shadows, quantiser, num_lights, num_materials, diffuse_bounce;
     float miss[3];
     // scene arena
     const BvhNode* nodes;

@@ -424,6 +424,10 @@ static cudaError_t launch_mode(const FrameParams& fp, int variant, cudaStream_t 
     dim3 grid((unsigned)fp.local_tiles), block(RT_BLOCK_THREADS);
     if (fp.accel == RT_ACCEL_BRUTE) { k_render_brute<MODE><<<grid, block, 0, stream>>>(fp); return cudaGetLastError(); }
     const bool fast = fp.fast_slab != 0;
+    // Bounce rays (max_depth > 1) are incoherent: the frame goes to the per-ray kernel, whose sample function
+    // carries TraceRayIterative's full loop; the packet kernels implement depth 1.
+    if (MODE != RT_MODE_HW1 && fp.max_depth > 1)
+        variant = (variant == RT_VARIANT_STATS || variant == RT_VARIANT_PER_RAY_STATS) ? RT_VARIANT_PER_RAY_STATS : RT_VARIANT_PER_RAY;
     switch (variant) {
     case RT_VARIANT_DEFAULT:
         if (fast) k_render_packet<MODE, false, true, 8><<<grid, block, 0, stream>>>(fp);

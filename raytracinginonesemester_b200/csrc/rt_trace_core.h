@@ -205,13 +205,67 @@ RT_HD f3 rt_shade_hw1(const FrameParams& P, const Ray& ray, const Hit& h) {
     return rt_shade_hw1_hit(ray, p, normal, P.lights[0]);
 }
 
-// One sample of one pixel through the BVH path: primary closest hit, shading, shadow rays.
+// ---------------------------------------------------------------- bounce loop ----
+// rng_next / make_rng_seed / random_unit_vector / random_on_hemisphere, GPUandCPU/include/query.h:32-70.
+RT_HD float rt_rng_next(uint32_t& state) {
+    state = state * 1664525u + 1013904223u;
+    uint32_t h = state;
+    h = (h ^ 61u) ^ (h >> 16u);
+    h *= 9u;
+    h ^= h >> 4u;
+    h *= 0x27d4eb2du;
+    h ^= h >> 15u;
+    return XDIV(RT_U2F(h), 4294967296.0f);          // float(h) / float(0xFFFFFFFFu); the divisor rounds to 2^32
+}
+RT_HD uint32_t rt_rng_seed(int x, int y, int sample) {
+    return (uint32_t)x * 73856093u ^ (uint32_t)y * 19349663u ^ (uint32_t)sample * 83492791u;
+}
+RT_HD f3 rt_random_on_hemisphere(f3 normal, uint32_t& state) {
+    f3 u;
+    for (;;) {
+        const float x = XSUB(XMUL(2.0f, rt_rng_next(state)), 1.0f);
+        const float y = XSUB(XMUL(2.0f, rt_rng_next(state)), 1.0f);
+        const float z = XSUB(XMUL(2.0f, rt_rng_next(state)), 1.0f);
+        const float lensq = XADD(XADD(XMUL(x, x), XMUL(y, y)), XMUL(z, z));
+        if (lensq > 1e-10f && lensq <= 1.0f) {
+            const float inv = XDIV(1.0f, XSQRT(lensq));
+            u = mk3(XMUL(x, inv), XMUL(y, inv), XMUL(z, inv));
+            break;
+        }
+    }
+    if (xdot(u, normal) > 0.0f) return u;
+    return xneg3(u);
+}
+// The ray that leaves a hit, query.h:193-216.  Returns false when the path ends (no reflecting material or
+// throughput below 1e-4 in every channel).
+RT_HD bool rt_bounce_hw2(const FrameParams& P, const Surface& sf, Ray& ray, f3& throughput, uint32_t& rng) {
+    const float kd = sf.mat.kd, kr = sf.mat.kr, total = XADD(kd, kr);
+    if (total <= 0.0f) return false;
+    const f3 N = sf.N;                                   // normalize(hitRecord.normal): the same three divides as unit_vector
+    const float xi = rt_rng_next(rng);
+    const f3 o = xadd3(sf.p, xmuls(N, 1e-3f));           // RT_EPS, shader.h:22
+    if (P.diffuse_bounce && xi < XDIV(kd, total)) {
+        const f3 d = rt_random_on_hemisphere(N, rng);
+        const float NdotL = fmaxf(xdot(N, d), 0.0f);
+        throughput = xmulv(throughput, xmuls(ld3(sf.mat.albedo), XMUL(2.0f, NdotL)));
+        ray.o = o; ray.d = d;
+    } else {
+        const f3 I = xunit(ray.d);
+        const f3 refl = xsub3(I, xmuls(N, XMUL(2.0f, xdot(I, N))));   // reflect_dir, shader.h:38-42
+        throughput = xmulv(throughput, xmuls(ld3(sf.mat.specular_color), kr));
+        ray.o = o; ray.d = refl;
+    }
+    return !(throughput.x < 1e-4f && throughput.y < 1e-4f && throughput.z < 1e-4f);
+}
+
+// One sample of one pixel through the BVH path: TraceRayIterative (query.h:156-220) — closest hit, shading,
+// shadow rays, then mirror / diffuse bounces up to P.max_depth.  h = the depth-0 hit.
 template <int MODE, int STRIDE, bool STATS>
 RT_HD f3 rt_sample_bvh(const FrameParams& P, int x, int y, int s, uint32_t* stk, Hit& h,
                        unsigned& nprim, unsigned& nshadow, TraceStats* st) {
     const float jx = P.jitter ? RT_LDG(P.jitter + 2 * s) : 0.0f;
     const float jy = P.jitter ? RT_LDG(P.jitter + 2 * s + 1) : 0.0f;
-    const Ray ray = rt_make_ray(P.cam, MODE, x, y, jx, jy);
+    Ray ray = rt_make_ray(P.cam, MODE, x, y, jx, jy);
     if (MODE != RT_MODE_HW1 && P.max_depth <= 0) {   // TraceRayIterative: maxDepth <= 0 -> black
         rt_hit_reset(h);
         return mk3(0.f, 0.f, 0.f);
@@ -219,20 +273,30 @@ RT_HD f3 rt_sample_bvh(const FrameParams& P, int x, int y, int s, uint32_t* stk,
     rt_trace_closest<MODE, STRIDE, STATS>(P, ray, stk, h, st);
     ++nprim;
     if (MODE == RT_MODE_HW1) return rt_shade_hw1(P, ray, h);
-    if (h.slot < 0) return rt_radiance_hw2(ld3(P.miss));
-    Surface sf;
-    rt_surface_hw2(P, ray, h, sf);
-    for (int l = 0; l < P.num_lights; ++l) {
-        const rt_light light = P.lights[l];
-        f3 L; float NdotL, dist; bool need; Ray sray;
-        if (!rt_light_setup_hw2(sf, light, L, NdotL, need, sray, dist)) continue;
-        if (need && P.shadows) {
-            ++nshadow;
-            if (rt_trace_any<MODE, STRIDE, STATS>(P, sray, dist, stk, st)) continue;
+    f3 radiance = mk3(0.f, 0.f, 0.f), throughput = mk3(1.f, 1.f, 1.f);
+    uint32_t rng = rt_rng_seed(x, y, s);
+    Hit cur = h;
+    for (int depth = 0;;) {
+        if (cur.slot < 0) { radiance = xadd3(radiance, xmulv(throughput, ld3(P.miss))); break; }
+        Surface sf;
+        rt_surface_hw2(P, ray, cur, sf);
+        for (int l = 0; l < P.num_lights; ++l) {
+            const rt_light light = P.lights[l];
+            f3 L; float NdotL, dist; bool need; Ray sray;
+            if (!rt_light_setup_hw2(sf, light, L, NdotL, need, sray, dist)) continue;
+            if (need && P.shadows) {
+                ++nshadow;
+                if (rt_trace_any<MODE, STRIDE, STATS>(P, sray, dist, stk, st)) continue;
+            }
+            rt_light_finish_hw2(sf, light, L, NdotL);
         }
-        rt_light_finish_hw2(sf, light, L, NdotL);
+        radiance = xadd3(radiance, xmulv(throughput, sf.Lo));
+        if (++depth >= P.max_depth) break;
+        if (!rt_bounce_hw2(P, sf, ray, throughput, rng)) break;
+        rt_trace_closest<MODE, STRIDE, STATS>(P, ray, stk, cur, st);
+        ++nprim;
     }
-    return rt_radiance_hw2(sf.Lo);
+    return rt_clamp01(radiance);
 }
 
 // Resolve: col / float(spp) (query.cu:163, render.cpp:110) + requested planes.

@@ -68,7 +68,7 @@ bool write_ppm(const std::string& path, int W, int H, const std::vector<float>& 
 
 int main(int argc, char** argv) {
     bool hw1 = false, gamma2 = false, brute = false;
-    int device = 0, width = 0, height = 0, spp_override = 0;
+    int device = 0, width = 0, height = 0, spp_override = 0, depth_override = 0;
     std::string out_path;
     std::vector<std::string> inputs;
     for (int i = 1; i < argc; ++i) {
@@ -80,9 +80,10 @@ int main(int argc, char** argv) {
         else if (a == "--width" && i + 1 < argc) width = std::atoi(argv[++i]);
         else if (a == "--height" && i + 1 < argc) height = std::atoi(argv[++i]);
         else if (a == "--spp" && i + 1 < argc) spp_override = std::atoi(argv[++i]);
+        else if (a == "--depth" && i + 1 < argc) depth_override = std::atoi(argv[++i]);
         else if ((a == "-o" || a == "--out") && i + 1 < argc) out_path = argv[++i];
         else if (a == "-h" || a == "--help") {
-            std::printf("usage: rt_render_cli [--hw1] [--brute] [--width W --height H] [--spp N] [--gamma2] [--device D] [-o out.ppm] [scene.json | mesh.obj ...]\n");
+            std::printf("usage: rt_render_cli [--hw1] [--brute] [--width W --height H] [--spp N] [--depth D] [--gamma2] [--device D] [-o out.ppm] [scene.json | mesh.obj ...]\n");
             return 0;
         } else inputs.push_back(a);
     }
@@ -166,11 +167,8 @@ int main(int argc, char** argv) {
         fr.spp = spp_override ? spp_override : (has_scene ? sd.spp : 1);
         jitter.resize(2 * (size_t)fr.spp); rt_jitter_table(jitter.data(), fr.spp, 42u, 1);
         std::memcpy(fr.miss_color, sd.miss_color, sizeof fr.miss_color);
-        fr.max_depth = has_scene ? sd.max_depth : 1;
-        if (fr.max_depth > 1) {
-            std::printf("note: max_bounces=%d requested; this build traces primary + direct light (depth 1)\n", fr.max_depth);
-            fr.max_depth = 1;
-        }
+        fr.max_depth = depth_override > 0 ? depth_override : (has_scene ? sd.max_depth : 1);   // main.cu:322-324
+        fr.diffuse_bounce = has_scene ? (sd.diffuse_bounce ? 1 : 0) : 1;
         fr.shadows = 1; fr.quantiser = RT_QUANT_HW2_TRUNC;
     }
     fr.lights = lights.data(); fr.num_lights = (int)lights.size(); fr.jitter = jitter.data();

@@ -94,3 +94,26 @@ def frog_frame(width=1920, height=1080, filling=False, outputs=A.RT_OUT_RGB_F32,
     return Frame(cam, width, height, mode=A.RT_MODE_HW2_BVH, accel=accel,
                  lights=[make_light((-3.0, 0.0, 1.0), (1.0, 1.0, 0.0), 5)], miss_color=(0, 0, 0), spp=1,
                  jitter=jitter_table(1, 42, True), max_depth=1, shadows=shadows, outputs=outputs, quantiser=quantiser)
+
+
+def cornell_bounce_scene(mesh_npz):
+    """Bounce-loop test scene: camera inside cornellbox.obj, every object partly mirror-like, one
+    pure mirror and one absorber.  Returns (Scene, (pos, look_at, up, focal_mm, sensor_mm), lights, miss_color)."""
+    d = np.load(mesh_npz)
+    nobj = int(d["tri_obj_ids"].max()) + 1
+    mats = [make_material(albedo=(0.7, 0.7, 0.7), kd=0.8, ks=0.1, kr=0.2, specular_color=(0.6, 0.6, 0.6)) for _ in range(nobj)]
+    mats[1] = make_material(albedo=(0.8, 0.1, 0.1), kd=0.6, kr=0.4, specular_color=(0.9, 0.9, 0.9))
+    mats[2] = make_material(albedo=(0.1, 0.8, 0.1), kd=0.0, kr=0.9, specular_color=(0.8, 0.8, 0.9))
+    mats[3] = make_material(albedo=(0.1, 0.1, 0.1), kd=0.0, kr=0.0)
+    sc = Scene(d["positions"], d["indices"], normals=d["normals"] if d["normals"].size else None,
+               tri_obj_ids=d["tri_obj_ids"], materials=mats)
+    cam = ((278.0, 273.0, -800.0), (278.0, 273.0, 0.0), (0.0, 1.0, 0.0), 35.0, 25.0)
+    lights = [make_light((278.0, 500.0, 279.5), (1, 1, 1), 2), make_light((100.0, 300.0, 100.0), (1.0, 0.5, 0.2), 1)]
+    return sc, cam, lights, (0.2, 0.3, 0.4)
+
+
+def cornell_bounce_frame(cam_args, lights, miss, width, height, spp, max_depth, diffuse_bounce, outputs=A.RT_OUT_RGB_F32):
+    cam = camera_init(cam_args[0], cam_args[1], cam_args[2], cam_args[3], cam_args[4], width, height)
+    return Frame(cam, width, height, mode=A.RT_MODE_HW2_BVH, accel=A.RT_ACCEL_BVH, lights=lights, miss_color=miss, spp=spp,
+                 jitter=jitter_table(spp, 42, True), max_depth=max_depth, shadows=True, outputs=outputs,
+                 quantiser=A.RT_QUANT_HW2_TRUNC, diffuse_bounce=bool(diffuse_bounce))

@@ -180,7 +180,7 @@ int emu_render_rank(void* h, const rt_frame* fr, rt_image* img, uint64_t* stats,
     EmuScene* es = (EmuScene*)h;
     FrameParams P{};
     P.cam = fr->cam; P.mode = fr->mode; P.accel = fr->accel; P.W = fr->width; P.H = fr->height; P.spp = fr->spp;
-    P.max_depth = fr->max_depth; P.shadows = fr->shadows; P.quantiser = fr->quantiser; P.num_lights = fr->num_lights;
+    P.max_depth = fr->max_depth; P.diffuse_bounce = fr->diffuse_bounce ? 1 : 0; P.shadows = fr->shadows; P.quantiser = fr->quantiser; P.num_lights = fr->num_lights;
     P.num_materials = (int)es->materials.size();
     memcpy(P.miss, fr->miss_color, sizeof P.miss);
     P.nodes = es->nodes.data(); P.geom = es->geom.data(); P.shade = es->shade.data(); P.num_tris = es->num_tris;

@@ -46,6 +46,17 @@ def assert_reference_bar(got, ref_id, ref_t, ref_rgb=None, quant=A.RT_QUANT_HW2_
         assert d[ok].max() <= 1, "%s: 8-bit image differs by %d LSB" % (what, d[ok].max())
 
 
+def _strided_bar(a, orc, rows, what):
+    n = orc["tri_id"][rows].size
+    mism = a["tri_id"][rows] != orc["tri_id"][rows]
+    assert mism.sum() <= 1e-4 * n, "%s: %d of %d ids differ" % (what, mism.sum(), n)
+    hit = (orc["tri_id"][rows] >= 0) & ~mism
+    if hit.any():
+        rel = np.abs(a["t"][rows][hit] - orc["t"][rows][hit]) / orc["t"][rows][hit]
+        assert rel.max() <= 1e-5, what
+    assert np.abs(a["rgb8"][rows].astype(int) - orc["rgb8"][rows].astype(int))[~mism].max() <= 1, what
+
+
 # ------------------------------------------------------------------------------ HW1 ----
 def test_hw1_frog_brute_matches_reference_fixture(renderer, frog_scene, golden):
     renderer.upload_scene(frog_scene)
@@ -235,6 +246,48 @@ def test_axis_parallel_rays_and_flat_boxes(renderer):
     assert got["tri_id"][16, 16] >= 0
 
 
+# ------------------------------------------------------------------------ bounce loop ----
+def test_hw2_bounce_loop_vs_reference_fixture(renderer, golden):
+    """max_depth > 1: mirror and hash-RNG diffuse bounces of TraceRayIterative on the device against
+    frames rendered by the reference (bit-exact ids, t and float rgb on this scene) and against the oracle."""
+    import os
+    g = golden("ref_hw2_bounce_cornell.npz")
+    sc, cam, lights, miss = scenes.cornell_bounce_scene(os.path.join(os.path.dirname(__file__), "golden", "cornell_mesh.npz"))
+    renderer.upload_scene(sc)
+    for name, W, H, spp, depth, diffuse in g["cases"]:
+        fr = scenes.cornell_bounce_frame(cam, lights, miss, int(W), int(H), int(spp), int(depth), int(diffuse), outputs=ALL)
+        a = run(renderer, fr)
+        assert a["rays_primary"] > int(W) * int(H) * int(spp)
+        for k in ("tri_id", "t"):
+            assert np.array_equal(a[k], g["%s_%s" % (name, k)]), (name, k)
+        assert np.abs(a["rgb"] - g["%s_rgb" % name]).max() <= 2e-6, name          # powf: fp64 pow narrowed vs glibc powf
+        o = orclib.oracle_render(sc, fr)
+        assert np.array_equal(a["rgb8"], o["rgb8"]), name
+        assert a["rays_primary"] == o["counters"]["rays_primary"] and a["rays_shadow"] == o["counters"]["rays_shadow"]
+
+
+def test_bounce_frame_at_size_terrain_mirror(renderer):
+    """A mirror-like terrain at 1920x1080, depth 4: determinism, more closest-hit queries than pixels, strided rows
+    against the reference-exact oracle."""
+    pos, idx = scenes.terrain(300, 150)
+    sc = api.Scene(pos, idx, tri_obj_ids=np.zeros(idx.shape[0], np.int32),
+                   materials=[api.make_material(albedo=(0.5, 0.5, 0.6), kd=0.5, ks=0.2, kr=0.5, specular_color=(0.9, 0.9, 0.9))])
+    renderer.upload_scene(sc)
+    W, H = 1920, 1080
+    cam = api.camera_init((0.3, -1.4, 0.6), (0, 0, 0), (0, 0, 1), 30.0, 24.0, W, H)
+    mk = lambda outs: api.Frame(cam, W, H, lights=[api.make_light((-2.0, -1.0, 1.5), (1, 1, 1), 5)], miss_color=(0.5, 0.7, 1.0), spp=1,
+                                jitter=api.jitter_table(1, 42, True), max_depth=4, diffuse_bounce=True, outputs=outs, quantiser=A.RT_QUANT_HW2_TRUNC)
+    a = run(renderer, mk(A.RT_OUT_RGB8 | A.RT_OUT_TRI_ID | A.RT_OUT_T))
+    b = run(renderer, mk(A.RT_OUT_RGB8 | A.RT_OUT_TRI_ID | A.RT_OUT_T))
+    for k in ("tri_id", "t", "rgb8"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["rays_primary"] > 1.2 * (a["tri_id"] >= 0).sum()
+    bvh = orclib.oracle_bvh(sc)
+    step = 120
+    orc = orclib.oracle_render(sc, mk(ALL), bvh=bvh, row_begin=9, row_step=step, want=("rgb8", "tri_id", "t"))
+    _strided_bar(a, orc, slice(9, H, step), "bounce terrain")
+
+
 # --------------------------------------------------------------- full-size properties ----
 def test_c4_full_size_properties(renderer):
     """BASELINE config C4 (1M-triangle terrain, 3840x2160, primary + shadow): properties that do not
@@ -272,17 +325,6 @@ def test_c4_full_size_properties(renderer):
     y = run(renderer, small)
     for k in ("tri_id", "t", "rgb8"):
         assert np.array_equal(x[k], y[k]), k
-
-
-def _strided_bar(a, orc, rows, what):
-    n = orc["tri_id"][rows].size
-    mism = a["tri_id"][rows] != orc["tri_id"][rows]
-    assert mism.sum() <= 1e-4 * n, "%s: %d of %d ids differ" % (what, mism.sum(), n)
-    hit = (orc["tri_id"][rows] >= 0) & ~mism
-    if hit.any():
-        rel = np.abs(a["t"][rows][hit] - orc["t"][rows][hit]) / orc["t"][rows][hit]
-        assert rel.max() <= 1e-5, what
-    assert np.abs(a["rgb8"][rows].astype(int) - orc["rgb8"][rows].astype(int))[~mism].max() <= 1, what
 
 
 def test_c2_full_size_hw1_brute_force(renderer, frog_scene):

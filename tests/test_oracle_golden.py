@@ -5,6 +5,8 @@ shims exist (oracle/_ref/, authoring container) — the reference itself, live."
 import ctypes as C
 import hashlib
 
+import os
+
 import numpy as np
 import pytest
 
@@ -86,6 +88,28 @@ def test_hw2_cornell_multi_material(golden):
     o = orclib.oracle_render(sc, fr, bvh=bvh)
     for k in ("tri_id", "t", "rgb"):
         assert np.array_equal(o[k], ref[k]), k
+
+
+def _bounce_cases(golden):
+    g = golden("ref_hw2_bounce_cornell.npz")
+    sc, cam, lights, miss = scenes.cornell_bounce_scene(os.path.join(os.path.dirname(__file__), "golden", "cornell_mesh.npz"))
+    for name, W, H, spp, depth, diffuse in g["cases"]:
+        fr = scenes.cornell_bounce_frame(cam, lights, miss, int(W), int(H), int(spp), int(depth), int(diffuse), outputs=ALL)
+        yield str(name), sc, fr, {k: g["%s_%s" % (name, k)] for k in ("rgb", "tri_id", "t")}
+
+
+def test_hw2_bounce_loop_matches_reference(golden):
+    """TraceRayIterative with max_depth > 1 (mirror and hash-RNG diffuse bounces, query.h:32-70,193-216): the oracle
+    over the reference LBVH, and the canonical brute force, reproduce the reference's frames bit for bit."""
+    for name, sc, fr, ref in _bounce_cases(golden):
+        bvh = orclib.oracle_bvh(sc)
+        o = orclib.oracle_render(sc, fr, bvh=bvh)
+        for k in ("tri_id", "t", "rgb"):
+            assert np.array_equal(o[k], ref[k]), (name, k)
+        assert o["counters"]["rays_primary"] > fr.width * fr.height * fr.spp      # bounce rays were traced
+        b = orclib.oracle_render(sc, fr, bvh=None)
+        for k in ("tri_id", "t", "rgb"):
+            assert np.array_equal(b[k], ref[k]), (name, "canonical", k)
 
 
 def test_canonical_brute_force_equals_reference_bvh(frog_scene, golden):
