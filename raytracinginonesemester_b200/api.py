@@ -34,7 +34,11 @@ def load_library():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError("%s is missing: run `python -m raytracinginonesemester_b200.build` "
                                "(the CUDA extension is the product; there is no CPU fallback)" % LIB_PATH)
-        _LIB = A.bind(C.CDLL(LIB_PATH))
+        lib = A.bind(C.CDLL(LIB_PATH))
+        if lib.rt_api_version() != A.RT_API_VERSION:
+            raise RuntimeError("%s has API version %d, this package expects %d: rebuild it (python -m raytracinginonesemester_b200.build)"
+                               % (LIB_PATH, lib.rt_api_version(), A.RT_API_VERSION))
+        _LIB = lib
     return _LIB
 
 
