@@ -45,7 +45,12 @@ extern "C" {
  * (SURVEY §8a "mode parameters"). */
 #define RT_MODE_HW1      0   /* HW1/src/render.cpp + HW1/include/{ray,raytracer}.h        */
 #define RT_MODE_HW2_BVH  1   /* HW2/HW2/GPUandCPU/include/{query,shader,brdf}.h           */
-#define RT_MODE_HW2_CPU  2   /* HW2/HW2/CPUOnly/include/{ray,raytracer,brdf}.h (direct)  */
+#define RT_MODE_HW2_CPU  2   /* HW2/HW2/CPUOnly/include/{ray,raytracer,brdf}.h: direct light + mirror bounces
+                                (TraceRay with diffuse_bounce == false and point lights — the deterministic part;
+                                its diffuse bounces and disk lights draw from std::random_device).  Sample position
+                                = pixel index + jitter (the reference uses +0.5 at 1 spp, render.cpp:127-131);
+                                rt_light.intensity_f; normals == NULL means per-triangle face normals
+                                (render.cpp:88-96); miss colour is the sky gradient (raytracer.h:224-230). */
 
 /* rt_frame.accel */
 #define RT_ACCEL_BRUTE   0   /* test every triangle (HW1/src/render.cpp:89-107)   */
@@ -62,6 +67,7 @@ extern "C" {
 #define RT_QUANT_PPM_GAMMA2   1  /* same with sqrt() first (ppm_p6 default gamma2=true)    */
 #define RT_QUANT_HW1_TRUNC    2  /* HW1/src/render.cpp:121-123   (uchar)(255.99f*c)        */
 #define RT_QUANT_HW2_TRUNC    3  /* GPUandCPU/src/main.cu:428-430 (uchar)(255*min(c,1))    */
+#define RT_QUANT_CPU_TRUNC    4  /* CPUOnly/src/render.cpp:157-163 clamp to [0,1], (uchar)(255.99f*c) */
 
 /* rt_frame.kernel_variant */
 #define RT_VARIANT_DEFAULT          0  /* warp-packet traversal (one 8x4 tile per warp), 8 blocks/SM    */
@@ -95,7 +101,10 @@ typedef struct rt_material {
 typedef struct rt_light {
     float   position[3];
     float   color[3];
-    int32_t intensity;
+    union {
+        int32_t intensity;      /* RT_MODE_HW1 / RT_MODE_HW2_BVH: int, as in GPUandCPU/include/scene.h:24 */
+        float   intensity_f;    /* RT_MODE_HW2_CPU: float, as in CPUOnly/include/raytracer.h:40-42 */
+    };
 } rt_light;
 
 /* Indexed triangle mesh exactly as the reference loaders hand it to render():
@@ -229,6 +238,10 @@ int  rt_frame_stats(rt_ctx* ctx, uint64_t* node_visits, uint64_t* tri_tests, uin
 int  rt_camera_init(rt_camera* out, const float pos[3], const float look_at[3],
                     const float up[3], double focal_length_mm,
                     double sensor_height_mm, int width, int height);
+/* The CPUOnly renderer's camera (CPUOnly/include/camera.h:64-104): explicit sensor width instead of the
+ * aspect-derived one.  Returns RT_ERR_ARG when width/height < 1 (the reference throws). */
+int  rt_camera_init_cpuonly(rt_camera* out, const float pos[3], const float look_at[3], const float up[3],
+                            double focal_length_mm, double sensor_height_mm, double sensor_width_mm, int width, int height);
 /* jittered_samples(spp, seed) of GPUandCPU/include/antialias.h:12-27:
  * std::mt19937 + uniform_real_distribution<float>(0,1) - 0.5.  out[2*spp]. */
 int  rt_jitter_table(float* out, int spp, uint32_t seed, int centered);

@@ -6,6 +6,7 @@ TEST INFRASTRUCTURE ONLY.  Produces
   oracle/_ref/libref_hw2.so       reference HW2/GPUandCPU sources (CPU build) compiled where they lie
   oracle/_ref/libref_ppm.so       reference ppm_p6_lib compiled where it lies
   oracle/_ref/libref_hw2_main.so  the reference's whole bvh_viz program (main renamed), for end-to-end fixtures
+  oracle/_ref/libref_cpuonly.so   reference HW2/CPUOnly sources (TraceRay, camera, transform, OBJ loader) compiled where they lie
 The _ref outputs need /root/reference (present in the authoring container only); on the GPU
 box the prebuilt files travel with the snapshot.  No reference source is copied into the repo.
 Flags: -O2 -ffp-contract=off, no -march=native (hit ids depend on no-FMA rounding).
@@ -47,7 +48,7 @@ def have_reference():
 
 def build_ref(force=False):
     """Compile the reference's own sources in place.  Returns dict name -> path (existing files)."""
-    outs = {n: os.path.join(REF_OUT, "lib%s.so" % n) for n in ("ref_hw1", "ref_hw2", "ref_ppm", "ref_hw2_main")}
+    outs = {n: os.path.join(REF_OUT, "lib%s.so" % n) for n in ("ref_hw1", "ref_hw2", "ref_ppm", "ref_hw2_main", "ref_cpuonly")}
     if have_reference():
         os.makedirs(REF_OUT, exist_ok=True)
         hw1, g = os.path.join(REF, "HW1"), os.path.join(REF, "HW2", "HW2", "GPUandCPU")
@@ -65,6 +66,11 @@ def build_ref(force=False):
             inc = ["-I", os.path.join(g, "third_party", "glm"), "-I", os.path.join(g, "include"), "-I", os.path.join(g, "src")]
             _run(["g++", "-x", "c++", "-std=c++14", "-w", "-D__device__="] + FP + inc + ["-o", outs["ref_hw2_main"],
                   s, os.path.join(g, "include", "bvh.cu"), os.path.join(g, "include", "query.cu")])
+        s = os.path.join(HERE, "ref_shim_cpuonly.cpp")
+        if force or _stale(outs["ref_cpuonly"], [s]):
+            c = os.path.join(REF, "HW2", "HW2", "CPUOnly")
+            _run(["g++", "-std=c++17", "-w"] + FP + ["-I", os.path.join(c, "include"), "-o", outs["ref_cpuonly"],
+                  s, os.path.join(c, "src", "MeshOBJ.cpp")])
         s = os.path.join(HERE, "ref_shim_ppm.cpp")
         if force or _stale(outs["ref_ppm"], [s]):
             p = os.path.join(hw1, "ppm_p6_lib")

@@ -6,7 +6,7 @@ RT_OK, RT_ERR_ARG, RT_ERR_CUDA, RT_ERR_STATE, RT_ERR_NCCL, RT_ERR_NOMEM = 0, -1,
 RT_MODE_HW1, RT_MODE_HW2_BVH, RT_MODE_HW2_CPU = 0, 1, 2
 RT_ACCEL_BRUTE, RT_ACCEL_BVH = 0, 1
 RT_OUT_RGB_F32, RT_OUT_RGB8, RT_OUT_TRI_ID, RT_OUT_T = 1, 2, 4, 8
-RT_QUANT_PPM_LROUND, RT_QUANT_PPM_GAMMA2, RT_QUANT_HW1_TRUNC, RT_QUANT_HW2_TRUNC = 0, 1, 2, 3
+RT_QUANT_PPM_LROUND, RT_QUANT_PPM_GAMMA2, RT_QUANT_HW1_TRUNC, RT_QUANT_HW2_TRUNC, RT_QUANT_CPU_TRUNC = 0, 1, 2, 3, 4
 RT_BUILD_DEFAULT, RT_BUILD_NO_BVH = 0, 1
 RT_VARIANT_DEFAULT, RT_VARIANT_PACKET_OCC6, RT_VARIANT_PACKET_OCC10, RT_VARIANT_PACKET_EXACT_SLAB, RT_VARIANT_PER_RAY = 0, 1, 2, 3, 10
 RT_VARIANT_STATS, RT_VARIANT_PER_RAY_STATS = 100, 110
@@ -28,8 +28,13 @@ class rt_material(C.Structure):
                 ("ks", C.c_float), ("shininess", C.c_float), ("kr", C.c_float), ("emission", C.c_float * 3)]
 
 
+class _rt_intensity(C.Union):
+    _fields_ = [("intensity", C.c_int32), ("intensity_f", C.c_float)]
+
+
 class rt_light(C.Structure):
-    _fields_ = [("position", C.c_float * 3), ("color", C.c_float * 3), ("intensity", C.c_int32)]
+    _anonymous_ = ("u",)
+    _fields_ = [("position", C.c_float * 3), ("color", C.c_float * 3), ("u", _rt_intensity)]
 
 
 class rt_scene(C.Structure):
@@ -86,6 +91,7 @@ EXPORTS = {
     "rt_sync": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "rt_frame_stats": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_uint64)] * 4),
     "rt_camera_init": (C.c_int, [C.POINTER(rt_camera), f32p, f32p, f32p, C.c_double, C.c_double, C.c_int, C.c_int]),
+    "rt_camera_init_cpuonly": (C.c_int, [C.POINTER(rt_camera), f32p, f32p, f32p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]),
     "rt_jitter_table": (C.c_int, [f32p, C.c_int, C.c_uint32, C.c_int]),
     "rt_mesh_load_obj": (C.c_int, [C.c_char_p, i32p, C.POINTER(C.c_void_p)]),
     "rt_mesh_create": (C.c_int, [C.POINTER(C.c_void_p)]),

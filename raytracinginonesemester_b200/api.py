@@ -90,11 +90,35 @@ def make_material(albedo=(0.8, 0.8, 0.8), kd=1.0, specular_color=(0.04, 0.04, 0.
 
 
 def make_light(position, color=(1.0, 1.0, 1.0), intensity=1):
+    """Light of the HW1 / HW2-BVH renderers: integer intensity (GPUandCPU/include/scene.h:21-25)."""
     l = A.rt_light()
     l.position[:] = position
     l.color[:] = color
     l.intensity = int(intensity)
     return l
+
+
+def make_light_f(position, color=(1.0, 1.0, 1.0), intensity=1.0):
+    """Point light of the CPUOnly renderer (RT_MODE_HW2_CPU): float intensity (CPUOnly/include/raytracer.h:37-46)."""
+    l = A.rt_light()
+    l.position[:] = position
+    l.color[:] = color
+    l.intensity_f = float(intensity)
+    return l
+
+
+def camera_init_cpuonly(pos, look_at, up, focal_length_mm, sensor_height_mm, sensor_width_mm, width, height):
+    """camera::initialize of the CPUOnly renderer (CPUOnly/include/camera.h:64-104) -> rt_camera."""
+    lib = load_library()
+    cam = A.rt_camera()
+    p, l, u = _f32(pos), _f32(look_at), _f32(up)
+    rc = lib.rt_camera_init_cpuonly(C.byref(cam), _ptr(p, A.f32p), _ptr(l, A.f32p), _ptr(u, A.f32p), float(focal_length_mm),
+                                    float(sensor_height_mm), float(sensor_width_mm), int(width), int(height))
+    if rc != A.RT_OK:
+        raise RtError(rc, "pixel_width and pixel_height must be >= 1 and sensor_width_mm > 0")
+    cam.params = dict(pos=tuple(float(x) for x in p), look_at=tuple(float(x) for x in l), up=tuple(float(x) for x in u),
+                      focal_mm=float(focal_length_mm), sensor_mm=float(sensor_height_mm), sensor_w_mm=float(sensor_width_mm))
+    return cam
 
 
 def load_obj(path, next_object_id=0, position=None, rotation=None, scale=None):

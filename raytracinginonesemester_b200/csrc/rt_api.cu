@@ -72,7 +72,7 @@ struct rt_ctx {
     std::string err;
     // scene
     BvhNode* nodes = nullptr; TriBlock* geom = nullptr; TriBlock* shade = nullptr; rt_material* materials = nullptr;
-    uint32_t num_tris = 0, num_nodes = 0; int num_materials = 0; bool has_scene = false, has_bvh = false;
+    uint32_t num_tris = 0, num_nodes = 0; int num_materials = 0; bool has_scene = false, has_bvh = false, has_normals = false;
     rt_build_info info{};
     // frame
     Plane lights, jitter, counters;
@@ -122,13 +122,13 @@ void free_scene(rt_ctx* c) {
 }
 
 
-struct SceneHeader { uint32_t num_tris, num_nodes, num_materials, has_bvh; float smin[3], smax[3]; };
+struct SceneHeader { uint32_t num_tris, num_nodes, num_materials, has_bvh, has_normals; float smin[3], smax[3]; };
 
 // Broadcast of the built arena from rank 0 (scene + BVH travel once per scene over NVLink).
 int broadcast_scene(rt_ctx* c) {
     SceneHeader h{};
     if (c->rank == 0) {
-        h.num_tris = c->num_tris; h.num_nodes = c->num_nodes; h.num_materials = (uint32_t)c->num_materials; h.has_bvh = c->has_bvh;
+        h.num_tris = c->num_tris; h.num_nodes = c->num_nodes; h.num_materials = (uint32_t)c->num_materials; h.has_bvh = c->has_bvh; h.has_normals = c->has_normals;
         memcpy(h.smin, c->info.scene_min, sizeof h.smin); memcpy(h.smax, c->info.scene_max, sizeof h.smax);
     }
     SceneHeader* dh = nullptr;
@@ -140,7 +140,7 @@ int broadcast_scene(rt_ctx* c) {
     cudaFree(dh);
     if (c->rank != 0) {
         free_scene(c);
-        c->num_tris = h.num_tris; c->num_nodes = h.num_nodes; c->num_materials = (int)h.num_materials; c->has_bvh = h.has_bvh != 0;
+        c->num_tris = h.num_tris; c->num_nodes = h.num_nodes; c->num_materials = (int)h.num_materials; c->has_bvh = h.has_bvh != 0; c->has_normals = h.has_normals != 0;
         if (c->num_nodes) CU(c, cudaMalloc(&c->nodes, sizeof(BvhNode) * (size_t)c->num_nodes));
         CU(c, cudaMalloc(&c->geom, sizeof(TriBlock) * (size_t)c->num_tris));
         CU(c, cudaMalloc(&c->shade, sizeof(TriBlock) * (size_t)c->num_tris));
@@ -463,7 +463,7 @@ int rt_upload_scene(rt_ctx* c, const rt_scene* sc) {
     cudaEventElapsedTime(&b_ms, e1, e2);
     cleanup();
 #undef CUS
-    c->num_tris = (uint32_t)nt; c->num_materials = sc->num_materials; c->has_scene = true;
+    c->num_tris = (uint32_t)nt; c->num_materials = sc->num_materials; c->has_scene = true; c->has_normals = sc->normals != nullptr;
     c->info.num_triangles = nt; c->info.num_nodes = c->num_nodes; c->info.build_ms = b_ms; c->info.upload_ms = up_ms;
     c->info.arena_bytes = sizeof(BvhNode) * (uint64_t)c->num_nodes + 2 * sizeof(TriBlock) * (uint64_t)nt +
                           sizeof(rt_material) * (uint64_t)sc->num_materials;
@@ -485,20 +485,25 @@ int rt_render(rt_ctx* c, const rt_frame* fr) {
     if (fr->width < 1 || fr->height < 1) return fail(c, RT_ERR_ARG, "rt_render: pixel_width/pixel_height must be >= 1");
     if ((uint64_t)fr->width * (uint64_t)fr->height > (1ull << 31)) return fail(c, RT_ERR_ARG, "rt_render: image too large");
     if (fr->spp < 1) return fail(c, RT_ERR_ARG, "rt_render: spp must be >= 1");
-    if (fr->mode != RT_MODE_HW1 && fr->mode != RT_MODE_HW2_BVH) return fail(c, RT_ERR_ARG, "rt_render: unsupported mode %d", fr->mode);
+    if (fr->mode != RT_MODE_HW1 && fr->mode != RT_MODE_HW2_BVH && fr->mode != RT_MODE_HW2_CPU) return fail(c, RT_ERR_ARG, "rt_render: unsupported mode %d", fr->mode);
+    if (fr->mode == RT_MODE_HW2_CPU) {
+        if (fr->accel != RT_ACCEL_BVH) return fail(c, RT_ERR_ARG, "rt_render: RT_MODE_HW2_CPU runs over the BVH (RT_ACCEL_BVH)");
+        if (fr->diffuse_bounce) return fail(c, RT_ERR_ARG, "rt_render: RT_MODE_HW2_CPU has no deterministic diffuse bounce (the reference draws from std::random_device)");
+        if (fr->max_depth > RT_CPU_MAX_DEPTH) return fail(c, RT_ERR_ARG, "rt_render: RT_MODE_HW2_CPU supports max_depth <= %d", RT_CPU_MAX_DEPTH);
+    }
     if (fr->accel != RT_ACCEL_BRUTE && fr->accel != RT_ACCEL_BVH) return fail(c, RT_ERR_ARG, "rt_render: unsupported accel %d", fr->accel);
     if (fr->accel == RT_ACCEL_BRUTE && fr->mode != RT_MODE_HW1 && fr->max_depth > 1)
         return fail(c, RT_ERR_ARG, "rt_render: bounces (max_depth > 1) need RT_ACCEL_BVH");
     if (fr->accel == RT_ACCEL_BVH && !c->has_bvh) return fail(c, RT_ERR_STATE, "rt_render: scene was uploaded with RT_BUILD_NO_BVH");
     if (fr->num_lights < 0 || (fr->num_lights > 0 && !fr->lights)) return fail(c, RT_ERR_ARG, "rt_render: lights");
     if (fr->mode == RT_MODE_HW1 && fr->num_lights < 1) return fail(c, RT_ERR_ARG, "rt_render: HW1 mode needs one light");
-    if (fr->quantiser < RT_QUANT_PPM_LROUND || fr->quantiser > RT_QUANT_HW2_TRUNC) return fail(c, RT_ERR_ARG, "rt_render: quantiser");
+    if (fr->quantiser < RT_QUANT_PPM_LROUND || fr->quantiser > RT_QUANT_CPU_TRUNC) return fail(c, RT_ERR_ARG, "rt_render: quantiser");
 
     FrameParams& P = c->fp;
     memset(&P, 0, sizeof P);
     P.cam = fr->cam; P.mode = fr->mode; P.accel = fr->accel; P.W = fr->width; P.H = fr->height; P.spp = fr->spp;
     P.max_depth = fr->max_depth; P.diffuse_bounce = fr->diffuse_bounce ? 1 : 0; P.shadows = fr->shadows; P.quantiser = fr->quantiser; P.num_lights = fr->num_lights;
-    P.num_materials = c->num_materials;
+    P.num_materials = c->num_materials; P.has_normals = c->has_normals ? 1 : 0;
     memcpy(P.miss, fr->miss_color, sizeof P.miss);
     P.nodes = c->nodes; P.geom = c->geom; P.shade = c->shade; P.num_tris = c->num_tris; P.materials = c->materials;
     P.tiles_x = (P.W + RT_TILE_W - 1) / RT_TILE_W; P.tiles_y = (P.H + RT_TILE_H - 1) / RT_TILE_H;

@@ -56,7 +56,13 @@ RT_HD Ray rt_make_ray(const rt_camera& cam, int mode, int x, int y, float jx, fl
     float px = XADD((float)x, jx), py = XADD((float)y, jy);
     f3 c = ld3(cam.center), p00 = ld3(cam.pixel00_loc), du = ld3(cam.pixel_delta_u), dv = ld3(cam.pixel_delta_v);
     Ray r; r.o = c;
-    if (mode == RT_MODE_HW1) {
+    if (mode == RT_MODE_HW2_CPU) {
+        // CPUOnly/src/render.cpp:124-135: u = double(i) + du, narrowed by get_pixel_position(double,double)
+        // (CPUOnly/include/camera.h:41-43); the Ray constructor normalises (CPUOnly/include/ray.h:13-14).
+        px = (float)((double)x + (double)jx); py = (float)((double)y + (double)jy);
+        f3 pp = xadd3(xadd3(p00, xmuls(du, px)), xmuls(dv, py));
+        r.d = xunit_c(xsub3(pp, c));
+    } else if (mode == RT_MODE_HW1) {
         px = (float)(int)px; py = (float)(int)py;
         f3 pp = xadd3(xadd3(p00, xmuls(du, px)), xmuls(dv, py));
         r.d = xunit(xsub3(pp, c));
@@ -192,6 +198,37 @@ RT_HD void rt_hit_frame_hw2(const Ray& r, f3 e1, f3 e2, f3 n0, f3 n1, f3 n2, flo
     normal = sn;
 }
 
+// ray_intersection's hit attributes in the CPUOnly renderer (CPUOnly/include/ray.h:74-94): face normal from the
+// winding, front/back by the ray, interpolated vertex normals normalised and negated on back faces.
+// has_normals == false: the triangle carries its face normal in all three slots (CPUOnly/src/render.cpp:88-96).
+RT_HD void rt_hit_frame_cpu(const Ray& r, f3 e1, f3 e2, f3 n0, f3 n1, f3 n2, bool has_normals, float t, float u, float v,
+                            f3& p, f3& normal) {
+    p = xadd3(r.o, xmuls(r.d, t));
+    const f3 faceN = xunit_c(xcross(e1, e2));
+    const bool front = xdot(r.d, faceN) < 0.0f;
+    if (!has_normals) { n0 = faceN; n1 = faceN; n2 = faceN; }
+    f3 sn = xadd3(xadd3(xmuls(n0, XSUB(XSUB(1.0f, u), v)), xmuls(n1, u)), xmuls(n2, v));
+    sn = xunit_c(sn);
+    if (!front) sn = xneg3(sn);
+    normal = sn;
+}
+
+// EvaluateBRDF of the CPUOnly renderer (CPUOnly/include/brdf.h:12-37): fs = specularColor * (ks * specLobe).
+RT_HD f3 rt_brdf_cpu(const rt_material& m, f3 N, f3 V, f3 L) {
+    float NdotL = fmaxf(xdot(N, L), 0.0f);
+    float NdotV = fmaxf(xdot(N, V), 0.0f);
+    if (NdotL <= 0.f || NdotV <= 0.f) return mk3(0.f, 0.f, 0.f);
+    const float invPi = 0.31830988618f;
+    f3 fd = xmuls(ld3(m.albedo), XMUL(m.kd, invPi));
+    f3 H = xunit_c(xadd3(L, V));
+    float NdotH = fmaxf(xdot(N, H), 0.0f);
+    const float inv2Pi = 0.15915494309f;
+    float specNorm = XMUL(XADD(m.shininess, 2.0f), inv2Pi);
+    float specLobe = XMUL(specNorm, XPOW(NdotH, m.shininess));
+    f3 fs = xmuls(ld3(m.specular_color), XMUL(m.ks, specLobe));
+    return xadd3(fd, fs);
+}
+
 // EvaluateBRDF, GPUandCPU/include/brdf.h:12-39.
 RT_HD f3 rt_brdf_hw2(const rt_material& m, f3 N, f3 V, f3 L) {
     float NdotL = fmaxf(xdot(N, L), 0.0f);
@@ -226,6 +263,7 @@ RT_HD rt_material rt_default_material() {   // Material(), GPUandCPU/include/mat
 RT_HD uint8_t rt_quantise(float c, int q) {
     if (q == RT_QUANT_HW1_TRUNC) return (uint8_t)(XMUL(255.99f, c));                 // HW1/src/render.cpp:121-123
     if (q == RT_QUANT_HW2_TRUNC) return (uint8_t)(XMUL(255.0f, (c < 1.0f ? c : 1.0f))); // GPUandCPU/src/main.cu:428-430
+    if (q == RT_QUANT_CPU_TRUNC) { float x = c > 1.0f ? 1.0f : c; if (x < 0.0f) x = 0.0f; return (uint8_t)(XMUL(255.99f, x)); }   // CPUOnly/src/render.cpp:157-163
     double x = (double)c;                                                            // ppm_p6.cpp:137-155
     if (q == RT_QUANT_PPM_GAMMA2) { if (x < 0.0) x = 0.0; x = sqrt(x); }
     if (x < 0.0) x = 0.0;

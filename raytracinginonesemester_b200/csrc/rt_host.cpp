@@ -24,9 +24,9 @@ inline V unit_or_z(V v) {
 inline void put(float* dst, V v) { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; }
 } // namespace
 
-extern "C" int rt_camera_init(rt_camera* out, const float pos[3], const float look_at[3], const float up[3],
-                              double focal_length_mm, double sensor_height_mm, int width, int height) {
-    // GPUandCPU/include/camera.h:72-94; HW1/include/camera.h:55-92 throws on width/height < 1.
+// sensor_width_mm <= 0: viewport width from the pixel aspect ratio (GPUandCPU, HW1); > 0: the sensor's own width (CPUOnly).
+static int camera_init(rt_camera* out, const float pos[3], const float look_at[3], const float up[3],
+                       double focal_length_mm, double sensor_height_mm, double sensor_width_mm, int width, int height) {
     if (!out || !pos || !look_at || !up || width < 1 || height < 1) return RT_ERR_ARG;
     const V center{pos[0], pos[1], pos[2]}, target{look_at[0], look_at[1], look_at[2]}, up_v{up[0], up[1], up[2]};
     const V forward = unit_or_z(sub(target, center));
@@ -34,7 +34,7 @@ extern "C" int rt_camera_init(rt_camera* out, const float pos[3], const float lo
     const V up_ortho = cross(right, forward);
     const double focal_m = focal_length_mm / 1000.0;
     const double vp_h = sensor_height_mm / 1000.0;
-    const double vp_w = vp_h * (double(width) / double(height));
+    const double vp_w = sensor_width_mm > 0.0 ? sensor_width_mm / 1000.0 : vp_h * (double(width) / double(height));
     // `double * Vec3` binds to operator*(float, Vec3): the scalar is narrowed before the multiply.
     const V vp_u = scale(right, (float)vp_w);
     const V vp_v = scale(up_ortho, (float)(-vp_h));
@@ -45,6 +45,19 @@ extern "C" int rt_camera_init(rt_camera* out, const float pos[3], const float lo
     const V p00 = add(upper_left, scale(add(du, dv), 0.5f));
     put(out->center, center); put(out->pixel00_loc, p00); put(out->pixel_delta_u, du); put(out->pixel_delta_v, dv);
     return RT_OK;
+}
+
+extern "C" int rt_camera_init(rt_camera* out, const float pos[3], const float look_at[3], const float up[3],
+                              double focal_length_mm, double sensor_height_mm, int width, int height) {
+    // GPUandCPU/include/camera.h:72-94; HW1/include/camera.h:55-92 throws on width/height < 1.
+    return camera_init(out, pos, look_at, up, focal_length_mm, sensor_height_mm, 0.0, width, height);
+}
+
+extern "C" int rt_camera_init_cpuonly(rt_camera* out, const float pos[3], const float look_at[3], const float up[3],
+                                      double focal_length_mm, double sensor_height_mm, double sensor_width_mm, int width, int height) {
+    // HW2/HW2/CPUOnly/include/camera.h:64-104 (same arithmetic; viewport width = sensor_width_mm / 1000).
+    if (!(sensor_width_mm > 0.0)) return RT_ERR_ARG;
+    return camera_init(out, pos, look_at, up, focal_length_mm, sensor_height_mm, sensor_width_mm, width, height);
 }
 
 extern "C" int rt_jitter_table(float* out, int spp, uint32_t seed, int centered) {

@@ -43,6 +43,7 @@
 #define RT_CLZ32(x) __clz((int)(x))
 #define RT_CLZ64(x) __clzll((long long)(x))
 #define RT_U2F(u) __uint2float_rn(u)
+#define RT_D2F_UP(d) __double2float_ru(d)
 #else
 #include <string.h>
 #define RT_LDG(p) (*(p))
@@ -53,6 +54,8 @@ static inline float rt_i2f_host(int i) { float f; memcpy(&f, &i, 4); return f; }
 #define RT_CLZ32(x) ((x) == 0 ? 32 : __builtin_clz((unsigned)(x)))
 #define RT_CLZ64(x) ((x) == 0 ? 64 : __builtin_clzll((unsigned long long)(x)))
 #define RT_U2F(u) ((float)(u))
+static inline float rt_d2f_up_host(double d) { float f = (float)d; return ((double)f < d) ? nextafterf(f, INFINITY) : f; }
+#define RT_D2F_UP(d) rt_d2f_up_host(d)
 #endif
 
 struct f3 { float x, y, z; };
@@ -81,6 +84,12 @@ RT_HD f3 xcross(f3 u, f3 v) {
 RT_HD float xlen3(f3 v) { return XSQRT(xdot(v, v)); }
 // global unit_vector(): vec3.h:53-56
 RT_HD f3 xunit(f3 v) { return xdivs(v, xlen3(v)); }
+// unit_vector() of the CPUOnly renderer: zero vector below 1e-12 (HW2/HW2/CPUOnly/include/vec3.h:53-57)
+RT_HD f3 xunit_c(f3 v) {
+    float len = xlen3(v);
+    if (len < 1e-12f) return mk3(0.0f, 0.0f, 0.0f);
+    return xdivs(v, len);
+}
 // Camera::unit_vector(): GPUandCPU/include/camera.h:64-69 (fallback (0,0,1) below 1e-12)
 RT_HD f3 xunit_cam(f3 v) {
     float len = xlen3(v);

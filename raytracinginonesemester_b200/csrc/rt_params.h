@@ -10,10 +10,11 @@
 #define RT_TILE_H 8
 #define RT_BLOCK_THREADS (RT_TILE_W * RT_TILE_H)
 #define RT_STACK_DEPTH 32
+#define RT_CPU_MAX_DEPTH 16          // RT_MODE_HW2_CPU: deepest mirror recursion kept on the per-thread fold stack
 
 struct FrameParams {
     rt_camera cam;
-    int mode, accel, W, H, spp, max_depth, shadows, quantiser, num_lights, num_materials, diffuse_bounce;
+    int mode, accel, W, H, spp, max_depth, shadows, quantiser, num_lights, num_materials, diffuse_bounce, has_normals;
     float miss[3];
     // scene arena
     const BvhNode* nodes;

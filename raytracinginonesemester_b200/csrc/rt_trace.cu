@@ -453,6 +453,13 @@ cudaError_t rt_launch_render(const FrameParams& fp, int kernel_variant, cudaStre
     switch (fp.mode) {
     case RT_MODE_HW1:     return launch_mode<RT_MODE_HW1>(fp, kernel_variant, stream);
     case RT_MODE_HW2_BVH: return launch_mode<RT_MODE_HW2_BVH>(fp, kernel_variant, stream);
+    case RT_MODE_HW2_CPU: {   // CPUOnly renderer's contract (N1): per-ray kernel over the BVH (mirror recursion is incoherent)
+        if (fp.accel != RT_ACCEL_BVH) return cudaErrorInvalidValue;
+        dim3 grid((unsigned)fp.local_tiles), block(RT_BLOCK_THREADS);
+        if (kernel_variant == RT_VARIANT_STATS || kernel_variant == RT_VARIANT_PER_RAY_STATS) k_render_bvh<RT_MODE_HW2_CPU, true><<<grid, block, 0, stream>>>(fp);
+        else k_render_bvh<RT_MODE_HW2_CPU, false><<<grid, block, 0, stream>>>(fp);
+        return cudaGetLastError();
+    }
     default:              return cudaErrorInvalidValue;
     }
 }

@@ -258,6 +258,86 @@ RT_HD bool rt_bounce_hw2(const FrameParams& P, const Surface& sf, Ray& ray, f3& 
     return !(throughput.x < 1e-4f && throughput.y < 1e-4f && throughput.z < 1e-4f);
 }
 
+// ------------------------------------------------------ CPUOnly renderer (N1) ----
+// TraceRay of HW2/HW2/CPUOnly/include/raytracer.h:215-260 with diffuse_bounce == false and point lights: direct light
+// (ShadeDirect :171-211, one shadow ray per lit hit, ShadowVisibility :121-168 with S == 1) plus perfect-mirror
+// recursion.  The recursion `Lo + kr * (tint * TraceRay(...))` is evaluated innermost-first like the reference: the
+// walk down records (Lo, kr, tint) per level, the fold runs back up.  Sky gradient on a miss (:224-230).
+template <int STRIDE, bool STATS>
+RT_HD f3 rt_sample_cpuonly(const FrameParams& P, const Ray& primary, uint32_t* stk, Hit& first,
+                           unsigned& nprim, unsigned& nshadow, TraceStats* st) {
+    const float EPS = 1e-4f;                                           // RT_EPS, raytracer.h:49
+    f3 lvl_Lo[RT_CPU_MAX_DEPTH], lvl_tint[RT_CPU_MAX_DEPTH];
+    float lvl_kr[RT_CPU_MAX_DEPTH];
+    int depth = P.max_depth > 1 ? P.max_depth : 1;                     // std::max(1, max_bounces), render.cpp:113
+    if (depth > RT_CPU_MAX_DEPTH) depth = RT_CPU_MAX_DEPTH;
+    Ray ray = primary;
+    rt_hit_reset(first);
+    int n = 0;
+    f3 tail = mk3(0.f, 0.f, 0.f);                                      // TraceRay(depth 0) = black
+    for (;;) {
+        Hit h;
+        rt_trace_closest<RT_MODE_HW2_CPU, STRIDE, STATS>(P, ray, stk, h, st);
+        ++nprim;
+        if (n == 0) first = h;
+        if (h.slot < 0) {
+            const f3 ud = xunit_c(ray.d);
+            const float t = XMUL(0.5f, XADD(ud.z, 1.0f));
+            tail = xadd3(xmuls(mk3(1.0f, 1.0f, 1.0f), XSUB(1.0f, t)), xmuls(mk3(0.5f, 0.7f, 1.0f), t));
+            break;
+        }
+        const Tri tr = rt_load_tri(P.geom, (uint32_t)h.slot);
+        f3 n0, n1, n2, p, normal; int obj;
+        rt_load_normals(P, h.slot, n0, n1, n2, obj);
+        rt_hit_frame_cpu(ray, tr.e1, tr.e2, n0, n1, n2, P.has_normals != 0, h.t, h.u, h.v, p, normal);
+        rt_material mat = rt_default_material();
+        if (P.materials != nullptr && obj >= 0 && obj < P.num_materials) mat = P.materials[obj];
+        const f3 N = xunit_c(normal);
+        const f3 V = xunit_c(xsub3(ray.o, p));
+        f3 Lo = mk3(0.f, 0.f, 0.f);
+        Lo = xadd3(Lo, xmuls(ld3(mat.albedo), 0.05f));
+        Lo = xadd3(Lo, ld3(mat.emission));
+        for (int l = 0; l < P.num_lights; ++l) {
+            const rt_light light = P.lights[l];
+            const f3 toL = xsub3(ld3(light.position), p);
+            const float dist = xlen3(toL);
+            if (dist <= 0.0f) continue;
+            const f3 L = xdivs(toL, dist);
+            const float NdotL = fmaxf(xdot(N, L), 0.0f);
+            if (NdotL <= 0.0f) continue;
+            if (P.shadows) {
+                Ray sray;
+                sray.o = xadd3(p, xmuls(N, EPS));
+                sray.d = xunit_c(L);                                   // the Ray constructor normalises again
+                // blocked iff some triangle has 1e-4 <= t and double(t) < double(dist) - double(1e-4f): as a float
+                // threshold, t < the smallest float >= that double
+                const float thr = RT_D2F_UP((double)dist - (double)EPS);
+                ++nshadow;
+                if (rt_trace_any<RT_MODE_HW2_CPU, STRIDE, STATS>(P, sray, thr, stk, st)) continue;
+            }
+            const f3 f = rt_brdf_cpu(mat, N, V, L);
+            const f3 radiance = xmuls(ld3(light.color), light.intensity_f);
+            Lo = xadd3(Lo, xmuls(xmulv(radiance, f), XMUL(NdotL, 1.0f)));
+        }
+        lvl_Lo[n] = Lo; lvl_kr[n] = 0.0f; lvl_tint[n] = mk3(0.f, 0.f, 0.f);
+        const bool bounce = XADD(mat.kd, mat.kr) > 0.0f && mat.kr > 0.0f;
+        if (!bounce) { ++n; tail = mk3(0.f, 0.f, 0.f); lvl_kr[n - 1] = -1.0f; break; }   // kr slot < 0: level returns Lo as is
+        lvl_kr[n] = mat.kr; lvl_tint[n] = ld3(mat.specular_color);
+        ++n;
+        if (n >= depth) { tail = mk3(0.f, 0.f, 0.f); break; }          // the next call has depth 0
+        const f3 I = xunit_c(ray.d);
+        const f3 refl = xsub3(I, xmuls(N, XMUL(2.0f, xdot(I, N))));    // reflect_dir, raytracer.h:70-74
+        ray.o = xadd3(p, xmuls(N, EPS));
+        ray.d = xunit_c(refl);
+    }
+    f3 v = tail;
+    for (int k = n - 1; k >= 0; --k) {
+        if (lvl_kr[k] < 0.0f) v = lvl_Lo[k];
+        else v = xadd3(lvl_Lo[k], xmuls(xmulv(lvl_tint[k], v), lvl_kr[k]));
+    }
+    return v;
+}
+
 // One sample of one pixel through the BVH path: TraceRayIterative (query.h:156-220) — closest hit, shading,
 // shadow rays, then mirror / diffuse bounces up to P.max_depth.  h = the depth-0 hit.
 template <int MODE, int STRIDE, bool STATS>
@@ -266,10 +346,11 @@ RT_HD f3 rt_sample_bvh(const FrameParams& P, int x, int y, int s, uint32_t* stk,
     const float jx = P.jitter ? RT_LDG(P.jitter + 2 * s) : 0.0f;
     const float jy = P.jitter ? RT_LDG(P.jitter + 2 * s + 1) : 0.0f;
     Ray ray = rt_make_ray(P.cam, MODE, x, y, jx, jy);
-    if (MODE != RT_MODE_HW1 && P.max_depth <= 0) {   // TraceRayIterative: maxDepth <= 0 -> black
+    if (MODE == RT_MODE_HW2_BVH && P.max_depth <= 0) {   // TraceRayIterative: maxDepth <= 0 -> black
         rt_hit_reset(h);
         return mk3(0.f, 0.f, 0.f);
     }
+    if (MODE == RT_MODE_HW2_CPU) return rt_sample_cpuonly<STRIDE, STATS>(P, ray, stk, h, nprim, nshadow, st);
     rt_trace_closest<MODE, STRIDE, STATS>(P, ray, stk, h, st);
     ++nprim;
     if (MODE == RT_MODE_HW1) return rt_shade_hw1(P, ray, h);

@@ -9,7 +9,7 @@ C4 = terrain(1000, 500, 42) = exactly 1 000 000 triangles; C5 = terrain(2500, 20
 import numpy as np
 
 from . import _abi as A
-from .api import Frame, Scene, camera_init, jitter_table, make_light, make_material
+from .api import Frame, Scene, camera_init, camera_init_cpuonly, jitter_table, make_light, make_light_f, make_material
 
 
 def wang_hash(seed):
@@ -117,3 +117,21 @@ def cornell_bounce_frame(cam_args, lights, miss, width, height, spp, max_depth, 
     return Frame(cam, width, height, mode=A.RT_MODE_HW2_BVH, accel=A.RT_ACCEL_BVH, lights=lights, miss_color=miss, spp=spp,
                  jitter=jitter_table(spp, 42, True), max_depth=max_depth, shadows=True, outputs=outputs,
                  quantiser=A.RT_QUANT_HW2_TRUNC, diffuse_bounce=bool(diffuse_bounce))
+
+
+def cpuonly_case(g, name, width=None, height=None, outputs=A.RT_OUT_RGB_F32, accel=A.RT_ACCEL_BVH):
+    """Scene + frame of an RT_MODE_HW2_CPU fixture (tests/golden/cpuonly_scenes.npz, tools/make_golden_cpuonly.py):
+    baked mesh, per-object materials, the CPUOnly camera (explicit sensor width), one point light with float intensity,
+    one sample at the pixel centre (+0.5, CPUOnly/src/render.cpp:127-131), max_bounces mirror recursion."""
+    nrm = g[name + "_normals"]
+    mats = []
+    for m in g[name + "_materials"]:
+        mats.append(make_material(albedo=m[0:3], kd=m[3], specular_color=m[4:7], ks=m[7], shininess=m[8], kr=m[9], emission=m[10:13]))
+    sc = Scene(g[name + "_positions"], g[name + "_indices"], normals=nrm if nrm.size else None, tri_obj_ids=g[name + "_tri_obj_ids"], materials=mats)
+    c, li = g[name + "_camera"], g[name + "_light"]
+    W, H, depth = (int(v) for v in g[name + "_frame"])
+    W, H = width or W, height or H
+    cam = camera_init_cpuonly(c[0:3], c[3:6], c[6:9], c[9], c[10], c[11], W, H)
+    fr = Frame(cam, W, H, mode=A.RT_MODE_HW2_CPU, accel=accel, lights=[make_light_f(li[0:3], li[3:6], li[6])], spp=1,
+               jitter=np.array([[0.5, 0.5]], np.float32), max_depth=depth, shadows=True, outputs=outputs, quantiser=A.RT_QUANT_CPU_TRUNC)
+    return sc, fr

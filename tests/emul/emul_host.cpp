@@ -18,6 +18,7 @@ struct EmuScene {
     std::vector<TriBlock> geom, shade;
     std::vector<rt_material> materials;
     uint32_t num_tris = 0;
+    bool has_normals = false;
 };
 
 extern "C" {
@@ -31,6 +32,7 @@ void* emu_build(const rt_scene* sc, uint32_t leaf_max) {
     EmuScene* es = new EmuScene;
     es->num_tris = (uint32_t)n;
     BuildParams bp{};
+    es->has_normals = sc->normals != nullptr;
     bp.positions = sc->positions; bp.normals = sc->normals; bp.indices = sc->indices; bp.obj_ids = sc->tri_obj_ids;
     bp.num_tris = (uint32_t)n; bp.leaf_max = leaf_max;
     if (sc->num_materials > 0) es->materials.assign(sc->materials, sc->materials + sc->num_materials);
@@ -181,7 +183,7 @@ int emu_render_rank(void* h, const rt_frame* fr, rt_image* img, uint64_t* stats,
     FrameParams P{};
     P.cam = fr->cam; P.mode = fr->mode; P.accel = fr->accel; P.W = fr->width; P.H = fr->height; P.spp = fr->spp;
     P.max_depth = fr->max_depth; P.diffuse_bounce = fr->diffuse_bounce ? 1 : 0; P.shadows = fr->shadows; P.quantiser = fr->quantiser; P.num_lights = fr->num_lights;
-    P.num_materials = (int)es->materials.size();
+    P.num_materials = (int)es->materials.size(); P.has_normals = es->has_normals ? 1 : 0;
     memcpy(P.miss, fr->miss_color, sizeof P.miss);
     P.nodes = es->nodes.data(); P.geom = es->geom.data(); P.shade = es->shade.data(); P.num_tris = es->num_tris;
     P.materials = es->materials.empty() ? nullptr : es->materials.data();
@@ -203,9 +205,9 @@ int emu_render_rank(void* h, const rt_frame* fr, rt_image* img, uint64_t* stats,
             TraceStats st{0, 0, 0, 0, 0};
             for (int s = 0; s < P.spp; ++s) {
                 Hit hh;
-                f3 color = fr->mode == RT_MODE_HW1
-                    ? rt_sample_bvh<RT_MODE_HW1, 1, true>(P, px.x, px.y, s, stk, hh, np, ns, &st)
-                    : rt_sample_bvh<RT_MODE_HW2_BVH, 1, true>(P, px.x, px.y, s, stk, hh, np, ns, &st);
+                f3 color = fr->mode == RT_MODE_HW1 ? rt_sample_bvh<RT_MODE_HW1, 1, true>(P, px.x, px.y, s, stk, hh, np, ns, &st)
+                         : fr->mode == RT_MODE_HW2_CPU ? rt_sample_bvh<RT_MODE_HW2_CPU, 1, true>(P, px.x, px.y, s, stk, hh, np, ns, &st)
+                         : rt_sample_bvh<RT_MODE_HW2_BVH, 1, true>(P, px.x, px.y, s, stk, hh, np, ns, &st);
                 if (s == 0) first = hh;
                 accum = xadd3(accum, color);
             }

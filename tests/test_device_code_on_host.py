@@ -116,6 +116,17 @@ def test_bounce_loop_matches_reference_fixture(golden):
             assert e["stats"]["rays_primary"] > int(W) * int(H) * int(spp)
 
 
+@pytest.mark.parametrize("name", ["sphere_point", "sphere", "cornell"])
+def test_cpuonly_mode_matches_reference_fixture(golden, name):
+    """RT_MODE_HW2_CPU through the product's per-ray sample function and BVH (host build of the device code)."""
+    g = golden("cpuonly_scenes.npz")
+    sc, fr = scenes.cpuonly_case(g, name, outputs=ALL)
+    for leaf in (1, 4):
+        e = orclib.emul_render(orclib.emul_build(sc, leaf), fr)
+        for k in ("tri_id", "t", "rgb"):
+            assert np.array_equal(e[k], g["%s_%s" % (name, k)]), (name, leaf, k)
+
+
 def test_tile_sharding_covers_the_frame_once():
     """rt_map_pixel / rt_unpack_index (used by the kernels): every pixel is owned by exactly one rank and
     pack -> unpack is the identity, for sizes that are not multiples of the 16x8 tile."""

@@ -288,6 +288,48 @@ def test_bounce_frame_at_size_terrain_mirror(renderer):
     _strided_bar(a, orc, slice(9, H, step), "bounce terrain")
 
 
+# --------------------------------------------------------------- CPUOnly renderer (N1) ----
+@pytest.mark.parametrize("name", ["sphere_point", "sphere", "cornell"])
+def test_cpuonly_mode_vs_reference_fixture(renderer, golden, name):
+    """RT_MODE_HW2_CPU on the device against frames rendered by the CPUOnly reference: ids and t bit-exact, float rgb to
+    powf rounding, 8-bit image equal to the oracle's."""
+    g = golden("cpuonly_scenes.npz")
+    sc, fr = scenes.cpuonly_case(g, name, outputs=ALL)
+    renderer.upload_scene(sc)
+    a = run(renderer, fr)
+    for k in ("tri_id", "t"):
+        assert np.array_equal(a[k], g["%s_%s" % (name, k)]), (name, k)
+    assert np.abs(a["rgb"] - g["%s_rgb" % name]).max() <= 2e-6, name
+    o = orclib.oracle_render(sc, fr)
+    assert np.abs(a["rgb8"].astype(int) - o["rgb8"].astype(int)).max() <= 1
+    assert a["rays_primary"] == o["counters"]["rays_primary"] and a["rays_shadow"] == o["counters"]["rays_shadow"]
+
+
+def test_cpuonly_committed_golden_png(renderer, golden):
+    """The reference's committed CPUOnly/output/sphere_point_output.png (360x240) from the device: within 1 LSB, and
+    identical where powf rounding does not sit on a quantiser boundary."""
+    g = golden("cpuonly_scenes.npz")
+    png = g["sphere_point_golden_png"]
+    sc, fr = scenes.cpuonly_case(g, "sphere_point", width=png.shape[1], height=png.shape[0], outputs=A.RT_OUT_RGB8)
+    renderer.upload_scene(sc)
+    a = run(renderer, fr)
+    d = np.abs(a["rgb8"].astype(int) - png.astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3, (d.max(), (d > 0).sum())
+
+
+def test_cpuonly_mode_rejects_what_has_no_deterministic_reference(renderer, golden):
+    g = golden("cpuonly_scenes.npz")
+    sc, fr = scenes.cpuonly_case(g, "sphere_point")
+    renderer.upload_scene(sc)
+    fr.diffuse_bounce = True
+    with pytest.raises(api.RtError):
+        renderer.render(fr)
+    fr.diffuse_bounce = False
+    fr.accel = A.RT_ACCEL_BRUTE
+    with pytest.raises(api.RtError):
+        renderer.render(fr)
+
+
 # --------------------------------------------------------------- full-size properties ----
 def test_c4_full_size_properties(renderer):
     """BASELINE config C4 (1M-triangle terrain, 3840x2160, primary + shadow): properties that do not

@@ -112,6 +112,28 @@ def test_hw2_bounce_loop_matches_reference(golden):
             assert np.array_equal(b[k], ref[k]), (name, "canonical", k)
 
 
+@pytest.mark.parametrize("name", ["sphere_point", "sphere", "cornell"])
+def test_cpuonly_mode_matches_reference(golden, name):
+    """RT_MODE_HW2_CPU: the oracle's restatement of the CPUOnly renderer (ray_intersection, IntersectScene,
+    ShadeDirect/ShadowVisibility, EvaluateBRDF, mirror TraceRay, sky) against frames rendered by the reference itself."""
+    g = golden("cpuonly_scenes.npz")
+    sc, fr = scenes.cpuonly_case(g, name, outputs=ALL)
+    o = orclib.oracle_render(sc, fr)
+    for k in ("tri_id", "t", "rgb"):
+        assert np.array_equal(o[k], g["%s_%s" % (name, k)]), (name, k)
+    if name != "sphere_point":
+        assert o["counters"]["rays_primary"] > fr.width * fr.height          # mirror bounces were traced
+
+
+def test_cpuonly_committed_golden_png_bit_exact(golden):
+    """CPUOnly/output/sphere_point_output.png (360x240), the one HW2 golden the reference still reproduces bit for bit."""
+    g = golden("cpuonly_scenes.npz")
+    png = g["sphere_point_golden_png"]
+    sc, fr = scenes.cpuonly_case(g, "sphere_point", width=png.shape[1], height=png.shape[0], outputs=A.RT_OUT_RGB8)
+    o = orclib.oracle_render(sc, fr, want=("rgb8",))
+    assert np.array_equal(o["rgb8"], png)
+
+
 def test_canonical_brute_force_equals_reference_bvh(frog_scene, golden):
     """SURVEY §8c last row: 'min t, then min id over intersectTriangle on all triangles' reproduces the
     reference BVH result (differences only at exact-t ties, far below the 99.99 % bar)."""
