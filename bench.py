@@ -10,9 +10,9 @@ terrain, 3840x2160, 1 spp with the reference jitter pair, primary 
 
 value   = rays (primary + shadow) per second, scene/BVH resident in HBM, L2 flushed between steps,
           device time from CUDA events on the library's stream, max over ranks.
-e2e     = the same metric through the public C ABI with host buffers: rt_render (frame description,
-          lights and jitter copied host->device) + rt_download_image of the 8-bit frame into pinned
-          host memory, every step, wall clock.  This is what the reference's own "GPU Render Time"
+e2e     = the same metric through the public C ABI with host buffers: rt_render_into (frame description,
+          lights and jitter copied host->device; render; 8-bit frame copied into pinned host memory,
+          band-pipelined on one GPU), every step, wall clock.  This is what the reference's own "GPU Render Time"
           brackets (render + D2H copy, GPUandCPU/src/main.cu:370-378).
 --impl reference: the reference's own CPU implementation of the path (oracle/_ref/libref_hw2.so,
           compiled in place from the reference sources; falls back to the oracle port) on all host
@@ -362,17 +362,16 @@ def run_ours(args, rank, world, local_rank):
         r.render(frame)
         ktimes.append(r.frame_times())
     kern_ms = float(np.mean([k for _, k in ktimes]))
+    clocks = sampler.stop() if sampler else None      # clocks were sampled during the device-timed steps
     # end to end through the C ABI with host buffers (render + blocking download), wall clock
     e2e_s = []
     for _ in range(args.steps):
         barrier()
         t0 = time.perf_counter()
-        r.render(frame)
-        r.download(into={"rgb8": pinned} if rank == 0 else None)
+        r.render_into(frame, into={"rgb8": pinned} if rank == 0 else None)     # rt_render_into: the user-facing "frame to host memory" call
         if dist is not None:
             dist.barrier()
         e2e_s.append(time.perf_counter() - t0)
-    clocks = sampler.stop() if sampler else None
     t = torch.tensor([step_ms, e2e_s + [0.0] * (len(step_ms) - len(e2e_s))], dtype=torch.float64, device="cuda")
     tw = torch.tensor(warm_ms + [kern_ms], dtype=torch.float64, device="cuda")
     if dist is not None:

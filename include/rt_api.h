@@ -214,6 +214,11 @@ int  rt_render(rt_ctx* ctx, const rt_frame* frame);
  * the gathered image).  Replaces the D2H copy + 8-bit conversion of
  * main.cu:374, 426-431 / render.cpp:119-124. */
 int  rt_download_image(rt_ctx* ctx, rt_image* img);
+/* rt_render + rt_download_image in one blocking call, with the same result.  On a single-GPU context the frame is
+ * rendered in horizontal bands on several streams and every finished band is copied to the caller's buffers while
+ * the following bands are still rendering (pinned host memory makes the copies asynchronous), which hides most of
+ * the device->host transfer that the reference pays after its kernel (GPUandCPU/src/main.cu:370-378). */
+int  rt_render_into(rt_ctx* ctx, const rt_frame* frame, rt_image* img);
 /* Blocks until the last rt_render finished; returns its device time. */
 int  rt_sync(rt_ctx* ctx, float* gpu_ms);
 /* Device times of the last frame on this rank: the whole rt_render (frame kernel + tile delivery to rank 0)

@@ -87,6 +87,7 @@ EXPORTS = {
     "rt_upload_scene": (C.c_int, [C.c_void_p, C.POINTER(rt_scene)]),
     "rt_build_info_get": (C.c_int, [C.c_void_p, C.POINTER(rt_build_info)]),
     "rt_render": (C.c_int, [C.c_void_p, C.POINTER(rt_frame)]),
+    "rt_render_into": (C.c_int, [C.c_void_p, C.POINTER(rt_frame), C.POINTER(rt_image)]),
     "rt_download_image": (C.c_int, [C.c_void_p, C.POINTER(rt_image)]),
     "rt_sync": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "rt_frame_stats": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_uint64)] * 4),

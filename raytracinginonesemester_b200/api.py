@@ -292,10 +292,7 @@ class Renderer:
         self._check(self.lib.rt_stream_handle(self.ctx, C.byref(h)))
         return int(h.value or 0)
 
-    def download(self, into=None):
-        """Blocking read-back of the planes requested in Frame.outputs -> dict of numpy arrays.
-        `into` may map plane name -> preallocated (e.g. pinned) array."""
-        fr = self._frame
+    def _image(self, fr, into):
         W, H = fr.width, fr.height
         img = A.rt_image()
         out = {}
@@ -318,7 +315,22 @@ class Renderer:
                 img.tri_id = _ptr(buf("tri_id", (H, W), np.int32), A.i32p)
             if fr.outputs & A.RT_OUT_T:
                 img.t = _ptr(buf("t", (H, W), np.float32), A.f32p)
+        return img, out
+
+    def download(self, into=None):
+        """Blocking read-back of the planes requested in Frame.outputs -> dict of numpy arrays.
+        `into` may map plane name -> preallocated (e.g. pinned) array."""
+        img, out = self._image(self._frame, into)
         self._check(self.lib.rt_download_image(self.ctx, C.byref(img)))
+        out["rays_primary"], out["rays_shadow"], out["gpu_ms"] = int(img.rays_primary), int(img.rays_shadow), float(img.gpu_ms)
+        return out
+
+    def render_into(self, frame, into=None):
+        """rt_render_into: render + download in one blocking call (band-pipelined on a single GPU)."""
+        self._frame = frame
+        f = frame.c_struct()
+        img, out = self._image(frame, into)
+        self._check(self.lib.rt_render_into(self.ctx, C.byref(f), C.byref(img)))
         out["rays_primary"], out["rays_shadow"], out["gpu_ms"] = int(img.rays_primary), int(img.rays_shadow), float(img.gpu_ms)
         return out
 

@@ -65,6 +65,9 @@ struct Plane {
 };
 } // namespace
 
+#define RT_BANDS 8
+#define RT_BAND_STREAMS 4
+
 struct rt_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -97,6 +100,9 @@ struct rt_ctx {
     std::vector<void*> retired;                   // rank 0: outgrown exported planes, freed at teardown
     unsigned seq = 0;                             // frame sequence number of the peer protocol
     int chunks_per_rank = 0;                      // tile ownership bands per rank (0 = RT_DEFAULT_CHUNKS_PER_RANK)
+    // rt_render_into: band-pipelined render + download (kernels of later bands overlap the D2H copy of earlier ones)
+    cudaStream_t band_stream[RT_BAND_STREAMS] = {}; cudaStream_t copy_stream = nullptr;
+    cudaEvent_t band_ev[RT_BANDS] = {}; cudaEvent_t copy_done = nullptr;
     int dbg_rank = 0, dbg_world = 0;              // rt_debug_set_shard: render one rank's share on a single GPU (timing only)
 };
 
@@ -332,6 +338,10 @@ int rt_destroy(rt_ctx* c) {
     Plane* planes[] = {&c->lights, &c->jitter, &c->counters, &c->loc_rgb, &c->loc_rgb8, &c->loc_id, &c->loc_t,
                        &c->img_rgb, &c->img_rgb8, &c->img_id, &c->img_t, &c->stage_rgb, &c->stage_rgb8, &c->stage_id, &c->stage_t};
     for (Plane* p : planes) p->release();
+    for (cudaStream_t s : c->band_stream) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (cudaEvent_t e : c->band_ev) if (e) cudaEventDestroy(e);
+    if (c->copy_done) cudaEventDestroy(c->copy_done);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->evk0) cudaEventDestroy(c->evk0);
@@ -478,7 +488,22 @@ int rt_build_info_get(const rt_ctx* c, rt_build_info* info) {
     return RT_OK;
 }
 
-int rt_render(rt_ctx* c, const rt_frame* fr) {
+} // extern "C"
+
+namespace {
+int ensure_band_resources(rt_ctx* c) {
+    if (c->copy_stream) return RT_OK;
+    for (cudaStream_t& s : c->band_stream) CU(c, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : c->band_ev) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(c, cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
+    return RT_OK;
+}
+
+// rt_render (into == NULL) and rt_render_into (into != NULL: single-GPU contexts render the frame in horizontal bands on
+// several streams and copy each finished band to the caller's host buffers while the next ones are still rendering).
+int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) {
+    if (pipelined) *pipelined = false;
     if (!c || !fr) return fail(c, RT_ERR_ARG, "rt_render: NULL argument");
     CU(c, cudaSetDevice(c->device));
     if (!c->has_scene) return fail(c, RT_ERR_STATE, "rt_render: no scene uploaded");
@@ -575,6 +600,42 @@ int rt_render(rt_ctx* c, const rt_frame* fr) {
         if (c->rank != 0) CU(c, rt_launch_flag_set(c->flags + (size_t)c->rank * RT_PEER_FLAG_STRIDE, seq, c->stream));
         else CU(c, rt_launch_flag_wait(c->flags + RT_PEER_FLAG_STRIDE, RT_PEER_FLAG_STRIDE, c->world - 1, seq, kPeerTimeoutNs, c->peer_err, c->stream));
         ++launches;
+    } else if (into && c->world == 1 && !dbg_shard && P.tiles_y >= 2) {
+        int rc = ensure_band_resources(c);
+        if (rc != RT_OK) return rc;
+        struct Out { void* host; uint32_t bit; size_t bpp; const void* dev; const char* name; };
+        const Out outs[4] = {{into->rgb, RT_OUT_RGB_F32, 12, P.rgb, "rgb"}, {into->rgb8, RT_OUT_RGB8, 3, P.rgb8, "rgb8"},
+                             {into->tri_id, RT_OUT_TRI_ID, 4, P.tri_id, "tri_id"}, {into->t, RT_OUT_T, 4, P.t, "t"}};
+        for (const Out& o : outs)
+            if (o.host && !(outputs & o.bit)) return fail(c, RT_ERR_STATE, "rt_render_into: plane '%s' was not requested in rt_frame.outputs", o.name);
+        const int B = P.tiles_y < RT_BANDS ? P.tiles_y : RT_BANDS;
+        CU(c, cudaEventRecord(c->evk0, c->stream));
+        for (int k = 0; k < B; ++k) {                 // all band kernels first: a pageable destination makes the copies host-synchronous
+            const int row_a = (int)((long long)P.tiles_y * k / B), row_b = (int)((long long)P.tiles_y * (k + 1) / B);
+            FrameParams Q = P;
+            Q.tile_offset = row_a * P.tiles_x; Q.local_tiles = (row_b - row_a) * P.tiles_x;
+            cudaStream_t s = c->band_stream[k % RT_BAND_STREAMS];
+            CU(c, cudaStreamWaitEvent(s, c->evk0, 0));
+            int l = 0;
+            CU(c, rt_launch_render(Q, fr->kernel_variant, s, &l));
+            launches += l;
+            CU(c, cudaEventRecord(c->band_ev[k], s));
+            CU(c, cudaStreamWaitEvent(c->stream, c->band_ev[k], 0));
+        }
+        CU(c, cudaEventRecord(c->evk1, c->stream));    // every band kernel has finished
+        for (int k = 0; k < B; ++k) {
+            const int row_a = (int)((long long)P.tiles_y * k / B), row_b = (int)((long long)P.tiles_y * (k + 1) / B);
+            const size_t y0 = (size_t)row_a * RT_TILE_H, y1 = (size_t)row_b * RT_TILE_H < (size_t)P.H ? (size_t)row_b * RT_TILE_H : (size_t)P.H;
+            CU(c, cudaStreamWaitEvent(c->copy_stream, c->band_ev[k], 0));
+            for (const Out& o : outs) {
+                if (!o.host) continue;
+                const size_t off = y0 * (size_t)P.W * o.bpp, bytes = (y1 - y0) * (size_t)P.W * o.bpp;
+                CU(c, cudaMemcpyAsync((char*)o.host + off, (const char*)o.dev + off, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+            }
+        }
+        CU(c, cudaEventRecord(c->copy_done, c->copy_stream));
+        CU(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));
+        if (pipelined) *pipelined = true;
     } else {
         CU(c, cudaEventRecord(c->evk0, c->stream));
         CU(c, rt_launch_render(P, fr->kernel_variant, c->stream, &launches));
@@ -628,6 +689,24 @@ int rt_render(rt_ctx* c, const rt_frame* fr) {
     c->outputs = outputs;
     c->launches = launches;
     c->frame_valid = true;
+    return RT_OK;
+}
+} // namespace
+
+extern "C" {
+
+int rt_render(rt_ctx* c, const rt_frame* fr) { return render_impl(c, fr, nullptr, nullptr); }
+
+int rt_render_into(rt_ctx* c, const rt_frame* fr, rt_image* img) {
+    if (!img) return fail(c, RT_ERR_ARG, "rt_render_into: NULL image");
+    bool pipelined = false;
+    int rc = render_impl(c, fr, img, &pipelined);
+    if (rc != RT_OK) return rc;
+    if (!pipelined) return rt_download_image(c, img);           // multi-GPU contexts: gather first, then one copy
+    rt_image meta{};                                            // planes are already on their way: fetch counters and times only
+    rc = rt_download_image(c, &meta);
+    if (rc != RT_OK) return rc;
+    img->width = meta.width; img->height = meta.height; img->rays_primary = meta.rays_primary; img->rays_shadow = meta.rays_shadow; img->gpu_ms = meta.gpu_ms;
     return RT_OK;
 }
 

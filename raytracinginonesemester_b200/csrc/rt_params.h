@@ -27,6 +27,7 @@ struct FrameParams {
     // tile sharding
     int tiles_x, tiles_y, rank, world;
     int local_tiles;                // tile slots of this rank (= grid size)
+    int tile_offset;                // first tile slot of this launch (band-pipelined frames launch one kernel per band)
     int chunk_tiles;                // tiles per ownership chunk (see rt_global_tile)
     int packed;                     // 1: planes are this rank's tile-packed buffers (NCCL gather); 0: row-major image
                                     //    (single GPU, or rank 0's image written in place over NVLink peer memory)

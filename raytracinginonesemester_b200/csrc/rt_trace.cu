@@ -16,7 +16,7 @@
 
 namespace {
 
-__device__ __forceinline__ Pixel map_pixel(const FrameParams& P) { return rt_map_pixel(P, (int)blockIdx.x, (int)threadIdx.x); }
+__device__ __forceinline__ Pixel map_pixel(const FrameParams& P) { return rt_map_pixel(P, (int)blockIdx.x + P.tile_offset, (int)threadIdx.x); }
 
 __device__ __forceinline__ void flush_counters(const FrameParams& P, unsigned nprim, unsigned nshadow) {
     for (int o = 16; o > 0; o >>= 1) {
@@ -317,7 +317,8 @@ k_render_packet(const __grid_constant__ FrameParams P) {
             }
             for (int l = 0; l < P.num_lights; ++l) {     // warp-uniform loop
                 bool need = false, lit = false, blocked = false;
-                {
+                f3 direct = mk3(0.f, 0.f, 0.f);          // this light's contribution, evaluated BEFORE the shadow trace so
+                {                                        // that only three floats stay live across it (no third surface rebuild)
                     Ray sray; sray.o = mk3(0.f, 0.f, 0.f); sray.d = mk3(0.f, 0.f, 1.f);
                     float dist = 0.f;
                     if (hit) {
@@ -326,19 +327,15 @@ k_render_packet(const __grid_constant__ FrameParams P) {
                         rt_surface_hw2(P, rt_make_ray(P.cam, MODE, x, y, jx, jy), h, sf);
                         lit = rt_light_setup_hw2(sf, P.lights[l], L, NdotL, need, sray, dist);
                         need = need && lit && P.shadows;
+                        if (lit) {
+                            sf.Lo = mk3(0.f, 0.f, 0.f);
+                            direct = rt_light_direct_hw2(sf, P.lights[l], L, NdotL);
+                        }
                     }
                     blocked = packet_trace<MODE, STATS, FAST>(P.nodes, P.geom, P.num_tris, sray, need, true, dist, &st).blocked;
                 }
                 if (need) ++nshadow;
-                if (lit && !blocked) {
-                    launder(h, x, y);
-                    Surface sf; f3 L; float NdotL, dist; bool n2; Ray sr;
-                    rt_surface_hw2(P, rt_make_ray(P.cam, MODE, x, y, jx, jy), h, sf);
-                    rt_light_setup_hw2(sf, P.lights[l], L, NdotL, n2, sr, dist);
-                    sf.Lo = Lo;
-                    rt_light_finish_hw2(sf, P.lights[l], L, NdotL);
-                    Lo = sf.Lo;
-                }
+                if (lit && !blocked) Lo = xadd3(Lo, direct);
             }
             if (live) color = hit ? rt_radiance_hw2(Lo) : rt_radiance_hw2(ld3(P.miss));
         }

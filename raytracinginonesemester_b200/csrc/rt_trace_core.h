@@ -182,11 +182,13 @@ RT_HD bool rt_light_setup_hw2(const Surface& s, const rt_light& light, f3& L, fl
     }
     return true;
 }
-RT_HD void rt_light_finish_hw2(Surface& s, const rt_light& light, f3 L, float NdotL) {
+RT_HD f3 rt_light_direct_hw2(const Surface& s, const rt_light& light, f3 L, float NdotL) {
     const f3 f = rt_brdf_hw2(s.mat, s.normal, s.V, L);
     const f3 radiance = xmuls(ld3(light.color), (float)light.intensity);
-    const f3 direct = xmuls(xmulv(radiance, f), NdotL);
-    s.Lo = xadd3(s.Lo, direct);
+    return xmuls(xmulv(radiance, f), NdotL);
+}
+RT_HD void rt_light_finish_hw2(Surface& s, const rt_light& light, f3 L, float NdotL) {
+    s.Lo = xadd3(s.Lo, rt_light_direct_hw2(s, light, L, NdotL));
 }
 // TraceRayIterative epilogue at depth 1 (query.h:186-191, 219)
 RT_HD f3 rt_radiance_hw2(f3 direct) {

@@ -5,6 +5,8 @@ Bars (BASELINE.json north_star): closest-hit triangle id bit-exact on >= 99.99 %
 the reference CPU path (mismatches only at exact-t ties), hit t within 1e-5 relative, 8-bit image
 within 1 LSB.  Against the canonical oracle (min t, then min id over the reference's
 intersectTriangle on every triangle) the bar is bit-exact ids, t and float rgb."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -427,6 +429,27 @@ def test_c5_scene_at_reduced_frame(renderer):
     step = 54
     orc = orclib.oracle_render(sc, scenes.terrain_frame(W, H, spp=16, outputs=ALL), bvh=bvh, row_begin=5, row_step=step, want=("rgb8", "tri_id", "t"))
     _strided_bar(a, orc, slice(5, H, step), "c5 scene")
+
+
+def test_render_into_equals_render_plus_download(renderer, frog_scene):
+    """rt_render_into (band-pipelined render + copy) must deliver exactly what rt_render + rt_download_image deliver,
+    for every plane, odd sizes, frames smaller than a band, all modes and multi-sample frames."""
+    renderer.upload_scene(frog_scene)
+    frames = [scenes.frog_frame(333, 201, filling=True, outputs=ALL), scenes.frog_frame(64, 8, filling=True, outputs=ALL),
+              scenes.frog_frame(17, 100, filling=True, outputs=A.RT_OUT_RGB8 | A.RT_OUT_T), scenes.hw1_frame(200, 120, accel=A.RT_ACCEL_BVH, outputs=ALL),
+              scenes.frog_frame(1920, 1080, filling=True, outputs=A.RT_OUT_RGB8)]
+    frames[0].spp = 3; frames[0].jitter = api.jitter_table(3, 42, True)
+    for fr in frames:
+        a = run(renderer, fr)
+        b = renderer.render_into(fr)
+        assert (a["rays_primary"], a["rays_shadow"]) == (b["rays_primary"], b["rays_shadow"])
+        for k in ("rgb", "rgb8", "tri_id", "t"):
+            if k in a:
+                assert np.array_equal(a[k], b[k]), (fr.width, fr.height, k)
+    fr = scenes.frog_frame(64, 64, filling=True, outputs=A.RT_OUT_RGB8)
+    img = A.rt_image(); buf = np.zeros((64, 64), np.float32); img.t = buf.ctypes.data_as(A.f32p)
+    f = fr.c_struct()
+    assert renderer.lib.rt_render_into(renderer.ctx, C.byref(f), C.byref(img)) == A.RT_ERR_STATE      # plane not requested
 
 
 # ----------------------------------------------------------------------- error behaviour ----
