@@ -95,6 +95,7 @@ struct rt_ctx {
     bool peer = false;                            // mode in effect
     unsigned* flags = nullptr;                    // rank 0: own allocation; others: IPC mapping of rank 0's
     unsigned* peer_err = nullptr;                 // local: set by a flag wait that timed out
+    unsigned* chunk_count = nullptr;              // local: finished tile slots per ownership chunk (rt_render_into)
     void* peer_img[4] = {nullptr, nullptr, nullptr, nullptr};   // ranks != 0: mapped rank-0 planes (rgb, rgb8, id, t)
     size_t gather_cap[4] = {0, 0, 0, 0};          // every rank tracks rank 0's plane capacities identically
     std::vector<void*> retired;                   // rank 0: outgrown exported planes, freed at teardown
@@ -186,7 +187,7 @@ int all_min(rt_ctx* c, int v, int* out) {                     // also a true bar
     return RT_OK;
 }
 
-const size_t kFlagBytes = sizeof(unsigned) * RT_PEER_FLAG_STRIDE * 16;   // [0]: ready, [r*STRIDE]: done by rank r
+const size_t kFlagBytes = sizeof(unsigned) * RT_PEER_CHUNK_FLAG(RT_PEER_MAX_RANKS, 0);   // layout: rt_kernels.h
 const unsigned long long kPeerTimeoutNs = 20ull * 1000000000ull;
 
 // Drops every peer mapping / exported allocation.  `collective`: all ranks are here and the communicator is
@@ -228,6 +229,7 @@ int peer_setup(rt_ctx* c) {
     c->peer = false;
     if (c->world <= 1) return RT_OK;
     if (!c->peer_err) { CU(c, cudaMalloc(&c->peer_err, sizeof(unsigned))); CU(c, cudaMemset(c->peer_err, 0, sizeof(unsigned))); }
+    if (!c->chunk_count) { CU(c, cudaMalloc(&c->chunk_count, sizeof(unsigned) * RT_PEER_MAX_CHUNKS)); CU(c, cudaMemset(c->chunk_count, 0, sizeof(unsigned) * RT_PEER_MAX_CHUNKS)); }
     cudaIpcMemHandle_t h; memset(&h, 0, sizeof h);
     int ok = 1;
     if (c->rank == 0) {
@@ -332,6 +334,7 @@ int rt_destroy(rt_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     peer_teardown(c, true);
     if (c->peer_err) cudaFree(c->peer_err);
+    if (c->chunk_count) cudaFree(c->chunk_count);
     if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
     free_scene(c);
     c->xfer.release();
@@ -588,6 +591,12 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
         // Frame k may overwrite rank 0's image only once rank 0 is done with frame k-1 (its downloads are
         // stream-ordered before this point): rank 0 publishes `ready = k`, the others wait for it.
         const unsigned seq = ++c->seq;
+        const int F = c->chunks_per_rank > 0 ? c->chunks_per_rank : RT_DEFAULT_CHUNKS_PER_RANK;
+        const bool chunked = into != nullptr && F <= RT_PEER_MAX_CHUNKS;     // rt_render_into (collective): publish chunk by chunk
+        if (chunked) {
+            P.chunk_flags = c->flags + RT_PEER_CHUNK_FLAG(c->rank, 0); P.chunk_count = c->chunk_count; P.seq = seq;
+            if (c->rank == 0) { int rc = ensure_band_resources(c); if (rc != RT_OK) return rc; }
+        }
         if (c->rank == 0) CU(c, rt_launch_flag_set(c->flags, seq, c->stream));
         else CU(c, rt_launch_flag_wait(c->flags, RT_PEER_FLAG_STRIDE, 1, seq, kPeerTimeoutNs, c->peer_err, c->stream));
         ++launches;
@@ -596,10 +605,40 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
         CU(c, rt_launch_render(P, fr->kernel_variant, c->stream, &l));
         CU(c, cudaEventRecord(c->evk1, c->stream));
         launches += l;
+        if (chunked && c->rank == 0) {
+            // Rank 0 copies the image to the host group by group: group j = chunk j of every rank = a contiguous range of
+            // row-major tiles; once all its flags arrived, the pixel rows it completes go out while later chunks render.
+            struct Out { void* host; uint32_t bit; size_t bpp; const void* dev; const char* name; };
+            const Out outs[4] = {{into->rgb, RT_OUT_RGB_F32, 12, P.rgb, "rgb"}, {into->rgb8, RT_OUT_RGB8, 3, P.rgb8, "rgb8"},
+                                 {into->tri_id, RT_OUT_TRI_ID, 4, P.tri_id, "tri_id"}, {into->t, RT_OUT_T, 4, P.t, "t"}};
+            for (const Out& o : outs)
+                if (o.host && !(outputs & o.bit)) return fail(c, RT_ERR_STATE, "rt_render_into: plane '%s' was not requested in rt_frame.outputs", o.name);
+            CU(c, cudaStreamWaitEvent(c->copy_stream, c->evk0, 0));
+            size_t y_prev = 0;
+            for (int j = 0; j < F; ++j) {
+                CU(c, rt_launch_flag_wait(c->flags + RT_PEER_CHUNK_FLAG(0, j), RT_PEER_MAX_CHUNKS * RT_PEER_FLAG_STRIDE, c->world, seq,
+                                          kPeerTimeoutNs, c->peer_err, c->copy_stream));
+                ++launches;
+                long long tiles_done = (long long)(j + 1) * c->world * P.chunk_tiles;
+                if (tiles_done > total_tiles) tiles_done = total_tiles;
+                size_t y_end = (j == F - 1) ? (size_t)P.H : (size_t)(tiles_done / P.tiles_x) * RT_TILE_H;
+                if (y_end > (size_t)P.H) y_end = (size_t)P.H;
+                if (y_end <= y_prev) continue;
+                for (const Out& o : outs) {
+                    if (!o.host) continue;
+                    const size_t off = y_prev * (size_t)P.W * o.bpp, bytes = (y_end - y_prev) * (size_t)P.W * o.bpp;
+                    CU(c, cudaMemcpyAsync((char*)o.host + off, (const char*)o.dev + off, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+                }
+                y_prev = y_end;
+            }
+            CU(c, cudaEventRecord(c->copy_done, c->copy_stream));
+            if (pipelined) *pipelined = true;
+        }
         // completion: one flag word per rank in rank 0's memory, written after the frame kernel
         if (c->rank != 0) CU(c, rt_launch_flag_set(c->flags + (size_t)c->rank * RT_PEER_FLAG_STRIDE, seq, c->stream));
         else CU(c, rt_launch_flag_wait(c->flags + RT_PEER_FLAG_STRIDE, RT_PEER_FLAG_STRIDE, c->world - 1, seq, kPeerTimeoutNs, c->peer_err, c->stream));
         ++launches;
+        if (chunked && c->rank == 0) CU(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));
     } else if (into && c->world == 1 && !dbg_shard && P.tiles_y >= 2) {
         int rc = ensure_band_resources(c);
         if (rc != RT_OK) return rc;

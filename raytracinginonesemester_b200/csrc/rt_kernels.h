@@ -21,7 +21,12 @@ cudaError_t rt_launch_unpack(const FrameParams& fp, int src_rank, const float* r
                              const int32_t* tri_id, const float* t, float* o_rgb, uint8_t* o_rgb8,
                              int32_t* o_tri_id, float* o_t, cudaStream_t stream);
 // Completion flags of the peer-store gather (see k_flag_set / k_flag_wait in rt_trace.cu).
-#define RT_PEER_FLAG_STRIDE 16            // one 64-byte line per rank
+#define RT_PEER_FLAG_STRIDE 16            // one 64-byte line per flag
+#define RT_PEER_MAX_RANKS 8
+#define RT_PEER_MAX_CHUNKS 16            // ownership chunks per rank that rt_render_into can pipeline
+// flag block layout (uints, each flag on its own line): [0] ready, [r] frame done by rank r (r >= 1),
+// [16 + r*RT_PEER_MAX_CHUNKS + j] chunk j of rank r done
+#define RT_PEER_CHUNK_FLAG(r, j) ((size_t)(16 + (r) * RT_PEER_MAX_CHUNKS + (j)) * RT_PEER_FLAG_STRIDE)
 cudaError_t rt_launch_flag_set(unsigned* flag, unsigned seq, cudaStream_t stream);
 cudaError_t rt_launch_flag_wait(const unsigned* flags, int stride, int n, unsigned seq, unsigned long long timeout_ns,
                                 unsigned* err, cudaStream_t stream);

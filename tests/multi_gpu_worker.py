@@ -52,6 +52,23 @@ def main():
                     print("MISMATCH", W, H, spp, k, int((got[k] != ref[k]).sum()))
                     ok = False
             assert int(cnt[1].item()) == ref["rays_shadow"]
+    # rt_render_into: chunk-pipelined delivery + download (peer gather), plain gather + download (NCCL gather)
+    for gm in ("peer", "nccl"):
+        for cpr, (W, H), outs in ((0, (517, 301), ALL), (3, (640, 360), A.RT_OUT_RGB8), (16, (333, 201), ALL), (64, (333, 201), ALL), (1, (40, 9), ALL)):
+            r.set_sharding(cpr)
+            r.set_gather(want_mode[gm])
+            fr = scenes.terrain_frame(W, H, outputs=outs)
+            for rep in range(3):
+                got = r.render_into(fr)
+            if rank == 0:
+                solo = api.Renderer(local_rank)
+                solo.upload_scene(sc)
+                ref = solo.render_into(fr)
+                solo.close()
+                for k in ("tri_id", "t", "rgb", "rgb8"):
+                    if k in ref and not np.array_equal(got[k], ref[k]):
+                        print("MISMATCH render_into", gm, cpr, W, H, k, int((got[k] != ref[k]).sum()))
+                        ok = False
     # back-to-back frames without a download in between (what bench.py's timed loop does), then one download
     r.set_sharding(0)
     r.set_gather(A.RT_GATHER_AUTO)
