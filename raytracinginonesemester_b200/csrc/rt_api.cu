@@ -6,6 +6,7 @@
 // RT_ERR_CUDA.
 #include "rt_kernels.h"
 
+#include <cuda.h>           // driver API types only; cuStreamWaitValue32 is fetched with cudaGetDriverEntryPoint
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>   // types and prototypes only: the library is resolved at run time, see NcclApi below
@@ -51,6 +52,19 @@ struct NcclApi {
 };
 NcclApi& nccl() { static NcclApi api; return api; }
 
+// Stream-ordered wait on a 32-bit word in device memory (no SM resources, unlike a spinning kernel, so it cannot queue
+// behind the frame kernel's pending blocks).  NULL when the driver does not offer it: callers fall back to k_flag_wait.
+typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamWaitValue32Fn stream_wait_value32() {
+    static StreamWaitValue32Fn fn = []() -> StreamWaitValue32Fn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; }
+        return (StreamWaitValue32Fn)p;
+    }();
+    return fn;
+}
+
 struct Plane {
     void* p = nullptr; size_t cap = 0;
     cudaError_t reserve(size_t bytes) {
@@ -95,14 +109,13 @@ struct rt_ctx {
     bool peer = false;                            // mode in effect
     unsigned* flags = nullptr;                    // rank 0: own allocation; others: IPC mapping of rank 0's
     unsigned* peer_err = nullptr;                 // local: set by a flag wait that timed out
-    unsigned* chunk_count = nullptr;              // local: finished tile slots per ownership chunk (rt_render_into)
     void* peer_img[4] = {nullptr, nullptr, nullptr, nullptr};   // ranks != 0: mapped rank-0 planes (rgb, rgb8, id, t)
     size_t gather_cap[4] = {0, 0, 0, 0};          // every rank tracks rank 0's plane capacities identically
     std::vector<void*> retired;                   // rank 0: outgrown exported planes, freed at teardown
     unsigned seq = 0;                             // frame sequence number of the peer protocol
     int chunks_per_rank = 0;                      // tile ownership bands per rank (0 = RT_DEFAULT_CHUNKS_PER_RANK)
     // rt_render_into: band-pipelined render + download (kernels of later bands overlap the D2H copy of earlier ones)
-    cudaStream_t band_stream[RT_BAND_STREAMS] = {}; cudaStream_t copy_stream = nullptr;
+    cudaStream_t band_stream[RT_BAND_STREAMS] = {}; cudaStream_t copy_stream = nullptr, sig_stream = nullptr;
     cudaEvent_t band_ev[RT_BANDS] = {}; cudaEvent_t copy_done = nullptr;
     int dbg_rank = 0, dbg_world = 0;              // rt_debug_set_shard: render one rank's share on a single GPU (timing only)
 };
@@ -229,7 +242,6 @@ int peer_setup(rt_ctx* c) {
     c->peer = false;
     if (c->world <= 1) return RT_OK;
     if (!c->peer_err) { CU(c, cudaMalloc(&c->peer_err, sizeof(unsigned))); CU(c, cudaMemset(c->peer_err, 0, sizeof(unsigned))); }
-    if (!c->chunk_count) { CU(c, cudaMalloc(&c->chunk_count, sizeof(unsigned) * RT_PEER_MAX_CHUNKS)); CU(c, cudaMemset(c->chunk_count, 0, sizeof(unsigned) * RT_PEER_MAX_CHUNKS)); }
     cudaIpcMemHandle_t h; memset(&h, 0, sizeof h);
     int ok = 1;
     if (c->rank == 0) {
@@ -334,7 +346,6 @@ int rt_destroy(rt_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     peer_teardown(c, true);
     if (c->peer_err) cudaFree(c->peer_err);
-    if (c->chunk_count) cudaFree(c->chunk_count);
     if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
     free_scene(c);
     c->xfer.release();
@@ -343,6 +354,7 @@ int rt_destroy(rt_ctx* c) {
     for (Plane* p : planes) p->release();
     for (cudaStream_t s : c->band_stream) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->sig_stream) { cudaStreamSynchronize(c->sig_stream); cudaStreamDestroy(c->sig_stream); }
     for (cudaEvent_t e : c->band_ev) if (e) cudaEventDestroy(e);
     if (c->copy_done) cudaEventDestroy(c->copy_done);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -497,7 +509,14 @@ namespace {
 int ensure_band_resources(rt_ctx* c) {
     if (c->copy_stream) return RT_OK;
     for (cudaStream_t& s : c->band_stream) CU(c, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    // The copy stream also runs the one-block flag waits of the multi-GPU path: highest priority, so that such a block is
+    // dispatched as soon as any SM slot frees up instead of queueing behind the frame kernel's pending blocks.
+    int prio_lo = 0, prio_hi = 0;
+    CU(c, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CU(c, cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, prio_hi));
+    // Chunk-completion flags are written by one-thread kernels: on a high-priority stream too, or they would only get an
+    // SM slot after the pending blocks of the following chunk kernels.
+    CU(c, cudaStreamCreateWithPriority(&c->sig_stream, cudaStreamNonBlocking, prio_hi));
     for (cudaEvent_t& e : c->band_ev) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CU(c, cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
     return RT_OK;
@@ -592,19 +611,38 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
         // stream-ordered before this point): rank 0 publishes `ready = k`, the others wait for it.
         const unsigned seq = ++c->seq;
         const int F = c->chunks_per_rank > 0 ? c->chunks_per_rank : RT_DEFAULT_CHUNKS_PER_RANK;
-        const bool chunked = into != nullptr && F <= RT_PEER_MAX_CHUNKS;     // rt_render_into (collective): publish chunk by chunk
-        if (chunked) {
-            P.chunk_flags = c->flags + RT_PEER_CHUNK_FLAG(c->rank, 0); P.chunk_count = c->chunk_count; P.seq = seq;
-            if (c->rank == 0) { int rc = ensure_band_resources(c); if (rc != RT_OK) return rc; }
-        }
+        // rt_render_into (collective): every rank renders its ownership chunks as separate kernels spread over a few streams
+        // (their tails overlap) and publishes a flag per finished chunk, so that rank 0 can copy finished rows to the host early
+        const bool chunked = into != nullptr && F <= RT_BANDS && F <= RT_PEER_MAX_CHUNKS;
+        if (chunked) { int rc = ensure_band_resources(c); if (rc != RT_OK) return rc; }
         if (c->rank == 0) CU(c, rt_launch_flag_set(c->flags, seq, c->stream));
         else CU(c, rt_launch_flag_wait(c->flags, RT_PEER_FLAG_STRIDE, 1, seq, kPeerTimeoutNs, c->peer_err, c->stream));
         ++launches;
         int l = 0;
         CU(c, cudaEventRecord(c->evk0, c->stream));
-        CU(c, rt_launch_render(P, fr->kernel_variant, c->stream, &l));
+        if (chunked) {
+            for (int j = 0; j < F; ++j) {
+                FrameParams Q = P;
+                Q.tile_offset = j * P.chunk_tiles; Q.local_tiles = P.chunk_tiles;
+                cudaStream_t sj = c->band_stream[j % RT_BAND_STREAMS];
+                CU(c, cudaStreamWaitEvent(sj, c->evk0, 0));
+                CU(c, rt_launch_render(Q, fr->kernel_variant, sj, &l));
+                launches += l;
+                CU(c, cudaEventRecord(c->band_ev[j], sj));
+                CU(c, cudaStreamWaitEvent(c->sig_stream, c->band_ev[j], 0));
+                CU(c, rt_launch_flag_set(c->flags + RT_PEER_CHUNK_FLAG(c->rank, j), seq, c->sig_stream));
+                ++launches;
+                CU(c, cudaStreamWaitEvent(c->stream, c->band_ev[j], 0));
+            }
+        } else {
+            CU(c, rt_launch_render(P, fr->kernel_variant, c->stream, &l));
+            launches += l;
+        }
         CU(c, cudaEventRecord(c->evk1, c->stream));
-        launches += l;
+        if (chunked) {                                  // the frame is over for this rank when its last chunk flag is out
+            CU(c, cudaEventRecord(c->copy_done, c->sig_stream));
+            CU(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));
+        }
         if (chunked && c->rank == 0) {
             // Rank 0 copies the image to the host group by group: group j = chunk j of every rank = a contiguous range of
             // row-major tiles; once all its flags arrived, the pixel rows it completes go out while later chunks render.
@@ -616,9 +654,15 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
             CU(c, cudaStreamWaitEvent(c->copy_stream, c->evk0, 0));
             size_t y_prev = 0;
             for (int j = 0; j < F; ++j) {
-                CU(c, rt_launch_flag_wait(c->flags + RT_PEER_CHUNK_FLAG(0, j), RT_PEER_MAX_CHUNKS * RT_PEER_FLAG_STRIDE, c->world, seq,
-                                          kPeerTimeoutNs, c->peer_err, c->copy_stream));
-                ++launches;
+                if (StreamWaitValue32Fn wait32 = stream_wait_value32()) {
+                    for (int r = 0; r < c->world; ++r)
+                        if (wait32((CUstream)c->copy_stream, (CUdeviceptr)(c->flags + RT_PEER_CHUNK_FLAG(r, j)), seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+                            return fail(c, RT_ERR_CUDA, "cuStreamWaitValue32 failed");
+                } else {
+                    CU(c, rt_launch_flag_wait(c->flags + RT_PEER_CHUNK_FLAG(0, j), RT_PEER_MAX_CHUNKS * RT_PEER_FLAG_STRIDE, c->world, seq,
+                                              kPeerTimeoutNs, c->peer_err, c->copy_stream));
+                    ++launches;
+                }
                 long long tiles_done = (long long)(j + 1) * c->world * P.chunk_tiles;
                 if (tiles_done > total_tiles) tiles_done = total_tiles;
                 size_t y_end = (j == F - 1) ? (size_t)P.H : (size_t)(tiles_done / P.tiles_x) * RT_TILE_H;
@@ -638,7 +682,12 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
         if (c->rank != 0) CU(c, rt_launch_flag_set(c->flags + (size_t)c->rank * RT_PEER_FLAG_STRIDE, seq, c->stream));
         else CU(c, rt_launch_flag_wait(c->flags + RT_PEER_FLAG_STRIDE, RT_PEER_FLAG_STRIDE, c->world - 1, seq, kPeerTimeoutNs, c->peer_err, c->stream));
         ++launches;
-        if (chunked && c->rank == 0) CU(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));
+        if (chunked && c->rank == 0) {
+            // had the wait above timed out (a rank died), release the stream-ordered chunk waits so that nothing hangs
+            CU(c, rt_launch_flag_unblock(c->peer_err, c->flags + RT_PEER_CHUNK_FLAG(0, 0), RT_PEER_FLAG_STRIDE, RT_PEER_MAX_RANKS * RT_PEER_MAX_CHUNKS, seq, c->stream));
+            ++launches;
+            CU(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));
+        }
     } else if (into && c->world == 1 && !dbg_shard && P.tiles_y >= 2) {
         int rc = ensure_band_resources(c);
         if (rc != RT_OK) return rc;

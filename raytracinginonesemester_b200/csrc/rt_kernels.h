@@ -30,3 +30,4 @@ cudaError_t rt_launch_unpack(const FrameParams& fp, int src_rank, const float* r
 cudaError_t rt_launch_flag_set(unsigned* flag, unsigned seq, cudaStream_t stream);
 cudaError_t rt_launch_flag_wait(const unsigned* flags, int stride, int n, unsigned seq, unsigned long long timeout_ns,
                                 unsigned* err, cudaStream_t stream);
+cudaError_t rt_launch_flag_unblock(const unsigned* err, unsigned* flags, int stride, int n, unsigned seq, cudaStream_t stream);

@@ -35,10 +35,6 @@ struct FrameParams {
     float* rgb; uint8_t* rgb8; int32_t* tri_id; float* t;
     unsigned long long* counters;   // [0] primary rays, [1] shadow rays, [2] node visits, [3] triangle tests (stats variants)
     int fast_slab;                  // 1: ray origins are close enough to the scene for rt_slab_fma (host decides)
-    // per-chunk completion signalling (multi-GPU rt_render_into): the last block of ownership chunk j publishes `seq`
-    // in chunk_flags[j * 16] (rank 0's memory, over NVLink for the other ranks) so that rank 0 can start copying the
-    // finished rows to the host while later chunks are still rendering.  NULL = off.
-    unsigned* chunk_flags; unsigned* chunk_count; unsigned seq;
 };
 
 struct BuildParams {

@@ -29,25 +29,6 @@ __device__ __forceinline__ void flush_counters(const FrameParams& P, unsigned np
     }
 }
 
-// Block epilogue of every frame kernel: counts the finished tile slots of the ownership chunk and lets the last one
-// publish the chunk (see FrameParams::chunk_flags).  Every thread fences its own pixel stores at system scope first.
-__device__ __forceinline__ void signal_chunk(const FrameParams& P) {
-    if (P.chunk_flags == nullptr) return;
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int j = ((int)blockIdx.x + P.tile_offset) / P.chunk_tiles;
-        __threadfence_system();
-        const unsigned done = atomicAdd(&P.chunk_count[j], 1u);
-        if (done == (unsigned)P.chunk_tiles - 1u) {
-            P.chunk_count[j] = 0u;                                   // re-armed for the next frame
-            __threadfence_system();
-            *((volatile unsigned*)(P.chunk_flags + (size_t)j * RT_PEER_FLAG_STRIDE)) = P.seq;
-            __threadfence_system();
-        }
-    }
-}
-
 // ------------------------------------------------------------------- BVH kernel ----
 template <int MODE, bool STATS>
 __global__ void __launch_bounds__(RT_BLOCK_THREADS)
@@ -81,7 +62,6 @@ k_render_bvh(const __grid_constant__ FrameParams P) {
             atomicAdd(&P.counters[5], (unsigned long long)nt);
         }
     }
-    signal_chunk(P);
 }
 
 // ------------------------------------------------------------ brute-force kernel ----
@@ -178,7 +158,6 @@ k_render_brute(const __grid_constant__ FrameParams P) {
     }
     if (px.inside) rt_write_pixel(P, px.out, accum, first);
     flush_counters(P, nprim, nshadow);
-    signal_chunk(P);
 }
 
 // ------------------------------------------------------------ warp-packet kernel ----
@@ -382,7 +361,6 @@ k_render_packet(const __grid_constant__ FrameParams P) {
             atomicAdd(&P.counters[5], (unsigned long long)st.wtris);    // one 48-byte triangle block per warp test
         }
     }
-    signal_chunk(P);
 }
 
 // -------------------------------------------------------------------- tile unpack ----
@@ -426,8 +404,19 @@ __global__ void k_flag_wait(const volatile unsigned* flags, int stride, int n, u
     __threadfence_system();
 }
 
+// After a timed-out wait: release every stream-ordered wait on the chunk flags (cuStreamWaitValue32 has no timeout).
+__global__ void k_flag_unblock(const unsigned* err, volatile unsigned* flags, int stride, int n, unsigned seq) {
+    if (*err == 0u) return;
+    for (int i = (int)threadIdx.x; i < n; i += (int)blockDim.x) flags[(size_t)i * stride] = seq;
+    __threadfence_system();
+}
+
 } // namespace
 
+cudaError_t rt_launch_flag_unblock(const unsigned* err, unsigned* flags, int stride, int n, unsigned seq, cudaStream_t stream) {
+    k_flag_unblock<<<1, 64, 0, stream>>>(err, flags, stride, n, seq);
+    return cudaGetLastError();
+}
 cudaError_t rt_launch_flag_set(unsigned* flag, unsigned seq, cudaStream_t stream) {
     k_flag_set<<<1, 1, 0, stream>>>(flag, seq);
     return cudaGetLastError();
