@@ -9,6 +9,7 @@ RT_OUT_RGB_F32, RT_OUT_RGB8, RT_OUT_TRI_ID, RT_OUT_T = 1, 2, 4, 8
 RT_QUANT_PPM_LROUND, RT_QUANT_PPM_GAMMA2, RT_QUANT_HW1_TRUNC, RT_QUANT_HW2_TRUNC, RT_QUANT_CPU_TRUNC = 0, 1, 2, 3, 4
 RT_BUILD_DEFAULT, RT_BUILD_NO_BVH = 0, 1
 RT_VARIANT_DEFAULT, RT_VARIANT_PACKET_OCC6, RT_VARIANT_PACKET_OCC10, RT_VARIANT_PACKET_EXACT_SLAB, RT_VARIANT_PER_RAY = 0, 1, 2, 3, 10
+RT_VARIANT_PACKET_PREFETCH, RT_VARIANT_PACKET_PIXEL_MAJOR = 4, 5
 RT_VARIANT_STATS, RT_VARIANT_PER_RAY_STATS = 100, 110
 RT_GATHER_AUTO, RT_GATHER_NCCL, RT_GATHER_PEER = 0, 1, 2
 

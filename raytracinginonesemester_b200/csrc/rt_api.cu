@@ -551,6 +551,9 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
     P.cam = fr->cam; P.mode = fr->mode; P.accel = fr->accel; P.W = fr->width; P.H = fr->height; P.spp = fr->spp;
     P.max_depth = fr->max_depth; P.diffuse_bounce = fr->diffuse_bounce ? 1 : 0; P.shadows = fr->shadows; P.quantiser = fr->quantiser; P.num_lights = fr->num_lights;
     P.num_materials = c->num_materials; P.has_normals = c->has_normals ? 1 : 0;
+    P.sample_group = 1;
+    while (P.sample_group < 32 && fr->spp % (2 * P.sample_group) == 0) P.sample_group *= 2;
+    if (fr->kernel_variant != RT_VARIANT_DEFAULT && fr->kernel_variant != RT_VARIANT_STATS) P.sample_group = 1;   // experimental variants: pixel-major
     memcpy(P.miss, fr->miss_color, sizeof P.miss);
     P.nodes = c->nodes; P.geom = c->geom; P.shade = c->shade; P.num_tris = c->num_tris; P.materials = c->materials;
     P.tiles_x = (P.W + RT_TILE_W - 1) / RT_TILE_W; P.tiles_y = (P.H + RT_TILE_H - 1) / RT_TILE_H;

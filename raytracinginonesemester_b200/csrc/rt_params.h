@@ -35,6 +35,7 @@ struct FrameParams {
     float* rgb; uint8_t* rgb8; int32_t* tri_id; float* t;
     unsigned long long* counters;   // [0] primary rays, [1] shadow rays, [2] node visits, [3] triangle tests (stats variants)
     int fast_slab;                  // 1: ray origins are close enough to the scene for rt_slab_fma (host decides)
+    int sample_group;               // packet kernel: samples of one pixel traced side by side (power of two dividing spp, <= 32)
 };
 
 struct BuildParams {

@@ -196,7 +196,7 @@ struct WarpStack {
 // `any` is a run-time, warp-uniform flag so that primary and shadow queries share one copy of the
 // loop (the first packet kernel spent 15 % of its issue slots waiting on instruction fetch).
 // FAST selects the fused slab test (rt_slab_fma).
-template <int MODE, bool STATS, bool FAST>
+template <int MODE, bool STATS, bool FAST, bool PF = false>
 __device__ __noinline__ TraceResult packet_trace(const BvhNode* __restrict__ nodes, const TriBlock* __restrict__ geom, const uint32_t num_tris,
                                                  const Ray ray, bool live, const bool any, float tlimit, TraceStats* st) {
     Hit best; rt_hit_reset(best);
@@ -233,7 +233,12 @@ __device__ __noinline__ TraceResult packet_trace(const BvhNode* __restrict__ nod
             const bool a0 = __any_sync(FULLMASK, h0 && live), a1 = __any_sync(FULLMASK, h1 && live);
             if (a0 && a1) {
                 const bool c1first = (dirneg >> ((unsigned)q.q3.w >> 30)) & 1u;
-                stk.push((uint32_t)(c1first ? q.q3.x : q.q3.y), lane);
+                const int far = c1first ? q.q3.x : q.q3.y;
+                stk.push((uint32_t)far, lane);
+                if (PF) {      // the deferred child will be popped later: start pulling its line into L1 now
+                    const void* a = far >= 0 ? (const void*)(nodes + far) : (const void*)(geom + rt_leaf_first(far));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(a));
+                }
                 cur = c1first ? q.q3.y : q.q3.x;
                 continue;
             }
@@ -281,27 +286,40 @@ __device__ __forceinline__ void launder(Hit& h, int& x, int& y) {
     asm volatile("" : "+f"(h.t), "+f"(h.u), "+f"(h.v), "+r"(h.slot), "+r"(x), "+r"(y));
 }
 
-template <int MODE, bool STATS, bool FAST, int MINB>
+template <int MODE, bool STATS, bool FAST, int MINB, bool PF = false, bool GROUPED = false>
 __global__ void __launch_bounds__(RT_BLOCK_THREADS, MINB)
 k_render_packet(const __grid_constant__ FrameParams P) {
     const Pixel px = map_pixel(P);
-    int x = px.inside ? px.x : 0, y = px.inside ? px.y : 0;
     unsigned nprim = 0, nshadow = 0;
     TraceStats st{0, 0, 0, 0, 0};
     f3 accum = mk3(0.f, 0.f, 0.f);
-    for (int s = 0; s < P.spp; ++s) {
+    // Sample-major packets: with G = P.sample_group samples of one pixel side by side in the warp, a pass traces
+    // 32/G neighbouring pixels x G samples — a footprint of 32/G pixels instead of 8x4, so the rays of a packet stay
+    // together much deeper into the tree when spp > 1 (G == 1: one sample of each of the warp's 32 pixels, as before).
+    // Lane q owns pixel q of the warp's 8x4 patch and sums its samples in sample order, like the reference's loop.
+    // GROUPED == false is the G == 1 instance without the shuffles (host picks the instance from P.sample_group).
+    const int lane = threadIdx.x & 31;
+    const int G = GROUPED ? P.sample_group : 1, gsh = GROUPED ? __ffs(G) - 1 : 0, PP = 32 >> gsh, chunks = P.spp >> gsh;
+    for (int pass = 0; pass < P.spp; ++pass) {
+        const int pb = GROUPED ? pass / chunks : 0, pc = pass - pb * chunks;
+        const int qi = GROUPED ? pb * PP + (lane >> gsh) : lane;
+        const int s = GROUPED ? (pc << gsh) + (lane & (G - 1)) : pass;
+        const bool inside = GROUPED ? __shfl_sync(FULLMASK, (int)px.inside, qi) != 0 : px.inside;
+        int x = GROUPED ? __shfl_sync(FULLMASK, px.x, qi) : px.x, y = GROUPED ? __shfl_sync(FULLMASK, px.y, qi) : px.y;
+        if (!inside) { x = 0; y = 0; }
+        const unsigned long long out_q = GROUPED ? __shfl_sync(FULLMASK, (unsigned long long)px.out, qi) : (unsigned long long)px.out;
         const float jx = P.jitter ? __ldg(P.jitter + 2 * s) : 0.0f;
         const float jy = P.jitter ? __ldg(P.jitter + 2 * s + 1) : 0.0f;
-        const bool live = px.inside && (MODE == RT_MODE_HW1 || P.max_depth > 0);
+        const bool live = inside && (MODE == RT_MODE_HW1 || P.max_depth > 0);
         Hit h; rt_hit_reset(h);
         {
             const Ray ray = rt_make_ray(P.cam, MODE, x, y, jx, jy);
-            h = packet_trace<MODE, STATS, FAST>(P.nodes, P.geom, P.num_tris, ray, live, false, 0.f, &st).hit;
+            h = packet_trace<MODE, STATS, FAST, PF>(P.nodes, P.geom, P.num_tris, ray, live, false, 0.f, &st).hit;
         }
         if (live) ++nprim;
-        if (s == 0 && px.inside) {                     // id / t planes describe sample 0
-            if (P.tri_id) P.tri_id[px.out] = h.slot >= 0 ? h.id : -1;
-            if (P.t) P.t[px.out] = h.slot >= 0 ? h.t : -1.0f;
+        if (s == 0 && inside) {                        // id / t planes describe sample 0
+            if (P.tri_id) P.tri_id[out_q] = h.slot >= 0 ? h.id : -1;
+            if (P.t) P.t[out_q] = h.slot >= 0 ? h.t : -1.0f;
         }
         f3 color = mk3(0.f, 0.f, 0.f);
         if (MODE == RT_MODE_HW1) {
@@ -332,14 +350,23 @@ k_render_packet(const __grid_constant__ FrameParams P) {
                             direct = rt_light_direct_hw2(sf, P.lights[l], L, NdotL);
                         }
                     }
-                    blocked = packet_trace<MODE, STATS, FAST>(P.nodes, P.geom, P.num_tris, sray, need, true, dist, &st).blocked;
+                    blocked = packet_trace<MODE, STATS, FAST, PF>(P.nodes, P.geom, P.num_tris, sray, need, true, dist, &st).blocked;
                 }
                 if (need) ++nshadow;
                 if (lit && !blocked) Lo = xadd3(Lo, direct);
             }
             if (live) color = hit ? rt_radiance_hw2(Lo) : rt_radiance_hw2(ld3(P.miss));
         }
-        accum = xadd3(accum, color);
+        if (!GROUPED) {
+            accum = xadd3(accum, color);
+        } else {                                         // owner lane q collects its pixel's G samples of this pass in order
+            const bool owner = lane >= pb * PP && lane < (pb + 1) * PP;
+            for (int k = 0; k < G; ++k) {
+                const int src = (((lane - pb * PP) << gsh) + k) & 31;
+                const f3 v = mk3(__shfl_sync(FULLMASK, color.x, src), __shfl_sync(FULLMASK, color.y, src), __shfl_sync(FULLMASK, color.z, src));
+                if (owner) accum = xadd3(accum, v);
+            }
+        }
     }
     if (px.inside) {
         const f3 fin = xdivs(accum, (float)P.spp);       // col / float(spp): query.cu:163, render.cpp:110
@@ -438,16 +465,31 @@ static cudaError_t launch_mode(const FrameParams& fp, int variant, cudaStream_t 
         variant = (variant == RT_VARIANT_STATS || variant == RT_VARIANT_PER_RAY_STATS) ? RT_VARIANT_PER_RAY_STATS : RT_VARIANT_PER_RAY;
     switch (variant) {
     case RT_VARIANT_DEFAULT:
-        if (fast) k_render_packet<MODE, false, true, 8><<<grid, block, 0, stream>>>(fp);
-        else k_render_packet<MODE, false, false, 8><<<grid, block, 0, stream>>>(fp);
+        if (fp.sample_group > 1) {
+            if (fast) k_render_packet<MODE, false, true, 8, false, true><<<grid, block, 0, stream>>>(fp);
+            else k_render_packet<MODE, false, false, 8, false, true><<<grid, block, 0, stream>>>(fp);
+        } else {
+            if (fast) k_render_packet<MODE, false, true, 8><<<grid, block, 0, stream>>>(fp);
+            else k_render_packet<MODE, false, false, 8><<<grid, block, 0, stream>>>(fp);
+        }
         break;
     case RT_VARIANT_STATS:
-        if (fast) k_render_packet<MODE, true, true, 8><<<grid, block, 0, stream>>>(fp);
-        else k_render_packet<MODE, true, false, 8><<<grid, block, 0, stream>>>(fp);
+        if (fp.sample_group > 1) {
+            if (fast) k_render_packet<MODE, true, true, 8, false, true><<<grid, block, 0, stream>>>(fp);
+            else k_render_packet<MODE, true, false, 8, false, true><<<grid, block, 0, stream>>>(fp);
+        } else {
+            if (fast) k_render_packet<MODE, true, true, 8><<<grid, block, 0, stream>>>(fp);
+            else k_render_packet<MODE, true, false, 8><<<grid, block, 0, stream>>>(fp);
+        }
         break;
     case RT_VARIANT_PACKET_OCC6:   k_render_packet<MODE, false, true, 6><<<grid, block, 0, stream>>>(fp); break;
     case RT_VARIANT_PACKET_OCC10:  k_render_packet<MODE, false, true, 10><<<grid, block, 0, stream>>>(fp); break;
     case RT_VARIANT_PACKET_EXACT_SLAB: k_render_packet<MODE, false, false, 8><<<grid, block, 0, stream>>>(fp); break;
+    case RT_VARIANT_PACKET_PREFETCH: k_render_packet<MODE, false, true, 8, true><<<grid, block, 0, stream>>>(fp); break;
+    case RT_VARIANT_PACKET_PIXEL_MAJOR:
+        if (fast) k_render_packet<MODE, false, true, 8><<<grid, block, 0, stream>>>(fp);
+        else k_render_packet<MODE, false, false, 8><<<grid, block, 0, stream>>>(fp);
+        break;
     case RT_VARIANT_PER_RAY:       k_render_bvh<MODE, false><<<grid, block, 0, stream>>>(fp); break;
     case RT_VARIANT_PER_RAY_STATS: k_render_bvh<MODE, true><<<grid, block, 0, stream>>>(fp); break;
     default: return cudaErrorInvalidValue;

@@ -431,6 +431,24 @@ def test_c5_scene_at_reduced_frame(renderer):
     _strided_bar(a, orc, slice(5, H, step), "c5 scene")
 
 
+@pytest.mark.parametrize("spp", [2, 3, 4, 6, 8, 16, 32, 64])
+def test_sample_major_packets_equal_pixel_major(renderer, frog_scene, spp):
+    """spp > 1: the default kernel traces G samples of one pixel side by side (G = largest power of two dividing spp, <= 32)
+    and sums them per pixel in sample order; it must equal the pixel-major kernel and the per-ray kernel bit for bit
+    (float accumulation order included), on frames that are not multiples of the tile."""
+    renderer.upload_scene(frog_scene)
+    out = {}
+    for variant in (A.RT_VARIANT_DEFAULT, A.RT_VARIANT_PACKET_PIXEL_MAJOR, A.RT_VARIANT_PER_RAY):
+        fr = scenes.frog_frame(203, 77, filling=True, outputs=ALL)
+        fr.spp, fr.jitter, fr.kernel_variant = spp, api.jitter_table(spp, 42, True), variant
+        out[variant] = run(renderer, fr)
+        assert out[variant]["rays_primary"] == 203 * 77 * spp
+    for variant in (A.RT_VARIANT_PACKET_PIXEL_MAJOR, A.RT_VARIANT_PER_RAY):
+        for k in ("rgb", "rgb8", "tri_id", "t"):
+            assert np.array_equal(out[A.RT_VARIANT_DEFAULT][k], out[variant][k]), (spp, variant, k)
+        assert out[A.RT_VARIANT_DEFAULT]["rays_shadow"] == out[variant]["rays_shadow"]
+
+
 def test_render_into_equals_render_plus_download(renderer, frog_scene):
     """rt_render_into (band-pipelined render + copy) must deliver exactly what rt_render + rt_download_image deliver,
     for every plane, odd sizes, frames smaller than a band, all modes and multi-sample frames."""
