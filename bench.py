@@ -363,14 +363,13 @@ def run_ours(args, rank, world, local_rank):
         ktimes.append(r.frame_times())
     kern_ms = float(np.mean([k for _, k in ktimes]))
     clocks = sampler.stop() if sampler else None      # clocks were sampled during the device-timed steps
-    # end to end through the C ABI with host buffers (render + blocking download), wall clock
+    # end to end through the C ABI with host buffers (render + copy into pinned host memory), wall clock per rank; the
+    # ranks are aligned before every step (outside the timed region) and the step's time is the max over ranks
     e2e_s = []
     for _ in range(args.steps):
         barrier()
         t0 = time.perf_counter()
         r.render_into(frame, into={"rgb8": pinned} if rank == 0 else None)     # rt_render_into: the user-facing "frame to host memory" call
-        if dist is not None:
-            dist.barrier()
         e2e_s.append(time.perf_counter() - t0)
     t = torch.tensor([step_ms, e2e_s + [0.0] * (len(step_ms) - len(e2e_s))], dtype=torch.float64, device="cuda")
     tw = torch.tensor(warm_ms + [kern_ms], dtype=torch.float64, device="cuda")
@@ -391,11 +390,12 @@ def run_ours(args, rank, world, local_rank):
         b_ray = bytes_launch / rays
         achieved = bytes_launch / (ms * 1e-3) / 1e9
         peak = peak * world
-        traffic, traffic_src = None, None          # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
+        traffic, traffic_src, winst = None, None, None   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
             if tj and world == 1 and args.variant == 0:
                 traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj["source"]
+                winst = float(tj.get("warp_instructions_per_launch", 0)) or None
         except Exception:
             pass
         if brute:
@@ -427,6 +427,13 @@ def run_ours(args, rank, world, local_rank):
                          "note": note},
             "clocks": clocks,
         }
+        if winst and not brute:
+            # the bound the profile actually shows: warp-instruction issue (4 schedulers per SM, one warp instruction per cycle each)
+            mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            pk = 148 * 4 * mhz * 1e6 / 1e9
+            line["issue_roofline"] = {"bound": "warp-instruction issue", "achieved": winst / (ms * 1e-3) / 1e9, "peak": pk, "unit": "G warp-instr/s",
+                                      "frac": winst / (ms * 1e-3) / 1e9 / pk, "warp_instructions_per_launch": winst, "source": traffic_src,
+                                      "peak_kind": "148 SMs x 4 schedulers x SM clock sampled during the run"}
         if brute:   # 51 flop per ray-triangle test in the reference's unfused formulation (27 mul, 23 add/sub, 1 div)
             tests_s = nt_all / (ms * 1e-3)
             pk = 148 * 128 * 2 * 1.965e9 / 1e12 * world
