@@ -296,9 +296,10 @@ def run_ours(args, rank, world, local_rank):
     W, H, spp = frame.width, frame.height, frame.spp
     brute = frame.accel == A.RT_ACCEL_BRUTE
     scene = wl["scene"]() if rank == 0 else None
-    first = r.upload_scene(scene)          # first call in the process: pays CUDA module loading and CUB temp sizing
+    first = r.upload_scene(scene)          # first call in the process: pays CUDA module loading and the pool's first allocations
+    r.upload_scene(scene)
     t0 = time.perf_counter()
-    info = r.upload_scene(scene)           # steady state (what a second scene or a re-upload costs)
+    info = r.upload_scene(scene)           # steady state (what another scene or a re-upload costs)
     upload_wall = time.perf_counter() - t0
     gather = {A.RT_GATHER_NCCL: "nccl send/recv + unpack", A.RT_GATHER_PEER: "peer stores into rank 0's image over NVLink + flag words"}[r.gather_mode()] if world > 1 else "none"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
