@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RT_API_VERSION 2
+#define RT_API_VERSION 3
 
 /* status codes */
 #define RT_OK            0
@@ -109,6 +109,18 @@ typedef struct rt_light {
     };
 } rt_light;
 
+/* Optional per-object transform baked ON THE DEVICE during rt_upload_scene, replacing the host loop of
+ * applyObjectTransform (GPUandCPU/src/main.cu:57-96): for the vertices [first_vertex, first_vertex + num_vertices)
+ * p' = Rz(Ry(Rx(p * scale))) + position, n' = normalize(Rz(Ry(Rx(n / scale)))) or (0,0,1) when degenerate —
+ * the same operation order and rounding (the six sin/cos values are taken on the host with the C library's
+ * sinf/cosf, like the reference).  Ranges must not overlap. */
+typedef struct rt_object_transform {
+    uint64_t first_vertex, num_vertices;
+    float    position[3];
+    float    rotation_deg[3];
+    float    scale[3];
+} rt_object_transform;
+
 /* Indexed triangle mesh exactly as the reference loaders hand it to render():
  * MeshView (GPUandCPU/include/MeshOBJ.h:24-40) + objectMaterials (main.cu:165-190). */
 typedef struct rt_scene {
@@ -121,6 +133,8 @@ typedef struct rt_scene {
     const rt_material* materials;      /* [num_materials] or NULL                  */
     int32_t            num_materials;
     uint32_t           build_flags;
+    const rt_object_transform* transforms;   /* [num_transforms] or NULL: positions/normals are already in world space */
+    int32_t            num_transforms;
 } rt_scene;
 
 /* The four vectors Camera::initialize leaves behind

@@ -1,7 +1,7 @@
 """ctypes mirror of include/rt_api.h (struct layouts and constants)."""
 import ctypes as C
 
-RT_API_VERSION = 2          # include/rt_api.h
+RT_API_VERSION = 3          # include/rt_api.h
 RT_OK, RT_ERR_ARG, RT_ERR_CUDA, RT_ERR_STATE, RT_ERR_NCCL, RT_ERR_NOMEM = 0, -1, -2, -3, -4, -5
 RT_MODE_HW1, RT_MODE_HW2_BVH, RT_MODE_HW2_CPU = 0, 1, 2
 RT_ACCEL_BRUTE, RT_ACCEL_BVH = 0, 1
@@ -38,10 +38,16 @@ class rt_light(C.Structure):
     _fields_ = [("position", C.c_float * 3), ("color", C.c_float * 3), ("u", _rt_intensity)]
 
 
+class rt_object_transform(C.Structure):
+    _fields_ = [("first_vertex", C.c_uint64), ("num_vertices", C.c_uint64), ("position", C.c_float * 3),
+                ("rotation_deg", C.c_float * 3), ("scale", C.c_float * 3)]
+
+
 class rt_scene(C.Structure):
     _fields_ = [("positions", f32p), ("normals", f32p), ("num_vertices", C.c_uint64),
                 ("indices", u32p), ("num_triangles", C.c_uint64), ("tri_obj_ids", i32p),
-                ("materials", C.POINTER(rt_material)), ("num_materials", C.c_int32), ("build_flags", C.c_uint32)]
+                ("materials", C.POINTER(rt_material)), ("num_materials", C.c_int32), ("build_flags", C.c_uint32),
+                ("transforms", C.POINTER(rt_object_transform)), ("num_transforms", C.c_int32)]
 
 
 class rt_camera(C.Structure):

@@ -149,7 +149,16 @@ def load_obj(path, next_object_id=0, position=None, rotation=None, scale=None):
 class Scene:
     """Indexed triangle mesh + per-object materials, as the reference loaders produce them."""
 
-    def __init__(self, positions, indices, normals=None, tri_obj_ids=None, materials=None, build_flags=0):
+    def __init__(self, positions, indices, normals=None, tri_obj_ids=None, materials=None, build_flags=0, transforms=None):
+        # transforms: [(first_vertex, num_vertices, position, rotation_deg, scale), ...] baked on the device at upload
+        self.transforms = list(transforms) if transforms else []
+        self._xf_arr = (A.rt_object_transform * max(1, len(self.transforms)))()
+        for k, (first, count, pos, rot, scl) in enumerate(self.transforms):
+            t = self._xf_arr[k]
+            t.first_vertex, t.num_vertices = int(first), int(count)
+            t.position[:] = [float(v) for v in pos]
+            t.rotation_deg[:] = [float(v) for v in rot]
+            t.scale[:] = [float(v) for v in scl]
         self.positions = _f32(positions).reshape(-1, 3)
         self.indices = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1, 3)
         self.normals = _f32(normals).reshape(-1, 3) if normals is not None and len(normals) else None
@@ -169,6 +178,8 @@ class Scene:
         s.materials = C.cast(self._mat_arr, C.POINTER(A.rt_material)) if self.materials else C.POINTER(A.rt_material)()
         s.num_materials = len(self.materials)
         s.build_flags = self.build_flags
+        s.transforms = C.cast(self._xf_arr, C.POINTER(A.rt_object_transform)) if self.transforms else C.POINTER(A.rt_object_transform)()
+        s.num_transforms = len(self.transforms)
         return s
 
 

@@ -5,6 +5,7 @@
 // There is no CPU rendering path here: without a usable CUDA device every entry point returns
 // RT_ERR_CUDA.
 #include "rt_kernels.h"
+#include "rt_build_core.h"
 
 #include <cuda.h>           // driver API types only; cuStreamWaitValue32 is fetched with cudaGetDriverEntryPoint
 #include <cuda_runtime.h>
@@ -456,6 +457,10 @@ int rt_upload_scene(rt_ctx* c, const rt_scene* sc) {
         fprintf(stderr, "[rt_upload_scene] %-22s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t - tp0).count());
         tp0 = t;
     };
+    if (sc->num_transforms < 0 || (sc->num_transforms > 0 && !sc->transforms)) return fail(c, RT_ERR_ARG, "rt_upload_scene: transforms");
+    for (int k = 0; k < sc->num_transforms; ++k)
+        if (sc->transforms[k].first_vertex > sc->num_vertices || sc->transforms[k].num_vertices > sc->num_vertices - sc->transforms[k].first_vertex)
+            return fail(c, RT_ERR_ARG, "rt_upload_scene: transform %d covers vertices outside the mesh", k);
     for (uint64_t i = 0; i < 3 * sc->num_triangles; ++i)
         if (sc->indices[i] >= sc->num_vertices) return fail(c, RT_ERR_ARG, "rt_upload_scene: index %llu out of range", (unsigned long long)i);
     lap("index validation");
@@ -486,6 +491,16 @@ int rt_upload_scene(rt_ctx* c, const rt_scene* sc) {
     if (d_nrm) CUS(cudaMemcpyAsync(d_nrm, sc->normals, sizeof(float) * 3 * nv, cudaMemcpyHostToDevice, c->stream));
     if (d_obj) CUS(cudaMemcpyAsync(d_obj, sc->tri_obj_ids, sizeof(int32_t) * nt, cudaMemcpyHostToDevice, c->stream));
     if (sc->num_materials) CUS(cudaMemcpyAsync(c->materials, sc->materials, sizeof(rt_material) * (size_t)sc->num_materials, cudaMemcpyHostToDevice, c->stream));
+    for (int k = 0; k < sc->num_transforms; ++k) {             // applyObjectTransform on the device (main.cu:75-96)
+        const rt_object_transform& o = sc->transforms[k];
+        const float d2r = 0.01745329251994329577f;             // deg2rad, main.cu:52-54
+        const float rx = o.rotation_deg[0] * d2r, ry = o.rotation_deg[1] * d2r, rz = o.rotation_deg[2] * d2r;
+        BakeXform T;
+        T.sx = o.scale[0]; T.sy = o.scale[1]; T.sz = o.scale[2];
+        T.cx_ = cosf(rx); T.sx_ = sinf(rx); T.cy_ = cosf(ry); T.sy_ = sinf(ry); T.cz_ = cosf(rz); T.sz_ = sinf(rz);
+        T.tx = o.position[0]; T.ty = o.position[1]; T.tz = o.position[2];
+        CUS(rt_bake_transform(d_pos, d_nrm, (size_t)o.first_vertex, (size_t)o.num_vertices, T, c->stream));
+    }
     CUS(cudaEventRecord(e1, c->stream));
     lap("enqueue H2D copies");
 

@@ -146,6 +146,26 @@ inline unsigned blocks_for(size_t n, unsigned t) { return (unsigned)((n + t - 1)
 
 } // namespace
 
+// Per-object transform bake in place (main.cu:75-96), one thread per vertex of the object.
+__global__ void k_bake_transform(float* pos, float* nrm, size_t first, size_t count, BakeXform T) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float* p = pos + 3 * (first + i);
+    const f3 q = rt_bake_point(mk3(p[0], p[1], p[2]), T);
+    p[0] = q.x; p[1] = q.y; p[2] = q.z;
+    if (nrm) {
+        float* n = nrm + 3 * (first + i);
+        const f3 m = rt_bake_normal(mk3(n[0], n[1], n[2]), T);
+        n[0] = m.x; n[1] = m.y; n[2] = m.z;
+    }
+}
+
+cudaError_t rt_bake_transform(float* pos, float* nrm, size_t first, size_t count, const BakeXform& T, cudaStream_t stream) {
+    if (count == 0) return cudaSuccess;
+    k_bake_transform<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(pos, nrm, first, count, T);
+    return cudaGetLastError();
+}
+
 cudaError_t rt_pack_triangles(const BuildParams& bp, TriBlock* geom, TriBlock* shade, cudaStream_t stream) {
     if (bp.num_tris == 0) return cudaSuccess;
     k_pack_tris<<<blocks_for(bp.num_tris, 256), 256, 0, stream>>>(bp, nullptr, geom, shade);

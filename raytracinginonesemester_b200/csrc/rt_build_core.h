@@ -140,3 +140,26 @@ RT_HD void rt_pack_tri(const BuildParams& bp, uint32_t tri, TriBlock* geom_k, Tr
     s[1] = make_float4(n1.x, n1.y, n1.z, 0.f);
     s[2] = make_float4(n2.x, n2.y, n2.z, 0.f);
 }
+
+// -------------------------------------------------------- per-object transform bake ----
+// applyObjectTransform / rotateXYZ, GPUandCPU/src/main.cu:52-96.  The trigonometric values come from the host.
+struct BakeXform { float sx, sy, sz, cx_, sx_, cy_, sy_, cz_, sz_, tx, ty, tz; };   // scale; cos/sin about X, Y, Z; translation
+RT_HD f3 rt_rotate_xyz(f3 v, const BakeXform& T) {
+    const float y1 = XSUB(XMUL(T.cx_, v.y), XMUL(T.sx_, v.z)), z1 = XADD(XMUL(T.sx_, v.y), XMUL(T.cx_, v.z));      // about X
+    const float x2 = XADD(XMUL(T.cy_, v.x), XMUL(T.sy_, z1)), z2 = XADD(XMUL(-T.sy_, v.x), XMUL(T.cy_, z1));       // about Y
+    const float x3 = XSUB(XMUL(T.cz_, x2), XMUL(T.sz_, y1)), y3 = XADD(XMUL(T.sz_, x2), XMUL(T.cz_, y1));          // about Z
+    return mk3(x3, y3, z2);
+}
+RT_HD f3 rt_bake_point(f3 p, const BakeXform& T) {
+    const f3 r = rt_rotate_xyz(mk3(XMUL(p.x, T.sx), XMUL(p.y, T.sy), XMUL(p.z, T.sz)), T);
+    return mk3(XADD(r.x, T.tx), XADD(r.y, T.ty), XADD(r.z, T.tz));
+}
+RT_HD f3 rt_bake_normal(f3 n, const BakeXform& T) {
+    if (fabsf(T.sx) > 1e-8f) n.x = XDIV(n.x, T.sx);
+    if (fabsf(T.sy) > 1e-8f) n.y = XDIV(n.y, T.sy);
+    if (fabsf(T.sz) > 1e-8f) n.z = XDIV(n.z, T.sz);
+    const f3 r = rt_rotate_xyz(n, T);
+    const float len2 = xdot(r, r);
+    if (len2 > 1e-12f) return xmuls(r, XDIV(1.0f, XSQRT(len2)));
+    return mk3(0.0f, 0.0f, 1.0f);
+}

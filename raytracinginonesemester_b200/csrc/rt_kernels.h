@@ -11,6 +11,9 @@
 struct BuildResult { uint32_t num_nodes; uint32_t num_leaves; float scene_min[3], scene_max[3]; };
 cudaError_t rt_build_bvh(const BuildParams& bp, BvhNode** nodes_out, TriBlock* geom, TriBlock* shade,
                          BuildResult* res, cudaStream_t stream);
+// Bakes an object's transform into its vertex range in place (device arrays), before the build.
+struct BakeXform;
+cudaError_t rt_bake_transform(float* pos, float* nrm, size_t first, size_t count, const BakeXform& T, cudaStream_t stream);
 // Pack triangles in input order without a BVH (brute-force-only scenes).
 cudaError_t rt_pack_triangles(const BuildParams& bp, TriBlock* geom, TriBlock* shade, cudaStream_t stream);
 

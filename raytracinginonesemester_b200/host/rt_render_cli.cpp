@@ -67,7 +67,7 @@ bool write_ppm(const std::string& path, int W, int H, const std::vector<float>& 
 } // namespace
 
 int main(int argc, char** argv) {
-    bool hw1 = false, gamma2 = false, brute = false;
+    bool hw1 = false, gamma2 = false, brute = false, host_transform = false;
     int device = 0, width = 0, height = 0, spp_override = 0, depth_override = 0;
     std::string out_path;
     std::vector<std::string> inputs;
@@ -76,6 +76,7 @@ int main(int argc, char** argv) {
         if (a == "--hw1") hw1 = true;
         else if (a == "--gamma2") gamma2 = true;
         else if (a == "--brute") brute = true;
+        else if (a == "--host-transform") host_transform = true;     // bake object transforms on the host instead of the device
         else if (a == "--device" && i + 1 < argc) device = std::atoi(argv[++i]);
         else if (a == "--width" && i + 1 < argc) width = std::atoi(argv[++i]);
         else if (a == "--height" && i + 1 < argc) height = std::atoi(argv[++i]);
@@ -83,7 +84,7 @@ int main(int argc, char** argv) {
         else if (a == "--depth" && i + 1 < argc) depth_override = std::atoi(argv[++i]);
         else if ((a == "-o" || a == "--out") && i + 1 < argc) out_path = argv[++i];
         else if (a == "-h" || a == "--help") {
-            std::printf("usage: rt_render_cli [--hw1] [--brute] [--width W --height H] [--spp N] [--depth D] [--gamma2] [--device D] [-o out.ppm] [scene.json | mesh.obj ...]\n");
+            std::printf("usage: rt_render_cli [--hw1] [--brute] [--host-transform] [--width W --height H] [--spp N] [--depth D] [--gamma2] [--device D] [-o out.ppm] [scene.json | mesh.obj ...]\n");
             return 0;
         } else inputs.push_back(a);
     }
@@ -112,6 +113,7 @@ int main(int argc, char** argv) {
 
     HostMesh mesh;
     std::vector<rt_material> materials;
+    std::vector<rt_object_transform> transforms;             // applyObjectTransform runs on the device at upload
     int next_id = 0;
     for (auto& o : objects) {
         std::printf("Loading OBJ: %s\n", o.path.c_str());
@@ -119,7 +121,14 @@ int main(int argc, char** argv) {
         const int first = next_id;
         std::string err;
         if (!load_obj(o.path, part, next_id, &err)) { std::fprintf(stderr, "Failed to load OBJ: %s (%s)\n", o.path.c_str(), err.c_str()); continue; }
-        transform_mesh(part, o.position, o.rotation, o.scale);
+        if (host_transform) transform_mesh(part, o.position, o.rotation, o.scale);
+        else {
+            rt_object_transform t{};
+            t.first_vertex = mesh.num_vertices(); t.num_vertices = part.num_vertices();
+            std::memcpy(t.position, o.position, sizeof t.position); std::memcpy(t.rotation_deg, o.rotation, sizeof t.rotation_deg);
+            std::memcpy(t.scale, o.scale, sizeof t.scale);
+            transforms.push_back(t);
+        }
         materials.resize((size_t)next_id, default_material());
         for (int id = first; id < next_id; ++id) materials[(size_t)id] = o.material;
         std::printf("  -> Loaded %zu triangles.\n", part.num_triangles());
@@ -135,6 +144,7 @@ int main(int argc, char** argv) {
     sc.num_vertices = mesh.num_vertices(); sc.indices = mesh.indices.data(); sc.num_triangles = mesh.num_triangles();
     sc.tri_obj_ids = mesh.tri_obj_ids.data(); sc.materials = materials.data(); sc.num_materials = (int)materials.size();
     sc.build_flags = (hw1 && brute) ? RT_BUILD_NO_BVH : RT_BUILD_DEFAULT;
+    sc.transforms = transforms.empty() ? nullptr : transforms.data(); sc.num_transforms = (int)transforms.size();
     if (rt_upload_scene(ctx, &sc) != RT_OK) return die(ctx, "rt_upload_scene");
     rt_build_info bi{};
     rt_build_info_get(ctx, &bi);

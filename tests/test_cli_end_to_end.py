@@ -1,7 +1,7 @@
 """Drop-in check of the C++ host driver: rt_render_cli (built here with g++ against the in-tree librt_b200.so) is
 run on the very scene JSON + OBJ files the reference's whole bvh_viz program was run on (fixture
 tests/golden/e2e_scene.npz, tools/make_golden_e2e.py), and its PPM is compared with the reference's 8-bit image.
-Covers the JSON dialect, OBJ ingest, transforms, per-object materials, two lights, 2 spp jitter, mirror and
+Covers the JSON dialect, OBJ ingest, transforms (baked on the device by default, on the host with --host-transform), per-object materials, two lights, 2 spp jitter, mirror and
 hash-RNG diffuse bounces (max_bounces 3) and the P6 writer."""
 import os
 import subprocess
@@ -44,13 +44,13 @@ def cli(tmp_path_factory):
     return exe
 
 
-@pytest.mark.parametrize("name", ["mirror", "diffuse"])
-def test_cli_matches_reference_program(cli, golden, tmp_path, name):
+@pytest.mark.parametrize("name,extra", [("mirror", []), ("diffuse", []), ("mirror", ["--host-transform"])])
+def test_cli_matches_reference_program(cli, golden, tmp_path, name, extra):
     g = golden("e2e_scene.npz")
     open(tmp_path / "ball.obj", "w").write(str(g["ball_obj"]))
     open(tmp_path / "ground.obj", "w").write(str(g["ground_obj"]))
     open(tmp_path / "scene.json", "w").write(str(g["json_" + name]))
-    r = subprocess.run([cli, "scene.json", "-o", "out.ppm"], cwd=str(tmp_path), capture_output=True, text=True, timeout=120)
+    r = subprocess.run([cli, "scene.json", "-o", "out.ppm"] + extra, cwd=str(tmp_path), capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
     assert "GPU LBVH Build Time" in r.stdout and "GPU Render Time" in r.stdout      # the reference's own progress lines
     got = read_p6(str(tmp_path / "out.ppm"))

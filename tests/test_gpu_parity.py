@@ -431,6 +431,49 @@ def test_c5_scene_at_reduced_frame(renderer):
     _strided_bar(a, orc, slice(5, H, step), "c5 scene")
 
 
+def test_device_transform_bake_matches_reference(renderer, golden, tmp_path):
+    """rt_scene.transforms (applyObjectTransform on the device, main.cu:57-96): the baked vertices, read back from the
+    triangle blocks, equal the positions the reference's own loader + applyObjectTransform produced (fixture
+    e2e_scene.npz) bit for bit, and the frame (normals included) equals the one rendered from the host-baked mesh
+    (host ingest is itself pinned to the reference by tests/test_host_ingest.py)."""
+    import json
+    import os
+    g = golden("e2e_scene.npz")
+    open(tmp_path / "ball.obj", "w").write(str(g["ball_obj"]))
+    open(tmp_path / "ground.obj", "w").write(str(g["ground_obj"]))
+    scene = json.loads(str(g["json_mirror"]))
+    raw_p, raw_n, host_p, host_n, idx, obj, xf = [], [], [], [], [], [], []
+    off = nid = 0
+    for k, o in enumerate(scene["scene"]):
+        path = os.path.join(str(tmp_path), o["path"][2:])
+        t = o["transform"]
+        p0, n0, i0, o0, nxt = api.load_obj(path, nid)
+        p1, n1, _, _, _ = api.load_obj(path, nid, position=t["position"], rotation=t["rotation"], scale=t["scale"])
+        assert np.array_equal(p1, g["obj%d_positions" % k])
+        xf.append((off, p0.shape[0], t["position"], t["rotation"], t["scale"]))
+        raw_p.append(p0); raw_n.append(n0); host_p.append(p1); host_n.append(n1); idx.append(i0 + off); obj.append(o0)
+        off += p0.shape[0]; nid = nxt
+    idx, obj, host_p = np.concatenate(idx), np.concatenate(obj), np.concatenate(host_p)
+    mats = [api.make_material(albedo=(0.7, 0.6, 0.5), ks=0.2) for _ in range(nid)]
+    dev = api.Scene(np.concatenate(raw_p), idx, normals=np.concatenate(raw_n), tri_obj_ids=obj, materials=mats, transforms=xf)
+    info = renderer.upload_scene(dev)
+    _, blocks, ids = renderer.download_bvh()
+    v0 = np.zeros((info.num_triangles, 3), np.float32)
+    v0[ids] = blocks[:, 0:3]
+    assert np.array_equal(v0, host_p[idx[:, 0]]), "device-baked vertices differ from applyObjectTransform"
+    cam = api.camera_init((0.0, -2.5, 1.2), (0.0, 0.0, 0.4), (0, 0, 1), 28.0, 24.0, 160, 96)
+    fr = api.Frame(cam, 160, 96, lights=[api.make_light((-2.0, -1.0, 1.5), (1, 1, 1), 5)], miss_color=(0.5, 0.7, 1.0), spp=1,
+                   jitter=api.jitter_table(1, 42, True), outputs=ALL)
+    a = run(renderer, fr)
+    renderer.upload_scene(api.Scene(host_p, idx, normals=np.concatenate(host_n), tri_obj_ids=obj, materials=mats))
+    b = run(renderer, fr)
+    for k in ("tri_id", "t", "rgb"):
+        assert np.array_equal(a[k], b[k]), k
+    bad = api.Scene(np.concatenate(raw_p), idx, tri_obj_ids=obj, materials=mats, transforms=[(10, 10 ** 9, (0, 0, 0), (0, 0, 0), (1, 1, 1))])
+    with pytest.raises(api.RtError):
+        renderer.upload_scene(bad)
+
+
 @pytest.mark.parametrize("spp", [2, 3, 4, 6, 8, 16, 32, 64])
 def test_sample_major_packets_equal_pixel_major(renderer, frog_scene, spp):
     """spp > 1: the default kernel traces G samples of one pixel side by side (G = largest power of two dividing spp, <= 32)
