@@ -33,24 +33,33 @@ __global__ void k_init_bounds(Bounds* b) {
     for (int a = 0; a < 3; ++a) { b->lo[a] = INFINITY; b->hi[a] = -INFINITY; }
 }
 
-// Scene bounds (thrust::reduce of main.cu:264-270): warp shuffle reduction + one float atomic per warp.
+// Scene bounds (thrust::reduce of main.cu:264-270): grid-stride accumulation in registers, warp shuffle + shared-memory
+// block reduction, six float atomics per block (min/max are exact, so the order of the reduction does not matter).
+// (One atomic set per warp — 1.9M contended atomics at 10M triangles — took 1.25 ms, DRAM at 2 % of peak.)
 __global__ void k_scene_bounds(BuildParams bp, Bounds* scene) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float s_red[8][6];
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    if (i < bp.num_tris) {
-        f3 a, b, c; uint32_t ia, ib, ic;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < bp.num_tris; i += gridDim.x * blockDim.x) {
+        f3 a, b, c; uint32_t ia, ib, ic; float l[3], h[3];
         rt_tri_verts(bp, i, a, b, c, ia, ib, ic);
-        rt_tri_box(a, b, c, lo, hi);
+        rt_tri_box(a, b, c, l, h);
+        for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], l[k]); hi[k] = fmaxf(hi[k], h[k]); }
     }
     for (int o = 16; o > 0; o >>= 1)
         for (int k = 0; k < 3; ++k) {
             lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
             hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
         }
-    if ((threadIdx.x & 31) == 0)
-        for (int k = 0; k < 3; ++k) {
-            if (lo[k] <= hi[k]) { atomic_min_f(&scene->lo[k], lo[k]); atomic_max_f(&scene->hi[k], hi[k]); }
-        }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) for (int k = 0; k < 3; ++k) { s_red[warp][k] = lo[k]; s_red[warp][3 + k] = hi[k]; }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int nw = (int)(blockDim.x >> 5), k = (int)threadIdx.x;
+        float v = s_red[0][k];
+        for (int w = 1; w < nw; ++w) v = k < 3 ? fminf(v, s_red[w][k]) : fmaxf(v, s_red[w][k]);
+        if (k < 3) { if (v != INFINITY) atomic_min_f(&scene->lo[k], v); }
+        else { if (v != -INFINITY) atomic_max_f(&scene->hi[k - 3], v); }
+    }
 }
 
 // Replaces ComputeMortonCodes (bvh.cu:34-55).
@@ -211,7 +220,7 @@ cudaError_t rt_build_bvh(const BuildParams& bp, BvhNode** nodes_out, TriBlock* g
     CKG(cudaMallocAsync(&d_tmp, tmp_bytes ? tmp_bytes : 16, stream));
 
     k_init_bounds<<<1, 1, 0, stream>>>(d_scene);
-    k_scene_bounds<<<blocks_for(n, T), T, 0, stream>>>(bp, d_scene);
+    { unsigned nb = blocks_for(n, T); if (nb > 148u * 8u) nb = 148u * 8u; k_scene_bounds<<<nb, T, 0, stream>>>(bp, d_scene); }
     k_morton<<<blocks_for(n, T), T, 0, stream>>>(bp, d_scene, d_keys, d_vals);
     CKG(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, n, 0, 63, stream));
     CKG(cudaMemsetAsync(d_flags, 0, sizeof(int) * (size_t)n, stream));
