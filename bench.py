@@ -428,6 +428,12 @@ def run_ours(args, rank, world, local_rank):
                          "note": note},
             "clocks": clocks,
         }
+        # SURVEY §8d's per-ray accounting (every ray pays for every node / triangle it takes part in: 64 B per node visit,
+        # 48 B per triangle test, 16 B of result), next to the per-request accounting above (a packet fetches a line once
+        # for its 32 rays).  Above 1 = served from cache, as §8d anticipates.
+        b_ray_8d = 64.0 * nv_all / rays + 48.0 * nt_all / rays + 16.0
+        line["roofline"]["survey_8d_per_ray"] = {"bytes_per_ray": b_ray_8d, "achieved": rays * b_ray_8d / (ms * 1e-3) / 1e9,
+                                                 "frac": rays * b_ray_8d / (ms * 1e-3) / 1e9 / peak}
         if winst and not brute:
             # the bound the profile actually shows: warp-instruction issue (4 schedulers per SM, one warp instruction per cycle each)
             mhz = (clocks or {}).get("sm_mhz") or 1965.0
