@@ -231,6 +231,49 @@ class CpuReference:
         return rows * W * fr.spp, dt
 
 
+def reference_cuda_leg(wl, rays, flush_bytes=256 << 20):
+    """The reference's OWN CUDA renderer (renderBatchCUDA + normalizeCUDA, GPUandCPU/include/query.cu:12-128, and its
+    Thrust LBVH build) compiled in place for sm_100 with the reference's flags (oracle/_ref/libref_hw2_cuda.so) and timed
+    on this GPU on the same scene and frame: the GPU bar of SURVEY §8d.  Measurement only — never on the product path.
+    Its GPU build jitters with a per-pixel wang hash (query.cu:36-45) instead of the mt19937 table, and uses
+    --use_fast_math, so its image is close to but not bit-comparable with the CPU reference."""
+    from raytracinginonesemester_b200 import _abi as A
+    p = os.path.join(ROOT, "oracle", "_ref", "libref_hw2_cuda.so")
+    if wl["mode"] != "hw2" or not os.path.exists(p):
+        return None
+    lib = C.CDLL(p)
+    lib.ref_cuda_world_create.restype = C.c_void_p
+    lib.ref_cuda_build_ms.restype = C.c_double
+    scene, fr = wl["scene"](), wl["frame"]
+    W, H, spp = fr.width, fr.height, fr.spp
+    f3 = lambda v: np.array(v, np.float32)
+    marr = (A.rt_material * len(scene.materials))(*scene.materials)
+    nrm = scene.normals.ctypes.data_as(A.f32p) if scene.normals is not None else None
+    h = lib.ref_cuda_world_create(scene.positions.ctypes.data_as(A.f32p), nrm, C.c_uint64(scene.positions.shape[0]),
+                                  scene.indices.ctypes.data_as(A.u32p), C.c_uint64(scene.indices.shape[0]),
+                                  scene.tri_obj_ids.ctypes.data_as(A.i32p), marr, len(scene.materials))
+    if not h:
+        return {"unavailable": "ref_cuda_world_create failed"}
+    cp = fr.cam.params
+    cpos, look, up, ms = f3(cp["pos"]), f3(cp["look_at"]), f3(cp["up"]), f3(fr.miss_color)
+    larr = (A.rt_light * len(fr.lights))(*fr.lights)
+    reps = 10 if W * H * spp <= 3840 * 2160 else 2
+    dev, e2e = np.zeros(reps, np.float32), np.zeros(reps, np.float32)
+    rc = lib.ref_cuda_render(C.c_void_p(h), cpos.ctypes.data_as(A.f32p), look.ctypes.data_as(A.f32p), up.ctypes.data_as(A.f32p),
+                             C.c_double(cp["focal_mm"]), C.c_double(cp["sensor_mm"]), W, H, ms.ctypes.data_as(A.f32p), 1, spp,
+                             larr, len(fr.lights), 1, 2, reps, C.c_uint64(flush_bytes), dev.ctypes.data_as(A.f32p), e2e.ctypes.data_as(A.f32p), None)
+    build_ms = float(lib.ref_cuda_build_ms(C.c_void_p(h)))
+    lib.ref_cuda_world_free(C.c_void_p(h))
+    if rc != 0:
+        return {"unavailable": "ref_cuda_render failed"}
+    return {"impl": "reference CUDA renderer (renderBatchCUDA, one thread per pixel, 512-entry local stack, fp64 slabs) built in place for sm_100 with --use_fast_math",
+            "value": rays / (float(dev.mean()) * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": float(dev.mean()), "frames": reps,
+            "e2e_ms_per_step": float(e2e.mean()), "e2e_value": rays / (float(e2e.mean()) * 1e-3) / 1e6,
+            "e2e_note": "render() + D2H of the float image = the reference's own 'GPU Render Time' (main.cu:370-378)",
+            "lbvh_build_ms": build_ms, "l2": "flushed before each frame (256 MiB memset)",
+            "rays": "the product's device count for the same frame (one shadow ray per lit hit - the same rule)"}
+
+
 # shadow rays per primary ray, counted by the device on each workload (one shadow ray per lit hit; the in-place
 # reference has no counters, the rule is the same)
 SHADOW_RATIO = {"c4": 0.81550, "c5": 0.70824, "c4small": 0.8155, "c2": 0.0, "c3": 0.020735, "c3fill": 0.274944}
@@ -367,11 +410,12 @@ def run_ours(args, rank, world, local_rank):
     # end to end through the C ABI with host buffers (render + copy into pinned host memory), wall clock per rank; the
     # ranks are aligned before every step (outside the timed region) and the step's time is the max over ranks
     e2e_s = []
-    for _ in range(args.steps):
+    for i in range(-max(args.warmup, 3), args.steps):      # the warm-up calls pay rt_render_into's one-time stream / event / band set-up
         barrier()
         t0 = time.perf_counter()
         r.render_into(frame, into={"rgb8": pinned} if rank == 0 else None)     # rt_render_into: the user-facing "frame to host memory" call
-        e2e_s.append(time.perf_counter() - t0)
+        if i >= 0:
+            e2e_s.append(time.perf_counter() - t0)
     t = torch.tensor([step_ms, e2e_s + [0.0] * (len(step_ms) - len(e2e_s))], dtype=torch.float64, device="cuda")
     tw = torch.tensor(warm_ms + [kern_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -382,6 +426,7 @@ def run_ours(args, rank, world, local_rank):
     ms = float(step_ms.mean())
     value = rays / (ms * 1e-3) / 1e6
     e2e_value = rays / float(e2e_s.mean()) / 1e6
+    e2e_spread = {"median_ms": 1e3 * float(np.median(e2e_s)), "min_ms": 1e3 * float(e2e_s.min()), "max_ms": 1e3 * float(e2e_s.max())}
 
     if rank == 0:
         peak, peak_kind = measured_peaks()
@@ -420,7 +465,7 @@ def run_ours(args, rank, world, local_rank):
             "scene_upload_wall_s": upload_wall,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": 1e3 * float(e2e_s.mean()),
                     "h2d_bytes_per_step": int(C.sizeof(A.rt_frame) + 28 * len(frame.lights) + 8 * spp),
-                    "d2h_bytes_per_step": int(3 * W * H + 32)},
+                    "d2h_bytes_per_step": int(3 * W * H + 32), "spread": e2e_spread},
             "gpu_launches": int(args.steps * launches_per_step),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_kind": peak_kind + (" x %d GPUs" % world if world > 1 else ""), "bytes_per_ray": b_ray, "bytes_per_launch": bytes_launch,
@@ -457,8 +502,19 @@ def run_ours(args, rank, world, local_rank):
             ratio = rays_shadow / max(rays_primary, 1.0)
             line["cpu_baseline"] = {"value": n * (1 + ratio) / dt / 1e6, "unit": "Mrays/s", "cores": ref.cores, "kind": ref.kind,
                                     "sample": "%d pass(es) over every %d-th row of the %dx%d frame, %.1f s of CPU work; shadow rays = primary x %.4f (device count)" % (passes, stp, W, H, dt, ratio)}
-        print(json.dumps(line))
     r.close()
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline and not args.profile:
+            try:
+                rc = reference_cuda_leg(make_workload(args.workload), rays)
+            except Exception as e:      # measurement of the other implementation must never take the product's line down
+                rc = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+            if rc is not None:
+                if "value" in rc:
+                    rc["speedup_device"] = value / rc["value"]
+                    rc["speedup_e2e"] = e2e_value / rc["e2e_value"]
+                line["reference_cuda"] = rc
+        print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 

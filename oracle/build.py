@@ -7,6 +7,8 @@ TEST INFRASTRUCTURE ONLY.  Produces
   oracle/_ref/libref_ppm.so       reference ppm_p6_lib compiled where it lies
   oracle/_ref/libref_hw2_main.so  the reference's whole bvh_viz program (main renamed), for end-to-end fixtures
   oracle/_ref/libref_cpuonly.so   reference HW2/CPUOnly sources (TraceRay, camera, transform, OBJ loader) compiled where they lie
+  oracle/_ref/libref_hw2_cuda.so  reference HW2/GPUandCPU sources compiled as CUDA (its ENABLE_GPU build) for sm_100: the
+                                  reference's own GPU renderer, timed next to the product by bench.py ("reference_cuda")
 The _ref outputs need /root/reference (present in the authoring container only); on the GPU
 box the prebuilt files travel with the snapshot.  No reference source is copied into the repo.
 Flags: -O2 -ffp-contract=off, no -march=native (hit ids depend on no-FMA rounding).
@@ -48,7 +50,7 @@ def have_reference():
 
 def build_ref(force=False):
     """Compile the reference's own sources in place.  Returns dict name -> path (existing files)."""
-    outs = {n: os.path.join(REF_OUT, "lib%s.so" % n) for n in ("ref_hw1", "ref_hw2", "ref_ppm", "ref_hw2_main", "ref_cpuonly")}
+    outs = {n: os.path.join(REF_OUT, "lib%s.so" % n) for n in ("ref_hw1", "ref_hw2", "ref_ppm", "ref_hw2_main", "ref_cpuonly", "ref_hw2_cuda")}
     if have_reference():
         os.makedirs(REF_OUT, exist_ok=True)
         hw1, g = os.path.join(REF, "HW1"), os.path.join(REF, "HW2", "HW2", "GPUandCPU")
@@ -76,6 +78,13 @@ def build_ref(force=False):
             p = os.path.join(hw1, "ppm_p6_lib")
             _run(["g++", "-std=c++17", "-w"] + FP + ["-I", os.path.join(p, "include"), "-o", outs["ref_ppm"],
                   s, os.path.join(p, "src", "ppm_p6.cpp")])
+        s = os.path.join(HERE, "ref_shim_hw2_cuda.cu")
+        if force or _stale(outs["ref_hw2_cuda"], [s]):
+            # the reference's own CUDA flags (GPUandCPU/CMakeLists.txt:27); it names no architecture, sm_100 is ours
+            inc = ["-I", os.path.join(g, "third_party", "glm"), "-I", os.path.join(g, "include"), "-I", os.path.join(g, "src")]
+            _run(["nvcc", "-std=c++17", "-O3", "-w", "--extended-lambda", "--expt-relaxed-constexpr", "--use_fast_math",
+                  "-gencode", "arch=compute_100,code=sm_100", "-Xcompiler", "-fPIC", "-shared"] + inc +
+                 ["-o", outs["ref_hw2_cuda"], s, os.path.join(g, "include", "bvh.cu"), os.path.join(g, "include", "query.cu")])
     return {k: v for k, v in outs.items() if os.path.exists(v)}
 
 
