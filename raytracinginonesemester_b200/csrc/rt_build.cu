@@ -125,7 +125,7 @@ __global__ void k_emit_nodes(const Topo* __restrict__ topo, int n, const uint32_
     const Topo tp = topo[i];
     const BvhNode nd = rt_make_node(blo[tp.left], bhi[tp.left], blo[tp.right], bhi[tp.right],
                                     rt_child_ref(tp.left, n, topo, keep, newidx), rt_child_ref(tp.right, n, topo, keep, newidx),
-                                    tp.first, (RT_TOPO_LAST(tp) - tp.first + 1u) | (RT_TOPO_AXIS(tp) << 30));
+                                    tp.first, (RT_TOPO_LAST(tp) - tp.first + 1u) | RT_NODE_AXIS_BITS(RT_TOPO_AXIS(tp)));
     float4* dst = reinterpret_cast<float4*>(nodes + newidx[i]);
     const float4* src = reinterpret_cast<const float4*>(&nd);
     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];

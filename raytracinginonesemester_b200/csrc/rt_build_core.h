@@ -9,6 +9,9 @@ struct Bounds { float lo[3]; float hi[3]; };
 struct Topo { uint32_t left, right, first, last; };   // last: bits 0..29 = index, bits 30..31 = split axis (0 z, 1 y, 2 x, 3 none)
 #define RT_TOPO_LAST(tp) ((tp).last & 0x3fffffffu)
 #define RT_TOPO_AXIS(tp) ((tp).last >> 30)
+// Node word slot_count: bits 0..28 = triangle slots of the subtree, bits 29..31 = one-hot split axis (29 z, 30 y, 31 x;
+// none set = no spatial split), so the packet kernel's descent order is one AND with its direction-sign mask.
+#define RT_NODE_AXIS_BITS(axis) ((axis) < 3u ? (1u << (29u + (axis))) : 0u)
 
 RT_HD void rt_tri_verts(const BuildParams& bp, uint32_t i, f3& a, f3& b, f3& c, uint32_t& ia, uint32_t& ib, uint32_t& ic) {
     ia = RT_LDG(bp.indices + 3 * (size_t)i); ib = RT_LDG(bp.indices + 3 * (size_t)i + 1); ic = RT_LDG(bp.indices + 3 * (size_t)i + 2);
@@ -116,7 +119,7 @@ RT_HD BvhNode rt_make_node(float4 l0, float4 h0, float4 l1, float4 h1, int32_t r
     BvhNode nd;
     rt_box_to_ch(l0.x, h0.x, nd.q[0], nd.q[3]); rt_box_to_ch(l0.y, h0.y, nd.q[1], nd.q[4]); rt_box_to_ch(l0.z, h0.z, nd.q[2], nd.q[5]);
     rt_box_to_ch(l1.x, h1.x, nd.q[6], nd.q[9]); rt_box_to_ch(l1.y, h1.y, nd.q[7], nd.q[10]); rt_box_to_ch(l1.z, h1.z, nd.q[8], nd.q[11]);
-    nd.ref0 = r0; nd.ref1 = r1; nd.first_slot = first; nd.slot_count = count;   // count: bits 30..31 carry the split axis
+    nd.ref0 = r0; nd.ref1 = r1; nd.first_slot = first; nd.slot_count = count;   // count: bits 29..31 carry the one-hot split axis (RT_NODE_AXIS_BITS)
     return nd;
 }
 

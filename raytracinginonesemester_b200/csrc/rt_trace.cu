@@ -177,12 +177,13 @@ k_render_brute(const __grid_constant__ FrameParams P) {
 struct TraceResult { Hit hit; bool blocked; };
 
 struct WarpStack {
-    uint32_t s0, s1; int sp; bool overflow;
-    __device__ __forceinline__ void reset() { sp = 0; overflow = false; s0 = s1 = 0u; }
+    uint32_t s0, s1; int sp;
+    __device__ __forceinline__ void reset() { sp = 0; s0 = s1 = 0u; }
+    // caller guarantees sp < RT_PACKET_STACK; entry sp lives in lane sp % 32 of s0 (sp < 32) or s1
     __device__ __forceinline__ void push(uint32_t v, int lane) {
-        if (sp < 32) { if (lane == sp) s0 = v; }
-        else if (sp < RT_PACKET_STACK) { if (lane == sp - 32) s1 = v; }
-        else { overflow = true; return; }
+        const bool mine = lane == (sp & 31);
+        if (mine && sp < 32) s0 = v;
+        if (mine && sp >= 32) s1 = v;
         ++sp;
     }
     __device__ __forceinline__ uint32_t pop() {
@@ -196,7 +197,9 @@ struct WarpStack {
 // `any` is a run-time, warp-uniform flag so that primary and shadow queries share one copy of the
 // loop (the first packet kernel spent 15 % of its issue slots waiting on instruction fetch).
 // FAST selects the fused slab test (rt_slab_fma).
-template <int MODE, bool STATS, bool FAST, bool PF = false>
+// TAG makes the instance private to one kernel: ptxas 12.9 crashes (-lineinfo) on a non-inlined function with
+// 256-bit loads that is shared by two entry points.
+template <int MODE, bool STATS, bool FAST, bool PF = false, int TAG = 0>
 __device__ __noinline__ TraceResult packet_trace(const BvhNode* __restrict__ nodes, const TriBlock* __restrict__ geom, const uint32_t num_tris,
                                                  const Ray ray, bool live, const bool any, float tlimit, TraceStats* st) {
     Hit best; rt_hit_reset(best);
@@ -207,6 +210,7 @@ __device__ __noinline__ TraceResult packet_trace(const BvhNode* __restrict__ nod
     if (FAST) kf = rt_ray_fma(ray); else k = rt_ray_inv(ray);
     WarpStack stk; stk.reset();
     int cur = 0;
+    bool overflow = false;
     const unsigned mlive = __ballot_sync(FULLMASK, live);
     if (!mlive) return TraceResult{best, blocked};
     // Descent order without a per-node vote: LBVH children are split along a known axis with the
@@ -232,8 +236,9 @@ __device__ __noinline__ TraceResult packet_trace(const BvhNode* __restrict__ nod
             }
             const bool a0 = __any_sync(FULLMASK, h0 && live), a1 = __any_sync(FULLMASK, h1 && live);
             if (a0 && a1) {
-                const bool c1first = (dirneg >> ((unsigned)q.q3.w >> 30)) & 1u;
+                const bool c1first = (((unsigned)q.q3.w >> 29) & dirneg) != 0u;
                 const int far = c1first ? q.q3.x : q.q3.y;
+                if (stk.sp >= RT_PACKET_STACK) { overflow = true; break; }     // deeper than 64 levels (never on an LBVH of < 2^64 keys; kept as the safety net)
                 stk.push((uint32_t)far, lane);
                 if (PF) {      // the deferred child will be popped later: start pulling its line into L1 now
                     const void* a = far >= 0 ? (const void*)(nodes + far) : (const void*)(geom + rt_leaf_first(far));
@@ -264,7 +269,7 @@ __device__ __noinline__ TraceResult packet_trace(const BvhNode* __restrict__ nod
         if (stk.sp == 0) break;
         cur = (int)stk.pop();
     }
-    if (stk.overflow) {        // deeper than 64 levels: finish by brute force, like the reference (query.h:297-308)
+    if (overflow) {            // finish by brute force, like the reference (query.h:297-308)
         for (uint32_t s = 0; s < num_tris; ++s) {
             const Tri tr = rt_load_tri(geom, s);
             if (!live) continue;
@@ -314,7 +319,7 @@ k_render_packet(const __grid_constant__ FrameParams P) {
         Hit h; rt_hit_reset(h);
         {
             const Ray ray = rt_make_ray(P.cam, MODE, x, y, jx, jy);
-            h = packet_trace<MODE, STATS, FAST, PF>(P.nodes, P.geom, P.num_tris, ray, live, false, 0.f, &st).hit;
+            h = packet_trace<MODE, STATS, FAST, PF, MINB * 2 + (GROUPED ? 1 : 0)>(P.nodes, P.geom, P.num_tris, ray, live, false, 0.f, &st).hit;
         }
         if (live) ++nprim;
         if (s == 0 && inside) {                        // id / t planes describe sample 0
@@ -350,7 +355,7 @@ k_render_packet(const __grid_constant__ FrameParams P) {
                             direct = rt_light_direct_hw2(sf, P.lights[l], L, NdotL);
                         }
                     }
-                    blocked = packet_trace<MODE, STATS, FAST, PF>(P.nodes, P.geom, P.num_tris, sray, need, true, dist, &st).blocked;
+                    blocked = packet_trace<MODE, STATS, FAST, PF, MINB * 2 + (GROUPED ? 1 : 0)>(P.nodes, P.geom, P.num_tris, sray, need, true, dist, &st).blocked;
                 }
                 if (need) ++nshadow;
                 if (lit && !blocked) Lo = xadd3(Lo, direct);

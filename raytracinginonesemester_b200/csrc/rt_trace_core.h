@@ -32,8 +32,19 @@ struct NodeQ { float4 q0, q1, q2; int4 q3; };
 RT_HD NodeQ rt_load_node(const BvhNode* __restrict__ nodes, int idx) {
     const float4* n = reinterpret_cast<const float4*>(nodes + idx);
     NodeQ q;
+#ifdef __CUDA_ARCH__
+    // sm_100: the 64-byte node line as two 256-bit read-only loads (LDG.E.ENL2.256.CONSTANT) instead of four
+    // 128-bit ones: half the load instructions and half the address set-up per node visit.
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(q.q0.x), "=f"(q.q0.y), "=f"(q.q0.z), "=f"(q.q0.w), "=f"(q.q1.x), "=f"(q.q1.y), "=f"(q.q1.z), "=f"(q.q1.w) : "l"(n));
+    float i0, i1, i2, i3;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(q.q2.x), "=f"(q.q2.y), "=f"(q.q2.z), "=f"(q.q2.w), "=f"(i0), "=f"(i1), "=f"(i2), "=f"(i3) : "l"(n + 2));
+    q.q3 = make_int4(__float_as_int(i0), __float_as_int(i1), __float_as_int(i2), __float_as_int(i3));
+#else
     q.q0 = RT_LDG(n); q.q1 = RT_LDG(n + 1); q.q2 = RT_LDG(n + 2);
     q.q3 = RT_LDG(reinterpret_cast<const int4*>(n + 3));
+#endif
     return q;
 }
 

@@ -98,7 +98,7 @@ void* emu_build(const rt_scene* sc, uint32_t leaf_max) {
             es->nodes[newidx[i]] = rt_make_node(blo[tp.left], bhi[tp.left], blo[tp.right], bhi[tp.right],
                                                 rt_child_ref(tp.left, n, topo.data(), keep.data(), newidx.data()),
                                                 rt_child_ref(tp.right, n, topo.data(), keep.data(), newidx.data()),
-                                                tp.first, (RT_TOPO_LAST(tp) - tp.first + 1u) | (RT_TOPO_AXIS(tp) << 30));
+                                                tp.first, (RT_TOPO_LAST(tp) - tp.first + 1u) | RT_NODE_AXIS_BITS(RT_TOPO_AXIS(tp)));
         }
     } else {
         float4 lo = make_float4(INFINITY, INFINITY, INFINITY, 0.f), hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
