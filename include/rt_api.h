@@ -76,8 +76,11 @@ extern "C" {
 #define RT_VARIANT_PACKET_EXACT_SLAB 3 /* same as default with the unfused (b-o)*inv slab test         */
 #define RT_VARIANT_PACKET_PREFETCH  4  /* default kernel + L1 prefetch of the deferred child at every push           */
 #define RT_VARIANT_PACKET_PIXEL_MAJOR 5 /* default kernel with one sample of 32 pixels per packet even when spp > 1     */
+#define RT_VARIANT_FRUSTUM          6  /* packet kernel with the frustum-culled wide traversal (one lane = one box, 32 boxes per round) */
+#define RT_VARIANT_PACKET           7  /* packet kernel with the per-lane traversal (every lane slab-tests both children of a node)       */
 #define RT_VARIANT_PER_RAY         10  /* independent per-thread stack traversal (shared-memory stack) */
 #define RT_VARIANT_STATS          100  /* default kernel, also counts BVH node visits / triangle tests per ray */
+#define RT_VARIANT_FRUSTUM_STATS  106  /* frustum kernel with the same counters                        */
 #define RT_VARIANT_PER_RAY_STATS  110  /* per-ray kernel with the same counters                        */
 
 /* rt_scene.build_flags */

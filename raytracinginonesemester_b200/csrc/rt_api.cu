@@ -91,6 +91,7 @@ struct rt_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;   // whole frame / frame kernel only
     std::string err;
     // scene
+    WideNode* wide = nullptr;            // 8-wide view of nodes, built after the BVH2 (every rank builds its own)
     BvhNode* nodes = nullptr; TriBlock* geom = nullptr; TriBlock* shade = nullptr; rt_material* materials = nullptr;
     uint32_t num_tris = 0, num_nodes = 0; int num_materials = 0; bool has_scene = false, has_bvh = false, has_normals = false;
     rt_build_info info{};
@@ -137,6 +138,8 @@ int fail(rt_ctx* c, int code, const char* fmt, ...) {
 
 void free_scene(rt_ctx* c) {
     if (c->nodes) cudaFree(c->nodes);
+    if (c->wide) cudaFree(c->wide);
+    c->wide = nullptr;
     if (c->geom) cudaFree(c->geom);
     if (c->shade) cudaFree(c->shade);
     if (c->materials) cudaFree(c->materials);
@@ -144,6 +147,17 @@ void free_scene(rt_ctx* c) {
     c->num_tris = c->num_nodes = 0; c->num_materials = 0; c->has_scene = c->has_bvh = false;
 }
 
+
+// 8-wide view of the BVH2 for the frustum traversal: derived data, rebuilt by every rank from its copy of the nodes.
+int build_wide_nodes(rt_ctx* c) {
+    if (c->wide) { cudaFree(c->wide); c->wide = nullptr; }
+    if (!c->has_bvh || !c->num_nodes) return RT_OK;
+    CU(c, cudaMalloc(&c->wide, sizeof(WideNode) * (size_t)c->num_nodes));
+    CU(c, rt_build_wide(c->nodes, c->num_nodes, c->wide, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->info.arena_bytes += sizeof(WideNode) * (uint64_t)c->num_nodes;
+    return RT_OK;
+}
 
 struct SceneHeader { uint32_t num_tris, num_nodes, num_materials, has_bvh, has_normals; float smin[3], smax[3]; };
 
@@ -182,7 +196,7 @@ int broadcast_scene(rt_ctx* c) {
     c->has_scene = true;
     c->info.arena_bytes = sizeof(BvhNode) * (uint64_t)c->num_nodes + 2 * sizeof(TriBlock) * (uint64_t)c->num_tris +
                           sizeof(rt_material) * (uint64_t)c->num_materials;
-    return RT_OK;
+    return build_wide_nodes(c);
 }
 
 // ---- small host-side collectives over the library's communicator (setup paths only) ----
@@ -534,7 +548,7 @@ int rt_upload_scene(rt_ctx* c, const rt_scene* sc) {
     c->info.arena_bytes = sizeof(BvhNode) * (uint64_t)c->num_nodes + 2 * sizeof(TriBlock) * (uint64_t)nt +
                           sizeof(rt_material) * (uint64_t)sc->num_materials;
     if (c->world > 1) return broadcast_scene(c);
-    return RT_OK;
+    return build_wide_nodes(c);
 }
 
 int rt_build_info_get(const rt_ctx* c, rt_build_info* info) {
@@ -594,9 +608,10 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
     P.num_materials = c->num_materials; P.has_normals = c->has_normals ? 1 : 0;
     P.sample_group = 1;
     while (P.sample_group < 32 && fr->spp % (2 * P.sample_group) == 0) P.sample_group *= 2;
-    if (fr->kernel_variant != RT_VARIANT_DEFAULT && fr->kernel_variant != RT_VARIANT_STATS) P.sample_group = 1;   // experimental variants: pixel-major
+    if (fr->kernel_variant != RT_VARIANT_DEFAULT && fr->kernel_variant != RT_VARIANT_STATS &&
+        fr->kernel_variant != RT_VARIANT_FRUSTUM && fr->kernel_variant != RT_VARIANT_FRUSTUM_STATS && fr->kernel_variant != RT_VARIANT_PACKET) P.sample_group = 1;   // experimental variants: pixel-major
     memcpy(P.miss, fr->miss_color, sizeof P.miss);
-    P.nodes = c->nodes; P.geom = c->geom; P.shade = c->shade; P.num_tris = c->num_tris; P.materials = c->materials;
+    P.nodes = c->nodes; P.wide = c->wide; P.geom = c->geom; P.shade = c->shade; P.num_tris = c->num_tris; P.materials = c->materials;
     P.tiles_x = (P.W + RT_TILE_W - 1) / RT_TILE_W; P.tiles_y = (P.H + RT_TILE_H - 1) / RT_TILE_H;
     P.rank = c->rank; P.world = c->world;
     const bool dbg_shard = c->world == 1 && c->dbg_world > 1;
@@ -619,6 +634,7 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
             far = fmaxf(far, fabsf(fr->cam.center[k]));
         }
         P.fast_slab = (c->has_bvh && far <= 8.0f * ext) ? 1 : 0;
+        P.frustum_eps = 1.6e-5f * fmaxf(ext, far) + 1e-30f;
     }
 
     if (fr->num_lights) {

@@ -27,6 +27,15 @@ struct alignas(64) BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be one 64-byte line");
 
+// 8-wide view of the same tree for the frustum traversal (rt_trace.cu, frustum_trace): wide[i] holds the boxes and
+// references reached from BVH2 node i by three left/right steps (entry k = path bits k2 k1 k0; a leaf met early sits in
+// the entry whose remaining path bits are zero, the other entries of that subtree are absent).  32 bytes per entry:
+// (c.x, c.y, c.z, h.x) (h.y, h.z, bits(ref), 0); absent: h = -1.  References are BVH2 node indices / leaf references
+// exactly as in BvhNode, so wide[ref] is the next wide node.  Built on the device from the finished BVH2 (k_build_wide).
+struct alignas(32) WideEntry { float cx, cy, cz, hx, hy, hz; int32_t ref; int32_t pad; };
+struct alignas(256) WideNode { WideEntry e[8]; };
+static_assert(sizeof(WideNode) == 256, "WideNode must be 256 bytes");
+
 #define RT_LEAF_MAX_LOG2 3
 RT_HD int32_t rt_leaf_ref(uint32_t first, uint32_t count) { return ~(int32_t)((first << RT_LEAF_MAX_LOG2) | (count - 1u)); }
 RT_HD uint32_t rt_leaf_first(int32_t ref) { return ((uint32_t)~ref) >> RT_LEAF_MAX_LOG2; }

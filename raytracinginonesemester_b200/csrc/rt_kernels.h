@@ -14,6 +14,8 @@ cudaError_t rt_build_bvh(const BuildParams& bp, BvhNode** nodes_out, TriBlock* g
 // Bakes an object's transform into its vertex range in place (device arrays), before the build.
 struct BakeXform;
 cudaError_t rt_bake_transform(float* pos, float* nrm, size_t first, size_t count, const BakeXform& T, cudaStream_t stream);
+// 8-wide view of a finished BVH2 (one WideNode per BVH2 node), for the frustum traversal.
+cudaError_t rt_build_wide(const BvhNode* nodes, uint32_t num_nodes, WideNode* wide, cudaStream_t stream);
 // Pack triangles in input order without a BVH (brute-force-only scenes).
 cudaError_t rt_pack_triangles(const BuildParams& bp, TriBlock* geom, TriBlock* shade, cudaStream_t stream);
 

@@ -283,6 +283,186 @@ __device__ __noinline__ TraceResult packet_trace(const BvhNode* __restrict__ nod
     return TraceResult{best, blocked};
 }
 
+// ------------------------------------------------------- frustum-culled wide traversal ----
+// packet_trace spends half of the frame's instructions on node visits in which all 32 lanes slab-test the SAME
+// two boxes.  Here the roles are swapped for the inner nodes: one LANE = one BOX.  The packet's rays are bounded
+// by four side planes and a depth range (a frustum that needs no common apex, see below); a round pops up to four
+// nodes from a warp-wide frontier stack in shared memory, every group of eight lanes reads that node's 8-wide view
+// (WideNode, rt_core.h: the boxes three left/right steps below it, one 32-byte entry per lane), and each lane tests
+// its box against the frustum — 32 boxes per round instead of 2 per visit.  Inner
+// boxes that pass are pushed with a ballot-ranked compaction; leaf boxes that pass are handed to the whole warp,
+// which culls them per ray with the ordinary slab test (own t limit) and then runs the same exactly-rounded
+// triangle tests as packet_trace.  A frustum test can only let a lane reach MORE triangles than its own
+// traversal would, so ids, t and colours are unchanged (canonical rule: min t, then min id).
+//
+// The frustum: for rays o_i + t d_i (t >= 0) pick any w with d_i.w > 0 and let sa_i = (d_i.u)/(d_i.w) for a
+// second vector u.  With n = u - s w and s <= min_i sa_i, f(x) = x.n has a non-negative coefficient of t along
+// every ray, so each ray stays in the half space x.n >= min_i o_i.n.  The other three sides follow with
+// (max sa, -u), (min sb, v), (max sb, -v).  Depth: x.w grows along every ray, so a box lies behind every
+// origin or beyond every ray's t limit when its depth interval misses [min o_i.w, max (o_i + tlimit_i d_i).w].
+// Rounding: the slope bounds are widened by 4e-6 (1 + |s|) (directions are within 60 degrees of w, so |s| < 1.8),
+// and every plane offset by feps = 1.6e-5 x the largest coordinate in play (host: scene bounds, camera) — an
+// order of magnitude more than the error of the 6-term FMA sums.
+#define RT_FSTACK 128
+
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+__device__ __forceinline__ float warp_fmin(float v) { return ord2f(__reduce_min_sync(FULLMASK, f2ord(v))); }
+__device__ __forceinline__ float warp_fmax(float v) { return ord2f(__reduce_max_sync(FULLMASK, f2ord(v))); }
+__device__ __forceinline__ float warp_bcast(float v, int src, int lane) { return __int_as_float((int)__reduce_or_sync(FULLMASK, lane == src ? (unsigned)__float_as_int(v) : 0u)); }
+__device__ __forceinline__ int ld_child_ref(const BvhNode* __restrict__ nodes, int node, int k) { return __ldg(reinterpret_cast<const int*>(nodes + node) + 12 + k); }
+
+template <int MODE, bool STATS, bool FAST, int TAG>
+__device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ nodes, const WideNode* __restrict__ wide, const TriBlock* __restrict__ geom, const uint32_t num_tris,
+                                                  const Ray ray, bool live, const bool any, float tlimit, TraceStats* st,
+                                                  int* __restrict__ wstack, float4* __restrict__ wfr, const float feps) {
+    Hit best; rt_hit_reset(best);
+    bool blocked = false;
+    const float det_eps = rt_det_eps(MODE), tmin = rt_tmin(MODE);
+    const int lane = threadIdx.x & 31;
+    const unsigned mlive = __ballot_sync(FULLMASK, live);
+    if (!mlive) return TraceResult{best, blocked};
+    // frame: w = bisector of the first and last live rays' directions (any w with d.w > 0 is valid; this one is central)
+    const int l0 = __ffs(mlive) - 1, l1 = 31 - __clz(mlive);
+    f3 w = mk3(warp_bcast(ray.d.x, l0, lane) + warp_bcast(ray.d.x, l1, lane), warp_bcast(ray.d.y, l0, lane) + warp_bcast(ray.d.y, l1, lane),
+               warp_bcast(ray.d.z, l0, lane) + warp_bcast(ray.d.z, l1, lane));
+    {
+        const float r = rsqrtf(w.x * w.x + w.y * w.y + w.z * w.z);
+        w = mk3(w.x * r, w.y * r, w.z * r);
+    }
+    f3 u = fabsf(w.x) < 0.7f ? mk3(0.f, w.z, -w.y) : mk3(-w.z, 0.f, w.x);        // w x e_x  or  w x e_y
+    {
+        const float r = rsqrtf(u.x * u.x + u.y * u.y + u.z * u.z);
+        u = mk3(u.x * r, u.y * r, u.z * r);
+    }
+    const f3 v = mk3(w.y * u.z - w.z * u.y, w.z * u.x - w.x * u.z, w.x * u.y - w.y * u.x);
+    const float dw = ray.d.x * w.x + ray.d.y * w.y + ray.d.z * w.z;
+    const float dl = sqrtf(ray.d.x * ray.d.x + ray.d.y * ray.d.y + ray.d.z * ray.d.z);
+    // every live direction within 60 degrees of w (NaN / zero directions fail the comparison), else the per-lane traversal
+    if (!__all_sync(FULLMASK, !live || dw >= 0.5f * dl))
+        return packet_trace<MODE, STATS, FAST, false, TAG>(nodes, geom, num_tris, ray, live, any, tlimit, st);
+    const float BIG = 3.0e38f;
+    float samin, samax, sbmin, sbmax;
+    {
+        const float idw = 1.0f / dw;
+        const float sa = (ray.d.x * u.x + ray.d.y * u.y + ray.d.z * u.z) * idw, sb = (ray.d.x * v.x + ray.d.y * v.y + ray.d.z * v.z) * idw;
+        samin = warp_fmin(live ? sa : BIG); samax = warp_fmax(live ? sa : -BIG);
+        sbmin = warp_fmin(live ? sb : BIG); sbmax = warp_fmax(live ? sb : -BIG);
+        samin -= 4e-6f * (1.0f + fabsf(samin)); samax += 4e-6f * (1.0f + fabsf(samax));
+        sbmin -= 4e-6f * (1.0f + fabsf(sbmin)); sbmax += 4e-6f * (1.0f + fabsf(sbmax));
+    }
+    float farD = BIG;
+    {
+        const f3 n0 = mk3(u.x - samin * w.x, u.y - samin * w.y, u.z - samin * w.z), n1 = mk3(samax * w.x - u.x, samax * w.y - u.y, samax * w.z - u.z);
+        const f3 n2 = mk3(v.x - sbmin * w.x, v.y - sbmin * w.y, v.z - sbmin * w.z), n3 = mk3(sbmax * w.x - v.x, sbmax * w.y - v.y, sbmax * w.z - v.z);
+        const f3 o = ray.o;
+        const float off0 = warp_fmin(live ? o.x * n0.x + o.y * n0.y + o.z * n0.z : BIG) - feps;
+        const float off1 = warp_fmin(live ? o.x * n1.x + o.y * n1.y + o.z * n1.z : BIG) - feps;
+        const float off2 = warp_fmin(live ? o.x * n2.x + o.y * n2.y + o.z * n2.z : BIG) - feps;
+        const float off3 = warp_fmin(live ? o.x * n3.x + o.y * n3.y + o.z * n3.z : BIG) - feps;
+        const float ow = o.x * w.x + o.y * w.y + o.z * w.z;
+        const float nearD = warp_fmin(live ? ow : BIG) - feps;
+        if (any) { farD = warp_fmax(live ? fmaf(tlimit, dw, ow) : -BIG); farD += fabsf(farD) * 2e-6f + feps; }
+        else tlimit = FLT_MAX;
+        // the frustum lives in shared memory (five broadcast 128-bit loads per round) instead of 20 registers per lane
+        if (lane == 0) {
+            wfr[0] = make_float4(n0.x, n0.y, n0.z, off0); wfr[1] = make_float4(n1.x, n1.y, n1.z, off1);
+            wfr[2] = make_float4(n2.x, n2.y, n2.z, off2); wfr[3] = make_float4(n3.x, n3.y, n3.z, off3);
+            wfr[4] = make_float4(w.x, w.y, w.z, nearD);
+            wstack[0] = 0;
+        }
+    }
+    RayInv k; RayFma kf;
+    if (FAST) kf = rt_ray_fma(ray); else k = rt_ray_inv(ray);
+    bool overflow = false;
+    __syncwarp();
+    int sp = 1;
+    while (sp > 0) {
+        const int npop = sp < 4 ? sp : 4;
+        bool valid = (lane >> 3) < npop;
+        int par = valid ? wstack[sp - 1 - (lane >> 3)] : 0;
+        sp -= npop;
+        __syncwarp();
+        // lane (g, k) reads entry k of wide node g: one 256-bit load, no dependent steps
+        float cx = 0.f, cy = 0.f, cz = 0.f, hx = -1.f, hy = -1.f, hz = -1.f;
+        int ref = -1;
+        const int lines = valid ? 1 : 0;
+        if (valid) {
+            const float* ep = reinterpret_cast<const float*>(wide + par) + 8 * (lane & 7);
+            float fr, fp;
+            asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(cx), "=f"(cy), "=f"(cz), "=f"(hx), "=f"(hy), "=f"(hz), "=f"(fr), "=f"(fp) : "l"(ep));
+            ref = __float_as_int(fr);
+        }
+        if (STATS) {
+            int tot = lines;
+            for (int q = 16; q > 0; q >>= 1) tot += __shfl_xor_sync(FULLMASK, tot, q);
+            if (lane == 0) { st->wnodes += (uint32_t)tot; st->nodes += (uint32_t)tot; }
+        }
+        bool hit = hx >= 0.f;                                // absent entries and idle lanes carry negative half extents
+        {
+            const float4 p0 = wfr[0], p1 = wfr[1], p2 = wfr[2], p3 = wfr[3], pw = wfr[4];
+            const float s0 = fmaf(hx, fabsf(p0.x), fmaf(hy, fabsf(p0.y), fmaf(hz, fabsf(p0.z), fmaf(cx, p0.x, fmaf(cy, p0.y, cz * p0.z)))));
+            const float s1 = fmaf(hx, fabsf(p1.x), fmaf(hy, fabsf(p1.y), fmaf(hz, fabsf(p1.z), fmaf(cx, p1.x, fmaf(cy, p1.y, cz * p1.z)))));
+            const float s2 = fmaf(hx, fabsf(p2.x), fmaf(hy, fabsf(p2.y), fmaf(hz, fabsf(p2.z), fmaf(cx, p2.x, fmaf(cy, p2.y, cz * p2.z)))));
+            const float s3 = fmaf(hx, fabsf(p3.x), fmaf(hy, fabsf(p3.y), fmaf(hz, fabsf(p3.z), fmaf(cx, p3.x, fmaf(cy, p3.y, cz * p3.z)))));
+            const float dep = fmaf(cx, pw.x, fmaf(cy, pw.y, cz * pw.z)), dh = fmaf(hx, fabsf(pw.x), fmaf(hy, fabsf(pw.y), hz * fabsf(pw.z)));
+            hit = hit && s0 >= p0.w && s1 >= p1.w && s2 >= p2.w && s3 >= p3.w && dep + dh >= pw.w && dep - dh <= farD;
+        }
+        const unsigned minner = __ballot_sync(FULLMASK, hit && ref >= 0);
+        unsigned mleaf = __ballot_sync(FULLMASK, hit && ref < 0);
+        const int ninner = __popc(minner);
+        if (sp + ninner > RT_FSTACK) { overflow = true; break; }
+        if (hit && ref >= 0) wstack[sp + __popc(minner & ((1u << lane) - 1u))] = ref;
+        sp += ninner;
+        __syncwarp();
+        bool improved = false;
+        while (mleaf) {
+            const int src = __ffs(mleaf) - 1;
+            mleaf &= mleaf - 1u;
+            const int lref = __shfl_sync(FULLMASK, ref, src);
+            const float lcx = __shfl_sync(FULLMASK, cx, src), lcy = __shfl_sync(FULLMASK, cy, src), lcz = __shfl_sync(FULLMASK, cz, src);
+            const float lhx = __shfl_sync(FULLMASK, hx, src), lhy = __shfl_sync(FULLMASK, hy, src), lhz = __shfl_sync(FULLMASK, hz, src);
+            bool lh; float tn;
+            if (FAST) lh = rt_slab_fma_tight(kf, lcx, lcy, lcz, lhx, lhy, lhz, tmin, tlimit);
+            else lh = rt_slab(k, lcx, lcy, lcz, lhx, lhy, lhz, tmin, tlimit, tn);
+            if (!__any_sync(FULLMASK, lh && live)) continue;
+            const uint32_t first = rt_leaf_first(lref), cnt = rt_leaf_count(lref);
+            for (uint32_t s = first; s < first + cnt; ++s) {
+                const Tri tr = rt_load_tri(geom, s);
+                if (STATS && lane == 0) st->wtris++;
+                if (live) {
+                    if (STATS) st->tris++;
+                    float t, uu, vv;
+                    if (rt_moller_trumbore(ray, tr.v0, tr.e1, tr.e2, det_eps, tmin, any ? FLT_MAX : tlimit, t, uu, vv)) {
+                        if (any) { if (t < tlimit) { blocked = true; live = false; } }
+                        else if (t < tlimit || tr.id < best.id) { best.t = t; best.u = uu; best.v = vv; best.slot = (int)s; best.id = tr.id; tlimit = t; improved = true; }
+                    }
+                }
+            }
+            if (any && !__any_sync(FULLMASK, live)) return TraceResult{best, blocked};
+        }
+        if (!any && __any_sync(FULLMASK, improved)) {        // closest: pull the far plane in to the farthest current hit
+            const float4 pw = wfr[4];
+            const float hx_ = fmaf(tlimit, ray.d.x, ray.o.x), hy_ = fmaf(tlimit, ray.d.y, ray.o.y), hz_ = fmaf(tlimit, ray.d.z, ray.o.z);
+            farD = warp_fmax(live ? fmaf(hx_, pw.x, fmaf(hy_, pw.y, hz_ * pw.z)) : -BIG);
+            farD += fabsf(farD) * 4e-6f + feps;
+        }
+    }
+    if (overflow) {            // frontier wider than the shared-memory stack: finish by brute force (as packet_trace does)
+        for (uint32_t s = 0; s < num_tris; ++s) {
+            const Tri tr = rt_load_tri(geom, s);
+            if (!live) continue;
+            float t, uu, vv;
+            if (rt_moller_trumbore(ray, tr.v0, tr.e1, tr.e2, det_eps, tmin, any ? FLT_MAX : tlimit, t, uu, vv)) {
+                if (any) { if (t < tlimit) { blocked = true; live = false; } }
+                else if (t < tlimit || tr.id < best.id) { best.t = t; best.u = uu; best.v = vv; best.slot = (int)s; best.id = tr.id; tlimit = t; }
+            }
+        }
+    }
+    return TraceResult{best, blocked};
+}
+
 // Values that are cheap to recompute are deliberately NOT kept in registers across a shadow
 // trace: laundering the hit through an empty asm makes the compiler rebuild the surface
 // (position, normals, material) afterwards instead of spilling ~60 registers around the loop,
@@ -291,9 +471,14 @@ __device__ __forceinline__ void launder(Hit& h, int& x, int& y) {
     asm volatile("" : "+f"(h.t), "+f"(h.u), "+f"(h.v), "+r"(h.slot), "+r"(x), "+r"(y));
 }
 
-template <int MODE, bool STATS, bool FAST, int MINB, bool PF = false, bool GROUPED = false>
+template <int MODE, bool STATS, bool FAST, int MINB, bool PF = false, bool GROUPED = false, bool FRUSTUM = false>
 __global__ void __launch_bounds__(RT_BLOCK_THREADS, MINB)
 k_render_packet(const __grid_constant__ FrameParams P) {
+    __shared__ int s_wstack[FRUSTUM ? (RT_BLOCK_THREADS / 32) * RT_FSTACK : 1];
+    int* const wstack = s_wstack + (FRUSTUM ? (threadIdx.x >> 5) * RT_FSTACK : 0);
+    __shared__ float4 s_wfr[FRUSTUM ? (RT_BLOCK_THREADS / 32) * 5 : 1];
+    float4* const wfr = s_wfr + (FRUSTUM ? (threadIdx.x >> 5) * 5 : 0);
+    constexpr int TAG = MINB * 4 + (GROUPED ? 1 : 0) + (FRUSTUM ? 2 : 0);
     const Pixel px = map_pixel(P);
     unsigned nprim = 0, nshadow = 0;
     TraceStats st{0, 0, 0, 0, 0};
@@ -319,7 +504,8 @@ k_render_packet(const __grid_constant__ FrameParams P) {
         Hit h; rt_hit_reset(h);
         {
             const Ray ray = rt_make_ray(P.cam, MODE, x, y, jx, jy);
-            h = packet_trace<MODE, STATS, FAST, PF, MINB * 2 + (GROUPED ? 1 : 0)>(P.nodes, P.geom, P.num_tris, ray, live, false, 0.f, &st).hit;
+            if (FRUSTUM) h = frustum_trace<MODE, STATS, FAST, TAG>(P.nodes, P.wide, P.geom, P.num_tris, ray, live, false, 0.f, &st, wstack, wfr, P.frustum_eps).hit;
+            else h = packet_trace<MODE, STATS, FAST, PF, TAG>(P.nodes, P.geom, P.num_tris, ray, live, false, 0.f, &st).hit;
         }
         if (live) ++nprim;
         if (s == 0 && inside) {                        // id / t planes describe sample 0
@@ -355,7 +541,8 @@ k_render_packet(const __grid_constant__ FrameParams P) {
                             direct = rt_light_direct_hw2(sf, P.lights[l], L, NdotL);
                         }
                     }
-                    blocked = packet_trace<MODE, STATS, FAST, PF, MINB * 2 + (GROUPED ? 1 : 0)>(P.nodes, P.geom, P.num_tris, sray, need, true, dist, &st).blocked;
+                    if (FRUSTUM) blocked = frustum_trace<MODE, STATS, FAST, TAG>(P.nodes, P.wide, P.geom, P.num_tris, sray, need, true, dist, &st, wstack, wfr, P.frustum_eps).blocked;
+                    else blocked = packet_trace<MODE, STATS, FAST, PF, TAG>(P.nodes, P.geom, P.num_tris, sray, need, true, dist, &st).blocked;
                 }
                 if (need) ++nshadow;
                 if (lit && !blocked) Lo = xadd3(Lo, direct);
@@ -467,9 +654,10 @@ static cudaError_t launch_mode(const FrameParams& fp, int variant, cudaStream_t 
     // Bounce rays (max_depth > 1) are incoherent: the frame goes to the per-ray kernel, whose sample function
     // carries TraceRayIterative's full loop; the packet kernels implement depth 1.
     if (MODE != RT_MODE_HW1 && fp.max_depth > 1)
-        variant = (variant == RT_VARIANT_STATS || variant == RT_VARIANT_PER_RAY_STATS) ? RT_VARIANT_PER_RAY_STATS : RT_VARIANT_PER_RAY;
+        variant = (variant == RT_VARIANT_STATS || variant == RT_VARIANT_PER_RAY_STATS || variant == RT_VARIANT_FRUSTUM_STATS) ? RT_VARIANT_PER_RAY_STATS : RT_VARIANT_PER_RAY;
     switch (variant) {
     case RT_VARIANT_DEFAULT:
+    case RT_VARIANT_PACKET:
         if (fp.sample_group > 1) {
             if (fast) k_render_packet<MODE, false, true, 8, false, true><<<grid, block, 0, stream>>>(fp);
             else k_render_packet<MODE, false, false, 8, false, true><<<grid, block, 0, stream>>>(fp);
@@ -494,6 +682,24 @@ static cudaError_t launch_mode(const FrameParams& fp, int variant, cudaStream_t 
     case RT_VARIANT_PACKET_PIXEL_MAJOR:
         if (fast) k_render_packet<MODE, false, true, 8><<<grid, block, 0, stream>>>(fp);
         else k_render_packet<MODE, false, false, 8><<<grid, block, 0, stream>>>(fp);
+        break;
+    case RT_VARIANT_FRUSTUM:
+        if (fp.sample_group > 1) {
+            if (fast) k_render_packet<MODE, false, true, 8, false, true, true><<<grid, block, 0, stream>>>(fp);
+            else k_render_packet<MODE, false, false, 8, false, true, true><<<grid, block, 0, stream>>>(fp);
+        } else {
+            if (fast) k_render_packet<MODE, false, true, 8, false, false, true><<<grid, block, 0, stream>>>(fp);
+            else k_render_packet<MODE, false, false, 8, false, false, true><<<grid, block, 0, stream>>>(fp);
+        }
+        break;
+    case RT_VARIANT_FRUSTUM_STATS:
+        if (fp.sample_group > 1) {
+            if (fast) k_render_packet<MODE, true, true, 8, false, true, true><<<grid, block, 0, stream>>>(fp);
+            else k_render_packet<MODE, true, false, 8, false, true, true><<<grid, block, 0, stream>>>(fp);
+        } else {
+            if (fast) k_render_packet<MODE, true, true, 8, false, false, true><<<grid, block, 0, stream>>>(fp);
+            else k_render_packet<MODE, true, false, 8, false, false, true><<<grid, block, 0, stream>>>(fp);
+        }
         break;
     case RT_VARIANT_PER_RAY:       k_render_bvh<MODE, false><<<grid, block, 0, stream>>>(fp); break;
     case RT_VARIANT_PER_RAY_STATS: k_render_bvh<MODE, true><<<grid, block, 0, stream>>>(fp); break;

@@ -197,7 +197,7 @@ def test_device_bvh_is_sound_and_host_walk_agrees(renderer):
         assert np.array_equal(pk[k], got[k]), k
 
 
-@pytest.mark.parametrize("variant", [A.RT_VARIANT_DEFAULT, A.RT_VARIANT_PACKET_OCC6, A.RT_VARIANT_PACKET_OCC10, A.RT_VARIANT_PACKET_EXACT_SLAB, A.RT_VARIANT_PER_RAY])
+@pytest.mark.parametrize("variant", [A.RT_VARIANT_DEFAULT, A.RT_VARIANT_PACKET_OCC6, A.RT_VARIANT_PACKET_OCC10, A.RT_VARIANT_PACKET_EXACT_SLAB, A.RT_VARIANT_PER_RAY, A.RT_VARIANT_PACKET, A.RT_VARIANT_FRUSTUM])
 def test_all_kernel_variants_agree(renderer, frog_scene, variant):
     renderer.upload_scene(frog_scene)
     base = run(renderer, scenes.frog_frame(200, 120, filling=True, outputs=ALL, accel=A.RT_ACCEL_BRUTE))
@@ -481,15 +481,67 @@ def test_sample_major_packets_equal_pixel_major(renderer, frog_scene, spp):
     (float accumulation order included), on frames that are not multiples of the tile."""
     renderer.upload_scene(frog_scene)
     out = {}
-    for variant in (A.RT_VARIANT_DEFAULT, A.RT_VARIANT_PACKET_PIXEL_MAJOR, A.RT_VARIANT_PER_RAY):
+    for variant in (A.RT_VARIANT_DEFAULT, A.RT_VARIANT_PACKET_PIXEL_MAJOR, A.RT_VARIANT_PER_RAY, A.RT_VARIANT_PACKET, A.RT_VARIANT_FRUSTUM):
         fr = scenes.frog_frame(203, 77, filling=True, outputs=ALL)
         fr.spp, fr.jitter, fr.kernel_variant = spp, api.jitter_table(spp, 42, True), variant
         out[variant] = run(renderer, fr)
         assert out[variant]["rays_primary"] == 203 * 77 * spp
-    for variant in (A.RT_VARIANT_PACKET_PIXEL_MAJOR, A.RT_VARIANT_PER_RAY):
+    for variant in (A.RT_VARIANT_PACKET_PIXEL_MAJOR, A.RT_VARIANT_PER_RAY, A.RT_VARIANT_PACKET, A.RT_VARIANT_FRUSTUM):
         for k in ("rgb", "rgb8", "tri_id", "t"):
             assert np.array_equal(out[A.RT_VARIANT_DEFAULT][k], out[variant][k]), (spp, variant, k)
         assert out[A.RT_VARIANT_DEFAULT]["rays_shadow"] == out[variant]["rays_shadow"]
+
+
+def _both_traversals(renderer, frame):
+    out = {}
+    for variant in (A.RT_VARIANT_PACKET, A.RT_VARIANT_FRUSTUM):
+        frame.kernel_variant = variant
+        out[variant] = run(renderer, frame)
+    a, b = out[A.RT_VARIANT_PACKET], out[A.RT_VARIANT_FRUSTUM]
+    for k in ("rgb", "rgb8", "tri_id", "t"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["rays_primary"] == b["rays_primary"] and a["rays_shadow"] == b["rays_shadow"]
+    return a
+
+
+def test_frustum_traversal_equals_per_lane_traversal(renderer, frog_scene, golden):
+    """The frustum-culled wide traversal (one lane = one box; inner nodes culled against the packet's bounding planes)
+    may only make a lane test MORE triangles than the per-lane traversal: every plane must be identical, bit for bit —
+    on terrain (primary + shadow packets, 1 and 4 spp, frame not a multiple of the tile), on the frog (mostly-miss stock
+    view, frame-filling view), inside the Cornell box (wide frusta, axis-aligned walls, lights behind the camera), on
+    tiny / degenerate / tied scenes, with two lights, and with the camera far outside the scene (exact-slab path)."""
+    renderer.upload_scene(scenes.terrain_scene(200, 100))
+    for W, H, spp in ((640, 360, 1), (333, 187, 4), (64, 40, 16)):
+        got = _both_traversals(renderer, scenes.terrain_frame(W, H, spp=spp, outputs=ALL))
+        assert (got["tri_id"] >= 0).mean() > 0.99 and got["rays_shadow"] > 0
+    fr = scenes.terrain_frame(320, 180, outputs=ALL)        # grazing view: long thin frusta, large depth range
+    fr.cam = api.camera_init((-1.4, -0.2, 0.12), (0.5, 0.1, 0.0), (0, 0, 1), 18.0, 24.0, 320, 180)
+    fr.lights = [api.make_light((-2.0, -1.0, 1.5), (1, 1, 1), 5), api.make_light((1.5, 0.8, 0.3), (1, 0.5, 0.2), 3)]
+    got = _both_traversals(renderer, fr)
+    assert (got["tri_id"] >= 0).any() and (got["tri_id"] < 0).any()
+    fr.cam = api.camera_init((0.0, 0.0, 400.0), (0, 0, 0), (0, 1, 0), 4000.0, 24.0, 320, 180)   # > 8 scene extents away
+    _both_traversals(renderer, fr)
+    renderer.upload_scene(frog_scene)
+    for filling in (False, True):
+        _both_traversals(renderer, scenes.frog_frame(320, 200, filling=filling, outputs=ALL))
+    d = golden("cornell_mesh.npz")
+    sc = api.Scene(d["positions"], d["indices"], normals=d["normals"] if d["normals"].size else None, tri_obj_ids=d["tri_obj_ids"],
+                   materials=[api.make_material(albedo=(0.7, 0.6, 0.5), kd=0.9, ks=0.2) for _ in range(int(d["tri_obj_ids"].max()) + 1)])
+    renderer.upload_scene(sc)
+    lo, hi = d["positions"].min(0), d["positions"].max(0)
+    mid = 0.5 * (lo + hi)
+    for pos, look, focal in (((mid[0], mid[1], lo[2] + 0.05 * (hi[2] - lo[2])), tuple(mid), 12.0), (tuple(mid), (hi[0], hi[1], mid[2]), 8.0),
+                             ((mid[0], mid[1], lo[2] - 1.5 * (hi[2] - lo[2])), tuple(mid), 35.0)):
+        cam = api.camera_init(pos, look, (0, 1, 0), focal, 24.0, 200, 160)
+        fr = api.Frame(cam, 200, 160, lights=[api.make_light((mid[0], hi[1] - 0.05 * (hi[1] - lo[1]), mid[2]), (1, 1, 1), 60000),
+                                              api.make_light(tuple(lo - 0.3 * (hi - lo)), (0.3, 0.4, 1.0), 90000)],
+                       miss_color=(0.1, 0.1, 0.2), outputs=ALL)
+        _both_traversals(renderer, fr)
+    pos = np.array([[-1, -1, 0], [1, -1, 0], [0, 1, 0], [0, 0, 0.5], [0, 0, 0.5], [0, 0, 0.5]], np.float32)
+    for idx in ([[0, 1, 2]], [[0, 1, 2], [0, 2, 1]], [[0, 1, 2], [3, 4, 5]], [[0, 1, 2]] * 7 + [[3, 4, 5]] * 3):
+        renderer.upload_scene(api.Scene(pos, np.array(idx, np.uint32)))
+        cam = api.camera_init((0.1, 0.05, 3), (0, 0, 0), (0, 1, 0), 50.0, 24.0, 40, 30)
+        _both_traversals(renderer, api.Frame(cam, 40, 30, lights=[api.make_light((1, 1, 2), (1, 1, 1), 3)], miss_color=(0.2, 0.3, 0.4), outputs=ALL))
 
 
 def test_render_into_equals_render_plus_download(renderer, frog_scene):
