@@ -337,14 +337,14 @@ __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ no
     }
     const f3 v = mk3(w.y * u.z - w.z * u.y, w.z * u.x - w.x * u.z, w.x * u.y - w.y * u.x);
     const float dw = ray.d.x * w.x + ray.d.y * w.y + ray.d.z * w.z;
-    const float dl = sqrtf(ray.d.x * ray.d.x + ray.d.y * ray.d.y + ray.d.z * ray.d.z);
+    const float dd = ray.d.x * ray.d.x + ray.d.y * ray.d.y + ray.d.z * ray.d.z;
     // every live direction within 60 degrees of w (NaN / zero directions fail the comparison), else the per-lane traversal
-    if (!__all_sync(FULLMASK, !live || dw >= 0.5f * dl))
+    if (!__all_sync(FULLMASK, !live || (dw > 0.f && dw * dw >= 0.25f * dd)))
         return packet_trace<MODE, STATS, FAST, false, TAG>(nodes, geom, num_tris, ray, live, any, tlimit, st);
     const float BIG = 3.0e38f;
     float samin, samax, sbmin, sbmax;
     {
-        const float idw = 1.0f / dw;
+        const float idw = __fdividef(1.0f, dw);
         const float sa = (ray.d.x * u.x + ray.d.y * u.y + ray.d.z * u.z) * idw, sb = (ray.d.x * v.x + ray.d.y * v.y + ray.d.z * v.z) * idw;
         samin = warp_fmin(live ? sa : BIG); samax = warp_fmax(live ? sa : -BIG);
         sbmin = warp_fmin(live ? sb : BIG); sbmax = warp_fmax(live ? sb : -BIG);
@@ -428,7 +428,8 @@ __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ no
             else lh = rt_slab(k, lcx, lcy, lcz, lhx, lhy, lhz, tmin, tlimit, tn);
             if (!__any_sync(FULLMASK, lh && live)) continue;
             const uint32_t first = rt_leaf_first(lref), cnt = rt_leaf_count(lref);
-            for (uint32_t s = first; s < first + cnt; ++s) {
+#pragma unroll 1
+            for (uint32_t s = first; s < first + cnt; ++s) {      // one copy of the test: the kernel is instruction-cache sensitive
                 const Tri tr = rt_load_tri(geom, s);
                 if (STATS && lane == 0) st->wtris++;
                 if (live) {
@@ -518,7 +519,7 @@ k_render_packet(const __grid_constant__ FrameParams P) {
         } else {
             const bool hit = live && h.slot >= 0;
             f3 Lo = mk3(0.f, 0.f, 0.f);
-            if (hit) {
+            if (hit && P.num_lights == 0) {              // with lights, the first light's surface rebuild supplies this term
                 launder(h, x, y);
                 Surface sf;
                 rt_surface_hw2(P, rt_make_ray(P.cam, MODE, x, y, jx, jy), h, sf);
@@ -534,6 +535,7 @@ k_render_packet(const __grid_constant__ FrameParams P) {
                         launder(h, x, y);
                         Surface sf; f3 L; float NdotL;
                         rt_surface_hw2(P, rt_make_ray(P.cam, MODE, x, y, jx, jy), h, sf);
+                        if (l == 0) Lo = sf.Lo;          // ambient + emission
                         lit = rt_light_setup_hw2(sf, P.lights[l], L, NdotL, need, sray, dist);
                         need = need && lit && P.shadows;
                         if (lit) {
