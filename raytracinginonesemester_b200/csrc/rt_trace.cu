@@ -300,6 +300,7 @@ __device__ __noinline__ TraceResult packet_trace(const BvhNode* __restrict__ nod
 // every ray, so each ray stays in the half space x.n >= min_i o_i.n.  The other three sides follow with
 // (max sa, -u), (min sb, v), (max sb, -v).  Depth: x.w grows along every ray, so a box lies behind every
 // origin or beyond every ray's t limit when its depth interval misses [min o_i.w, max (o_i + tlimit_i d_i).w].
+// same_origin: the caller guarantees one origin for all live lanes (camera rays), which saves the five reductions.
 // Rounding: the slope bounds are widened by 4e-6 (1 + |s|) (directions are within 60 degrees of w, so |s| < 1.8),
 // and every plane offset by feps = 1.6e-5 x the largest coordinate in play (host: scene bounds, camera) — an
 // order of magnitude more than the error of the 6-term FMA sums.
@@ -314,7 +315,7 @@ __device__ __forceinline__ int ld_child_ref(const BvhNode* __restrict__ nodes, i
 
 template <int MODE, bool STATS, bool FAST, int TAG>
 __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ nodes, const WideNode* __restrict__ wide, const TriBlock* __restrict__ geom, const uint32_t num_tris,
-                                                  const Ray ray, bool live, const bool any, float tlimit, TraceStats* st,
+                                                  const Ray ray, bool live, const bool any, const bool same_origin, float tlimit, TraceStats* st,
                                                   int* __restrict__ wstack, float4* __restrict__ wfr, const float feps) {
     Hit best; rt_hit_reset(best);
     bool blocked = false;
@@ -356,12 +357,20 @@ __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ no
         const f3 n0 = mk3(u.x - samin * w.x, u.y - samin * w.y, u.z - samin * w.z), n1 = mk3(samax * w.x - u.x, samax * w.y - u.y, samax * w.z - u.z);
         const f3 n2 = mk3(v.x - sbmin * w.x, v.y - sbmin * w.y, v.z - sbmin * w.z), n3 = mk3(sbmax * w.x - v.x, sbmax * w.y - v.y, sbmax * w.z - v.z);
         const f3 o = ray.o;
-        const float off0 = warp_fmin(live ? o.x * n0.x + o.y * n0.y + o.z * n0.z : BIG) - feps;
-        const float off1 = warp_fmin(live ? o.x * n1.x + o.y * n1.y + o.z * n1.z : BIG) - feps;
-        const float off2 = warp_fmin(live ? o.x * n2.x + o.y * n2.y + o.z * n2.z : BIG) - feps;
-        const float off3 = warp_fmin(live ? o.x * n3.x + o.y * n3.y + o.z * n3.z : BIG) - feps;
+        float off0 = o.x * n0.x + o.y * n0.y + o.z * n0.z, off1 = o.x * n1.x + o.y * n1.y + o.z * n1.z;
+        float off2 = o.x * n2.x + o.y * n2.y + o.z * n2.z, off3 = o.x * n3.x + o.y * n3.y + o.z * n3.z;
         const float ow = o.x * w.x + o.y * w.y + o.z * w.z;
-        const float nearD = warp_fmin(live ? ow : BIG) - feps;
+        float nearD = ow;
+        if (!same_origin) {                               // (lane 0 writes the frustum; with one origin its values are everyone's)
+            off0 = warp_fmin(live ? off0 : BIG); off1 = warp_fmin(live ? off1 : BIG);
+            off2 = warp_fmin(live ? off2 : BIG); off3 = warp_fmin(live ? off3 : BIG);
+            nearD = warp_fmin(live ? ow : BIG);
+        } else {
+            const int l0b = __ffs(mlive) - 1;
+            off0 = __shfl_sync(FULLMASK, off0, l0b); off1 = __shfl_sync(FULLMASK, off1, l0b);
+            off2 = __shfl_sync(FULLMASK, off2, l0b); off3 = __shfl_sync(FULLMASK, off3, l0b); nearD = __shfl_sync(FULLMASK, nearD, l0b);
+        }
+        off0 -= feps; off1 -= feps; off2 -= feps; off3 -= feps; nearD -= feps;
         if (any) { farD = warp_fmax(live ? fmaf(tlimit, dw, ow) : -BIG); farD += fabsf(farD) * 2e-6f + feps; }
         else tlimit = FLT_MAX;
         // the frustum lives in shared memory (five broadcast 128-bit loads per round) instead of 20 registers per lane
@@ -420,9 +429,14 @@ __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ no
         while (mleaf) {
             const int src = __ffs(mleaf) - 1;
             mleaf &= mleaf - 1u;
-            const int lref = __shfl_sync(FULLMASK, ref, src);
-            const float lcx = __shfl_sync(FULLMASK, cx, src), lcy = __shfl_sync(FULLMASK, cy, src), lcz = __shfl_sync(FULLMASK, cz, src);
-            const float lhx = __shfl_sync(FULLMASK, hx, src), lhy = __shfl_sync(FULLMASK, hy, src), lhz = __shfl_sync(FULLMASK, hz, src);
+            // the candidate's entry again, this time by every lane (uniform address, the line is in L1): one shuffle
+            // and one 256-bit load instead of seven shuffles
+            const int eidx = __shfl_sync(FULLMASK, par * 8 + (lane & 7), src);
+            float lcx, lcy, lcz, lhx, lhy, lhz, lfr, lfp;
+            asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(lcx), "=f"(lcy), "=f"(lcz), "=f"(lhx), "=f"(lhy), "=f"(lhz), "=f"(lfr), "=f"(lfp)
+                         : "l"(reinterpret_cast<const float*>(wide) + 8 * (size_t)eidx));
+            const int lref = __float_as_int(lfr);
             bool lh; float tn;
             if (FAST) lh = rt_slab_fma_tight(kf, lcx, lcy, lcz, lhx, lhy, lhz, tmin, tlimit);
             else lh = rt_slab(k, lcx, lcy, lcz, lhx, lhy, lhz, tmin, tlimit, tn);
@@ -505,7 +519,7 @@ k_render_packet(const __grid_constant__ FrameParams P) {
         Hit h; rt_hit_reset(h);
         {
             const Ray ray = rt_make_ray(P.cam, MODE, x, y, jx, jy);
-            if (FRUSTUM) h = frustum_trace<MODE, STATS, FAST, TAG>(P.nodes, P.wide, P.geom, P.num_tris, ray, live, false, 0.f, &st, wstack, wfr, P.frustum_eps).hit;
+            if (FRUSTUM) h = frustum_trace<MODE, STATS, FAST, TAG>(P.nodes, P.wide, P.geom, P.num_tris, ray, live, false, true, 0.f, &st, wstack, wfr, P.frustum_eps).hit;
             else h = packet_trace<MODE, STATS, FAST, PF, TAG>(P.nodes, P.geom, P.num_tris, ray, live, false, 0.f, &st).hit;
         }
         if (live) ++nprim;
@@ -543,7 +557,7 @@ k_render_packet(const __grid_constant__ FrameParams P) {
                             direct = rt_light_direct_hw2(sf, P.lights[l], L, NdotL);
                         }
                     }
-                    if (FRUSTUM) blocked = frustum_trace<MODE, STATS, FAST, TAG>(P.nodes, P.wide, P.geom, P.num_tris, sray, need, true, dist, &st, wstack, wfr, P.frustum_eps).blocked;
+                    if (FRUSTUM) blocked = frustum_trace<MODE, STATS, FAST, TAG>(P.nodes, P.wide, P.geom, P.num_tris, sray, need, true, false, dist, &st, wstack, wfr, P.frustum_eps).blocked;
                     else blocked = packet_trace<MODE, STATS, FAST, PF, TAG>(P.nodes, P.geom, P.num_tris, sray, need, true, dist, &st).blocked;
                 }
                 if (need) ++nshadow;
