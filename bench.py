@@ -378,7 +378,8 @@ def run_ours(args, rank, world, local_rank):
     timed(args.warmup if args.profile else max(args.warmup, 3))
     # traversal statistics (untimed): bytes per ray for the roofline
     if not brute:
-        frame.kernel_variant = A.RT_VARIANT_PER_RAY_STATS if args.variant >= 10 else A.RT_VARIANT_STATS
+        frame.kernel_variant = (A.RT_VARIANT_PER_RAY_STATS if args.variant >= 10 else
+                                A.RT_VARIANT_STATS if args.variant in (A.RT_VARIANT_DEFAULT, A.RT_VARIANT_FRUSTUM) else A.RT_VARIANT_PACKET_STATS)
     r.render(frame)
     st = r.download(into={"rgb8": pinned} if rank == 0 else None)
     nv, nt, nl, nb = r.frame_stats()
@@ -430,8 +431,9 @@ def run_ours(args, rank, world, local_rank):
 
     if rank == 0:
         peak, peak_kind = measured_peaks()
-        # algorithmic bytes per launch: 64-byte node lines and 48-byte triangle blocks the kernel requests
-        # (one per warp visit), one 48-byte shading block per hit pixel, the 8-bit frame written once
+        # algorithmic bytes per launch: node data and 48-byte triangle blocks the kernel requests (frustum traversal: one
+        # 32-byte wide entry per lane-box test, counted in 64-byte units; per-lane traversal: one 64-byte line per warp
+        # visit), one 48-byte shading block per hit pixel, the 8-bit frame written once
         bytes_launch = 64.0 * nl_all + 48.0 * nb_all + 48.0 * rays_primary + 3.0 * W * H
         b_ray = bytes_launch / rays
         achieved = bytes_launch / (ms * 1e-3) / 1e9
@@ -447,8 +449,8 @@ def run_ours(args, rank, world, local_rank):
         if brute:
             note = "FP32-issue bound, not HBM-bound: triangles are streamed through shared memory once per 128 rays; see fp32_issue"
         else:
-            note = ("instruction-issue/latency bound, not HBM-bound: the arena is L2/L1-resident (ncu: issue slots 79 % busy, DRAM < 1 % of peak); "
-                    "achieved = bytes the kernel REQUESTS (64 B per warp node visit, 48 B per warp triangle test), most served by L1/L2 - see traffic and profiles/")
+            note = ("instruction-issue/latency bound, not HBM-bound: the arena is L2/L1-resident (ncu: issue slots 76 % busy, DRAM < 1 % of peak); "
+                    "achieved = bytes the kernel REQUESTS (32 B per lane-box test of the frustum traversal, 48 B per warp triangle test), most served by L1/L2 - see traffic and profiles/")
         line = {
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -70,7 +70,7 @@ extern "C" {
 #define RT_QUANT_CPU_TRUNC    4  /* CPUOnly/src/render.cpp:157-163 clamp to [0,1], (uchar)(255.99f*c) */
 
 /* rt_frame.kernel_variant */
-#define RT_VARIANT_DEFAULT          0  /* warp-packet traversal (one 8x4 tile per warp), 8 blocks/SM    */
+#define RT_VARIANT_DEFAULT          0  /* packet kernel (one 8x4 tile per warp) with the frustum-culled wide traversal (= RT_VARIANT_FRUSTUM) */
 #define RT_VARIANT_PACKET_OCC6      1  /* same, compiled for >= 6 resident blocks per SM               */
 #define RT_VARIANT_PACKET_OCC10     2  /* same, >= 10 resident blocks per SM                           */
 #define RT_VARIANT_PACKET_EXACT_SLAB 3 /* same as default with the unfused (b-o)*inv slab test         */
@@ -79,7 +79,8 @@ extern "C" {
 #define RT_VARIANT_FRUSTUM          6  /* packet kernel with the frustum-culled wide traversal (one lane = one box, 32 boxes per round) */
 #define RT_VARIANT_PACKET           7  /* packet kernel with the per-lane traversal (every lane slab-tests both children of a node)       */
 #define RT_VARIANT_PER_RAY         10  /* independent per-thread stack traversal (shared-memory stack) */
-#define RT_VARIANT_STATS          100  /* default kernel, also counts BVH node visits / triangle tests per ray */
+#define RT_VARIANT_STATS          100  /* default kernel, also counts node data requested / triangle tests (= RT_VARIANT_FRUSTUM_STATS) */
+#define RT_VARIANT_PACKET_STATS   107  /* per-lane packet traversal with the same counters               */
 #define RT_VARIANT_FRUSTUM_STATS  106  /* frustum kernel with the same counters                        */
 #define RT_VARIANT_PER_RAY_STATS  110  /* per-ray kernel with the same counters                        */
 

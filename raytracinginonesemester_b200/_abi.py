@@ -11,7 +11,7 @@ RT_BUILD_DEFAULT, RT_BUILD_NO_BVH = 0, 1
 RT_VARIANT_DEFAULT, RT_VARIANT_PACKET_OCC6, RT_VARIANT_PACKET_OCC10, RT_VARIANT_PACKET_EXACT_SLAB, RT_VARIANT_PER_RAY = 0, 1, 2, 3, 10
 RT_VARIANT_PACKET_PREFETCH, RT_VARIANT_PACKET_PIXEL_MAJOR = 4, 5
 RT_VARIANT_STATS, RT_VARIANT_PER_RAY_STATS = 100, 110
-RT_VARIANT_FRUSTUM, RT_VARIANT_FRUSTUM_STATS, RT_VARIANT_PACKET = 6, 106, 7
+RT_VARIANT_FRUSTUM, RT_VARIANT_FRUSTUM_STATS, RT_VARIANT_PACKET, RT_VARIANT_PACKET_STATS = 6, 106, 7, 107
 RT_GATHER_AUTO, RT_GATHER_NCCL, RT_GATHER_PEER = 0, 1, 2
 
 

@@ -609,7 +609,8 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
     P.sample_group = 1;
     while (P.sample_group < 32 && fr->spp % (2 * P.sample_group) == 0) P.sample_group *= 2;
     if (fr->kernel_variant != RT_VARIANT_DEFAULT && fr->kernel_variant != RT_VARIANT_STATS &&
-        fr->kernel_variant != RT_VARIANT_FRUSTUM && fr->kernel_variant != RT_VARIANT_FRUSTUM_STATS && fr->kernel_variant != RT_VARIANT_PACKET) P.sample_group = 1;   // experimental variants: pixel-major
+        fr->kernel_variant != RT_VARIANT_FRUSTUM && fr->kernel_variant != RT_VARIANT_FRUSTUM_STATS && fr->kernel_variant != RT_VARIANT_PACKET &&
+        fr->kernel_variant != RT_VARIANT_PACKET_STATS) P.sample_group = 1;   // experimental variants: pixel-major
     memcpy(P.miss, fr->miss_color, sizeof P.miss);
     P.nodes = c->nodes; P.wide = c->wide; P.geom = c->geom; P.shade = c->shade; P.num_tris = c->num_tris; P.materials = c->materials;
     P.tiles_x = (P.W + RT_TILE_W - 1) / RT_TILE_W; P.tiles_y = (P.H + RT_TILE_H - 1) / RT_TILE_H;
@@ -635,6 +636,23 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
         }
         P.fast_slab = (c->has_bvh && far <= 8.0f * ext) ? 1 : 0;
         P.frustum_eps = 1.6e-5f * fmaxf(ext, far) + 1e-30f;
+        float r2 = 0.f;
+        for (int k = 0; k < 3; ++k) {
+            P.scene_c[k] = 0.5f * c->info.scene_min[k] + 0.5f * c->info.scene_max[k];
+            const float e = c->info.scene_max[k] - c->info.scene_min[k];
+            r2 += 0.25f * e * e;
+        }
+        P.scene_r2 = r2 * 1.03f + 1e-30f;   // 3 %: far beyond the 2^-17 padding of the node boxes
+        {   // rounding of (c-o).d and |c-o|^2 must stay far below the padding: coordinates <= 1000 r, camera within 30 r
+            const float r = sqrtf(r2);
+            float dc2 = 0.f, maxabs = 0.f;
+            for (int k = 0; k < 3; ++k) {
+                const float d = fr->cam.center[k] - P.scene_c[k];
+                dc2 += d * d;
+                maxabs = fmaxf(maxabs, fmaxf(fabsf(fr->cam.center[k]), fmaxf(fabsf(c->info.scene_min[k]), fabsf(c->info.scene_max[k]))));
+            }
+            if (!(r > 0.f) || !(maxabs <= 1000.f * r) || !(dc2 <= 900.f * r2)) P.scene_r2 = INFINITY;
+        }
     }
 
     if (fr->num_lights) {

@@ -36,6 +36,7 @@ struct FrameParams {
     float* rgb; uint8_t* rgb8; int32_t* tri_id; float* t;
     unsigned long long* counters;   // [0] primary rays, [1] shadow rays, [2] node visits, [3] triangle tests (stats variants)
     int fast_slab;                  // 1: ray origins are close enough to the scene for rt_slab_fma (host decides)
+    float scene_c[3], scene_r2;     // scene bounding sphere (centre, padded squared radius): packets that miss it skip the traversal set-up
     float frustum_eps;              // frustum traversal: absolute slack of the plane tests = 1.6e-5 x largest coordinate in play (host)
     int sample_group;               // packet kernel: samples of one pixel traced side by side (power of two dividing spp, <= 32)
 };

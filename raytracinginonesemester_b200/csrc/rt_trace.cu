@@ -316,11 +316,20 @@ __device__ __forceinline__ int ld_child_ref(const BvhNode* __restrict__ nodes, i
 template <int MODE, bool STATS, bool FAST, int TAG>
 __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ nodes, const WideNode* __restrict__ wide, const TriBlock* __restrict__ geom, const uint32_t num_tris,
                                                   const Ray ray, bool live, const bool any, const bool same_origin, float tlimit, TraceStats* st,
-                                                  int* __restrict__ wstack, float4* __restrict__ wfr, const float feps) {
+                                                  int* __restrict__ wstack, float4* __restrict__ wfr, const float feps, const f3 sc, const float sr2) {
     Hit best; rt_hit_reset(best);
     bool blocked = false;
     const float det_eps = rt_det_eps(MODE), tmin = rt_tmin(MODE);
     const int lane = threadIdx.x & 31;
+    if (!any) {   // (shadow rays start on the scene: nothing to gain)
+        // packets that miss the scene's bounding sphere altogether (sky, mostly-empty frames) leave before any set-up.
+        // Division-free, a dozen instructions.  The host pads the squared radius by 3 % and passes +inf (test always
+        // true) unless the origins are close enough for the cancellation error of the expression to stay far below that.
+        const f3 oc = mk3(sc.x - ray.o.x, sc.y - ray.o.y, sc.z - ray.o.z);
+        const float b = oc.x * ray.d.x + oc.y * ray.d.y + oc.z * ray.d.z, c2 = oc.x * oc.x + oc.y * oc.y + oc.z * oc.z;
+        const float dd = ray.d.x * ray.d.x + ray.d.y * ray.d.y + ray.d.z * ray.d.z;
+        live = live && (b * b >= dd * (c2 - sr2)) && (b >= 0.f || c2 <= sr2);
+    }
     const unsigned mlive = __ballot_sync(FULLMASK, live);
     if (!mlive) return TraceResult{best, blocked};
     // frame: w = bisector of the first and last live rays' directions (any w with d.w > 0 is valid; this one is central)
@@ -406,7 +415,7 @@ __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ no
         if (STATS) {
             int tot = lines;
             for (int q = 16; q > 0; q >>= 1) tot += __shfl_xor_sync(FULLMASK, tot, q);
-            if (lane == 0) { st->wnodes += (uint32_t)tot; st->nodes += (uint32_t)tot; }
+            if (lane == 0) { st->wnodes += (uint32_t)tot; st->nodes += (uint32_t)tot; }     // 32-byte entries requested
         }
         bool hit = hx >= 0.f;                                // absent entries and idle lanes carry negative half extents
         {
@@ -437,6 +446,7 @@ __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ no
                          : "=f"(lcx), "=f"(lcy), "=f"(lcz), "=f"(lhx), "=f"(lhy), "=f"(lhz), "=f"(lfr), "=f"(lfp)
                          : "l"(reinterpret_cast<const float*>(wide) + 8 * (size_t)eidx));
             const int lref = __float_as_int(lfr);
+            if (STATS && lane == 0) { st->wnodes++; st->nodes++; }
             bool lh; float tn;
             if (FAST) lh = rt_slab_fma_tight(kf, lcx, lcy, lcz, lhx, lhy, lhz, tmin, tlimit);
             else lh = rt_slab(k, lcx, lcy, lcz, lhx, lhy, lhz, tmin, tlimit, tn);
@@ -519,7 +529,7 @@ k_render_packet(const __grid_constant__ FrameParams P) {
         Hit h; rt_hit_reset(h);
         {
             const Ray ray = rt_make_ray(P.cam, MODE, x, y, jx, jy);
-            if (FRUSTUM) h = frustum_trace<MODE, STATS, FAST, TAG>(P.nodes, P.wide, P.geom, P.num_tris, ray, live, false, true, 0.f, &st, wstack, wfr, P.frustum_eps).hit;
+            if (FRUSTUM) h = frustum_trace<MODE, STATS, FAST, TAG>(P.nodes, P.wide, P.geom, P.num_tris, ray, live, false, true, 0.f, &st, wstack, wfr, P.frustum_eps, ld3(P.scene_c), P.scene_r2).hit;
             else h = packet_trace<MODE, STATS, FAST, PF, TAG>(P.nodes, P.geom, P.num_tris, ray, live, false, 0.f, &st).hit;
         }
         if (live) ++nprim;
@@ -557,7 +567,7 @@ k_render_packet(const __grid_constant__ FrameParams P) {
                             direct = rt_light_direct_hw2(sf, P.lights[l], L, NdotL);
                         }
                     }
-                    if (FRUSTUM) blocked = frustum_trace<MODE, STATS, FAST, TAG>(P.nodes, P.wide, P.geom, P.num_tris, sray, need, true, false, dist, &st, wstack, wfr, P.frustum_eps).blocked;
+                    if (FRUSTUM) blocked = frustum_trace<MODE, STATS, FAST, TAG>(P.nodes, P.wide, P.geom, P.num_tris, sray, need, true, false, dist, &st, wstack, wfr, P.frustum_eps, ld3(P.scene_c), P.scene_r2).blocked;
                     else blocked = packet_trace<MODE, STATS, FAST, PF, TAG>(P.nodes, P.geom, P.num_tris, sray, need, true, dist, &st).blocked;
                 }
                 if (need) ++nshadow;
@@ -592,7 +602,7 @@ k_render_packet(const __grid_constant__ FrameParams P) {
         if ((threadIdx.x & 31) == 0 && P.counters) {
             atomicAdd(&P.counters[2], (unsigned long long)nn);
             atomicAdd(&P.counters[3], (unsigned long long)nt);
-            atomicAdd(&P.counters[4], (unsigned long long)st.wnodes);   // one 64-byte node line per warp visit
+            atomicAdd(&P.counters[4], (unsigned long long)(FRUSTUM ? (st.wnodes + 1u) / 2u : st.wnodes));   // 64-byte units: one node line per warp visit (per-lane traversal), two 32-byte wide entries (frustum traversal)
             atomicAdd(&P.counters[5], (unsigned long long)st.wtris);    // one 48-byte triangle block per warp test
         }
     }
@@ -670,9 +680,12 @@ static cudaError_t launch_mode(const FrameParams& fp, int variant, cudaStream_t 
     // Bounce rays (max_depth > 1) are incoherent: the frame goes to the per-ray kernel, whose sample function
     // carries TraceRayIterative's full loop; the packet kernels implement depth 1.
     if (MODE != RT_MODE_HW1 && fp.max_depth > 1)
-        variant = (variant == RT_VARIANT_STATS || variant == RT_VARIANT_PER_RAY_STATS || variant == RT_VARIANT_FRUSTUM_STATS) ? RT_VARIANT_PER_RAY_STATS : RT_VARIANT_PER_RAY;
+        variant = (variant == RT_VARIANT_STATS || variant == RT_VARIANT_PER_RAY_STATS || variant == RT_VARIANT_FRUSTUM_STATS || variant == RT_VARIANT_PACKET_STATS) ? RT_VARIANT_PER_RAY_STATS : RT_VARIANT_PER_RAY;
+    // default = frustum traversal (needs the 8-wide view, which every scene with a BVH has)
+    if (variant == RT_VARIANT_DEFAULT) variant = fp.wide ? RT_VARIANT_FRUSTUM : RT_VARIANT_PACKET;
+    if (variant == RT_VARIANT_STATS) variant = fp.wide ? RT_VARIANT_FRUSTUM_STATS : RT_VARIANT_PACKET_STATS;
+    if ((variant == RT_VARIANT_FRUSTUM || variant == RT_VARIANT_FRUSTUM_STATS) && !fp.wide) return cudaErrorInvalidValue;
     switch (variant) {
-    case RT_VARIANT_DEFAULT:
     case RT_VARIANT_PACKET:
         if (fp.sample_group > 1) {
             if (fast) k_render_packet<MODE, false, true, 8, false, true><<<grid, block, 0, stream>>>(fp);
@@ -682,7 +695,7 @@ static cudaError_t launch_mode(const FrameParams& fp, int variant, cudaStream_t 
             else k_render_packet<MODE, false, false, 8><<<grid, block, 0, stream>>>(fp);
         }
         break;
-    case RT_VARIANT_STATS:
+    case RT_VARIANT_PACKET_STATS:
         if (fp.sample_group > 1) {
             if (fast) k_render_packet<MODE, true, true, 8, false, true><<<grid, block, 0, stream>>>(fp);
             else k_render_packet<MODE, true, false, 8, false, true><<<grid, block, 0, stream>>>(fp);

@@ -188,13 +188,19 @@ def test_device_bvh_is_sound_and_host_walk_agrees(renderer):
     nv, nt, nl, nb = renderer.frame_stats()
     assert (nv, nt) == (emu["stats"]["nodes"], emu["stats"]["tris"]) and (nl, nb) == (nv, nt)
     assert np.array_equal(st["tri_id"], got["tri_id"])
-    fr.kernel_variant = A.RT_VARIANT_STATS                  # packet kernel: a lane tests a superset, results identical
+    fr.kernel_variant = A.RT_VARIANT_PACKET_STATS           # per-lane packet traversal: a lane tests a superset, results identical
     pk = run(renderer, fr)
     nvp, ntp, nlp, nbp = renderer.frame_stats()
     assert nvp >= nv and ntp >= nt
     assert nlp * 32 >= nvp and nbp * 32 >= ntp and nlp < nvp          # one line per warp visit, shared by its lanes
     for k in ("tri_id", "t", "rgb8"):
         assert np.array_equal(pk[k], got[k]), k
+    fr.kernel_variant = A.RT_VARIANT_STATS                  # default = frustum traversal: a lane still tests a superset of its own triangles
+    fk = run(renderer, fr)
+    _, ntf, nlf, nbf = renderer.frame_stats()
+    assert ntf >= nt and nbf * 32 >= ntf and nlf > 0
+    for k in ("tri_id", "t", "rgb8"):
+        assert np.array_equal(fk[k], got[k]), k
 
 
 @pytest.mark.parametrize("variant", [A.RT_VARIANT_DEFAULT, A.RT_VARIANT_PACKET_OCC6, A.RT_VARIANT_PACKET_OCC10, A.RT_VARIANT_PACKET_EXACT_SLAB, A.RT_VARIANT_PER_RAY, A.RT_VARIANT_PACKET, A.RT_VARIANT_FRUSTUM])
