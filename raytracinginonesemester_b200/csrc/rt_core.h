@@ -94,7 +94,7 @@ RT_HD bool rt_moller_trumbore(const Ray& r, f3 v0, f3 e1, f3 e2, float det_eps, 
     f3 pvec = xcross(r.d, e2);
     float det = xdot(e1, pvec);
     if (fabsf(det) < det_eps) return false;
-    float invDet = XDIV(1.0f, det);
+    float invDet = XRCP(det);
     f3 tvec = xsub3(r.o, v0);
     float u = XMUL(xdot(tvec, pvec), invDet);
     if (u < 0.0f || u > 1.0f) return false;

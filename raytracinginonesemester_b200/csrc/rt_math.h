@@ -24,6 +24,7 @@
 #define XMUL(a, b) __fmul_rn((a), (b))
 #define XDIV(a, b) __fdiv_rn((a), (b))
 #define XSQRT(a)   __fsqrt_rn((a))
+#define XRCP(a)    __frcp_rn((a))       // == __fdiv_rn(1.0f, a): both are the correctly rounded quotient, this one is two instructions shorter
 // glibc powf is computed in double and is correctly rounded in all but ~1e-8 of cases;
 // an fp64 pow narrowed to float reproduces it (CUDA powf is 4+ ulp off).
 #define XPOW(a, b) ((float)pow((double)(a), (double)(b)))
@@ -33,6 +34,7 @@
 #define XMUL(a, b) ((a) * (b))
 #define XDIV(a, b) ((a) / (b))
 #define XSQRT(a)   sqrtf((a))
+#define XRCP(a)    (1.0f / (a))
 #define XPOW(a, b) powf((a), (b))
 #endif
 
