@@ -152,9 +152,21 @@ void free_scene(rt_ctx* c) {
 int build_wide_nodes(rt_ctx* c) {
     if (c->wide) { cudaFree(c->wide); c->wide = nullptr; }
     if (!c->has_bvh || !c->num_nodes) return RT_OK;
-    CU(c, cudaMalloc(&c->wide, sizeof(WideNode) * (size_t)c->num_nodes));
+    if (cudaMalloc(&c->wide, sizeof(WideNode) * (size_t)c->num_nodes) != cudaSuccess) {
+        (void)cudaGetLastError();          // not enough memory for the 8-wide view: frames use the per-lane traversal
+        c->wide = nullptr;
+        return RT_OK;
+    }
+    cudaEvent_t e0, e1;
+    CU(c, cudaEventCreate(&e0)); CU(c, cudaEventCreate(&e1));
+    CU(c, cudaEventRecord(e0, c->stream));
     CU(c, rt_build_wide(c->nodes, c->num_nodes, c->wide, c->stream));
+    CU(c, cudaEventRecord(e1, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    c->info.build_ms += ms;
     c->info.arena_bytes += sizeof(WideNode) * (uint64_t)c->num_nodes;
     return RT_OK;
 }
