@@ -449,7 +449,7 @@ def run_ours(args, rank, world, local_rank):
         if brute:
             note = "FP32-issue bound, not HBM-bound: triangles are streamed through shared memory once per 128 rays; see fp32_issue"
         else:
-            note = ("instruction-issue/latency bound, not HBM-bound: the arena is L2/L1-resident (ncu: issue slots 76 % busy, DRAM < 1 % of peak); "
+            note = ("instruction-issue/latency bound, not HBM-bound: the arena is L2/L1-resident (ncu: issue slots 78 % busy, DRAM < 1 % of peak); "
                     "achieved = bytes the kernel REQUESTS (32 B per lane-box test of the frustum traversal, 48 B per warp triangle test), most served by L1/L2 - see traffic and profiles/")
         line = {
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
