@@ -591,10 +591,29 @@ k_render_packet(const __grid_constant__ FrameParams P) {
     if (px.inside) {
         const f3 fin = xdivs(accum, (float)P.spp);       // col / float(spp): query.cu:163, render.cpp:110
         if (P.rgb) { P.rgb[3 * px.out] = fin.x; P.rgb[3 * px.out + 1] = fin.y; P.rgb[3 * px.out + 2] = fin.z; }
-        if (P.rgb8) {
-            P.rgb8[3 * px.out] = rt_quantise(fin.x, P.quantiser);
-            P.rgb8[3 * px.out + 1] = rt_quantise(fin.y, P.quantiser);
-            P.rgb8[3 * px.out + 2] = rt_quantise(fin.z, P.quantiser);
+    }
+    if (P.rgb8) {
+        // 8-bit plane: a row of the warp's 8x4 patch is 24 contiguous bytes.  Six lanes per row assemble one 32-bit word
+        // each from two neighbours' packed pixels and store it — 4 partial-sector writes per warp instead of ~12 with
+        // byte stores, which is what the NVLink ingress of rank 0 has to absorb from 7 peers in the fused gather.
+        uint32_t pk = 0u;
+        if (px.inside) {
+            const f3 fin = xdivs(accum, (float)P.spp);
+            pk = (uint32_t)rt_quantise(fin.x, P.quantiser) | ((uint32_t)rt_quantise(fin.y, P.quantiser) << 8) | ((uint32_t)rt_quantise(fin.z, P.quantiser) << 16);
+        }
+        const int row0 = lane & ~7, kx = lane & 7;
+        const unsigned rowmask = 0xffu << row0;
+        const bool row_ok = (__ballot_sync(FULLMASK, px.inside) & rowmask) == rowmask;
+        const unsigned long long out0 = __shfl_sync(FULLMASK, (unsigned long long)px.out, row0);
+        const int p = (4 * kx) / 3, o = (4 * kx) - 3 * p;                  // first pixel / first channel of word kx (kx < 6)
+        const uint32_t a = __shfl_sync(FULLMASK, pk, row0 + (p & 7)), b = __shfl_sync(FULLMASK, pk, row0 + ((p + 1) & 7));
+        if (row_ok && (out0 & 3ull) == 0ull) {
+            if (kx < 6) {
+                const uint32_t word = __funnelshift_r(a | (b << 24), b >> 8, 8 * o);
+                *reinterpret_cast<uint32_t*>(P.rgb8 + 3ull * out0 + 4 * kx) = word;
+            }
+        } else if (px.inside) {
+            P.rgb8[3 * px.out] = (uint8_t)pk; P.rgb8[3 * px.out + 1] = (uint8_t)(pk >> 8); P.rgb8[3 * px.out + 2] = (uint8_t)(pk >> 16);
         }
     }
     flush_counters(P, nprim, nshadow);
