@@ -471,14 +471,18 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(args.steps * launches_per_step),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_kind": peak_kind + (" x %d GPUs" % world if world > 1 else ""), "bytes_per_ray": b_ray, "bytes_per_launch": bytes_launch,
-                         "nodes_per_ray": nv_all / rays, "tris_per_ray": nt_all / rays, "node_lines_per_ray": nl_all / rays, "tri_blocks_per_ray": nb_all / rays,
+                         ("wide_entries_per_ray" if args.variant in (A.RT_VARIANT_DEFAULT, A.RT_VARIANT_FRUSTUM) and not brute else "nodes_per_ray"): nv_all / rays,
+                         "tris_per_ray": nt_all / rays, "node_lines_per_ray": nl_all / rays, "tri_blocks_per_ray": nb_all / rays,
                          "note": note},
             "clocks": clocks,
         }
         # SURVEY §8d's per-ray accounting (every ray pays for every node / triangle it takes part in: 64 B per node visit,
         # 48 B per triangle test, 16 B of result), next to the per-request accounting above (a packet fetches a line once
         # for its 32 rays).  Above 1 = served from cache, as §8d anticipates.
-        b_ray_8d = 64.0 * nv_all / rays + 48.0 * nt_all / rays + 16.0
+        frustum = args.variant in (A.RT_VARIANT_DEFAULT, A.RT_VARIANT_FRUSTUM) and not brute
+        # frustum traversal: rays take no part in the inner-node tests (one lane = one box); the node term is the packet's
+        # 32-byte wide entries shared over its rays
+        b_ray_8d = (32.0 if frustum else 64.0) * nv_all / rays + 48.0 * nt_all / rays + 16.0
         line["roofline"]["survey_8d_per_ray"] = {"bytes_per_ray": b_ray_8d, "achieved": rays * b_ray_8d / (ms * 1e-3) / 1e9,
                                                  "frac": rays * b_ray_8d / (ms * 1e-3) / 1e9 / peak}
         if winst and not brute:
