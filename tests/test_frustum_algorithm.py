@@ -1,0 +1,57 @@
+"""CPU check of the ALGORITHM behind the default frame kernel's traversal (csrc/rt_trace.cu, frustum_trace): on the BVH
+the host emulation of the device build produces, the frustum-culled wide traversal (8-wide view, four bounding planes that
+need no common apex, depth range, per-ray leaf cull) must find exactly the closest hits / occlusion flags of the per-lane
+packet traversal, for camera packets and for their point-light shadow packets.  tools/packet_sim.py is the float64 model
+both kernels were designed with; the device code itself is covered by the GPU tier (test_gpu_parity.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+@pytest.mark.parametrize("width,height,levels,batch", [(320, 180, 3, 4), (96, 54, 3, 4), (640, 360, 2, 8)])
+def test_frustum_traversal_is_sound_on_terrain(width, height, levels, batch):
+    import packet_sim as ps
+    from raytracinginonesemester_b200 import scenes
+    b = ps.Bvh(*ps.load_bvh(60, 30))
+    fr = scenes.terrain_frame(width, height)
+    cam = fr.cam
+    c3 = lambda v: np.array(list(v), np.float64)
+    cen, p00, du, dv = c3(cam.center), c3(cam.pixel00_loc), c3(cam.pixel_delta_u), c3(cam.pixel_delta_v)
+    L = np.array([-2.0, -1.0, 1.5])
+    slot_of = np.zeros(b.ids.max() + 1, np.int64)
+    slot_of[b.ids] = np.arange(len(b.ids))
+    rng = np.random.default_rng(7)
+    rounds = visits = 0
+    for _ in range(25):
+        tx, ty = rng.integers(0, width // 8), rng.integers(0, height // 4)
+        xs, ys = np.meshgrid(tx * 8 + np.arange(8), ty * 4 + np.arange(4))
+        d = p00 + (xs.ravel() + 0.1)[:, None] * du + (ys.ravel() - 0.2)[:, None] * dv - cen
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        o = np.broadcast_to(cen, d.shape).copy()
+        live = np.ones(32, bool)
+        live[rng.integers(0, 32)] = False                       # a dead lane (pixel outside the frame)
+        s1, t1, id1, _ = ps.trace_current(b, o, d, live, False, np.full(32, np.inf))
+        s2, t2, id2, _ = ps.trace_wide(b, o, d, live, False, np.full(32, np.inf), batch, "none", levels)
+        assert np.array_equal(id1[live], id2[live]) and np.array_equal(t1[live], t2[live])
+        rounds += s2["rounds"]; visits += s1["visits"]
+        hit = np.isfinite(t1) & live
+        if not hit.any():
+            continue
+        P = o + d * np.where(hit, t1, 0.0)[:, None]
+        g = b.geom[slot_of[np.where(hit, id1, 0)]]
+        n = np.cross(g[:, 4:7], g[:, 8:11]); n /= np.linalg.norm(n, axis=1, keepdims=True)
+        n[np.einsum("ij,ij->i", n, d) > 0] *= -1
+        toL = L - P
+        dist = np.linalg.norm(toL, axis=1)
+        sd = toL / dist[:, None]
+        need = hit & (np.einsum("ij,ij->i", n, sd) > 0)
+        if need.any():
+            _, _, _, b1 = ps.trace_current(b, P + n * 1e-3, sd, need, True, dist)
+            _, _, _, b2 = ps.trace_wide(b, P + n * 1e-3, sd, need, True, dist, batch, "none", levels)
+            assert np.array_equal(b1[need], b2[need])
+    assert rounds < visits          # and it gets there in fewer steps than one node visit at a time
