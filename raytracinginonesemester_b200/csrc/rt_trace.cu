@@ -308,10 +308,9 @@ __device__ __noinline__ TraceResult packet_trace(const BvhNode* __restrict__ nod
 // 9 resident blocks (36 warps, 56 registers) measured best for the frustum kernel on C4: 6 -> 2.21 ms, 8 -> 2.07, 9 -> 2.01, 10 -> 2.05, 12 -> 2.04
 #define RT_FRUSTUM_MINB 9
 
-__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
-__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
-__device__ __forceinline__ float warp_fmin(float v) { return ord2f(__reduce_min_sync(FULLMASK, f2ord(v))); }
-__device__ __forceinline__ float warp_fmax(float v) { return ord2f(__reduce_max_sync(FULLMASK, f2ord(v))); }
+// sm_100a: float min/max reductions are one instruction (CREDUX.MIN/MAX.F32, result in a uniform register)
+__device__ __forceinline__ float warp_fmin(float v) { float r; asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float warp_fmax(float v) { float r; asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v)); return r; }
 __device__ __forceinline__ float warp_bcast(float v, int src, int lane) { return __int_as_float((int)__reduce_or_sync(FULLMASK, lane == src ? (unsigned)__float_as_int(v) : 0u)); }
 __device__ __forceinline__ int ld_child_ref(const BvhNode* __restrict__ nodes, int node, int k) { return __ldg(reinterpret_cast<const int*>(nodes + node) + 12 + k); }
 
@@ -322,7 +321,8 @@ __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ no
     Hit best; rt_hit_reset(best);
     bool blocked = false;
     const float det_eps = rt_det_eps(MODE), tmin = rt_tmin(MODE);
-    const int lane = threadIdx.x & 31;
+    int lane;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));       // volatile: kept in a register instead of an S2R + mask per use in the round loop
     if (!any) {   // (shadow rays start on the scene: nothing to gain)
         // packets that miss the scene's bounding sphere altogether (sky, mostly-empty frames) leave before any set-up.
         // Division-free, a dozen instructions.  The host pads the squared radius by 3 % and passes +inf (test always
