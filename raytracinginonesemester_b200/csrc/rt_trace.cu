@@ -433,6 +433,8 @@ __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ no
         unsigned mleaf = __ballot_sync(FULLMASK, hit && ref < 0);
         const int ninner = __popc(minner);
         if (sp + ninner > RT_FSTACK) { overflow = true; break; }
+        // (prefetching the pushed wide nodes / the candidates' triangle blocks into L1 was measured: 2.05 vs 2.00 ms —
+        // the kernel is issue-bound, the extra instructions cost more than the latency they hide)
         if (hit && ref >= 0) wstack[sp + __popc(minner & ((1u << lane) - 1u))] = ref;
         sp += ninner;
         __syncwarp();
