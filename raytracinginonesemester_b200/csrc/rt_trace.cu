@@ -403,11 +403,12 @@ __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ no
         int par = valid ? wstack[sp - 1 - (lane >> 3)] : 0;
         sp -= npop;
         __syncwarp();
-        // lane (g, k) reads entry k of wide node g: one 256-bit load, no dependent steps
-        float cx = 0.f, cy = 0.f, cz = 0.f, hx = -1.f, hy = -1.f, hz = -1.f;
-        int ref = -1;
+        // lane (g, k) reads entry k of wide node g: one 256-bit load, no dependent steps.  Idle lanes read node 0's entry
+        // (harmless, already cached) and are masked out of the result: cheaper than eight predicated defaults per round.
+        float cx, cy, cz, hx, hy, hz;
+        int ref;
         const int lines = valid ? 1 : 0;
-        if (valid) {
+        {
             const float* ep = reinterpret_cast<const float*>(wide + par) + 8 * (lane & 7);
             float fr, fp;
             asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -419,7 +420,7 @@ __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ no
             for (int q = 16; q > 0; q >>= 1) tot += __shfl_xor_sync(FULLMASK, tot, q);
             if (lane == 0) { st->wnodes += (uint32_t)tot; st->nodes += (uint32_t)tot; }     // 32-byte entries requested
         }
-        bool hit = hx >= 0.f;                                // absent entries and idle lanes carry negative half extents
+        bool hit = valid && hx >= 0.f;                       // absent entries carry negative half extents
         {
             const float4 p0 = wfr[0], p1 = wfr[1], p2 = wfr[2], p3 = wfr[3], pw = wfr[4];
             const float s0 = fmaf(hx, fabsf(p0.x), fmaf(hy, fabsf(p0.y), fmaf(hz, fabsf(p0.z), fmaf(cx, p0.x, fmaf(cy, p0.y, cz * p0.z)))));
@@ -458,7 +459,9 @@ __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ no
             const uint32_t first = rt_leaf_first(lref), cnt = rt_leaf_count(lref);
 #pragma unroll 1
             for (uint32_t s = first; s < first + cnt; ++s) {      // one copy of the test: the kernel is instruction-cache sensitive
-                const Tri tr = rt_load_tri(geom, s);
+                uint32_t sv = s;
+                asm volatile("" : "+r"(sv));      // address arithmetic in vector registers: one IMAD.WIDE for the three loads
+                const Tri tr = rt_load_tri(geom, sv);   // instead of a uniform address re-materialised into a register pair per load
                 if (STATS && lane == 0) st->wtris++;
                 if (live) {
                     if (STATS) st->tris++;
