@@ -425,6 +425,7 @@ def run_ours(args, rank, world, local_rank):
     step_ms = t[0].cpu().numpy()
     e2e_s = t[1].cpu().numpy()
     ms = float(step_ms.mean())
+    step_spread = {"median_ms": float(np.median(step_ms)), "min_ms": float(step_ms.min()), "max_ms": float(step_ms.max())}
     value = rays / (ms * 1e-3) / 1e6
     e2e_value = rays / float(e2e_s.mean()) / 1e6
     e2e_spread = {"median_ms": 1e3 * float(np.median(e2e_s)), "min_ms": 1e3 * float(e2e_s.min()), "max_ms": 1e3 * float(e2e_s.max())}
@@ -459,6 +460,7 @@ def run_ours(args, rank, world, local_rank):
                        "rays": "primary+shadow" if rays_shadow else "primary", "rays_primary": rays_primary, "rays_shadow": rays_shadow,
                        "l2": "flushed between timed steps (256 MiB memset); warm-L2 figure in value_warm_l2",
                        "tile_sharding": "16x8-px tiles in %d contiguous bands per rank, band c -> rank c %% %d" % (args.chunks or parallel.DEFAULT_CHUNKS_PER_RANK, world), "gather": gather, "leaf_max": args.leaf_max, "variant": args.variant},
+            "ms_per_step_spread": step_spread,
             "primary_mrays_s": rays_primary / (ms * 1e-3) / 1e6,
             "value_warm_l2": rays / (float(tw[:-1].mean()) * 1e-3) / 1e6,
             "frame_kernel_ms_max_rank": float(tw[-1]), "gather_overhead_ms": ms - float(tw[-1]),
