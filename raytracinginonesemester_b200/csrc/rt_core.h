@@ -10,7 +10,7 @@
 
 // ----------------------------------------------------------------- layout ----
 // One BVH2 node = one 64-byte line: both children's boxes + both child references, so a
-// node visit is four 16-byte loads from a single aligned line (ld.global.nc.v4).
+// node visit is two 32-byte loads from a single aligned line (ld.global.nc.v8 = LDG.256 on sm_100).
 // Boxes are stored as centre + half-extent: the slab distances are then m -+ h*|1/d| with
 // m = (c - o)/d, i.e. nine FMAs per box and no per-axis min/max (those run on the half-rate
 // ALU pipe, which ncu showed to be the busiest pipe of the first packet kernel).

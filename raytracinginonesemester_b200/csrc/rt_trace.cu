@@ -3,12 +3,14 @@
 // Replaces renderBatchCUDA / normalizeCUDA / render() of the reference
 // (HW2/HW2/GPUandCPU/include/query.cu:12-167) and the HW1 pixel loop (HW1/src/render.cpp:72-124).
 // Not a port: the reference walks a 16-byte-node + separate-AABB LBVH with a 512-entry local
-// stack and fp64 slabs per thread; here a thread block owns a 16x8 pixel tile (4 warps of 8x4
-// pixels), nodes are single 64-byte lines carrying both child boxes, the traversal stack is a
-// bank-conflict-free shared-memory column per thread, triangles are 48-byte pre-differenced
-// blocks in leaf order, and shadow rays are any-hit queries in the same kernel.  The
-// Möller–Trumbore and shading arithmetic is exactly rounded (rt_math.h) so hit ids, t and
-// colours equal the reference CPU build.
+// stack and fp64 slabs per thread.  Here a thread block owns a 16x8 pixel tile and a warp is a
+// 32-ray packet (an 8x4 patch); inner nodes are culled against the packet's bounding frustum
+// with one LANE per BOX of an 8-wide view of the tree (frustum_trace, the default), leaves are
+// culled per ray and their triangles — 48-byte pre-differenced blocks in leaf order — tested by
+// every lane; shadow rays are any-hit queries in the same kernel.  A per-lane packet traversal
+// (packet_trace) and a per-ray kernel with a shared-memory stack column (k_render_bvh) are kept
+// as cross-checks and for incoherent rays.  The Möller–Trumbore and shading arithmetic is
+// exactly rounded (rt_math.h) so hit ids, t and colours equal the reference CPU build.
 #include "rt_kernels.h"
 #include "rt_trace_core.h"
 
@@ -312,7 +314,6 @@ __device__ __noinline__ TraceResult packet_trace(const BvhNode* __restrict__ nod
 __device__ __forceinline__ float warp_fmin(float v) { float r; asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v)); return r; }
 __device__ __forceinline__ float warp_fmax(float v) { float r; asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v)); return r; }
 __device__ __forceinline__ float warp_bcast(float v, int src, int lane) { return __int_as_float((int)__reduce_or_sync(FULLMASK, lane == src ? (unsigned)__float_as_int(v) : 0u)); }
-__device__ __forceinline__ int ld_child_ref(const BvhNode* __restrict__ nodes, int node, int k) { return __ldg(reinterpret_cast<const int*>(nodes + node) + 12 + k); }
 
 template <int MODE, bool STATS, bool FAST, int TAG>
 __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ nodes, const WideNode* __restrict__ wide, const TriBlock* __restrict__ geom, const uint32_t num_tris,
