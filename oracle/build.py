@@ -82,9 +82,12 @@ def build_ref(force=False):
         if force or _stale(outs["ref_hw2_cuda"], [s]):
             # the reference's own CUDA flags (GPUandCPU/CMakeLists.txt:27); it names no architecture, sm_100 is ours
             inc = ["-I", os.path.join(g, "third_party", "glm"), "-I", os.path.join(g, "include"), "-I", os.path.join(g, "src")]
-            _run(["nvcc", "-std=c++17", "-O3", "-w", "--extended-lambda", "--expt-relaxed-constexpr", "--use_fast_math",
-                  "-gencode", "arch=compute_100,code=sm_100", "-Xcompiler", "-fPIC", "-shared"] + inc +
-                 ["-o", outs["ref_hw2_cuda"], s, os.path.join(g, "include", "bvh.cu"), os.path.join(g, "include", "query.cu")])
+            try:        # timing aid only (bench.py "reference_cuda"): a failure here must not fail the build of the checker
+                _run(["nvcc", "-std=c++17", "-O3", "-w", "--extended-lambda", "--expt-relaxed-constexpr", "--use_fast_math",
+                      "-gencode", "arch=compute_100,code=sm_100", "-Xcompiler", "-fPIC", "-shared"] + inc +
+                     ["-o", outs["ref_hw2_cuda"], s, os.path.join(g, "include", "bvh.cu"), os.path.join(g, "include", "query.cu")])
+            except (RuntimeError, OSError) as e:
+                sys.stderr.write("oracle/build.py: reference CUDA build skipped: %s\n" % str(e)[:400])
     return {k: v for k, v in outs.items() if os.path.exists(v)}
 
 
