@@ -175,30 +175,11 @@ cudaError_t rt_bake_transform(float* pos, float* nrm, size_t first, size_t count
     return cudaGetLastError();
 }
 
-// One thread per BVH2 node: expand three levels into the node's eight wide entries.
+// One thread per BVH2 node: expand three levels into the node's eight wide entries (rt_wide_node, rt_build_core.h).
 __global__ void k_build_wide(const BvhNode* __restrict__ nodes, uint32_t num_nodes, WideNode* __restrict__ wide) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= num_nodes) return;
-    WideNode out;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        bool valid = true;
-        uint32_t par = i;
-        int pb = (k >> 2) & 1;
-        int ref = pb ? nodes[par].ref1 : nodes[par].ref0;
-        if (ref < 0) valid = (k & 3) == 0;
-        else {
-            par = (uint32_t)ref; pb = (k >> 1) & 1; ref = pb ? nodes[par].ref1 : nodes[par].ref0;
-            if (ref < 0) valid = (k & 1) == 0;
-            else { par = (uint32_t)ref; pb = k & 1; ref = pb ? nodes[par].ref1 : nodes[par].ref0; }
-        }
-        const float* q = nodes[par].q + 6 * pb;
-        WideEntry e;
-        e.cx = q[0]; e.cy = q[1]; e.cz = q[2]; e.hx = q[3]; e.hy = q[4]; e.hz = q[5]; e.ref = ref; e.pad = 0;
-        if (!valid || !(e.hx >= 0.f)) { e.cx = e.cy = e.cz = 0.f; e.hx = e.hy = e.hz = -1.f; e.ref = -1; }
-        out.e[k] = e;
-    }
-    wide[i] = out;
+    wide[i] = rt_wide_node(nodes, i);
 }
 
 cudaError_t rt_build_wide(const BvhNode* nodes, uint32_t num_nodes, WideNode* wide, cudaStream_t stream) {

@@ -123,6 +123,31 @@ RT_HD BvhNode rt_make_node(float4 l0, float4 h0, float4 l1, float4 h1, int32_t r
     return nd;
 }
 
+// 8-wide view of BVH2 node i (WideNode, rt_core.h): entry k = the box reached by the left/right steps k2 k1 k0; a leaf met
+// early sits in the entry whose remaining path bits are zero; everything else below it, and absent children, are "absent"
+// entries (negative half extents, ref -1).
+RT_HD WideNode rt_wide_node(const BvhNode* __restrict__ nodes, uint32_t i) {
+    WideNode out;
+    for (int k = 0; k < 8; ++k) {
+        bool valid = true;
+        uint32_t par = i;
+        int pb = (k >> 2) & 1;
+        int ref = pb ? nodes[par].ref1 : nodes[par].ref0;
+        if (ref < 0) valid = (k & 3) == 0;
+        else {
+            par = (uint32_t)ref; pb = (k >> 1) & 1; ref = pb ? nodes[par].ref1 : nodes[par].ref0;
+            if (ref < 0) valid = (k & 1) == 0;
+            else { par = (uint32_t)ref; pb = k & 1; ref = pb ? nodes[par].ref1 : nodes[par].ref0; }
+        }
+        const float* q = nodes[par].q + 6 * pb;
+        WideEntry e;
+        e.cx = q[0]; e.cy = q[1]; e.cz = q[2]; e.hx = q[3]; e.hy = q[4]; e.hz = q[5]; e.ref = ref; e.pad = 0;
+        if (!valid || !(e.hx >= 0.f)) { e.cx = e.cy = e.cz = 0.f; e.hx = e.hy = e.hz = -1.f; e.ref = -1; }
+        out.e[k] = e;
+    }
+    return out;
+}
+
 // Triangle blocks of slot k (triangle `tri`).  e1/e2 are the same rounded differences the
 // reference forms inside every test (query.h:80-81, HW1 ray.h:72-73).
 RT_HD void rt_pack_tri(const BuildParams& bp, uint32_t tri, TriBlock* geom_k, TriBlock* shade_k) {

@@ -139,6 +139,13 @@ void emu_export(void* h, void* nodes64, void* geom48) {
     if (geom48) memcpy(geom48, es->geom.data(), sizeof(TriBlock) * es->geom.size());
 }
 
+// 8-wide view of the emulated BVH, node by node with the product's rt_wide_node (what k_build_wide runs per thread).
+void emu_wide(void* h, void* wide256) {
+    EmuScene* es = (EmuScene*)h;
+    WideNode* w = (WideNode*)wide256;
+    for (size_t i = 0; i < es->nodes.size(); ++i) w[i] = rt_wide_node(es->nodes.data(), (uint32_t)i);
+}
+
 // Structural check of a flattened BVH: every slot reachable exactly once, child boxes contain
 // their triangles, refs in range.  Returns 0 when sound, else a negative code.
 int emu_validate(void* h) {

@@ -55,3 +55,59 @@ def test_frustum_traversal_is_sound_on_terrain(width, height, levels, batch):
             _, _, _, b2 = ps.trace_wide(b, P + n * 1e-3, sd, need, True, dist, batch, "none", levels)
             assert np.array_equal(b1[need], b2[need])
     assert rounds < visits          # and it gets there in fewer steps than one node visit at a time
+
+
+@pytest.mark.parametrize("nx,ny,leaf_max", [(60, 30, 2), (17, 9, 1), (8, 4, 4), (1, 1, 2)])
+def test_wide_view_of_the_bvh(nx, ny, leaf_max):
+    """rt_wide_node (what k_build_wide runs per BVH2 node) against an independent expansion of the same nodes: entry k is
+    the box three left/right steps down (path bits k2 k1 k0), a leaf met early sits where the remaining bits are zero,
+    everything else is absent; and walking the wide view from the root reaches every triangle slot exactly once."""
+    import ctypes as C
+    import orclib
+    import packet_sim as ps
+    from raytracinginonesemester_b200 import scenes
+    sc = scenes.terrain_scene(nx, ny)
+    h = orclib.emul_build(sc, leaf_max)
+    lib = orclib.emul()
+    lib.emu_num_nodes.restype = C.c_uint32
+    nn = lib.emu_num_nodes(C.c_void_p(h))
+    nodes = np.zeros((nn, 16), np.uint32)
+    lib.emu_export(C.c_void_p(h), nodes.ctypes.data_as(C.c_void_p), None)
+    wide = np.zeros((nn, 8, 8), np.uint32)
+    lib.emu_wide(C.c_void_p(h), wide.ctypes.data_as(C.c_void_p))
+    q = nodes[:, :12].view(np.float32)
+    refs = nodes[:, 12:14].view(np.int32)
+    wf, wref = wide[..., :6].view(np.float32), wide[..., 6].view(np.int32)
+
+    def child(n, k):
+        return q[n, 6 * k:6 * k + 6], int(refs[n, k])
+    for i in range(nn):
+        for k in range(8):
+            box, ref = child(i, (k >> 2) & 1)
+            ok = True
+            if ref >= 0:
+                box, ref2 = child(ref, (k >> 1) & 1)
+                if ref2 >= 0:
+                    box, ref = child(ref2, k & 1)
+                else:
+                    ok, ref = (k & 1) == 0, ref2
+            else:
+                ok = (k & 3) == 0
+            if ok and box[3] >= 0:
+                assert np.array_equal(wf[i, k], box) and wref[i, k] == ref, (i, k)
+            else:
+                assert wf[i, k, 3] < 0 and wref[i, k] == -1, (i, k)
+    seen = np.zeros(sc.indices.shape[0], int)
+    stack = [0]
+    while stack:
+        n = stack.pop()
+        for k in range(8):
+            if wf[n, k, 3] < 0:
+                continue
+            r = int(wref[n, k])
+            if r >= 0:
+                stack.append(r)
+            else:
+                first, cnt = ps.leaf_range(r)
+                seen[first:first + cnt] += 1
+    assert (seen == 1).all()
