@@ -223,6 +223,7 @@ def main():
     ap.add_argument("--width", type=int, default=3840); ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--packets", type=int, default=200); ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--levels", type=int, default=3); ap.add_argument("--order", default="depth")
+    ap.add_argument("--tile", default="8x4", help="pixel footprint of a packet, WxH with W*H = 32")
     args = ap.parse_args()
     from raytracinginonesemester_b200 import scenes
     b = Bvh(*load_bvh(args.nx, args.ny))
@@ -236,8 +237,9 @@ def main():
     tot = {k: np.zeros(2) for k in ("cur_visits", "cur_blocks", "w_rounds", "w_boxes", "w_blocks", "w_leaves", "fallback", "n")}
     mism = 0
     for _ in range(args.packets):
-        tx, ty = rng.integers(0, args.width // 8), rng.integers(0, args.height // 4)
-        xs, ys = np.meshgrid(tx * 8 + np.arange(8), ty * 4 + np.arange(4))
+        tw, th = [int(v) for v in args.tile.split("x")]
+        tx, ty = rng.integers(0, args.width // tw), rng.integers(0, args.height // th)
+        xs, ys = np.meshgrid(tx * tw + np.arange(tw), ty * th + np.arange(th))
         px, py = xs.ravel() + jit[0], ys.ravel() + jit[1]
         d = p00 + px[:, None] * du + py[:, None] * dv - cen
         d /= np.linalg.norm(d, axis=1, keepdims=True)
