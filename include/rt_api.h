@@ -71,11 +71,11 @@ extern "C" {
 
 /* rt_frame.kernel_variant */
 #define RT_VARIANT_DEFAULT          0  /* packet kernel (one 8x4 tile per warp) with the frustum-culled wide traversal (= RT_VARIANT_FRUSTUM) */
-#define RT_VARIANT_PACKET_OCC6      1  /* same, compiled for >= 6 resident blocks per SM               */
-#define RT_VARIANT_PACKET_OCC10     2  /* same, >= 10 resident blocks per SM                           */
-#define RT_VARIANT_PACKET_EXACT_SLAB 3 /* same as default with the unfused (b-o)*inv slab test         */
-#define RT_VARIANT_PACKET_PREFETCH  4  /* default kernel + L1 prefetch of the deferred child at every push           */
-#define RT_VARIANT_PACKET_PIXEL_MAJOR 5 /* default kernel with one sample of 32 pixels per packet even when spp > 1     */
+#define RT_VARIANT_PACKET_OCC6      1  /* per-lane packet traversal compiled for >= 6 resident blocks per SM (experiments 1..5 all use it) */
+#define RT_VARIANT_PACKET_OCC10     2  /* >= 10 resident blocks per SM                                 */
+#define RT_VARIANT_PACKET_EXACT_SLAB 3 /* with the unfused (b-o)*inv slab test                         */
+#define RT_VARIANT_PACKET_PREFETCH  4  /* + L1 prefetch of the deferred child at every push            */
+#define RT_VARIANT_PACKET_PIXEL_MAJOR 5 /* one sample of 32 pixels per packet even when spp > 1         */
 #define RT_VARIANT_FRUSTUM          6  /* packet kernel with the frustum-culled wide traversal (one lane = one box, 32 boxes per round) */
 #define RT_VARIANT_PACKET           7  /* packet kernel with the per-lane traversal (every lane slab-tests both children of a node)       */
 #define RT_VARIANT_PER_RAY         10  /* independent per-thread stack traversal (shared-memory stack) */
