@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RT_API_VERSION 3
+#define RT_API_VERSION 4
 
 /* status codes */
 #define RT_OK            0
@@ -70,14 +70,19 @@ extern "C" {
 #define RT_QUANT_CPU_TRUNC    4  /* CPUOnly/src/render.cpp:157-163 clamp to [0,1], (uchar)(255.99f*c) */
 
 /* rt_frame.kernel_variant */
-#define RT_VARIANT_DEFAULT          0  /* packet kernel (one 8x4 tile per warp) with the frustum-culled wide traversal (= RT_VARIANT_FRUSTUM) */
-#define RT_VARIANT_PACKET_OCC6      1  /* per-lane packet traversal compiled for >= 6 resident blocks per SM (experiments 1..5 all use it) */
-#define RT_VARIANT_PACKET_OCC10     2  /* >= 10 resident blocks per SM                                 */
-#define RT_VARIANT_PACKET_EXACT_SLAB 3 /* with the unfused (b-o)*inv slab test                         */
-#define RT_VARIANT_PACKET_PREFETCH  4  /* + L1 prefetch of the deferred child at every push            */
-#define RT_VARIANT_PACKET_PIXEL_MAJOR 5 /* one sample of 32 pixels per packet even when spp > 1         */
-#define RT_VARIANT_FRUSTUM          6  /* packet kernel with the frustum-culled wide traversal (one lane = one box, 32 boxes per round) */
-#define RT_VARIANT_PACKET           7  /* packet kernel with the per-lane traversal (every lane slab-tests both children of a node)       */
+#define RT_VARIANT_DEFAULT          0  /* persistent packet kernel: warps pull 8x4 packets from a tile queue; frustum-culled wide traversal;
+                                          division-free front end of the triangle test (= RT_VARIANT_PERSIST) */
+#define RT_VARIANT_PACKET_OCC6      1  /* retired round-1 experiments 1, 2, 4: accepted, run RT_VARIANT_PACKET */
+#define RT_VARIANT_PACKET_OCC10     2
+#define RT_VARIANT_PACKET_EXACT_SLAB 3 /* per-lane packet traversal with the unfused (b-o)*inv slab test */
+#define RT_VARIANT_PACKET_PREFETCH  4
+#define RT_VARIANT_PACKET_PIXEL_MAJOR 5 /* one sample of 32 pixels per packet even when spp > 1 (per-lane traversal) */
+#define RT_VARIANT_FRUSTUM          6  /* round-1 default: one block per 16x8 tile, frustum-culled wide traversal (one lane = one box, 32 boxes per round) */
+#define RT_VARIANT_PACKET           7  /* one block per tile, per-lane traversal (every lane slab-tests both children of a node) */
+#define RT_VARIANT_PERSIST          8  /* the default, by name */
+#define RT_VARIANT_PERSIST_EXACT_MT 9  /* persistent kernel with the reference-order triangle test (IEEE divide first): A/B of the lazy front end */
+#define RT_VARIANT_PERSIST_OCC8    11  /* persistent kernel compiled for >= 8 resident blocks per SM (64 registers) */
+#define RT_VARIANT_PERSIST_OCC10   12  /* ... >= 10 resident blocks per SM (48 registers) */
 #define RT_VARIANT_PER_RAY         10  /* independent per-thread stack traversal (shared-memory stack) */
 #define RT_VARIANT_STATS          100  /* default kernel, also counts node data requested / triangle tests (= RT_VARIANT_FRUSTUM_STATS) */
 #define RT_VARIANT_PACKET_STATS   107  /* per-lane packet traversal with the same counters               */
@@ -217,6 +222,12 @@ int  rt_comm_set_gather(rt_ctx* ctx, int mode);
  * must use the same value. */
 int  rt_comm_set_sharding(rt_ctx* ctx, int chunks_per_rank);
 int  rt_comm_gather_mode(const rt_ctx* ctx, int* mode);   /* mode in effect: RT_GATHER_NCCL or RT_GATHER_PEER */
+/* Upper bound (seconds, default 120) of every device-side wait on another rank in the fused gather: a rank's frame kernel
+ * waiting for rank 0 to release its image (rank 0 publishes that when ITS host calls rt_render for the same frame, so the
+ * bound also limits how far apart the ranks' hosts may call rt_render), and rank 0 waiting for the other ranks' bands.
+ * A wait that runs out makes the next rt_sync / rt_download_image on that rank fail with RT_ERR_STATE; the late rank
+ * stores nothing into rank 0's image.  Not collective. */
+int  rt_comm_set_timeout(rt_ctx* ctx, double seconds);
 
 /* -- scene --------------------------------------------------------------- */
 /* Pack triangles, build the BVH on the device and (world>1) broadcast the arena

@@ -1,7 +1,7 @@
 """ctypes mirror of include/rt_api.h (struct layouts and constants)."""
 import ctypes as C
 
-RT_API_VERSION = 3          # include/rt_api.h
+RT_API_VERSION = 4          # include/rt_api.h
 RT_OK, RT_ERR_ARG, RT_ERR_CUDA, RT_ERR_STATE, RT_ERR_NCCL, RT_ERR_NOMEM = 0, -1, -2, -3, -4, -5
 RT_MODE_HW1, RT_MODE_HW2_BVH, RT_MODE_HW2_CPU = 0, 1, 2
 RT_ACCEL_BRUTE, RT_ACCEL_BVH = 0, 1
@@ -12,6 +12,7 @@ RT_VARIANT_DEFAULT, RT_VARIANT_PACKET_OCC6, RT_VARIANT_PACKET_OCC10, RT_VARIANT_
 RT_VARIANT_PACKET_PREFETCH, RT_VARIANT_PACKET_PIXEL_MAJOR = 4, 5
 RT_VARIANT_STATS, RT_VARIANT_PER_RAY_STATS = 100, 110
 RT_VARIANT_FRUSTUM, RT_VARIANT_FRUSTUM_STATS, RT_VARIANT_PACKET, RT_VARIANT_PACKET_STATS = 6, 106, 7, 107
+RT_VARIANT_PERSIST, RT_VARIANT_PERSIST_EXACT_MT, RT_VARIANT_PERSIST_OCC8, RT_VARIANT_PERSIST_OCC10 = 8, 9, 11, 12
 RT_GATHER_AUTO, RT_GATHER_NCCL, RT_GATHER_PEER = 0, 1, 2
 
 
@@ -90,6 +91,7 @@ EXPORTS = {
     "rt_comm_set_gather": (C.c_int, [C.c_void_p, C.c_int]),
     "rt_comm_set_sharding": (C.c_int, [C.c_void_p, C.c_int]),
     "rt_comm_gather_mode": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "rt_comm_set_timeout": (C.c_int, [C.c_void_p, C.c_double]),
     "rt_frame_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "rt_stream_handle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "rt_upload_scene": (C.c_int, [C.c_void_p, C.POINTER(rt_scene)]),

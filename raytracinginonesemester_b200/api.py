@@ -18,7 +18,8 @@ import numpy as np
 from . import _abi as A
 
 _LIB = None
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "librt_b200.so")
+# RT_B200_LIB: another build of the same library (kernel experiments are compiled side by side and A/B-timed in one GPU session)
+LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "librt_b200.so")
 
 
 class RtError(RuntimeError):

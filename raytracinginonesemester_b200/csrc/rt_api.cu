@@ -84,6 +84,7 @@ struct Plane {
 
 #define RT_BANDS 8
 #define RT_BAND_STREAMS 4
+#define RT_COUNTER_BYTES 64           // 8 x u64 ray / traversal counters, followed by the persistent kernel's PersistCtl
 
 struct rt_ctx {
     int device = 0;
@@ -121,6 +122,7 @@ struct rt_ctx {
     // rt_render_into: band-pipelined render + download (kernels of later bands overlap the D2H copy of earlier ones)
     cudaStream_t band_stream[RT_BAND_STREAMS] = {}; cudaStream_t copy_stream = nullptr, sig_stream = nullptr;
     cudaEvent_t band_ev[RT_BANDS] = {}; cudaEvent_t copy_done = nullptr;
+    unsigned long long peer_timeout_ns = 120ull * 1000000000ull;   // bound of every in-kernel / flag-kernel wait on another rank (rt_comm_set_timeout)
     int dbg_rank = 0, dbg_world = 0;              // rt_debug_set_shard: render one rank's share on a single GPU (timing only)
 };
 
@@ -171,13 +173,16 @@ int build_wide_nodes(rt_ctx* c) {
     return RT_OK;
 }
 
-struct SceneHeader { uint32_t num_tris, num_nodes, num_materials, has_bvh, has_normals; float smin[3], smax[3]; };
+struct SceneHeader { int32_t status; uint32_t num_tris, num_nodes, num_leaves, num_materials, has_bvh, has_normals; float smin[3], smax[3]; };
 
-// Broadcast of the built arena from rank 0 (scene + BVH travel once per scene over NVLink).
-int broadcast_scene(rt_ctx* c) {
+// Broadcast of the built arena from rank 0 (scene + BVH travel once per scene over NVLink).  Collective: rank 0 ALWAYS
+// gets here, also when its own upload failed (root_status != RT_OK) — the header carries the status, so every rank
+// returns an error together instead of the others waiting forever in ncclBroadcast.
+int broadcast_scene(rt_ctx* c, int root_status) {
     SceneHeader h{};
     if (c->rank == 0) {
-        h.num_tris = c->num_tris; h.num_nodes = c->num_nodes; h.num_materials = (uint32_t)c->num_materials; h.has_bvh = c->has_bvh; h.has_normals = c->has_normals;
+        h.status = root_status;
+        h.num_tris = c->num_tris; h.num_nodes = c->num_nodes; h.num_leaves = (uint32_t)c->info.num_leaves; h.num_materials = (uint32_t)c->num_materials; h.has_bvh = c->has_bvh; h.has_normals = c->has_normals;
         memcpy(h.smin, c->info.scene_min, sizeof h.smin); memcpy(h.smax, c->info.scene_max, sizeof h.smax);
     }
     SceneHeader* dh = nullptr;
@@ -187,6 +192,11 @@ int broadcast_scene(rt_ctx* c) {
     CU(c, cudaMemcpyAsync(&h, dh, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     cudaFree(dh);
+    if (h.status != RT_OK) {
+        if (c->rank == 0) return root_status;                  // (its message is already set)
+        free_scene(c);
+        return fail(c, RT_ERR_STATE, "rt_upload_scene: rank 0 failed to upload the scene (status %d); no scene on this rank", h.status);
+    }
     if (c->rank != 0) {
         free_scene(c);
         c->num_tris = h.num_tris; c->num_nodes = h.num_nodes; c->num_materials = (int)h.num_materials; c->has_bvh = h.has_bvh != 0; c->has_normals = h.has_normals != 0;
@@ -195,7 +205,7 @@ int broadcast_scene(rt_ctx* c) {
         CU(c, cudaMalloc(&c->shade, sizeof(TriBlock) * (size_t)c->num_tris));
         if (c->num_materials) CU(c, cudaMalloc(&c->materials, sizeof(rt_material) * (size_t)c->num_materials));
         memset(&c->info, 0, sizeof c->info);
-        c->info.num_triangles = h.num_tris; c->info.num_nodes = h.num_nodes;
+        c->info.num_triangles = h.num_tris; c->info.num_nodes = h.num_nodes; c->info.num_leaves = h.num_leaves;
         memcpy(c->info.scene_min, h.smin, sizeof h.smin); memcpy(c->info.scene_max, h.smax, sizeof h.smax);
     }
     NC(c, GroupStart());
@@ -230,7 +240,6 @@ int all_min(rt_ctx* c, int v, int* out) {                     // also a true bar
 }
 
 const size_t kFlagBytes = sizeof(unsigned) * RT_PEER_CHUNK_FLAG(RT_PEER_MAX_RANKS, 0);   // layout: rt_kernels.h
-const unsigned long long kPeerTimeoutNs = 20ull * 1000000000ull;
 
 // Drops every peer mapping / exported allocation.  `collective`: all ranks are here and the communicator is
 // healthy, so rank 0 can wait for the importers to unmap before it frees (otherwise the exported memory is
@@ -261,7 +270,7 @@ void peer_teardown(rt_ctx* c, bool collective) {
 int peer_timeout(rt_ctx* c, unsigned code) {
     cudaMemset(c->peer_err, 0, sizeof(unsigned));
     c->frame_valid = false;
-    return fail(c, RT_ERR_STATE, "peer-store gather: rank %d waited more than %llu s for %s", c->rank, kPeerTimeoutNs / 1000000000ull,
+    return fail(c, RT_ERR_STATE, "peer-store gather: rank %d waited more than %llu s for %s", c->rank, c->peer_timeout_ns / 1000000000ull,
                 c->rank == 0 ? "another rank's completion flag" : "rank 0 to start the frame");
     (void)code;
 }
@@ -373,7 +382,7 @@ int rt_create(rt_ctx** out, int device) {
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     if (e == cudaSuccess) e = cudaEventCreate(&c->evk0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->evk1);
-    if (e == cudaSuccess) e = c->counters.reserve(8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = c->counters.reserve(RT_COUNTER_BYTES + RT_PERSIST_CTL_BYTES);
     if (e != cudaSuccess) { int r = fail(nullptr, RT_ERR_CUDA, "rt_create: %s", cudaGetErrorString(e)); delete c; return r; }
     *out = c;
     return RT_OK;
@@ -383,7 +392,9 @@ int rt_destroy(rt_ctx* c) {
     if (!c) return RT_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    peer_teardown(c, true);
+    // NOT a collective (ranks may destroy in any order, or after another rank died): mappings are closed, rank 0's
+    // exported planes are left to process teardown because an importer may still have them mapped.
+    peer_teardown(c, false);
     if (c->peer_err) cudaFree(c->peer_err);
     if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
     free_scene(c);
@@ -449,6 +460,12 @@ int rt_comm_set_sharding(rt_ctx* c, int chunks_per_rank) {
     return RT_OK;
 }
 
+int rt_comm_set_timeout(rt_ctx* c, double seconds) {
+    if (!c || !(seconds > 0.0) || seconds > 86400.0) return fail(c, RT_ERR_ARG, "rt_comm_set_timeout: seconds must be in (0, 86400]");
+    c->peer_timeout_ns = (unsigned long long)(seconds * 1e9);
+    return RT_OK;
+}
+
 int rt_comm_gather_mode(const rt_ctx* c, int* mode) {
     if (!c || !mode) return fail(nullptr, RT_ERR_ARG, "rt_comm_gather_mode: NULL");
     *mode = c->peer ? RT_GATHER_PEER : RT_GATHER_NCCL;
@@ -462,15 +479,8 @@ int rt_comm_rank(const rt_ctx* c, int* rank, int* world) {
     return RT_OK;
 }
 
-int rt_upload_scene(rt_ctx* c, const rt_scene* sc) {
-    if (!c) return fail(nullptr, RT_ERR_ARG, "rt_upload_scene: NULL ctx");
-    CU(c, cudaSetDevice(c->device));
-    c->frame_valid = false;
-    if (!sc) {
-        if (c->world > 1 && c->rank != 0) return broadcast_scene(c);
-        return fail(c, RT_ERR_ARG, "rt_upload_scene: scene is NULL (only ranks != 0 of a multi-GPU context may receive)");
-    }
-    if (c->world > 1 && c->rank != 0) return broadcast_scene(c);   // rank 0's scene wins
+// Rank 0 / single GPU: validate, copy, bake transforms, build.  No collective step in here (see rt_upload_scene).
+static int upload_local(rt_ctx* c, const rt_scene* sc) {
     if (!sc->positions || !sc->indices || sc->num_triangles == 0 || sc->num_vertices == 0)
         return fail(c, RT_ERR_ARG, "rt_upload_scene: empty mesh (positions/indices NULL or zero counts)");
     if (sc->num_triangles >= (1ull << 28)) return fail(c, RT_ERR_ARG, "rt_upload_scene: more than 2^28 triangles");
@@ -487,9 +497,7 @@ int rt_upload_scene(rt_ctx* c, const rt_scene* sc) {
     for (int k = 0; k < sc->num_transforms; ++k)
         if (sc->transforms[k].first_vertex > sc->num_vertices || sc->transforms[k].num_vertices > sc->num_vertices - sc->transforms[k].first_vertex)
             return fail(c, RT_ERR_ARG, "rt_upload_scene: transform %d covers vertices outside the mesh", k);
-    for (uint64_t i = 0; i < 3 * sc->num_triangles; ++i)
-        if (sc->indices[i] >= sc->num_vertices) return fail(c, RT_ERR_ARG, "rt_upload_scene: index %llu out of range", (unsigned long long)i);
-    lap("index validation");
+    if (sc->num_vertices >= (1ull << 32)) return fail(c, RT_ERR_ARG, "rt_upload_scene: more than 2^32 vertices");
     free_scene(c);
     lap("free previous scene");
 
@@ -527,8 +535,22 @@ int rt_upload_scene(rt_ctx* c, const rt_scene* sc) {
         T.tx = o.position[0]; T.ty = o.position[1]; T.tz = o.position[2];
         CUS(rt_bake_transform(d_pos, d_nrm, (size_t)o.first_vertex, (size_t)o.num_vertices, T, c->stream));
     }
+    {   // index range check on the device, on the copy that the build will read (the reference's loaders trust the file,
+        // MeshOBJ.h:389-401; a host loop over 30 M indices of C5 took longer than the whole build)
+        unsigned long long bad = ~0ull, *d_bad = nullptr;
+        CUS(cudaMallocAsync(&d_bad, sizeof bad, c->stream));
+        CUS(cudaMemcpyAsync(d_bad, &bad, sizeof bad, cudaMemcpyHostToDevice, c->stream));
+        CUS(rt_validate_indices(d_idx, 3 * nt, (uint32_t)nv, d_bad, c->stream));
+        CUS(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, c->stream));
+        CUS(cudaFreeAsync(d_bad, c->stream));
+        CUS(cudaStreamSynchronize(c->stream));
+        if (bad != ~0ull) {
+            cleanup(); free_scene(c);
+            return fail(c, RT_ERR_ARG, "rt_upload_scene: index %llu out of range", bad);
+        }
+    }
     CUS(cudaEventRecord(e1, c->stream));
-    lap("enqueue H2D copies");
+    lap("H2D copies + index check");
 
     BuildParams bp{};
     bp.positions = d_pos; bp.normals = d_nrm; bp.indices = d_idx; bp.obj_ids = d_obj;
@@ -542,7 +564,7 @@ int rt_upload_scene(rt_ctx* c, const rt_scene* sc) {
         c->has_bvh = false; c->num_nodes = 0;
     } else {
         CUS(rt_build_bvh(bp, &c->nodes, c->geom, c->shade, &br, c->stream));
-        c->has_bvh = true; c->num_nodes = br.num_nodes;
+        c->has_bvh = true; c->num_nodes = br.num_nodes; c->info.num_leaves = br.num_leaves;
         memcpy(c->info.scene_min, br.scene_min, sizeof br.scene_min);
         memcpy(c->info.scene_max, br.scene_max, sizeof br.scene_max);
     }
@@ -559,7 +581,18 @@ int rt_upload_scene(rt_ctx* c, const rt_scene* sc) {
     c->info.num_triangles = nt; c->info.num_nodes = c->num_nodes; c->info.build_ms = b_ms; c->info.upload_ms = up_ms;
     c->info.arena_bytes = sizeof(BvhNode) * (uint64_t)c->num_nodes + 2 * sizeof(TriBlock) * (uint64_t)nt +
                           sizeof(rt_material) * (uint64_t)sc->num_materials;
-    if (c->world > 1) return broadcast_scene(c);
+    return RT_OK;
+}
+
+int rt_upload_scene(rt_ctx* c, const rt_scene* sc) {
+    if (!c) return fail(nullptr, RT_ERR_ARG, "rt_upload_scene: NULL ctx");
+    CU(c, cudaSetDevice(c->device));
+    c->frame_valid = false;
+    if (c->world > 1 && c->rank != 0) return broadcast_scene(c, RT_OK);   // collective: rank 0's scene (and status) arrives here
+    int rc = sc ? upload_local(c, sc)
+                : fail(c, RT_ERR_ARG, "rt_upload_scene: scene is NULL (only ranks != 0 of a multi-GPU context may receive)");
+    if (c->world > 1) return broadcast_scene(c, rc);           // also on failure: the other ranks are waiting in the broadcast
+    if (rc != RT_OK) return rc;
     return build_wide_nodes(c);
 }
 
@@ -589,8 +622,21 @@ int ensure_band_resources(rt_ctx* c) {
     return RT_OK;
 }
 
-// rt_render (into == NULL) and rt_render_into (into != NULL: single-GPU contexts render the frame in horizontal bands on
-// several streams and copy each finished band to the caller's host buffers while the next ones are still rendering).
+// Local flag block for single-GPU band pipelining (multi-GPU contexts get theirs from peer_setup).
+int ensure_flags(rt_ctx* c) {
+    if (c->flags) return RT_OK;
+    CU(c, cudaMalloc(&c->flags, kFlagBytes));
+    CU(c, cudaMemset(c->flags, 0, kFlagBytes));
+    return RT_OK;
+}
+
+struct HostOut { void* host; uint32_t bit; size_t bpp; const void* dev; const char* name; };
+
+// rt_render (into == NULL) and rt_render_into (into != NULL: finished bands of the frame are copied to the caller's host
+// buffers while later bands are still rendering).  One frame = ONE launch of the persistent kernel per rank: it
+// publishes a flag word per finished band itself (and, on several GPUs, runs the ready / done handshake with rank 0),
+// the copy stream waits on those words with cuStreamWaitValue32.  Kernels that do not publish their own completion
+// (brute force, per-ray, the block-per-tile variants) get the flag kernels around them.
 int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) {
     if (pipelined) *pipelined = false;
     if (!c || !fr) return fail(c, RT_ERR_ARG, "rt_render: NULL argument");
@@ -612,6 +658,13 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
     if (fr->num_lights < 0 || (fr->num_lights > 0 && !fr->lights)) return fail(c, RT_ERR_ARG, "rt_render: lights");
     if (fr->mode == RT_MODE_HW1 && fr->num_lights < 1) return fail(c, RT_ERR_ARG, "rt_render: HW1 mode needs one light");
     if (fr->quantiser < RT_QUANT_PPM_LROUND || fr->quantiser > RT_QUANT_CPU_TRUNC) return fail(c, RT_ERR_ARG, "rt_render: quantiser");
+    const uint32_t outputs = fr->outputs ? fr->outputs : RT_OUT_RGB_F32;
+    if (into) {   // checked before any device work or collective step, so that an error leaves every rank in the same state
+        const HostOut chk[4] = {{into->rgb, RT_OUT_RGB_F32, 12, nullptr, "rgb"}, {into->rgb8, RT_OUT_RGB8, 3, nullptr, "rgb8"},
+                                {into->tri_id, RT_OUT_TRI_ID, 4, nullptr, "tri_id"}, {into->t, RT_OUT_T, 4, nullptr, "t"}};
+        for (const HostOut& o : chk)
+            if (o.host && !(outputs & o.bit)) return fail(c, RT_ERR_STATE, "rt_render_into: plane '%s' was not requested in rt_frame.outputs", o.name);
+    }
 
     FrameParams& P = c->fp;
     memset(&P, 0, sizeof P);
@@ -620,16 +673,15 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
     P.num_materials = c->num_materials; P.has_normals = c->has_normals ? 1 : 0;
     P.sample_group = 1;
     while (P.sample_group < 32 && fr->spp % (2 * P.sample_group) == 0) P.sample_group *= 2;
-    if (fr->kernel_variant != RT_VARIANT_DEFAULT && fr->kernel_variant != RT_VARIANT_STATS &&
-        fr->kernel_variant != RT_VARIANT_FRUSTUM && fr->kernel_variant != RT_VARIANT_FRUSTUM_STATS && fr->kernel_variant != RT_VARIANT_PACKET &&
-        fr->kernel_variant != RT_VARIANT_PACKET_STATS) P.sample_group = 1;   // experimental variants: pixel-major
+    if (fr->kernel_variant == RT_VARIANT_PACKET_PIXEL_MAJOR || fr->kernel_variant == RT_VARIANT_PERSIST_EXACT_MT ||
+        fr->kernel_variant == RT_VARIANT_PERSIST_OCC8 || fr->kernel_variant == RT_VARIANT_PERSIST_OCC10 || fr->kernel_variant == RT_VARIANT_PACKET_EXACT_SLAB)
+        P.sample_group = 1;   // experimental variants: pixel-major
     memcpy(P.miss, fr->miss_color, sizeof P.miss);
     P.nodes = c->nodes; P.wide = c->wide; P.geom = c->geom; P.shade = c->shade; P.num_tris = c->num_tris; P.materials = c->materials;
     P.tiles_x = (P.W + RT_TILE_W - 1) / RT_TILE_W; P.tiles_y = (P.H + RT_TILE_H - 1) / RT_TILE_H;
     P.rank = c->rank; P.world = c->world;
     const bool dbg_shard = c->world == 1 && c->dbg_world > 1;
     if (dbg_shard) { P.rank = c->dbg_rank; P.world = c->dbg_world; }
-    const uint32_t outputs = fr->outputs ? fr->outputs : RT_OUT_RGB_F32;
     if (c->world > 1 && c->peer) {                 // collective; may fall back to the NCCL gather
         int rc = peer_planes(c, outputs, (size_t)fr->width * fr->height);
         if (rc != RT_OK) return rc;
@@ -691,101 +743,119 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
         if (outputs & RT_OUT_TRI_ID) { CU(c, c->loc_id.reserve(4 * npix_loc + 16)); P.tri_id = (int32_t*)c->loc_id.p; }
         if (outputs & RT_OUT_T) { CU(c, c->loc_t.reserve(4 * npix_loc + 16)); P.t = (float*)c->loc_t.p; }
     }
+    // ray counters (8 x u64) and the persistent kernel's work queue share one allocation and one memset per frame
     P.counters = (unsigned long long*)c->counters.p;
-    CU(c, cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
+    P.queue = (unsigned*)((char*)c->counters.p + RT_COUNTER_BYTES);
+    CU(c, cudaMemsetAsync(c->counters.p, 0, RT_COUNTER_BYTES + RT_PERSIST_CTL_BYTES, c->stream));
+    P.peer_timeout_ns = c->peer_timeout_ns;
+    P.peer_err = c->peer_err;
+    const bool persistent = rt_render_is_persistent(P, fr->kernel_variant);
+    const HostOut outs[4] = {{into ? into->rgb : nullptr, RT_OUT_RGB_F32, 12, P.rgb, "rgb"}, {into ? into->rgb8 : nullptr, RT_OUT_RGB8, 3, P.rgb8, "rgb8"},
+                             {into ? into->tri_id : nullptr, RT_OUT_TRI_ID, 4, P.tri_id, "tri_id"}, {into ? into->t : nullptr, RT_OUT_T, 4, P.t, "t"}};
+    // copies rows [y0, y1) of every requested plane to the caller's buffers
+    auto copy_rows = [&](size_t y0, size_t y1) -> int {
+        for (const HostOut& o : outs) {
+            if (!o.host) continue;
+            const size_t off = y0 * (size_t)P.W * o.bpp, bytes = (y1 - y0) * (size_t)P.W * o.bpp;
+            CU(c, cudaMemcpyAsync((char*)o.host + off, (const char*)o.dev + off, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+        }
+        return RT_OK;
+    };
 
     CU(c, cudaEventRecord(c->ev0, c->stream));
     int launches = 0;
     if (peer) {
-        // Frame k may overwrite rank 0's image only once rank 0 is done with frame k-1 (its downloads are
-        // stream-ordered before this point): rank 0 publishes `ready = k`, the others wait for it.
+        // Frame k may overwrite rank 0's image only once rank 0 is done with frame k-1 (its downloads are stream-ordered
+        // before this point): rank 0 publishes `ready = k`, the others wait for it — inside the persistent kernel.
         const unsigned seq = ++c->seq;
         const int F = c->chunks_per_rank > 0 ? c->chunks_per_rank : RT_DEFAULT_CHUNKS_PER_RANK;
-        // rt_render_into (collective): every rank renders its ownership chunks as separate kernels spread over a few streams
-        // (their tails overlap) and publishes a flag per finished chunk, so that rank 0 can copy finished rows to the host early
-        const bool chunked = into != nullptr && F <= RT_BANDS && F <= RT_PEER_MAX_CHUNKS;
-        if (chunked) { int rc = ensure_band_resources(c); if (rc != RT_OK) return rc; }
-        if (c->rank == 0) CU(c, rt_launch_flag_set(c->flags, seq, c->stream));
-        else CU(c, rt_launch_flag_wait(c->flags, RT_PEER_FLAG_STRIDE, 1, seq, kPeerTimeoutNs, c->peer_err, c->stream));
-        ++launches;
+        const bool banded = F <= RT_PEER_MAX_CHUNKS;            // one flag per ownership band, else one per rank
+        P.num_chunks = banded ? F : 1; P.band_tiles = banded ? P.chunk_tiles : P.local_tiles;
+        P.seq = seq;
+        P.flags = c->flags + RT_PEER_CHUNK_FLAG(c->rank, 0);
+        const bool root = c->rank == 0;
+        if (persistent) {
+            if (root) { P.ready_out = c->flags; P.wait_ranks = c->world - 1; P.flags_base = c->flags; }
+            else P.ready_in = c->flags;
+        } else {
+            if (root) CU(c, rt_launch_flag_set(c->flags, 1, 1, seq, c->stream));
+            else CU(c, rt_launch_flag_wait(c->flags, 0, 1, 0, 1, seq, c->peer_timeout_ns, c->peer_err, c->stream));
+            ++launches;
+        }
+        const bool pipe = into != nullptr && root && banded;
+        if (pipe) { int rc = ensure_band_resources(c); if (rc != RT_OK) return rc; }
         int l = 0;
         CU(c, cudaEventRecord(c->evk0, c->stream));
-        if (chunked) {
-            for (int j = 0; j < F; ++j) {
-                FrameParams Q = P;
-                Q.tile_offset = j * P.chunk_tiles; Q.local_tiles = P.chunk_tiles;
-                cudaStream_t sj = c->band_stream[j % RT_BAND_STREAMS];
-                CU(c, cudaStreamWaitEvent(sj, c->evk0, 0));
-                CU(c, rt_launch_render(Q, fr->kernel_variant, sj, &l));
-                launches += l;
-                CU(c, cudaEventRecord(c->band_ev[j], sj));
-                CU(c, cudaStreamWaitEvent(c->sig_stream, c->band_ev[j], 0));
-                CU(c, rt_launch_flag_set(c->flags + RT_PEER_CHUNK_FLAG(c->rank, j), seq, c->sig_stream));
-                ++launches;
-                CU(c, cudaStreamWaitEvent(c->stream, c->band_ev[j], 0));
-            }
-        } else {
-            CU(c, rt_launch_render(P, fr->kernel_variant, c->stream, &l));
-            launches += l;
+        CU(c, rt_launch_render(P, fr->kernel_variant, c->stream, &l));
+        launches += l;
+        if (!persistent) { CU(c, rt_launch_flag_set(P.flags, RT_PEER_FLAG_STRIDE, P.num_chunks, seq, c->stream)); ++launches; }
+        if (root && !persistent) {
+            CU(c, rt_launch_flag_wait(c->flags + RT_PEER_CHUNK_FLAG(1, 0), RT_PEER_MAX_CHUNKS * RT_PEER_FLAG_STRIDE, c->world - 1, RT_PEER_FLAG_STRIDE, P.num_chunks,
+                                      seq, c->peer_timeout_ns, c->peer_err, c->stream));
+            ++launches;
         }
-        CU(c, cudaEventRecord(c->evk1, c->stream));
-        if (chunked) {                                  // the frame is over for this rank when its last chunk flag is out
-            CU(c, cudaEventRecord(c->copy_done, c->sig_stream));
-            CU(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));
-        }
-        if (chunked && c->rank == 0) {
-            // Rank 0 copies the image to the host group by group: group j = chunk j of every rank = a contiguous range of
-            // row-major tiles; once all its flags arrived, the pixel rows it completes go out while later chunks render.
-            struct Out { void* host; uint32_t bit; size_t bpp; const void* dev; const char* name; };
-            const Out outs[4] = {{into->rgb, RT_OUT_RGB_F32, 12, P.rgb, "rgb"}, {into->rgb8, RT_OUT_RGB8, 3, P.rgb8, "rgb8"},
-                                 {into->tri_id, RT_OUT_TRI_ID, 4, P.tri_id, "tri_id"}, {into->t, RT_OUT_T, 4, P.t, "t"}};
-            for (const Out& o : outs)
-                if (o.host && !(outputs & o.bit)) return fail(c, RT_ERR_STATE, "rt_render_into: plane '%s' was not requested in rt_frame.outputs", o.name);
+        CU(c, cudaEventRecord(c->evk1, c->stream));             // rank 0: every rank's pixels have landed
+        if (pipe) {
+            // Rank 0 copies the image to the host group by group: group j = band j of every rank = a contiguous range of
+            // row-major tiles; once all its flags arrived, the pixel rows it completes go out while later bands render.
             CU(c, cudaStreamWaitEvent(c->copy_stream, c->evk0, 0));
+            StreamWaitValue32Fn wait32 = stream_wait_value32();
             size_t y_prev = 0;
             for (int j = 0; j < F; ++j) {
-                if (StreamWaitValue32Fn wait32 = stream_wait_value32()) {
+                if (wait32) {
                     for (int r = 0; r < c->world; ++r)
                         if (wait32((CUstream)c->copy_stream, (CUdeviceptr)(c->flags + RT_PEER_CHUNK_FLAG(r, j)), seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
                             return fail(c, RT_ERR_CUDA, "cuStreamWaitValue32 failed");
-                } else {
-                    CU(c, rt_launch_flag_wait(c->flags + RT_PEER_CHUNK_FLAG(0, j), RT_PEER_MAX_CHUNKS * RT_PEER_FLAG_STRIDE, c->world, seq,
-                                              kPeerTimeoutNs, c->peer_err, c->copy_stream));
-                    ++launches;
+                } else if (j == 0) {                            // no stream-ordered waits on this driver: copy after the frame
+                    CU(c, cudaStreamWaitEvent(c->copy_stream, c->evk1, 0));
                 }
                 long long tiles_done = (long long)(j + 1) * c->world * P.chunk_tiles;
                 if (tiles_done > total_tiles) tiles_done = total_tiles;
                 size_t y_end = (j == F - 1) ? (size_t)P.H : (size_t)(tiles_done / P.tiles_x) * RT_TILE_H;
                 if (y_end > (size_t)P.H) y_end = (size_t)P.H;
                 if (y_end <= y_prev) continue;
-                for (const Out& o : outs) {
-                    if (!o.host) continue;
-                    const size_t off = y_prev * (size_t)P.W * o.bpp, bytes = (y_end - y_prev) * (size_t)P.W * o.bpp;
-                    CU(c, cudaMemcpyAsync((char*)o.host + off, (const char*)o.dev + off, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
-                }
+                int rc = copy_rows(y_prev, y_end);
+                if (rc != RT_OK) return rc;
                 y_prev = y_end;
             }
             CU(c, cudaEventRecord(c->copy_done, c->copy_stream));
             if (pipelined) *pipelined = true;
-        }
-        // completion: one flag word per rank in rank 0's memory, written after the frame kernel
-        if (c->rank != 0) CU(c, rt_launch_flag_set(c->flags + (size_t)c->rank * RT_PEER_FLAG_STRIDE, seq, c->stream));
-        else CU(c, rt_launch_flag_wait(c->flags + RT_PEER_FLAG_STRIDE, RT_PEER_FLAG_STRIDE, c->world - 1, seq, kPeerTimeoutNs, c->peer_err, c->stream));
-        ++launches;
-        if (chunked && c->rank == 0) {
-            // had the wait above timed out (a rank died), release the stream-ordered chunk waits so that nothing hangs
+            // had a wait timed out (a rank died), release the stream-ordered band waits so that nothing hangs
             CU(c, rt_launch_flag_unblock(c->peer_err, c->flags + RT_PEER_CHUNK_FLAG(0, 0), RT_PEER_FLAG_STRIDE, RT_PEER_MAX_RANKS * RT_PEER_MAX_CHUNKS, seq, c->stream));
             ++launches;
             CU(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));
         }
+    } else if (into && c->world == 1 && !dbg_shard && P.tiles_y >= 2 && persistent && stream_wait_value32()) {
+        // single GPU: one persistent launch; bands of whole tile rows, each published as it completes
+        int rc = ensure_band_resources(c);
+        if (rc == RT_OK) rc = ensure_flags(c);
+        if (rc != RT_OK) return rc;
+        const unsigned seq = ++c->seq;
+        const int rows_per_band = (P.tiles_y + RT_BANDS - 1) / RT_BANDS;
+        const int B = (P.tiles_y + rows_per_band - 1) / rows_per_band;
+        P.num_chunks = B; P.band_tiles = rows_per_band * P.tiles_x; P.seq = seq;
+        P.flags = c->flags + RT_PEER_CHUNK_FLAG(0, 0);
+        CU(c, cudaEventRecord(c->evk0, c->stream));
+        CU(c, rt_launch_render(P, fr->kernel_variant, c->stream, &launches));
+        CU(c, cudaEventRecord(c->evk1, c->stream));
+        CU(c, cudaStreamWaitEvent(c->copy_stream, c->evk0, 0));
+        StreamWaitValue32Fn wait32 = stream_wait_value32();
+        for (int k = 0; k < B; ++k) {
+            if (wait32((CUstream)c->copy_stream, (CUdeviceptr)(c->flags + RT_PEER_CHUNK_FLAG(0, k)), seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+                return fail(c, RT_ERR_CUDA, "cuStreamWaitValue32 failed");
+            const size_t y0 = (size_t)k * rows_per_band * RT_TILE_H;
+            size_t y1 = (size_t)(k + 1) * rows_per_band * RT_TILE_H;
+            if (y1 > (size_t)P.H) y1 = (size_t)P.H;
+            rc = copy_rows(y0, y1);
+            if (rc != RT_OK) return rc;
+        }
+        CU(c, cudaEventRecord(c->copy_done, c->copy_stream));
+        CU(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));
+        if (pipelined) *pipelined = true;
     } else if (into && c->world == 1 && !dbg_shard && P.tiles_y >= 2) {
+        // kernels without in-kernel completion flags: one launch per band on a few streams, copies chained with events
         int rc = ensure_band_resources(c);
         if (rc != RT_OK) return rc;
-        struct Out { void* host; uint32_t bit; size_t bpp; const void* dev; const char* name; };
-        const Out outs[4] = {{into->rgb, RT_OUT_RGB_F32, 12, P.rgb, "rgb"}, {into->rgb8, RT_OUT_RGB8, 3, P.rgb8, "rgb8"},
-                             {into->tri_id, RT_OUT_TRI_ID, 4, P.tri_id, "tri_id"}, {into->t, RT_OUT_T, 4, P.t, "t"}};
-        for (const Out& o : outs)
-            if (o.host && !(outputs & o.bit)) return fail(c, RT_ERR_STATE, "rt_render_into: plane '%s' was not requested in rt_frame.outputs", o.name);
         const int B = P.tiles_y < RT_BANDS ? P.tiles_y : RT_BANDS;
         CU(c, cudaEventRecord(c->evk0, c->stream));
         for (int k = 0; k < B; ++k) {                 // all band kernels first: a pageable destination makes the copies host-synchronous
@@ -805,11 +875,8 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
             const int row_a = (int)((long long)P.tiles_y * k / B), row_b = (int)((long long)P.tiles_y * (k + 1) / B);
             const size_t y0 = (size_t)row_a * RT_TILE_H, y1 = (size_t)row_b * RT_TILE_H < (size_t)P.H ? (size_t)row_b * RT_TILE_H : (size_t)P.H;
             CU(c, cudaStreamWaitEvent(c->copy_stream, c->band_ev[k], 0));
-            for (const Out& o : outs) {
-                if (!o.host) continue;
-                const size_t off = y0 * (size_t)P.W * o.bpp, bytes = (y1 - y0) * (size_t)P.W * o.bpp;
-                CU(c, cudaMemcpyAsync((char*)o.host + off, (const char*)o.dev + off, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
-            }
+            rc = copy_rows(y0, y1);
+            if (rc != RT_OK) return rc;
         }
         CU(c, cudaEventRecord(c->copy_done, c->copy_stream));
         CU(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));

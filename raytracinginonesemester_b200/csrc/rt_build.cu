@@ -20,12 +20,17 @@ namespace {
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
 
+// Float min/max through integer atomics: non-negative floats order like signed ints, negative floats like unsigned ints
+// reversed.  -0.0f (bit pattern 0x80000000 = INT_MIN) satisfies `v >= 0.f` but would win every signed atomicMin and lose
+// every signed atomicMax, so the value is canonicalised first (v + 0.0f maps -0.0 to +0.0; the branch is on the sign BIT).
 __device__ __forceinline__ void atomic_min_f(float* a, float v) {
-    if (v >= 0.f) atomicMin(reinterpret_cast<int*>(a), __float_as_int(v));
+    v += 0.0f;
+    if (!(__float_as_uint(v) >> 31)) atomicMin(reinterpret_cast<int*>(a), __float_as_int(v));
     else atomicMax(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
 }
 __device__ __forceinline__ void atomic_max_f(float* a, float v) {
-    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(a), __float_as_int(v));
+    v += 0.0f;
+    if (!(__float_as_uint(v) >> 31)) atomicMax(reinterpret_cast<int*>(a), __float_as_int(v));
     else atomicMin(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
 }
 
@@ -153,7 +158,23 @@ __global__ void k_pack_tris(BuildParams bp, const uint32_t* __restrict__ vals, T
 
 inline unsigned blocks_for(size_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
 
+// first position whose vertex index is out of range (atomicMin over 64-bit positions; ~0 = none)
+__global__ void k_validate_indices(const uint32_t* __restrict__ idx, size_t n, uint32_t num_vertices, unsigned long long* bad) {
+    unsigned long long first = ~0ull;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        if (idx[i] >= num_vertices && (unsigned long long)i < first) first = (unsigned long long)i;
+    if (first != ~0ull) atomicMin(bad, first);
+}
+
 } // namespace
+
+cudaError_t rt_validate_indices(const uint32_t* idx, size_t n, uint32_t num_vertices, unsigned long long* bad, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    unsigned nb = blocks_for(n, 256);
+    if (nb > 148u * 16u) nb = 148u * 16u;
+    k_validate_indices<<<nb, 256, 0, stream>>>(idx, n, num_vertices, bad);
+    return cudaGetLastError();
+}
 
 // Per-object transform bake in place (main.cu:75-96), one thread per vertex of the object.
 __global__ void k_bake_transform(float* pos, float* nrm, size_t first, size_t count, BakeXform T) {
@@ -263,7 +284,7 @@ cudaError_t rt_build_bvh(const BuildParams& bp, BvhNode** nodes_out, TriBlock* g
         CKG(cudaStreamSynchronize(stream));
         if (res) {
             res->num_nodes = num_nodes;
-            res->num_leaves = 0;
+            res->num_leaves = (uint32_t)n > leaf_max ? num_nodes + 1u : 1u;   // every kept node has two children, each a kept node or a leaf
             for (int k = 0; k < 3; ++k) { res->scene_min[k] = hb.lo[k]; res->scene_max[k] = hb.hi[k]; }
         }
     }

@@ -107,6 +107,58 @@ RT_HD bool rt_moller_trumbore(const Ray& r, f3 v0, f3 e1, f3 e2, float det_eps, 
     return true;
 }
 
+// The same test with a division-free front end (what the packet kernels run): most warp-level tests of a packet
+// accept no lane, and the reference's formulation pays an IEEE divide before its first reject.  Here the three
+// barycentric numerators are first judged with an APPROXIMATE reciprocal `ra` of det (rcp.approx on the device,
+// relative error <= 2^-22); a lane leaves early only when the exactly-rounded test below could not accept either:
+//   ua = fl(U*ra) < -2^-100        =>  U/det < -2^-101                 =>  u = fl(U*fl(1/det)) < 0
+//   ua > 1 + 2^-20                 =>  U/det > 1 + 2^-21               =>  u > 1
+//   va < -2^-100                   =>  v < 0                           (same argument)
+//   fl(ua+va) > 1 + 2^-19          =>  u + v > 1 + 2^-21 (u, v >= -2^-100 here, |u-ua| <= 2^-20 |ua|)  =>  fl(u+v) > 1
+//   ta < 0.999996 tmin - 2^-100    =>  t < tmin          ta > 1.000004 tmax + 2^-100  =>  t > tmax
+// (the 2^-100 guard keeps products that underflow to -0 — which the reference accepts — on the exact path; NaNs
+// fail every comparison and stay on it too).  Survivors run the reference's operations in the reference's order, so
+// an accepted hit carries bit-identical (t, u, v).  tests/test_device_code_on_host.py sweeps the reference's
+// 57-point barycentric grid and random near-edge probes with adversarially perturbed `ra`.
+#define RT_LAZY_TINY 7.8886091e-31f          /* 2^-100 */
+RT_HD bool rt_moller_trumbore_lazy_r(const Ray& r, f3 v0, f3 e1, f3 e2, float det_eps, float tmin, float tmax, float ra_scale,
+                                     float& t_out, float& u_out, float& v_out) {
+    f3 pvec = xcross(r.d, e2);
+    float det = xdot(e1, pvec);
+    if (fabsf(det) < det_eps) return false;
+#if defined(__CUDA_ARCH__)
+    float ra;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(det));
+    (void)ra_scale;
+#else
+    const float ra = (1.0f / det) * ra_scale;       // host model: tests pass 1 +- 2^-22 to emulate the worst approximation
+#endif
+    f3 tvec = xsub3(r.o, v0);
+    const float U = xdot(tvec, pvec);
+    const float ua = U * ra;
+    if (ua < -RT_LAZY_TINY || ua > 1.00000095367431640625f) return false;
+    f3 qvec = xcross(tvec, e1);
+    const float V = xdot(r.d, qvec);
+    const float va = V * ra;
+    if (va < -RT_LAZY_TINY || ua + va > 1.0000019073486328125f) return false;
+    const float T = xdot(e2, qvec);
+    const float ta = T * ra;
+    if (ta < 0.999996f * tmin - RT_LAZY_TINY || ta > 1.000004f * tmax + RT_LAZY_TINY) return false;
+    const float invDet = XRCP(det);
+    const float u = XMUL(U, invDet);
+    if (u < 0.0f || u > 1.0f) return false;
+    const float v = XMUL(V, invDet);
+    if (v < 0.0f || XADD(u, v) > 1.0f) return false;
+    const float t = XMUL(T, invDet);
+    if (t < tmin || t > tmax) return false;
+    t_out = t; u_out = u; v_out = v;
+    return true;
+}
+RT_HD bool rt_moller_trumbore_lazy(const Ray& r, f3 v0, f3 e1, f3 e2, float det_eps, float tmin, float tmax,
+                                   float& t_out, float& u_out, float& v_out) {
+    return rt_moller_trumbore_lazy_r(r, v0, e1, e2, det_eps, tmin, tmax, 1.0f, t_out, u_out, v_out);
+}
+
 RT_HD float rt_det_eps(int mode) { return mode == RT_MODE_HW2_BVH ? 1e-8f : FLT_EPSILON; }
 RT_HD float rt_tmin(int mode) { return mode == RT_MODE_HW1 ? 0.0f : 1e-4f; }
 
@@ -269,7 +321,7 @@ RT_HD rt_material rt_default_material() {   // Material(), GPUandCPU/include/mat
 }
 
 // -------------------------------------------------------------- quantiser ----
-RT_HD uint8_t rt_quantise(float c, int q) {
+RT_UNIT_FN uint8_t rt_quantise(float c, int q) {      // (one copy in device code, see rt_math.h RT_UNIT_FN)
     if (q == RT_QUANT_HW1_TRUNC) return (uint8_t)(XMUL(255.99f, c));                 // HW1/src/render.cpp:121-123
     if (q == RT_QUANT_HW2_TRUNC) return (uint8_t)(XMUL(255.0f, (c < 1.0f ? c : 1.0f))); // GPUandCPU/src/main.cu:428-430
     if (q == RT_QUANT_CPU_TRUNC) { float x = c > 1.0f ? 1.0f : c; if (x < 0.0f) x = 0.0f; return (uint8_t)(XMUL(255.99f, x)); }   // CPUOnly/src/render.cpp:157-163

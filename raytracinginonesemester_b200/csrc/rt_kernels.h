@@ -11,6 +11,8 @@
 struct BuildResult { uint32_t num_nodes; uint32_t num_leaves; float scene_min[3], scene_max[3]; };
 cudaError_t rt_build_bvh(const BuildParams& bp, BvhNode** nodes_out, TriBlock* geom, TriBlock* shade,
                          BuildResult* res, cudaStream_t stream);
+// Writes the first position i with idx[i] >= num_vertices into *bad (device, preset to ~0 by the caller).
+cudaError_t rt_validate_indices(const uint32_t* idx, size_t n, uint32_t num_vertices, unsigned long long* bad, cudaStream_t stream);
 // Bakes an object's transform into its vertex range in place (device arrays), before the build.
 struct BakeXform;
 cudaError_t rt_bake_transform(float* pos, float* nrm, size_t first, size_t count, const BakeXform& T, cudaStream_t stream);
@@ -21,6 +23,11 @@ cudaError_t rt_pack_triangles(const BuildParams& bp, TriBlock* geom, TriBlock* s
 
 // rt_trace.cu --------------------------------------------------------------------------
 cudaError_t rt_launch_render(const FrameParams& fp, int kernel_variant, cudaStream_t stream, int* launches);
+// True when rt_launch_render will run this frame on the persistent kernel, which publishes band-completion flags and
+// runs the multi-GPU handshake itself (FrameParams.queue / flags / ready_* / wait_ranks); other kernels need the flag
+// kernels below around them.
+bool rt_render_is_persistent(const FrameParams& fp, int kernel_variant);
+#define RT_PERSIST_CTL_BYTES 128          // device bytes behind FrameParams.queue
 // Scatter tile-packed planes of rank `src_rank` into the row-major image (rank 0, world > 1).
 cudaError_t rt_launch_unpack(const FrameParams& fp, int src_rank, const float* rgb, const uint8_t* rgb8,
                              const int32_t* tri_id, const float* t, float* o_rgb, uint8_t* o_rgb8,
@@ -29,10 +36,12 @@ cudaError_t rt_launch_unpack(const FrameParams& fp, int src_rank, const float* r
 #define RT_PEER_FLAG_STRIDE 16            // one 64-byte line per flag
 #define RT_PEER_MAX_RANKS 8
 #define RT_PEER_MAX_CHUNKS 16            // ownership chunks per rank that rt_render_into can pipeline
-// flag block layout (uints, each flag on its own line): [0] ready, [r] frame done by rank r (r >= 1),
-// [16 + r*RT_PEER_MAX_CHUNKS + j] chunk j of rank r done
+// flag block layout (uints, each flag on its own line): [0] ready (rank 0 -> everybody: the previous image has been read),
+// [16 + r*RT_PEER_MAX_CHUNKS + j] band j of rank r done
 #define RT_PEER_CHUNK_FLAG(r, j) ((size_t)(16 + (r) * RT_PEER_MAX_CHUNKS + (j)) * RT_PEER_FLAG_STRIDE)
-cudaError_t rt_launch_flag_set(unsigned* flag, unsigned seq, cudaStream_t stream);
-cudaError_t rt_launch_flag_wait(const unsigned* flags, int stride, int n, unsigned seq, unsigned long long timeout_ns,
-                                unsigned* err, cudaStream_t stream);
+// (only around kernels that do not publish their own completion: brute force, per-ray, the block-per-tile variants)
+cudaError_t rt_launch_flag_set(unsigned* flags, int stride, int n, unsigned seq, cudaStream_t stream);
+// waits for flags[a * rank_stride + b * stride] >= seq for a < nranks, b < nper
+cudaError_t rt_launch_flag_wait(const unsigned* flags, int rank_stride, int nranks, int stride, int nper, unsigned seq,
+                                unsigned long long timeout_ns, unsigned* err, cudaStream_t stream);
 cudaError_t rt_launch_flag_unblock(const unsigned* err, unsigned* flags, int stride, int n, unsigned seq, cudaStream_t stream);

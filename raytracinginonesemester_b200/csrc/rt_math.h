@@ -84,16 +84,28 @@ RT_HD f3 xcross(f3 u, f3 v) {
                XSUB(XMUL(u.x, v.y), XMUL(u.y, v.x)));
 }
 RT_HD float xlen3(f3 v) { return XSQRT(xdot(v, v)); }
+// The three unit-vector routines are NOT inlined in device code: each is an IEEE square root and three IEEE divides
+// (~45 SASS instructions with their range checks), shading calls them eight times per hit, and the frame kernel is
+// instruction-cache bound outside its traversal loop (ncu r2: 19 % of the warp stalls were instruction fetches, almost
+// all of them in straight-line shading code that every packet streams through once).  One copy, eight calls.
+#ifndef RT_X_NOINLINE_UNIT
+#define RT_X_NOINLINE_UNIT 0
+#endif
+#if defined(__CUDA_ARCH__) && RT_X_NOINLINE_UNIT
+#define RT_UNIT_FN static __device__ __noinline__
+#else
+#define RT_UNIT_FN RT_HD
+#endif
 // global unit_vector(): vec3.h:53-56
-RT_HD f3 xunit(f3 v) { return xdivs(v, xlen3(v)); }
+RT_UNIT_FN f3 xunit(f3 v) { return xdivs(v, xlen3(v)); }
 // unit_vector() of the CPUOnly renderer: zero vector below 1e-12 (HW2/HW2/CPUOnly/include/vec3.h:53-57)
-RT_HD f3 xunit_c(f3 v) {
+RT_UNIT_FN f3 xunit_c(f3 v) {
     float len = xlen3(v);
     if (len < 1e-12f) return mk3(0.0f, 0.0f, 0.0f);
     return xdivs(v, len);
 }
 // Camera::unit_vector(): GPUandCPU/include/camera.h:64-69 (fallback (0,0,1) below 1e-12)
-RT_HD f3 xunit_cam(f3 v) {
+RT_UNIT_FN f3 xunit_cam(f3 v) {
     float len = xlen3(v);
     if ((double)len < 1e-12) return mk3(0.0f, 0.0f, 1.0f);
     return xdivs(v, len);

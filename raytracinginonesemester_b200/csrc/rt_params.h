@@ -39,6 +39,17 @@ struct FrameParams {
     float scene_c[3], scene_r2;     // scene bounding sphere (centre, padded squared radius): packets that miss it skip the traversal set-up
     float frustum_eps;              // frustum traversal: absolute slack of the plane tests = 1.6e-5 x largest coordinate in play (host)
     int sample_group;               // packet kernel: samples of one pixel traced side by side (power of two dividing spp, <= 32)
+    // persistent kernel (rt_trace.cu, k_render_persist): work queue + in-kernel completion protocol
+    unsigned* queue;                // PersistCtl, zeroed by the host before the launch
+    int num_chunks, band_tiles;     // the rank's tile slots in num_chunks bands of band_tiles slots whose completion is published (0: none)
+    unsigned seq;                   // frame sequence number written into flag words
+    unsigned* flags;                // this rank's band flags: band j -> flags[j * RT_PEER_FLAG_STRIDE] (own memory, or rank 0's over NVLink)
+    const unsigned* flags_base;     // rank 0 of the fused gather: the whole flag block (all ranks' band flags), else unused
+    int wait_ranks;                 // rank 0 of the fused gather: ranks 1..wait_ranks are awaited by the last warp; else 0
+    const unsigned* ready_in;       // ranks != 0 of the fused gather: rank 0's `ready` word, awaited before the first store; else NULL
+    unsigned* ready_out;            // rank 0 of the fused gather: where `ready = seq` is published at kernel start; else NULL
+    unsigned long long peer_timeout_ns;
+    unsigned* peer_err;             // set when a wait above timed out
 };
 
 struct BuildParams {

@@ -175,6 +175,7 @@ k_render_brute(const __grid_constant__ FrameParams P) {
 // single ray's while SIMD efficiency goes from ~44 % (per-ray, ncu r1_v1) to ~100 %.
 #define FULLMASK 0xffffffffu
 #define RT_PACKET_STACK 64
+#define RT_SLOT_DEAD (-2)                         // Hit.slot of a lane that traced nothing (outside the frame, depth 0)
 
 struct TraceResult { Hit hit; bool blocked; };
 
@@ -205,6 +206,7 @@ template <int MODE, bool STATS, bool FAST, bool PF = false, int TAG = 0>
 __device__ __noinline__ TraceResult packet_trace(const BvhNode* __restrict__ nodes, const TriBlock* __restrict__ geom, const uint32_t num_tris,
                                                  const Ray ray, bool live, const bool any, float tlimit, TraceStats* st) {
     Hit best; rt_hit_reset(best);
+    if (!live) best.slot = RT_SLOT_DEAD;          // lets the caller tell "traced nothing" from "missed" without keeping `live` across the call
     bool blocked = false;
     const float det_eps = rt_det_eps(MODE), tmin = rt_tmin(MODE);
     const int lane = threadIdx.x & 31;
@@ -306,7 +308,9 @@ __device__ __noinline__ TraceResult packet_trace(const BvhNode* __restrict__ nod
 // Rounding: the slope bounds are widened by 4e-6 (1 + |s|) (directions are within 60 degrees of w, so |s| < 1.8),
 // and every plane offset by feps = 1.6e-5 x the largest coordinate in play (host: scene bounds, camera) — an
 // order of magnitude more than the error of the 6-term FMA sums.
+#ifndef RT_FSTACK
 #define RT_FSTACK 128
+#endif
 // 9 resident blocks (36 warps, 56 registers) measured best for the frustum kernel on C4: 6 -> 2.21 ms, 8 -> 2.07, 9 -> 2.01, 10 -> 2.05, 12 -> 2.04
 #define RT_FRUSTUM_MINB 9
 
@@ -315,11 +319,12 @@ __device__ __forceinline__ float warp_fmin(float v) { float r; asm volatile("red
 __device__ __forceinline__ float warp_fmax(float v) { float r; asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v)); return r; }
 __device__ __forceinline__ float warp_bcast(float v, int src, int lane) { return __int_as_float((int)__reduce_or_sync(FULLMASK, lane == src ? (unsigned)__float_as_int(v) : 0u)); }
 
-template <int MODE, bool STATS, bool FAST, int TAG>
+template <int MODE, bool STATS, bool FAST, int TAG, bool LAZY = false>
 __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ nodes, const WideNode* __restrict__ wide, const TriBlock* __restrict__ geom, const uint32_t num_tris,
                                                   const Ray ray, bool live, const bool any, const bool same_origin, float tlimit, TraceStats* st,
                                                   int* __restrict__ wstack, float4* __restrict__ wfr, const float feps, const f3 sc, const float sr2) {
     Hit best; rt_hit_reset(best);
+    if (!live) best.slot = RT_SLOT_DEAD;          // lets the caller tell "traced nothing" from "missed" without keeping `live` across the call
     bool blocked = false;
     const float det_eps = rt_det_eps(MODE), tmin = rt_tmin(MODE);
     int lane;
@@ -460,14 +465,32 @@ __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ no
             const uint32_t first = rt_leaf_first(lref), cnt = rt_leaf_count(lref);
 #pragma unroll 1
             for (uint32_t s = first; s < first + cnt; ++s) {      // one copy of the test: the kernel is instruction-cache sensitive
-                uint32_t sv = s;
-                asm volatile("" : "+r"(sv));      // address arithmetic in vector registers: one IMAD.WIDE for the three loads
-                const Tri tr = rt_load_tri(geom, sv);   // instead of a uniform address re-materialised into a register pair per load
+                // all three 16-byte loads of the block are issued together, up front (volatile asm: ptxas otherwise sinks the
+                // v0 load below the determinant test, which nearly every test passes — a second full memory latency per test)
+#ifndef RT_X_EARLY_LOAD
+#define RT_X_EARLY_LOAD 1
+#endif
+                Tri tr;
+                if (!RT_X_EARLY_LOAD) {
+                    uint32_t sv = s;
+                    asm volatile("" : "+r"(sv));
+                    tr = rt_load_tri(geom, sv);
+                } else {
+                    const float4* tp = reinterpret_cast<const float4*>(geom + s);
+                    float idf;
+                    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(tr.v0.x), "=f"(tr.v0.y), "=f"(tr.v0.z), "=f"(idf) : "l"(tp));
+                    float p0, p1;
+                    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(tr.e1.x), "=f"(tr.e1.y), "=f"(tr.e1.z), "=f"(p0) : "l"(tp + 1));
+                    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(tr.e2.x), "=f"(tr.e2.y), "=f"(tr.e2.z), "=f"(p1) : "l"(tp + 2));
+                    tr.id = __float_as_int(idf);
+                }
                 if (STATS && lane == 0) st->wtris++;
                 if (live) {
                     if (STATS) st->tris++;
                     float t, uu, vv;
-                    if (rt_moller_trumbore(ray, tr.v0, tr.e1, tr.e2, det_eps, tmin, any ? FLT_MAX : tlimit, t, uu, vv)) {
+                    // LAZY: division-free front end, exact test for the survivors (rt_core.h, rt_moller_trumbore_lazy)
+                    if (LAZY ? rt_moller_trumbore_lazy(ray, tr.v0, tr.e1, tr.e2, det_eps, tmin, any ? FLT_MAX : tlimit, t, uu, vv)
+                             : rt_moller_trumbore(ray, tr.v0, tr.e1, tr.e2, det_eps, tmin, any ? FLT_MAX : tlimit, t, uu, vv)) {
                         if (any) { if (t < tlimit) { blocked = true; live = false; } }
                         else if (t < tlimit || tr.id < best.id) { best.t = t; best.u = uu; best.v = vv; best.slot = (int)s; best.id = tr.id; tlimit = t; improved = true; }
                     }
@@ -496,116 +519,144 @@ __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ no
     return TraceResult{best, blocked};
 }
 
-// Values that are cheap to recompute are deliberately NOT kept in registers across a shadow
-// trace: laundering the hit through an empty asm makes the compiler rebuild the surface
-// (position, normals, material) afterwards instead of spilling ~60 registers around the loop,
-// which is what buys the occupancy (ncu r1: 140 regs -> 64, 16 -> 32 warps/SM).
-__device__ __forceinline__ void launder(Hit& h, int& x, int& y) {
-    asm volatile("" : "+f"(h.t), "+f"(h.u), "+f"(h.v), "+r"(h.slot), "+r"(x), "+r"(y));
+// One packet = the 32 pixels of one 8x4 patch (lane q owns pixel q): ray generation, closest-hit trace, one any-hit
+// shadow trace per light, shading, resolve into the requested planes.  Shared by the block-per-tile kernel
+// (k_render_packet) and the persistent kernel (k_render_persist).
+//
+// NOTHING stays in registers across a trace call.  ptxas allocates the registers of the (non-inlined) traversal
+// function together with its callers': every value that is live across a call site is one register less for the
+// traversal loop, and with the 56-register budget of 9 resident blocks the loop then spills (ncu r2: eight LDL/STL per
+// round, +13 % instructions, 3x the local-memory traffic, after a version of this function that merely let the compiler
+// hoist the surface set-up above the shadow trace).  So the few values that must survive a trace — ray direction, hit,
+// the light's contribution, the pixel sum, the packet's tile — live in a shared-memory STASH (one column of
+// RT_STASH_WORDS words per thread, stride RT_BLOCK_THREADS, conflict-free; volatile, so that nothing is cached in
+// registers or hoisted), and everything else is recomputed from them.  Side effect: the ray is generated once per
+// sample instead of three times, and the surface code exists once — the kernel is instruction-cache bound outside the
+// traversal loop, so code that is not there is the cheapest code.
+enum { ST_DX = 0, ST_DY, ST_DZ, ST_HT, ST_HU, ST_HV, ST_HSLOT, ST_LOX, ST_LOY, ST_LOZ, ST_DIX, ST_DIY, ST_DIZ, ST_ACX, ST_ACY, ST_ACZ, RT_STASH_WORDS };
+#define STASH(k) stash[(k) * RT_BLOCK_THREADS]
+struct WarpSlot { unsigned tile, sub, nprim, nshadow; };       // per warp, shared memory: the packet in flight + ray counters
+
+template <bool GROUPED>
+__device__ __forceinline__ Pixel packet_pixel(const FrameParams& P, const volatile WarpSlot* ws, int lane) {
+    return rt_map_pixel(P, (int)ws->tile, (int)(ws->sub * 32u) + lane);
 }
 
-template <int MODE, bool STATS, bool FAST, int MINB, bool PF = false, bool GROUPED = false, bool FRUSTUM = false>
-__global__ void __launch_bounds__(RT_BLOCK_THREADS, MINB)
-k_render_packet(const __grid_constant__ FrameParams P) {
-    __shared__ int s_wstack[FRUSTUM ? (RT_BLOCK_THREADS / 32) * RT_FSTACK : 1];
-    int* const wstack = s_wstack + (FRUSTUM ? (threadIdx.x >> 5) * RT_FSTACK : 0);
-    __shared__ float4 s_wfr[FRUSTUM ? (RT_BLOCK_THREADS / 32) * 5 : 1];
-    float4* const wfr = s_wfr + (FRUSTUM ? (threadIdx.x >> 5) * 5 : 0);
-    constexpr int TAG = MINB * 4 + (GROUPED ? 1 : 0) + (FRUSTUM ? 2 : 0);
-    const Pixel px = map_pixel(P);
-    unsigned nprim = 0, nshadow = 0;
-    TraceStats st{0, 0, 0, 0, 0};
-    f3 accum = mk3(0.f, 0.f, 0.f);
+template <int MODE, bool STATS, bool FAST, bool PF, bool GROUPED, bool FRUSTUM, bool LAZY, int TAG>
+__device__ __forceinline__ void render_packet(const FrameParams& P, volatile WarpSlot* const ws, volatile float* const stash,
+                                              int* const wstack, float4* const wfr, TraceStats* const st) {
+    const int lane = (int)(threadIdx.x & 31);
+    STASH(ST_ACX) = 0.f; STASH(ST_ACY) = 0.f; STASH(ST_ACZ) = 0.f;    // pixel sum
     // Sample-major packets: with G = P.sample_group samples of one pixel side by side in the warp, a pass traces
     // 32/G neighbouring pixels x G samples — a footprint of 32/G pixels instead of 8x4, so the rays of a packet stay
     // together much deeper into the tree when spp > 1 (G == 1: one sample of each of the warp's 32 pixels, as before).
     // Lane q owns pixel q of the warp's 8x4 patch and sums its samples in sample order, like the reference's loop.
     // GROUPED == false is the G == 1 instance without the shuffles (host picks the instance from P.sample_group).
-    const int lane = threadIdx.x & 31;
-    const int G = GROUPED ? P.sample_group : 1, gsh = GROUPED ? __ffs(G) - 1 : 0, PP = 32 >> gsh, chunks = P.spp >> gsh;
     for (int pass = 0; pass < P.spp; ++pass) {
+        const int G = GROUPED ? P.sample_group : 1, gsh = GROUPED ? __ffs(G) - 1 : 0, PP = 32 >> gsh, chunks = P.spp >> gsh;
         const int pb = GROUPED ? pass / chunks : 0, pc = pass - pb * chunks;
-        const int qi = GROUPED ? pb * PP + (lane >> gsh) : lane;
-        const int s = GROUPED ? (pc << gsh) + (lane & (G - 1)) : pass;
-        const bool inside = GROUPED ? __shfl_sync(FULLMASK, (int)px.inside, qi) != 0 : px.inside;
-        int x = GROUPED ? __shfl_sync(FULLMASK, px.x, qi) : px.x, y = GROUPED ? __shfl_sync(FULLMASK, px.y, qi) : px.y;
-        if (!inside) { x = 0; y = 0; }
-        const unsigned long long out_q = GROUPED ? __shfl_sync(FULLMASK, (unsigned long long)px.out, qi) : (unsigned long long)px.out;
-        const float jx = P.jitter ? __ldg(P.jitter + 2 * s) : 0.0f;
-        const float jy = P.jitter ? __ldg(P.jitter + 2 * s + 1) : 0.0f;
-        const bool live = inside && (MODE == RT_MODE_HW1 || P.max_depth > 0);
-        Hit h; rt_hit_reset(h);
-        {
+        const int qi = GROUPED ? pb * PP + (lane >> gsh) : lane;                 // the pixel (lane of the patch) this lane samples
+        const int s = GROUPED ? (pc << gsh) + (lane & (G - 1)) : pass;           // ... and which of its samples
+        {   // ---- camera ray + closest hit
+            const Pixel px = packet_pixel<GROUPED>(P, ws, lane);
+            const bool inside = GROUPED ? __shfl_sync(FULLMASK, (int)px.inside, qi) != 0 : px.inside;
+            int x = GROUPED ? __shfl_sync(FULLMASK, px.x, qi) : px.x, y = GROUPED ? __shfl_sync(FULLMASK, px.y, qi) : px.y;
+            if (!inside) { x = 0; y = 0; }
+            const bool live = inside && (MODE == RT_MODE_HW1 || P.max_depth > 0);
+            const float jx = P.jitter ? __ldg(P.jitter + 2 * s) : 0.0f;
+            const float jy = P.jitter ? __ldg(P.jitter + 2 * s + 1) : 0.0f;
             const Ray ray = rt_make_ray(P.cam, MODE, x, y, jx, jy);
-            if (FRUSTUM) h = frustum_trace<MODE, STATS, FAST, TAG>(P.nodes, P.wide, P.geom, P.num_tris, ray, live, false, true, 0.f, &st, wstack, wfr, P.frustum_eps, ld3(P.scene_c), P.scene_r2).hit;
-            else h = packet_trace<MODE, STATS, FAST, PF, TAG>(P.nodes, P.geom, P.num_tris, ray, live, false, 0.f, &st).hit;
-        }
-        if (live) ++nprim;
-        if (s == 0 && inside) {                        // id / t planes describe sample 0
-            if (P.tri_id) P.tri_id[out_q] = h.slot >= 0 ? h.id : -1;
-            if (P.t) P.t[out_q] = h.slot >= 0 ? h.t : -1.0f;
+            STASH(ST_DX) = ray.d.x; STASH(ST_DY) = ray.d.y; STASH(ST_DZ) = ray.d.z;
+            const unsigned nlive = (unsigned)__popc(__ballot_sync(FULLMASK, live));
+            if (lane == 0) ws->nprim += nlive;
+            Hit h;
+            if (FRUSTUM) h = frustum_trace<MODE, STATS, FAST, TAG, LAZY>(P.nodes, P.wide, P.geom, P.num_tris, ray, live, false, true, 0.f, st, wstack, wfr, P.frustum_eps, ld3(P.scene_c), P.scene_r2).hit;
+            else h = packet_trace<MODE, STATS, FAST, PF, TAG>(P.nodes, P.geom, P.num_tris, ray, live, false, 0.f, st).hit;
+            // (a lane that traced nothing comes back with slot == RT_SLOT_DEAD)
+            STASH(ST_HT) = h.t; STASH(ST_HU) = h.u; STASH(ST_HV) = h.v; STASH(ST_HSLOT) = __int_as_float(h.slot);
+            if (P.tri_id || P.t) {                         // id / t planes describe sample 0
+                const Pixel p2 = packet_pixel<GROUPED>(P, ws, lane);
+                const bool in2 = GROUPED ? __shfl_sync(FULLMASK, (int)p2.inside, qi) != 0 : p2.inside;
+                const unsigned long long out_q = GROUPED ? __shfl_sync(FULLMASK, (unsigned long long)p2.out, qi) : (unsigned long long)p2.out;
+                if (s == 0 && in2) {
+                    if (P.tri_id) P.tri_id[out_q] = h.slot >= 0 ? h.id : -1;
+                    if (P.t) P.t[out_q] = h.slot >= 0 ? h.t : -1.0f;
+                }
+            }
         }
         f3 color = mk3(0.f, 0.f, 0.f);
         if (MODE == RT_MODE_HW1) {
-            if (live) color = rt_shade_hw1(P, rt_make_ray(P.cam, MODE, x, y, jx, jy), h);
+            Hit h; h.t = STASH(ST_HT); h.u = STASH(ST_HU); h.v = STASH(ST_HV); h.slot = __float_as_int(STASH(ST_HSLOT)); h.id = 0;
+            Ray ray; ray.o = ld3(P.cam.center); ray.d = mk3(STASH(ST_DX), STASH(ST_DY), STASH(ST_DZ));
+            if (h.slot != RT_SLOT_DEAD) color = rt_shade_hw1(P, ray, h);
         } else {
-            const bool hit = live && h.slot >= 0;
-            f3 Lo = mk3(0.f, 0.f, 0.f);
-            if (hit && P.num_lights == 0) {              // with lights, the first light's surface rebuild supplies this term
-                launder(h, x, y);
-                Surface sf;
-                rt_surface_hw2(P, rt_make_ray(P.cam, MODE, x, y, jx, jy), h, sf);
-                Lo = sf.Lo;                              // ambient + emission
-            }
-            for (int l = 0; l < P.num_lights; ++l) {     // warp-uniform loop
-                bool need = false, lit = false, blocked = false;
-                f3 direct = mk3(0.f, 0.f, 0.f);          // this light's contribution, evaluated BEFORE the shadow trace so
-                {                                        // that only three floats stay live across it (no third surface rebuild)
-                    Ray sray; sray.o = mk3(0.f, 0.f, 0.f); sray.d = mk3(0.f, 0.f, 1.f);
-                    float dist = 0.f;
-                    if (hit) {
-                        launder(h, x, y);
-                        Surface sf; f3 L; float NdotL;
-                        rt_surface_hw2(P, rt_make_ray(P.cam, MODE, x, y, jx, jy), h, sf);
-                        if (l == 0) Lo = sf.Lo;          // ambient + emission
-                        lit = rt_light_setup_hw2(sf, P.lights[l], L, NdotL, need, sray, dist);
+            // one iteration per light; a frame without lights still takes one (for the ambient + emission term): a single
+            // copy of the surface code in the binary.  The surface is rebuilt from the stash in every iteration.
+            STASH(ST_LOX) = 0.f; STASH(ST_LOY) = 0.f; STASH(ST_LOZ) = 0.f;
+            for (int l = 0; l < (P.num_lights > 0 ? P.num_lights : 1); ++l) {     // warp-uniform loop
+                bool need = false;
+                Ray sray; sray.o = mk3(0.f, 0.f, 0.f); sray.d = mk3(0.f, 0.f, 1.f);
+                float dist = 0.f;
+                STASH(ST_DIX) = 0.f; STASH(ST_DIY) = 0.f; STASH(ST_DIZ) = 0.f;      // this light's contribution, evaluated BEFORE its shadow trace
+                const int slot = __float_as_int(STASH(ST_HSLOT));
+                if (slot >= 0) {
+                    Hit h; h.t = STASH(ST_HT); h.u = STASH(ST_HU); h.v = STASH(ST_HV); h.slot = slot; h.id = 0;
+                    Ray ray; ray.o = ld3(P.cam.center); ray.d = mk3(STASH(ST_DX), STASH(ST_DY), STASH(ST_DZ));
+                    Surface sf; f3 L; float NdotL;
+                    rt_surface_hw2(P, ray, h, sf);
+                    if (l == 0) { STASH(ST_LOX) = sf.Lo.x; STASH(ST_LOY) = sf.Lo.y; STASH(ST_LOZ) = sf.Lo.z; }     // ambient + emission
+                    if (l < P.num_lights) {
+                        bool lit = rt_light_setup_hw2(sf, P.lights[l], L, NdotL, need, sray, dist);
                         need = need && lit && P.shadows;
                         if (lit) {
                             sf.Lo = mk3(0.f, 0.f, 0.f);
-                            direct = rt_light_direct_hw2(sf, P.lights[l], L, NdotL);
+                            const f3 direct = rt_light_direct_hw2(sf, P.lights[l], L, NdotL);
+                            STASH(ST_DIX) = direct.x; STASH(ST_DIY) = direct.y; STASH(ST_DIZ) = direct.z;
                         }
                     }
-                    if (FRUSTUM) blocked = frustum_trace<MODE, STATS, FAST, TAG>(P.nodes, P.wide, P.geom, P.num_tris, sray, need, true, false, dist, &st, wstack, wfr, P.frustum_eps, ld3(P.scene_c), P.scene_r2).blocked;
-                    else blocked = packet_trace<MODE, STATS, FAST, PF, TAG>(P.nodes, P.geom, P.num_tris, sray, need, true, dist, &st).blocked;
                 }
-                if (need) ++nshadow;
-                if (lit && !blocked) Lo = xadd3(Lo, direct);
+                if (P.num_lights > 0) {
+                    const unsigned nneed = (unsigned)__popc(__ballot_sync(FULLMASK, need));
+                    if (lane == 0) ws->nshadow += nneed;
+                    bool blocked;
+                    if (FRUSTUM) blocked = frustum_trace<MODE, STATS, FAST, TAG, LAZY>(P.nodes, P.wide, P.geom, P.num_tris, sray, need, true, false, dist, st, wstack, wfr, P.frustum_eps, ld3(P.scene_c), P.scene_r2).blocked;
+                    else blocked = packet_trace<MODE, STATS, FAST, PF, TAG>(P.nodes, P.geom, P.num_tris, sray, need, true, dist, st).blocked;
+                    // an unlit light left a zero contribution: Lo + 0 == Lo bit for bit (no -0 can arise: Lo >= +0)
+                    if (!blocked) {
+                        const f3 Lo = xadd3(mk3(STASH(ST_LOX), STASH(ST_LOY), STASH(ST_LOZ)), mk3(STASH(ST_DIX), STASH(ST_DIY), STASH(ST_DIZ)));
+                        STASH(ST_LOX) = Lo.x; STASH(ST_LOY) = Lo.y; STASH(ST_LOZ) = Lo.z;
+                    }
+                }
             }
-            if (live) color = hit ? rt_radiance_hw2(Lo) : rt_radiance_hw2(ld3(P.miss));
+            const int slot = __float_as_int(STASH(ST_HSLOT));
+            if (slot != RT_SLOT_DEAD) color = slot >= 0 ? rt_radiance_hw2(mk3(STASH(ST_LOX), STASH(ST_LOY), STASH(ST_LOZ))) : rt_radiance_hw2(ld3(P.miss));
         }
+        f3 acc = mk3(STASH(ST_ACX), STASH(ST_ACY), STASH(ST_ACZ));
         if (!GROUPED) {
-            accum = xadd3(accum, color);
+            acc = xadd3(acc, color);
         } else {                                         // owner lane q collects its pixel's G samples of this pass in order
             const bool owner = lane >= pb * PP && lane < (pb + 1) * PP;
             for (int k = 0; k < G; ++k) {
                 const int src = (((lane - pb * PP) << gsh) + k) & 31;
                 const f3 v = mk3(__shfl_sync(FULLMASK, color.x, src), __shfl_sync(FULLMASK, color.y, src), __shfl_sync(FULLMASK, color.z, src));
-                if (owner) accum = xadd3(accum, v);
+                if (owner) acc = xadd3(acc, v);
             }
         }
+        STASH(ST_ACX) = acc.x; STASH(ST_ACY) = acc.y; STASH(ST_ACZ) = acc.z;
     }
-    if (px.inside) {
-        const f3 fin = xdivs(accum, (float)P.spp);       // col / float(spp): query.cu:163, render.cpp:110
-        if (P.rgb) { P.rgb[3 * px.out] = fin.x; P.rgb[3 * px.out + 1] = fin.y; P.rgb[3 * px.out + 2] = fin.z; }
-    }
+    // col / float(spp): query.cu:163, render.cpp:110
+    const Pixel px = packet_pixel<GROUPED>(P, ws, lane);
+    const f3 fin = xdivs(mk3(STASH(ST_ACX), STASH(ST_ACY), STASH(ST_ACZ)), (float)P.spp);
+    if (px.inside && P.rgb) { P.rgb[3 * px.out] = fin.x; P.rgb[3 * px.out + 1] = fin.y; P.rgb[3 * px.out + 2] = fin.z; }
     if (P.rgb8) {
         // 8-bit plane: a row of the warp's 8x4 patch is 24 contiguous bytes.  Six lanes per row assemble one 32-bit word
         // each from two neighbours' packed pixels and store it — 4 partial-sector writes per warp instead of ~12 with
         // byte stores, which is what the NVLink ingress of rank 0 has to absorb from 7 peers in the fused gather.
         uint32_t pk = 0u;
         if (px.inside) {
-            const f3 fin = xdivs(accum, (float)P.spp);
-            pk = (uint32_t)rt_quantise(fin.x, P.quantiser) | ((uint32_t)rt_quantise(fin.y, P.quantiser) << 8) | ((uint32_t)rt_quantise(fin.z, P.quantiser) << 16);
+#pragma unroll 1
+            for (int ch = 0; ch < 3; ++ch)
+                pk |= (uint32_t)rt_quantise(ch == 0 ? fin.x : ch == 1 ? fin.y : fin.z, P.quantiser) << (8 * ch);
         }
         const int row0 = lane & ~7, kx = lane & 7;
         const unsigned rowmask = 0xffu << row0;
@@ -622,15 +673,171 @@ k_render_packet(const __grid_constant__ FrameParams P) {
             P.rgb8[3 * px.out] = (uint8_t)pk; P.rgb8[3 * px.out + 1] = (uint8_t)(pk >> 8); P.rgb8[3 * px.out + 2] = (uint8_t)(pk >> 16);
         }
     }
-    flush_counters(P, nprim, nshadow);
-    if (STATS) {
-        unsigned nn = st.nodes, nt = st.tris;
-        for (int o = 16; o > 0; o >>= 1) { nn += __shfl_xor_sync(FULLMASK, nn, o); nt += __shfl_xor_sync(FULLMASK, nt, o); }
-        if ((threadIdx.x & 31) == 0 && P.counters) {
-            atomicAdd(&P.counters[2], (unsigned long long)nn);
-            atomicAdd(&P.counters[3], (unsigned long long)nt);
-            atomicAdd(&P.counters[4], (unsigned long long)(FRUSTUM ? (st.wnodes + 1u) / 2u : st.wnodes));   // 64-byte units: one node line per warp visit (per-lane traversal), two 32-byte wide entries (frustum traversal)
-            atomicAdd(&P.counters[5], (unsigned long long)st.wtris);    // one 48-byte triangle block per warp test
+}
+
+__device__ __forceinline__ void flush_stats(const FrameParams& P, const TraceStats& st, bool frustum) {
+    unsigned nn = st.nodes, nt = st.tris;
+    for (int o = 16; o > 0; o >>= 1) { nn += __shfl_xor_sync(FULLMASK, nn, o); nt += __shfl_xor_sync(FULLMASK, nt, o); }
+    if ((threadIdx.x & 31) == 0 && P.counters) {
+        atomicAdd(&P.counters[2], (unsigned long long)nn);
+        atomicAdd(&P.counters[3], (unsigned long long)nt);
+        atomicAdd(&P.counters[4], (unsigned long long)(frustum ? (st.wnodes + 1u) / 2u : st.wnodes));   // 64-byte units: one node line per warp visit (per-lane traversal), two 32-byte wide entries (frustum traversal)
+        atomicAdd(&P.counters[5], (unsigned long long)st.wtris);    // one 48-byte triangle block per warp test
+    }
+}
+__device__ __forceinline__ void flush_warp_counters(const FrameParams& P, const volatile WarpSlot* ws) {
+    if ((threadIdx.x & 31) == 0 && P.counters) {
+        if (ws->nprim) atomicAdd(&P.counters[0], (unsigned long long)ws->nprim);
+        if (ws->nshadow) atomicAdd(&P.counters[1], (unsigned long long)ws->nshadow);
+    }
+}
+
+// Block-per-tile launch (one 128-thread block = one 16x8 tile, grid = the rank's tile slots): kept as the comparison
+// point of the persistent kernel below and for the experimental traversal variants.
+template <int MODE, bool STATS, bool FAST, int MINB, bool PF = false, bool GROUPED = false, bool FRUSTUM = false>
+__global__ void __launch_bounds__(RT_BLOCK_THREADS, MINB)
+k_render_packet(const __grid_constant__ FrameParams P) {
+    __shared__ int s_wstack[FRUSTUM ? (RT_BLOCK_THREADS / 32) * RT_FSTACK : 1];
+    int* const wstack = s_wstack + (FRUSTUM ? (threadIdx.x >> 5) * RT_FSTACK : 0);
+    __shared__ float4 s_wfr[FRUSTUM ? (RT_BLOCK_THREADS / 32) * 5 : 1];
+    float4* const wfr = s_wfr + (FRUSTUM ? (threadIdx.x >> 5) * 5 : 0);
+    __shared__ float s_stash[RT_STASH_WORDS * RT_BLOCK_THREADS];
+    __shared__ WarpSlot s_ws[RT_BLOCK_THREADS / 32];
+    constexpr int TAG = MINB * 4 + (GROUPED ? 1 : 0) + (FRUSTUM ? 2 : 0);
+    volatile WarpSlot* const ws = s_ws + (threadIdx.x >> 5);
+    if ((threadIdx.x & 31) == 0) { ws->tile = blockIdx.x + (unsigned)P.tile_offset; ws->sub = threadIdx.x >> 5; ws->nprim = 0u; ws->nshadow = 0u; }
+    __syncwarp();
+    TraceStats st{0, 0, 0, 0, 0};
+    render_packet<MODE, STATS, FAST, PF, GROUPED, FRUSTUM, false, TAG>(P, ws, s_stash + threadIdx.x, wstack, wfr, STATS ? &st : nullptr);
+    __syncwarp();
+    flush_warp_counters(P, ws);
+    if (STATS) flush_stats(P, st, FRUSTUM);
+}
+
+// --------------------------------------------------------------- persistent frame kernel ----
+// The default frame kernel.  The grid is sized to the machine (SMs x resident blocks), not to the frame: every block
+// pulls 16x8 tiles from the rank's tile queue (one atomicAdd per tile, issued one tile ahead) until it is empty; its
+// four warps take the tile's four 8x4 packets and meet at one barrier per tile.
+// Completion is published by the kernel itself — no flag kernels, no launch gaps: the rank's tile slots are cut into
+// P.num_chunks bands of P.band_tiles slots; a block counts the tiles it finished per band and, when it moves on to
+// another band (or runs dry), releases them: a block barrier, then one release-ordered atomicAdd on the band's counter
+// by thread 0; the block whose add completes a band writes the band's flag word P.flags[band] = P.seq — in this GPU's
+// memory or, in the fused multi-GPU gather, in rank 0's memory over NVLink, where the pixels went as well.
+// Stream-ordered waits (cuStreamWaitValue32) on those words start the device->host copy of finished rows while later
+// bands render.  (Release-only on purpose: atom.release / st.release compile to MEMBAR.ALL.SYS + the access, whereas
+// __threadfence_system() and the acquire forms also emit CCTL.IVALL, which throws away the SM's whole L1 — the cache
+// this kernel lives on — every time any block of the SM changes band.)
+// Multi-GPU handshake, same kernel: rank 0 publishes `ready = seq` at its kernel start (its stream has finished
+// reading the previous image by then); the other ranks' blocks wait for it before their first store; rank 0's last
+// block waits for every other rank's band flags before the kernel ends (bounded by P.peer_timeout_ns), so the end of
+// rank 0's kernel is the end of the gathered frame.
+//
+// Why the warps of a block stay in step (measured, B200, C4; block-per-tile launch = 1.91 ms):
+//   * warp-granular pulling (each warp claims the next packet of the queue the moment it is free: no warp ever idles,
+//     tail of one packet): 2.30-2.45 ms;
+//   * block-granular tiles with a split barrier of depth two (a warp may run one tile ahead of its siblings): 2.29 ms;
+//   * block-granular tiles, one barrier per tile (this kernel): 1.96 ms.
+// The four packets of a tile share most of their nodes and triangles; started together they hit each other's lines
+// in L1 (hit rate 77 %), drifting apart they do not (60 %), and 36 desynchronised warps per SM stream the ~30 KB of
+// straight-line shading code through the instruction cache independently (instruction-fetch stalls 19 % of all stall
+// samples against 5 %).  Locality beats the few per cent of idle warp slots.
+struct PersistCtl {               // P.queue, zeroed by the host before every launch
+    unsigned next_tile;           // global tile-slot counter
+    unsigned blocks_done;         // blocks that left the loop
+    unsigned pad[2];
+    unsigned chunk_done[RT_PEER_MAX_CHUNKS];   // tiles finished per band
+};
+static_assert(sizeof(PersistCtl) <= RT_PERSIST_CTL_BYTES, "PersistCtl must fit the host's allocation");
+
+__device__ __forceinline__ unsigned long long rt_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned rt_atom_add_release_sys(unsigned* p, unsigned v) { unsigned o; asm volatile("atom.add.release.sys.global.u32 %0, [%1], %2;" : "=r"(o) : "l"(p), "r"(v) : "memory"); return o; }
+__device__ __forceinline__ void rt_store_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+
+template <int MODE, bool STATS, bool FAST, int MINB, bool GROUPED, bool LAZY>
+__global__ void __launch_bounds__(RT_BLOCK_THREADS, MINB)
+k_render_persist(const __grid_constant__ FrameParams P) {
+    __shared__ int s_wstack[(RT_BLOCK_THREADS / 32) * RT_FSTACK];
+    __shared__ float4 s_wfr[(RT_BLOCK_THREADS / 32) * 5];
+    __shared__ float s_stash[RT_STASH_WORDS * RT_BLOCK_THREADS];
+    __shared__ WarpSlot s_ws[RT_BLOCK_THREADS / 32];
+    __shared__ unsigned s_tile[2];                    // double-buffered: one barrier per tile
+    __shared__ int s_go, s_band;
+    __shared__ unsigned s_band_cnt, s_last;
+    int* const wstack = s_wstack + (threadIdx.x >> 5) * RT_FSTACK;
+    float4* const wfr = s_wfr + (threadIdx.x >> 5) * 5;
+    volatile WarpSlot* const ws = s_ws + (threadIdx.x >> 5);
+    constexpr int TAG = 1000 + MINB * 8 + (GROUPED ? 1 : 0) + (LAZY ? 2 : 0) + (STATS ? 4 : 0);
+    PersistCtl* const ctl = reinterpret_cast<PersistCtl*>(P.queue);
+    if ((threadIdx.x & 31) == 0) { ws->sub = threadIdx.x >> 5; ws->nprim = 0u; ws->nshadow = 0u; }
+    if (threadIdx.x == 0) {
+        s_tile[0] = atomicAdd(&ctl->next_tile, 1u);
+        s_band = -1; s_band_cnt = 0u;
+        int go = 1;
+        if (P.ready_out && blockIdx.x == 0) { *(volatile unsigned*)P.ready_out = P.seq; }
+        if (P.ready_in) {                             // ranks != 0 of the fused gather: rank 0 must be done with its previous image
+            const unsigned long long t0 = rt_globaltimer();
+            while ((int)(*(volatile const unsigned*)P.ready_in - P.seq) < 0) {
+                if (rt_globaltimer() - t0 > P.peer_timeout_ns) { go = 0; if (P.peer_err) atomicExch(P.peer_err, 1u); break; }
+                __nanosleep(100);
+            }
+        }
+        s_go = go;                                    // 0: timed out — trace nothing, store nothing, still publish (rank 0 must not hang on us)
+    }
+    TraceStats st{0, 0, 0, 0, 0};
+    // Releases the tiles this block finished in its current band.  Called by the whole block (block-uniform condition).
+    auto release_band = [&]() {
+        __syncthreads();                              // every thread's pixel stores happen-before thread 0's release below
+        if (threadIdx.x == 0 && s_band_cnt) {
+            const unsigned band = (unsigned)s_band, cnt = s_band_cnt, ntiles = (unsigned)P.local_tiles;
+            const unsigned first = band * (unsigned)P.band_tiles;
+            unsigned n = ntiles > first ? ntiles - first : 0u;
+            if (n > (unsigned)P.band_tiles) n = (unsigned)P.band_tiles;
+            const unsigned old = rt_atom_add_release_sys(&ctl->chunk_done[band], cnt);
+            if (old + cnt == n) rt_store_release_sys(P.flags + (size_t)band * RT_PEER_FLAG_STRIDE, P.seq);
+            s_band_cnt = 0u;
+        }
+    };
+    for (unsigned it = 0;; ++it) {
+        __syncthreads();                              // s_tile[it & 1] is published; everybody is done with the previous tile
+        // broadcast with a warp reduction: the result is warp-uniform FOR THE COMPILER (uniform datapath for the tile arithmetic)
+        const unsigned tile = __reduce_max_sync(FULLMASK, *(volatile unsigned*)&s_tile[it & 1u]);
+        if (tile >= (unsigned)P.local_tiles) break;
+        if (threadIdx.x == 0) s_tile[(it + 1u) & 1u] = atomicAdd(&ctl->next_tile, 1u);      // one tile ahead: the atomic's latency is off the critical path
+        if (P.num_chunks > 0) {
+            const int b = (int)(tile / (unsigned)P.band_tiles);
+            if (b != *(volatile int*)&s_band) {       // block-uniform
+                if (*(volatile int*)&s_band >= 0) release_band();
+                __syncthreads();
+                if (threadIdx.x == 0) s_band = b;
+            }
+            if (threadIdx.x == 0) s_band_cnt = s_band_cnt + 1u;
+        }
+        if ((threadIdx.x & 31) == 0) ws->tile = tile;
+        __syncwarp();
+        if (*(volatile int*)&s_go)
+            render_packet<MODE, STATS, FAST, false, GROUPED, true, LAZY, TAG>(P, ws, s_stash + threadIdx.x, wstack, wfr, STATS ? &st : nullptr);
+    }
+    if (P.num_chunks > 0 && *(volatile int*)&s_band >= 0) release_band();
+    __syncwarp();
+    flush_warp_counters(P, ws);
+    if (STATS) flush_stats(P, st, true);
+    if (P.wait_ranks > 0) {
+        // rank 0 of the fused gather: the last block out waits for the other ranks' band flags (they live in this GPU's memory)
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(&ctl->blocks_done, 1u) + 1u == gridDim.x ? 1u : 0u;
+        __syncthreads();
+        if (s_last) {
+            const int nflags = P.wait_ranks * P.num_chunks;
+            const unsigned long long t0 = rt_globaltimer();
+            for (int i = (int)threadIdx.x; i < nflags; i += RT_BLOCK_THREADS) {
+                const int r = 1 + i / P.num_chunks, j = i - (r - 1) * P.num_chunks;
+                const volatile unsigned* f = P.flags_base + RT_PEER_CHUNK_FLAG(r, j);
+                while ((int)(*f - P.seq) < 0) {
+                    if (rt_globaltimer() - t0 > P.peer_timeout_ns) { if (P.peer_err) atomicExch(P.peer_err, 1u + (unsigned)r); break; }
+                    __nanosleep(100);
+                }
+            }
+            __threadfence_system();
         }
     }
 }
@@ -656,20 +863,22 @@ __global__ void k_unpack(FrameParams P, int src_rank, const float* rgb, const ui
 // a flag word per rank in rank 0's memory.  k_flag_set publishes a frame sequence number after
 // everything the stream did before it (kernel boundary + system fence); k_flag_wait spins until
 // all `n` flags reached it, bounded by a wall-clock timeout so a dead peer cannot hang the GPU.
-__global__ void k_flag_set(volatile unsigned* flag, unsigned seq) {
+__global__ void k_flag_set(volatile unsigned* flags, int stride, int n, unsigned seq) {
     __threadfence_system();
-    *flag = seq;
+    for (int i = (int)threadIdx.x; i < n; i += (int)blockDim.x) flags[(size_t)i * stride] = seq;
     __threadfence_system();
 }
-__global__ void k_flag_wait(const volatile unsigned* flags, int stride, int n, unsigned seq, unsigned long long timeout_ns, unsigned* err) {
-    const int i = (int)threadIdx.x;
-    if (i < n) {
+// waits for flags[(r0 + a) * rank_stride + b * stride] >= seq, a < nranks, b < nper
+__global__ void k_flag_wait(const volatile unsigned* flags, int rank_stride, int nranks, int stride, int nper, unsigned seq, unsigned long long timeout_ns, unsigned* err) {
+    for (int i = (int)threadIdx.x; i < nranks * nper; i += (int)blockDim.x) {
+        const int a = i / nper, b = i - a * nper;
+        const volatile unsigned* f = flags + (size_t)a * rank_stride + (size_t)b * stride;
         unsigned long long t0;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        while ((int)(flags[(size_t)i * stride] - seq) < 0) {
+        while ((int)(*f - seq) < 0) {
             unsigned long long t1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > timeout_ns) { atomicExch(err, 1u + (unsigned)i); break; }
+            if (t1 - t0 > timeout_ns) { atomicExch(err, 1u + (unsigned)a); break; }
             __nanosleep(200);
         }
     }
@@ -689,14 +898,48 @@ cudaError_t rt_launch_flag_unblock(const unsigned* err, unsigned* flags, int str
     k_flag_unblock<<<1, 64, 0, stream>>>(err, flags, stride, n, seq);
     return cudaGetLastError();
 }
-cudaError_t rt_launch_flag_set(unsigned* flag, unsigned seq, cudaStream_t stream) {
-    k_flag_set<<<1, 1, 0, stream>>>(flag, seq);
+cudaError_t rt_launch_flag_set(unsigned* flags, int stride, int n, unsigned seq, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    k_flag_set<<<1, 32, 0, stream>>>(flags, stride, n, seq);
     return cudaGetLastError();
 }
-cudaError_t rt_launch_flag_wait(const unsigned* flags, int stride, int n, unsigned seq, unsigned long long timeout_ns, unsigned* err, cudaStream_t stream) {
-    if (n <= 0) return cudaSuccess;
-    k_flag_wait<<<1, 32, 0, stream>>>(flags, stride, n, seq, timeout_ns, err);
+cudaError_t rt_launch_flag_wait(const unsigned* flags, int rank_stride, int nranks, int stride, int nper, unsigned seq, unsigned long long timeout_ns, unsigned* err, cudaStream_t stream) {
+    if (nranks <= 0 || nper <= 0) return cudaSuccess;
+    k_flag_wait<<<1, 128, 0, stream>>>(flags, rank_stride, nranks, stride, nper, seq, timeout_ns, err);
     return cudaGetLastError();
+}
+
+// Grid of the persistent kernel: every SM filled to the kernel's occupancy (never more blocks than tiles).
+// (All instantiations share one function-pointer type, so the cache is keyed by the pointer.)
+static cudaError_t persist_grid(void (*kernel)(const FrameParams), int tiles, unsigned* grid) {
+    struct Entry { void (*k)(const FrameParams); int blocks; };
+    static Entry cache[32];
+    static int ncache = 0;
+    int blocks = 0;
+    for (int i = 0; i < ncache; ++i) if (cache[i].k == kernel) blocks = cache[i].blocks;
+    if (!blocks) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RT_BLOCK_THREADS, 0);
+        if (e != cudaSuccess) return e;
+        blocks = (per_sm < 1 ? 1 : per_sm) * (sms < 1 ? 1 : sms);
+        if (ncache < 32) { cache[ncache].k = kernel; cache[ncache].blocks = blocks; ++ncache; }
+    }
+    long long g = blocks;
+    if (g > tiles) g = tiles;
+    *grid = (unsigned)(g < 1 ? 1 : g);
+    return cudaSuccess;
+}
+#define RT_LAUNCH_PERSIST(...) do { unsigned g_ = 1; cudaError_t e_ = persist_grid(k_render_persist<__VA_ARGS__>, fp.local_tiles, &g_); if (e_ != cudaSuccess) return e_; \
+                                    k_render_persist<__VA_ARGS__><<<g_, block, 0, stream>>>(fp); } while (0)
+
+// Which frames run on the persistent kernel (the host layer asks: it then leaves the completion protocol to the kernel).
+bool rt_render_is_persistent(const FrameParams& fp, int variant) {
+    if (fp.accel != RT_ACCEL_BVH || !fp.wide || fp.mode == RT_MODE_HW2_CPU) return false;
+    if (fp.mode != RT_MODE_HW1 && fp.max_depth > 1) return false;
+    return variant == RT_VARIANT_DEFAULT || variant == RT_VARIANT_STATS || variant == RT_VARIANT_PERSIST || variant == RT_VARIANT_PERSIST_EXACT_MT ||
+           variant == RT_VARIANT_PERSIST_OCC8 || variant == RT_VARIANT_PERSIST_OCC10;
 }
 
 template <int MODE>
@@ -704,15 +947,34 @@ static cudaError_t launch_mode(const FrameParams& fp, int variant, cudaStream_t 
     dim3 grid((unsigned)fp.local_tiles), block(RT_BLOCK_THREADS);
     if (fp.accel == RT_ACCEL_BRUTE) { k_render_brute<MODE><<<grid, block, 0, stream>>>(fp); return cudaGetLastError(); }
     const bool fast = fp.fast_slab != 0;
+    if (rt_render_is_persistent(fp, variant)) {
+        const bool grouped = fp.sample_group > 1;
+        switch (variant) {
+        case RT_VARIANT_STATS:
+            if (grouped) { if (fast) RT_LAUNCH_PERSIST(MODE, true, true, RT_FRUSTUM_MINB, true, true); else RT_LAUNCH_PERSIST(MODE, true, false, RT_FRUSTUM_MINB, true, true); }
+            else { if (fast) RT_LAUNCH_PERSIST(MODE, true, true, RT_FRUSTUM_MINB, false, true); else RT_LAUNCH_PERSIST(MODE, true, false, RT_FRUSTUM_MINB, false, true); }
+            break;
+        case RT_VARIANT_PERSIST_EXACT_MT: RT_LAUNCH_PERSIST(MODE, false, true, RT_FRUSTUM_MINB, false, false); break;
+        case RT_VARIANT_PERSIST_OCC8:     RT_LAUNCH_PERSIST(MODE, false, true, 8, false, true); break;
+        case RT_VARIANT_PERSIST_OCC10:    RT_LAUNCH_PERSIST(MODE, false, true, 10, false, true); break;
+        default:
+            if (grouped) { if (fast) RT_LAUNCH_PERSIST(MODE, false, true, RT_FRUSTUM_MINB, true, true); else RT_LAUNCH_PERSIST(MODE, false, false, RT_FRUSTUM_MINB, true, true); }
+            else { if (fast) RT_LAUNCH_PERSIST(MODE, false, true, RT_FRUSTUM_MINB, false, true); else RT_LAUNCH_PERSIST(MODE, false, false, RT_FRUSTUM_MINB, false, true); }
+        }
+        return cudaGetLastError();
+    }
     // Bounce rays (max_depth > 1) are incoherent: the frame goes to the per-ray kernel, whose sample function
     // carries TraceRayIterative's full loop; the packet kernels implement depth 1.
     if (MODE != RT_MODE_HW1 && fp.max_depth > 1)
         variant = (variant == RT_VARIANT_STATS || variant == RT_VARIANT_PER_RAY_STATS || variant == RT_VARIANT_FRUSTUM_STATS || variant == RT_VARIANT_PACKET_STATS) ? RT_VARIANT_PER_RAY_STATS : RT_VARIANT_PER_RAY;
-    // default = frustum traversal (needs the 8-wide view, which every scene with a BVH has)
-    if (variant == RT_VARIANT_DEFAULT) variant = fp.wide ? RT_VARIANT_FRUSTUM : RT_VARIANT_PACKET;
-    if (variant == RT_VARIANT_STATS) variant = fp.wide ? RT_VARIANT_FRUSTUM_STATS : RT_VARIANT_PACKET_STATS;
+    // no 8-wide view (it could not be allocated): per-lane packet traversal
+    if (variant == RT_VARIANT_DEFAULT || variant == RT_VARIANT_PERSIST || variant == RT_VARIANT_PERSIST_EXACT_MT || variant == RT_VARIANT_PERSIST_OCC8 || variant == RT_VARIANT_PERSIST_OCC10)
+        variant = RT_VARIANT_PACKET;
+    if (variant == RT_VARIANT_STATS) variant = RT_VARIANT_PACKET_STATS;
     if ((variant == RT_VARIANT_FRUSTUM || variant == RT_VARIANT_FRUSTUM_STATS) && !fp.wide) return cudaErrorInvalidValue;
     switch (variant) {
+    case RT_VARIANT_PACKET_OCC6: case RT_VARIANT_PACKET_OCC10: case RT_VARIANT_PACKET_PREFETCH:   // retired round-1 experiments: the plain per-lane kernel
+    case RT_VARIANT_PACKET_PIXEL_MAJOR:
     case RT_VARIANT_PACKET:
         if (fp.sample_group > 1) {
             if (fast) k_render_packet<MODE, false, true, 8, false, true><<<grid, block, 0, stream>>>(fp);
@@ -731,15 +993,8 @@ static cudaError_t launch_mode(const FrameParams& fp, int variant, cudaStream_t 
             else k_render_packet<MODE, true, false, 8><<<grid, block, 0, stream>>>(fp);
         }
         break;
-    case RT_VARIANT_PACKET_OCC6:   k_render_packet<MODE, false, true, 6><<<grid, block, 0, stream>>>(fp); break;
-    case RT_VARIANT_PACKET_OCC10:  k_render_packet<MODE, false, true, 10><<<grid, block, 0, stream>>>(fp); break;
     case RT_VARIANT_PACKET_EXACT_SLAB: k_render_packet<MODE, false, false, 8><<<grid, block, 0, stream>>>(fp); break;
-    case RT_VARIANT_PACKET_PREFETCH: k_render_packet<MODE, false, true, 8, true><<<grid, block, 0, stream>>>(fp); break;
-    case RT_VARIANT_PACKET_PIXEL_MAJOR:
-        if (fast) k_render_packet<MODE, false, true, 8><<<grid, block, 0, stream>>>(fp);
-        else k_render_packet<MODE, false, false, 8><<<grid, block, 0, stream>>>(fp);
-        break;
-    case RT_VARIANT_FRUSTUM:
+    case RT_VARIANT_FRUSTUM:            // round-1 default: block-per-tile launch of the frustum traversal
         if (fp.sample_group > 1) {
             if (fast) k_render_packet<MODE, false, true, RT_FRUSTUM_MINB, false, true, true><<<grid, block, 0, stream>>>(fp);
             else k_render_packet<MODE, false, false, RT_FRUSTUM_MINB, false, true, true><<<grid, block, 0, stream>>>(fp);

@@ -245,4 +245,84 @@ void emu_unpack_rgb8(int W, int H, int world, int chunks_per_rank, int src_rank,
         }
 }
 
+
+// ---- division-free front end of the triangle test (rt_core.h, rt_moller_trumbore_lazy_r) vs the reference-order test ----
+// Single probe, for the reference's own unit vectors.  mode 0 = HW1 contract, 1 = HW2-BVH contract.
+int emu_mt_lazy(int mode, const float* o, const float* d, int normalise, const float* v0, const float* v1, const float* v2, float ra_scale, float* t_out) {
+    Ray r; r.o = ld3(o); r.d = normalise ? xunit(ld3(d)) : ld3(d);      // both reference Ray constructors / get_ray normalise
+    const f3 a = ld3(v0), e1 = xsub3(ld3(v1), a), e2 = xsub3(ld3(v2), a);
+    const int m = mode == 0 ? RT_MODE_HW1 : RT_MODE_HW2_BVH;
+    float t, u, v;
+    const bool hit = rt_moller_trumbore_lazy_r(r, a, e1, e2, rt_det_eps(m), rt_tmin(m), FLT_MAX, ra_scale, t, u, v);
+    if (t_out) *t_out = hit ? t : -1.0f;
+    return hit ? 1 : 0;
+}
+
+static inline uint64_t xs64(uint64_t& s) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; }
+static inline double urand(uint64_t& s) { return (double)(xs64(s) >> 11) * (1.0 / 9007199254740992.0); }
+
+// n random probes aimed at the places where the two tests could disagree: hit points within 10^-9..10^-1 of an edge, a
+// vertex or the t limits, triangles of size 10^-3..10^3 (also slivers), origins near and far, unit and non-unit directions;
+// every probe is judged with the approximate reciprocal at its worst (x (1 -+ 2^-22)) and exact.  Returns the number of
+// probes where the lazy test rejected something the exact test accepts or returned different (t, u, v): must be 0.
+// stats[0] = exact accepts, [1] = probes that left before the IEEE divide, [2] = exact rejects that still paid for it.
+uint64_t emu_mt_lazy_sweep(uint64_t n, uint64_t seed, uint64_t* stats) {
+    uint64_t s = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull, bad = 0, acc = 0, early = 0, late = 0;
+    const float scales[3] = {1.0f - 2.3841858e-7f, 1.0f, 1.0f + 2.3841858e-7f};
+    for (uint64_t i = 0; i < n; ++i) {
+        const double size = pow(10.0, -3.0 + 6.0 * urand(s));
+        double V[3][3];
+        for (int k = 0; k < 3; ++k) for (int c = 0; c < 3; ++c) V[k][c] = (urand(s) - 0.5) * size;
+        if (xs64(s) % 8 == 0) for (int c = 0; c < 3; ++c) V[2][c] = V[0][c] + (V[1][c] - V[0][c]) * urand(s) + (urand(s) - 0.5) * size * 1e-4;   // sliver
+        const double off = (urand(s) - 0.5) * size * (xs64(s) % 4 == 0 ? 100.0 : 1.0);
+        for (int k = 0; k < 3; ++k) for (int c = 0; c < 3; ++c) V[k][c] += off;
+        // barycentric target near the boundary
+        const double eps = pow(10.0, -9.0 + 8.0 * urand(s)) * (xs64(s) & 1 ? 1.0 : -1.0);
+        double bu = urand(s), bv = urand(s) * (1.0 - bu);
+        switch (xs64(s) % 6) {
+            case 0: bu = eps; break;                       // edge u = 0
+            case 1: bv = eps; break;                       // edge v = 0
+            case 2: bv = 1.0 - bu + eps; break;            // edge u + v = 1
+            case 3: bu = eps; bv = eps * urand(s); break;  // vertex 0
+            case 4: bu = 1.0 + eps; bv = eps * urand(s); break;
+            default: break;                                // interior / anywhere
+        }
+        double Pt[3];
+        for (int c = 0; c < 3; ++c) Pt[c] = V[0][c] + bu * (V[1][c] - V[0][c]) + bv * (V[2][c] - V[0][c]);
+        double O[3], D[3], len = 0;
+        const double dist = size * pow(10.0, -4.0 + 6.0 * urand(s));
+        for (int c = 0; c < 3; ++c) { D[c] = urand(s) - 0.5; len += D[c] * D[c]; }
+        len = sqrt(len) + 1e-300;
+        const double dscale = (xs64(s) & 1) ? 1.0 : pow(10.0, -2.0 + 4.0 * urand(s));     // non-unit directions too (HW1 rays are not all unit)
+        const double tsign = (xs64(s) % 16 == 0) ? -1.0 : 1.0;                                 // sometimes behind the origin
+        for (int c = 0; c < 3; ++c) { D[c] /= len; O[c] = Pt[c] - tsign * dist * D[c]; D[c] *= dscale; }
+        Ray r; r.o = mk3((float)O[0], (float)O[1], (float)O[2]); r.d = mk3((float)D[0], (float)D[1], (float)D[2]);
+        const f3 a = mk3((float)V[0][0], (float)V[0][1], (float)V[0][2]);
+        const f3 e1 = xsub3(mk3((float)V[1][0], (float)V[1][1], (float)V[1][2]), a), e2 = xsub3(mk3((float)V[2][0], (float)V[2][1], (float)V[2][2]), a);
+        const int m = (xs64(s) & 1) ? RT_MODE_HW1 : RT_MODE_HW2_BVH;
+        const float tmin = rt_tmin(m);
+        // t limits: unbounded, or close to the true t (the closest-hit loop passes its best t as tmax)
+        float tmax = FLT_MAX;
+        if (xs64(s) % 3 == 0) tmax = (float)(dist / dscale * (1.0 + eps));
+        float t0, u0, v0;
+        const bool h0 = rt_moller_trumbore(r, a, e1, e2, rt_det_eps(m), tmin, tmax, t0, u0, v0);
+        acc += h0;
+        for (int k = 0; k < 3; ++k) {
+            float t1, u1, v1;
+            const bool h1 = rt_moller_trumbore_lazy_r(r, a, e1, e2, rt_det_eps(m), tmin, tmax, scales[k], t1, u1, v1);
+            if (h0 != h1 || (h0 && (t0 != t1 || u0 != u1 || v0 != v1))) ++bad;
+        }
+        if (!h0) {   // did the front end save the divide?  (re-run its comparisons with the exact reciprocal)
+            const f3 pvec = xcross(r.d, e2); const float det = xdot(e1, pvec);
+            if (fabsf(det) < rt_det_eps(m)) { ++early; continue; }
+            const float ra = 1.0f / det; const f3 tvec = xsub3(r.o, a); const float ua = xdot(tvec, pvec) * ra;
+            const f3 qvec = xcross(tvec, e1); const float va = xdot(r.d, qvec) * ra, ta = xdot(e2, qvec) * ra;
+            if (ua < -RT_LAZY_TINY || ua > 1.00000095367431640625f || va < -RT_LAZY_TINY || ua + va > 1.0000019073486328125f ||
+                ta < 0.999996f * tmin - RT_LAZY_TINY || ta > 1.000004f * tmax + RT_LAZY_TINY) ++early; else ++late;
+        }
+    }
+    if (stats) { stats[0] = acc; stats[1] = early; stats[2] = late; }
+    return bad;
+}
+
 } // extern "C"
