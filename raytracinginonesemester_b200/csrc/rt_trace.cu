@@ -175,6 +175,9 @@ k_render_brute(const __grid_constant__ FrameParams P) {
 // single ray's while SIMD efficiency goes from ~44 % (per-ray, ncu r1_v1) to ~100 %.
 #define FULLMASK 0xffffffffu
 #define RT_PACKET_STACK 64
+#ifndef RT_FSTACK
+#define RT_FSTACK 128                             // frontier stack of the frustum traversal, entries per warp
+#endif
 #define RT_SLOT_DEAD (-2)                         // Hit.slot of a lane that traced nothing (outside the frame, depth 0)
 
 struct TraceResult { Hit hit; bool blocked; };
@@ -308,9 +311,6 @@ __device__ __noinline__ TraceResult packet_trace(const BvhNode* __restrict__ nod
 // Rounding: the slope bounds are widened by 4e-6 (1 + |s|) (directions are within 60 degrees of w, so |s| < 1.8),
 // and every plane offset by feps = 1.6e-5 x the largest coordinate in play (host: scene bounds, camera) — an
 // order of magnitude more than the error of the 6-term FMA sums.
-#ifndef RT_FSTACK
-#define RT_FSTACK 128
-#endif
 // 9 resident blocks (36 warps, 56 registers) measured best for the frustum kernel on C4: 6 -> 2.21 ms, 8 -> 2.07, 9 -> 2.01, 10 -> 2.05, 12 -> 2.04
 #define RT_FRUSTUM_MINB 9
 
@@ -417,7 +417,10 @@ __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ no
         {
             const float* ep = reinterpret_cast<const float*>(wide + par) + 8 * (lane & 7);
             float fr, fp;
-            asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#ifndef RT_X_NODE_HINT
+#define RT_X_NODE_HINT ""
+#endif
+            asm volatile("ld.global.nc" RT_X_NODE_HINT ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                          : "=f"(cx), "=f"(cy), "=f"(cz), "=f"(hx), "=f"(hy), "=f"(hz), "=f"(fr), "=f"(fp) : "l"(ep));
             ref = __float_as_int(fr);
         }
@@ -478,10 +481,13 @@ __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ no
                 } else {
                     const float4* tp = reinterpret_cast<const float4*>(geom + s);
                     float idf;
-                    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(tr.v0.x), "=f"(tr.v0.y), "=f"(tr.v0.z), "=f"(idf) : "l"(tp));
+#ifndef RT_X_TRI_HINT
+#define RT_X_TRI_HINT ""
+#endif
+                    asm volatile("ld.global.nc" RT_X_TRI_HINT ".v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(tr.v0.x), "=f"(tr.v0.y), "=f"(tr.v0.z), "=f"(idf) : "l"(tp));
                     float p0, p1;
-                    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(tr.e1.x), "=f"(tr.e1.y), "=f"(tr.e1.z), "=f"(p0) : "l"(tp + 1));
-                    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(tr.e2.x), "=f"(tr.e2.y), "=f"(tr.e2.z), "=f"(p1) : "l"(tp + 2));
+                    asm volatile("ld.global.nc" RT_X_TRI_HINT ".v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(tr.e1.x), "=f"(tr.e1.y), "=f"(tr.e1.z), "=f"(p0) : "l"(tp + 1));
+                    asm volatile("ld.global.nc" RT_X_TRI_HINT ".v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(tr.e2.x), "=f"(tr.e2.y), "=f"(tr.e2.z), "=f"(p1) : "l"(tp + 2));
                     tr.id = __float_as_int(idf);
                 }
                 if (STATS && lane == 0) st->wtris++;
