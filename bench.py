@@ -196,9 +196,24 @@ class CpuReference:
             self.h = None if self.hw1 else orclib.oracle_bvh(scene)
         self.build_s = time.perf_counter() - t0
 
+    def census(self, row_begin, row_step):
+        """(primary, shadow) rays of a row-strided pass, counted by the reference shim itself (ref_hw2_count_rays_rows:
+        the reference's SearchBVH + the two conditions that gate IsInShadow); None when only the port is available."""
+        if not self.lib or self.hw1:
+            return None
+        fr, A = self.frame, self.A
+        cp = fr.cam.params
+        f3 = lambda v: np.array(v, np.float32)
+        cpos, look, up = f3(cp["pos"]), f3(cp["look_at"]), f3(cp["up"])
+        larr = (A.rt_light * max(1, len(fr.lights)))(*fr.lights)
+        a, b = C.c_uint64(), C.c_uint64()
+        self.lib.ref_hw2_count_rays_rows(C.c_void_p(self.h), cpos.ctypes.data_as(A.f32p), look.ctypes.data_as(A.f32p), up.ctypes.data_as(A.f32p),
+                                         C.c_double(cp["focal_mm"]), C.c_double(cp["sensor_mm"]), fr.width, fr.height, fr.spp, larr, len(fr.lights),
+                                         row_begin, row_step, self.cores, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
     def rays_in_rows(self, row_begin, row_step):
-        """Times one row-strided pass; returns (primary rays, seconds).  The in-place reference has no ray counters:
-        shadow rays are taken from the device count (one per lit hit — the same rule)."""
+        """Times one row-strided pass; returns (primary rays, seconds)."""
         fr, A, scene = self.frame, self.A, self.scene
         W, H = fr.width, fr.height
         rows = len(range(row_begin, H, row_step))
@@ -274,9 +289,6 @@ def reference_cuda_leg(wl, rays, flush_bytes=256 << 20):
             "rays": "the product's device count for the same frame (one shadow ray per lit hit - the same rule)"}
 
 
-# shadow rays per primary ray, counted by the device on each workload (one shadow ray per lit hit; the in-place
-# reference has no counters, the rule is the same)
-SHADOW_RATIO = {"c4": 0.81550, "c5": 0.70824, "c4small": 0.8155, "c2": 0.0, "c3": 0.020735, "c3fill": 0.274944}
 METRIC = "Mrays/s closest-hit (BVH+tri)"
 
 
@@ -290,51 +302,60 @@ def cpu_sample(ref, seconds, max_passes=64):
     return stp
 
 
-def run_reference(args, rank, world):
-    if rank != 0:
-        return
-    wl = make_workload(args.workload)
+def reference_record(workload, steps, warmup, seconds_per_step=6.0, n_gpus=1):
+    """The reference's CPU path on `workload`: K steps, each a bounded row sample of the frame (~seconds_per_step of CPU work on
+    all host threads).  Rays = primary + shadow, both counted by the reference shim on the sampled rows."""
+    wl = make_workload(workload)
     ref = CpuReference(wl)
     fr = wl["frame"]
     W, H, spp = fr.width, fr.height, fr.spp
-    shadow_ratio = args.shadow_ratio if args.shadow_ratio >= 0 else SHADOW_RATIO.get(args.workload, 0.0)
-    step = cpu_sample(ref, 6.0)                    # a step = ~6 s of CPU work on a row sample of the same frame
-    for _ in range(args.warmup if args.warmup < 2 else 1):
+    step = cpu_sample(ref, seconds_per_step)
+    for _ in range(min(warmup, 1)):
         ref.rays_in_rows(1 % step, step)
-    tot_rays, tot_s = 0, 0.0
-    for k in range(args.steps):
+    tot_rays, tot_s, prim, shad = 0, 0.0, 0, 0
+    for k in range(steps):
         rays, dt = ref.rays_in_rows(k % step, step)
         tot_rays += rays
         tot_s += dt
-    mrays = tot_rays * (1.0 + shadow_ratio) / tot_s / 1e6
-    line = {
-        "impl": "reference", "metric": METRIC, "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
+    cen = ref.census(0, step)                      # untimed: shadow rays per primary ray on a sampled row set
+    if cen is not None:
+        prim, shad = cen
+        ratio, how = shad / max(prim, 1), "counted by the reference shim on the sampled rows"
+    else:
+        ratio, how = 0.0, "primary rays only (no counters in this build)"
+    mrays = tot_rays * (1.0 + ratio) / tot_s / 1e6
+    return {
+        "impl": "reference", "metric": METRIC, "value": mrays, "unit": "Mrays/s", "n_gpus": n_gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * tot_s / steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "description": wl["desc"], "triangles": wl["triangles"], "width": W, "height": H, "spp": spp,
-                   "rays": "primary+shadow" if shadow_ratio else "primary"},
+        "config": {"workload": workload, "description": wl["desc"], "triangles": wl["triangles"], "width": W, "height": H, "spp": spp,
+                   "rays": "primary+shadow" if ratio else "primary"},
         "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": ref.cores, "kind": ref.kind,
-                         "sample": "every %d-th row of the %dx%d frame per step (%d rows), full-frame rate extrapolated; shadow rays = primary x %.4f" % (step, W, H, len(range(0, H, step)), shadow_ratio),
+                         "sample": "every %d-th row of the %dx%d frame per step (%d rows), full-frame rate extrapolated; shadow rays = primary x %.4f, %s" % (step, W, H, len(range(0, H, step)), ratio, how),
                          "lbvh_build_s": ref.build_s},
         "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    line = reference_record(args.workload, args.steps, args.warmup, n_gpus=args.gpus)
+    if args.gpus >= 8 and args.workload == "c4" and not args.no_c5:
+        # BASELINE config 5 (10M triangles, 8K, 16 spp) beside the headline, like the product arm: a thin sample (BASELINE.md §3)
+        try:
+            line["configs"] = [reference_record("c5", max(1, min(args.steps, 3)), 0, seconds_per_step=4.0, n_gpus=args.gpus)]
+        except Exception as e:
+            line["configs"] = [{"config": {"workload": "c5"}, "unavailable": "%s: %s" % (type(e).__name__, e)}]
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------ our arm ----
-def run_ours(args, rank, world, local_rank):
+def bench_workload(args, r, dist, rank, world, local_rank, workload, steps, with_cpu=True):
+    """Benchmarks one workload on the already-created renderer(s); returns the record (rank 0) or None."""
     import torch
-    from raytracinginonesemester_b200 import _abi as A, api, scenes
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU baseline)")
-    from raytracinginonesemester_b200 import parallel
-    torch.cuda.set_device(local_rank)
-    dist, rank, world, local_rank = parallel.init_process_group("nccl")
-    r = parallel.make_renderer(dist, rank, world, local_rank)
-    if world > 1:
-        r.set_sharding(args.chunks)
-        r.set_gather({"auto": A.RT_GATHER_AUTO, "nccl": A.RT_GATHER_NCCL, "peer": A.RT_GATHER_PEER}[args.gather])
-    wl = make_workload(args.workload, args.leaf_max, args.variant, not args.no_shadows)
+    from raytracinginonesemester_b200 import _abi as A, api, parallel
+    wl = make_workload(workload, args.leaf_max, args.variant, not args.no_shadows)
     frame = wl["frame"]
     W, H, spp = frame.width, frame.height, frame.spp
     brute = frame.accel == A.RT_ACCEL_BRUTE
@@ -344,7 +365,7 @@ def run_ours(args, rank, world, local_rank):
     t0 = time.perf_counter()
     info = r.upload_scene(scene)           # steady state (what another scene or a re-upload costs)
     upload_wall = time.perf_counter() - t0
-    gather = {A.RT_GATHER_NCCL: "nccl send/recv + unpack", A.RT_GATHER_PEER: "peer stores into rank 0's image over NVLink + flag words"}[r.gather_mode()] if world > 1 else "none"
+    gather = {A.RT_GATHER_NCCL: "nccl send/recv + unpack", A.RT_GATHER_PEER: "peer stores into rank 0's image over NVLink; band flags and the ready/done handshake inside the frame kernel"}[r.gather_mode()] if world > 1 else "none"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     pinned = torch.empty((H, W, 3), dtype=torch.uint8, pin_memory=True).numpy() if rank == 0 else None
 
@@ -376,10 +397,19 @@ def run_ours(args, rank, world, local_rank):
         return [a.elapsed_time(b) for a, b in ev]
 
     timed(args.warmup if args.profile else max(args.warmup, 3))
-    # traversal statistics (untimed): bytes per ray for the roofline
+    # traversal statistics (untimed).  (1) the frame kernel's own counters (STATS instance): wide entries / triangle blocks it
+    # requests; (2) SURVEY §8(d)'s N_node / N_tri: a SINGLE-RAY walk of the same BVH, counted by the per-ray kernel, whose
+    # counters equal the host walk of the downloaded BVH (tests/test_gpu_parity.py) — the gap between the two is the
+    # redundancy a packet pays (every lane tests every triangle any lane reaches).
+    single = None
     if not brute:
+        frame.kernel_variant = A.RT_VARIANT_PER_RAY_STATS
+        r.render(frame)
+        r.download(into={"rgb8": pinned} if rank == 0 else None)
+        single = r.frame_stats()
         frame.kernel_variant = (A.RT_VARIANT_PER_RAY_STATS if args.variant >= 10 else
-                                A.RT_VARIANT_STATS if args.variant in (A.RT_VARIANT_DEFAULT, A.RT_VARIANT_FRUSTUM) else A.RT_VARIANT_PACKET_STATS)
+                                A.RT_VARIANT_STATS if args.variant in (A.RT_VARIANT_DEFAULT, A.RT_VARIANT_PERSIST) else
+                                A.RT_VARIANT_FRUSTUM_STATS if args.variant == A.RT_VARIANT_FRUSTUM else A.RT_VARIANT_PACKET_STATS)
     r.render(frame)
     st = r.download(into={"rgb8": pinned} if rank == 0 else None)
     nv, nt, nl, nb = r.frame_stats()
@@ -389,16 +419,22 @@ def run_ours(args, rank, world, local_rank):
         nt = st["rays_primary"] * ntri
         nb = (st["rays_primary"] // 128) * ntri
     frame.kernel_variant = args.variant
-    cnt = torch.tensor([st["rays_primary"], st["rays_shadow"], nv, nt, nl, nb], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([st["rays_primary"], st["rays_shadow"], nv, nt, nl, nb] + list(single[:2] if single else (0, 0)), dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(cnt)
-    rays_primary, rays_shadow, nv_all, nt_all, nl_all, nb_all = [float(x) for x in cnt.cpu()]
+    rays_primary, rays_shadow, nv_all, nt_all, nl_all, nb_all, n_node_1, n_tri_1 = [float(x) for x in cnt.cpu()]
     rays = rays_primary + rays_shadow
 
-    launches_per_step = 1 if world == 1 else (3 if r.gather_mode() == A.RT_GATHER_PEER else 1 + world)   # rank 0: frame kernel + flag set/wait, or + unpack per rank
+    persistent = (not brute) and args.variant in (A.RT_VARIANT_DEFAULT, A.RT_VARIANT_PERSIST, A.RT_VARIANT_PERSIST_EXACT_MT, A.RT_VARIANT_PERSIST_OCC8, A.RT_VARIANT_PERSIST_OCC10)
+    if world == 1:
+        launches_per_step = 1
+    elif r.gather_mode() == A.RT_GATHER_PEER:
+        launches_per_step = 1 if persistent else 3      # per rank: the frame kernel; other kernels need a flag kernel either side
+    else:
+        launches_per_step = 1 + world                   # rank 0: frame kernel + one unpack per rank
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    step_ms = timed(args.steps)
-    warm_ms = timed(min(args.steps, 5), do_flush=False)
+    step_ms = timed(steps)
+    warm_ms = timed(min(steps, 5), do_flush=False)
     # frame kernel alone vs the whole rt_render, per rank (host-synchronised frames, untimed for the headline)
     ktimes = []
     for _ in range(3):
@@ -411,12 +447,34 @@ def run_ours(args, rank, world, local_rank):
     # end to end through the C ABI with host buffers (render + copy into pinned host memory), wall clock per rank; the
     # ranks are aligned before every step (outside the timed region) and the step's time is the max over ranks
     e2e_s = []
-    for i in range(-max(args.warmup, 3), args.steps):      # the warm-up calls pay rt_render_into's one-time stream / event / band set-up
+    for i in range(-max(args.warmup, 3), steps):      # the warm-up calls pay rt_render_into's one-time stream / event / band set-up
         barrier()
         t0 = time.perf_counter()
-        r.render_into(frame, into={"rgb8": pinned} if rank == 0 else None)     # rt_render_into: the user-facing "frame to host memory" call
+        e2e_out = r.render_into(frame, into={"rgb8": pinned} if rank == 0 else None)     # rt_render_into: the user-facing "frame to host memory" call
         if i >= 0:
             e2e_s.append(time.perf_counter() - t0)
+    # PARITY OF WHAT WAS TIMED (world > 1): rank 0 renders the same frame alone and compares it with the gathered planes —
+    # the 8-bit frame the e2e loop just delivered, and one extra untimed frame with ids and t
+    gather_parity = None
+    if world > 1:
+        allp = A.RT_OUT_RGB8 | A.RT_OUT_TRI_ID | A.RT_OUT_T
+        keep = frame.outputs
+        frame.outputs = allp
+        r.render(frame)
+        got = r.download()
+        frame.outputs = keep
+        if rank == 0:
+            solo = api.Renderer(local_rank)
+            solo.upload_scene(scene)
+            frame.outputs = allp
+            solo.render(frame)
+            ref = solo.download()
+            frame.outputs = keep
+            solo.close()
+            gather_parity = {"rgb8_equal": bool(np.array_equal(got["rgb8"], ref["rgb8"])), "tri_id_equal": bool(np.array_equal(got["tri_id"], ref["tri_id"])),
+                             "t_equal": bool(np.array_equal(got["t"], ref["t"])), "e2e_rgb8_equal": bool(np.array_equal(e2e_out["rgb8"], ref["rgb8"])),
+                             "pixels": int(W * H), "against": "the same frame rendered by rank 0 alone (single-GPU context, same scene)"}
+        barrier()
     t = torch.tensor([step_ms, e2e_s + [0.0] * (len(step_ms) - len(e2e_s))], dtype=torch.float64, device="cuda")
     tw = torch.tensor(warm_ms + [kern_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -429,89 +487,124 @@ def run_ours(args, rank, world, local_rank):
     value = rays / (ms * 1e-3) / 1e6
     e2e_value = rays / float(e2e_s.mean()) / 1e6
     e2e_spread = {"median_ms": 1e3 * float(np.median(e2e_s)), "min_ms": 1e3 * float(e2e_s.min()), "max_ms": 1e3 * float(e2e_s.max())}
+    if rank != 0:
+        return None
 
-    if rank == 0:
-        peak, peak_kind = measured_peaks()
-        # algorithmic bytes per launch: node data and 48-byte triangle blocks the kernel requests (frustum traversal: one
-        # 32-byte wide entry per lane-box test, counted in 64-byte units; per-lane traversal: one 64-byte line per warp
-        # visit), one 48-byte shading block per hit pixel, the 8-bit frame written once
-        bytes_launch = 64.0 * nl_all + 48.0 * nb_all + 48.0 * rays_primary + 3.0 * W * H
-        b_ray = bytes_launch / rays
-        achieved = bytes_launch / (ms * 1e-3) / 1e9
-        peak = peak * world
-        traffic, traffic_src, winst = None, None, None   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
+    peak, peak_kind = measured_peaks()
+    peak = peak * world
+    # ncu capture of the dominant kernel on this workload (profiles/traffic.json, re-captured whenever the kernel changes; the
+    # record names the kernel and the profile it came from): DRAM bytes and warp instructions per launch
+    traffic, traffic_src, winst, tkern = None, None, None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload)
+        if tj and world == 1 and args.variant == 0:
+            traffic, traffic_src, tkern = float(tj["dram_bytes_per_launch"]), tj["source"], tj.get("kernel")
+            winst = float(tj.get("warp_instructions_per_launch", 0)) or None
+    except Exception:
+        pass
+    # algorithmic bytes, SURVEY §8(d): B_ray = 64 N_node + 48 N_tri + 16 with N_node / N_tri of a single-ray walk of the uploaded BVH
+    b_ray_8d = (64.0 * n_node_1 + 48.0 * n_tri_1) / max(rays, 1.0) + 16.0 if not brute else 48.0 * nt_all / max(rays, 1.0) + 16.0
+    hbm_achieved = rays * b_ray_8d / (ms * 1e-3) / 1e9
+    # bytes the frame kernel itself requests at L1 (frustum traversal: one 32-byte wide entry per lane-box test, counted in 64-byte
+    # units; one 48-byte triangle block per warp test), one shading block per hit pixel, the 8-bit frame
+    bytes_requested = 64.0 * nl_all + 48.0 * nb_all + 48.0 * rays_primary + 3.0 * W * H
+    compulsory = float(info.arena_bytes) + 3.0 * W * H        # every byte of the arena once + the frame
+    hbm = {"bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak,
+           "peak_kind": peak_kind + (" x %d GPUs" % world if world > 1 else ""),
+           "bytes_per_ray": b_ray_8d, "n_node_single_ray": n_node_1 / max(rays, 1.0), "n_tri_single_ray": n_tri_1 / max(rays, 1.0),
+           "counted_by": "per-ray kernel walking the uploaded BVH one ray at a time (== host walk of the downloaded BVH, tested)",
+           "kernel_requested_bytes_per_launch_at_l1": bytes_requested, "kernel_tri_tests_per_ray": nt_all / max(rays, 1.0),
+           "packet_redundancy_tri_tests": (nt_all / n_tri_1) if n_tri_1 else None,
+           "dram_bytes_per_launch_ncu": traffic, "dram_frac_of_peak": (traffic / (ms * 1e-3) / 1e9 / peak) if traffic else None,
+           "compulsory_bytes_per_launch": compulsory,
+           "note": "the working set is cache-resident (ncu: L1 hit 78 %, L2 hit 84-92 %, DRAM < 1 % of peak): this kernel is NOT HBM-bound; "
+                   "the figure above 1.0 x peak that SURVEY 8(d) anticipates would mean 'served from cache'"}
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "description": wl["desc"], "triangles": wl["triangles"], "width": W, "height": H, "spp": spp,
+                   "rays": "primary+shadow" if rays_shadow else "primary", "rays_primary": rays_primary, "rays_shadow": rays_shadow,
+                   "l2": "flushed between timed steps (256 MiB memset); warm-L2 figure in value_warm_l2",
+                   "tile_sharding": "16x8-px tiles in %d contiguous bands per rank, band c -> rank c %% %d" % (args.chunks or parallel.DEFAULT_CHUNKS_PER_RANK, world), "gather": gather, "leaf_max": args.leaf_max, "variant": args.variant},
+        "ms_per_step_spread": step_spread,
+        "primary_mrays_s": rays_primary / (ms * 1e-3) / 1e6,
+        "value_warm_l2": rays / (float(tw[:-1].mean()) * 1e-3) / 1e6,
+        "frame_kernel_ms_max_rank": float(tw[-1]), "gather_overhead_ms": ms - float(tw[-1]),
+        "bvh_nodes": int(info.num_nodes), "bvh_build_ms": float(info.build_ms), "bvh_build_first_call_ms": float(first.build_ms),
+        "scene_upload_ms": float(info.upload_ms),
+        "scene_upload_wall_s": upload_wall,
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": 1e3 * float(e2e_s.mean()),
+                "h2d_bytes_per_step": int(C.sizeof(A.rt_frame) + 28 * len(frame.lights) + 8 * spp),
+                "d2h_bytes_per_step": int(3 * W * H + 32), "spread": e2e_spread},
+        "gpu_launches": int(steps * launches_per_step),
+        "clocks": clocks,
+    }
+    if gather_parity is not None:
+        line["gather_parity"] = gather_parity
+    if brute:   # 51 flop per ray-triangle test in the reference's unfused formulation (27 mul, 23 add/sub, 1 div)
+        tests_s = nt_all / (ms * 1e-3)
+        pk = 148 * 128 * 2 * 1.965e9 / 1e12 * world
+        line["roofline"] = {"bound": "fp32-issue", "achieved": tests_s * 51 / 1e12, "peak": pk, "unit": "TFLOP/s", "frac": tests_s * 51 / 1e12 / pk, "traffic": traffic,
+                            "ray_triangle_tests_per_s": tests_s, "flop_per_test": 51,
+                            "note": "peak counts FMA as 2 flop; the exactly-rounded test cannot use FMA, so 0.5 is its ceiling; triangles are streamed through shared memory once per 128 rays",
+                            "hbm": hbm}
+    else:
+        # The bound the profile shows: warp-instruction issue (4 schedulers per SM, one warp instruction per cycle each).
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        pk = 148 * 4 * mhz * 1e6 / 1e9 * world
+        if winst:
+            line["roofline"] = {"bound": "issue", "achieved": winst / (ms * 1e-3) / 1e9, "peak": pk, "unit": "G warp-instr/s", "frac": winst / (ms * 1e-3) / 1e9 / pk,
+                                "traffic": traffic, "warp_instructions_per_launch": winst, "source": traffic_src, "kernel": tkern,
+                                "peak_kind": "148 SMs x 4 schedulers x SM clock sampled during the run",
+                                "note": "issue-slot roofline: smsp__inst_executed.sum of the ncu capture named in `source` / this run's kernel time; traffic = dram bytes of the same capture",
+                                "hbm": hbm}
+        else:   # no capture for this workload / variant / rank count: only the byte roofline can be formed from this run
+            line["roofline"] = dict(hbm, traffic=traffic, issue_peak_g_warp_instr_s=pk,
+                                    note="no ncu capture on file for this workload/variant/rank count (profiles/traffic.json): HBM byte roofline of SURVEY 8(d) only; the kernel is issue-bound (see the c4 record) - " + hbm["note"])
+    if world == 1 and with_cpu and not args.no_cpu_baseline and not args.profile:
+        ref = CpuReference(make_workload(workload))
+        stp = cpu_sample(ref, 12.0)
+        n, dt, passes = 0, 0.0, 0
+        while dt < 10.0 and passes < 64:                  # bounded sample: ~10 s of CPU work
+            a, b = ref.rays_in_rows(passes % stp, stp)
+            n += a; dt += b; passes += 1
+        cen = ref.census(0, stp)
+        ratio = (cen[1] / max(cen[0], 1)) if cen else rays_shadow / max(rays_primary, 1.0)
+        line["cpu_baseline"] = {"value": n * (1 + ratio) / dt / 1e6, "unit": "Mrays/s", "cores": ref.cores, "kind": ref.kind,
+                                "sample": "%d pass(es) over every %d-th row of the %dx%d frame, %.1f s of CPU work; shadow rays = primary x %.4f (%s)" %
+                                          (passes, stp, W, H, dt, ratio, "counted by the reference shim on the sampled rows" if cen else "device count")}
+    line["_rays"] = rays
+    line["_e2e_value"] = e2e_value
+    return line
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from raytracinginonesemester_b200 import _abi as A
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU baseline)")
+    from raytracinginonesemester_b200 import parallel
+    torch.cuda.set_device(local_rank)
+    dist, rank, world, local_rank = parallel.init_process_group("nccl")
+    r = parallel.make_renderer(dist, rank, world, local_rank)
+    if world > 1:
+        r.set_sharding(args.chunks)
+        r.set_gather({"auto": A.RT_GATHER_AUTO, "nccl": A.RT_GATHER_NCCL, "peer": A.RT_GATHER_PEER}[args.gather])
+    line = bench_workload(args, r, dist, rank, world, local_rank, args.workload, args.steps)
+    extra = None
+    if world >= 8 and args.workload == "c4" and not args.no_c5 and not args.profile:
+        # BASELINE config 5 (10M triangles, 7680x4320, 16 spp, 8 GPUs) as a driver-timed record beside the headline
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-            if tj and world == 1 and args.variant == 0:
-                traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj["source"]
-                winst = float(tj.get("warp_instructions_per_launch", 0)) or None
-        except Exception:
-            pass
-        if brute:
-            note = "FP32-issue bound, not HBM-bound: triangles are streamed through shared memory once per 128 rays; see fp32_issue"
-        else:
-            note = ("instruction-issue/latency bound, not HBM-bound: the arena is L2/L1-resident (ncu: issue slots 78 % busy, DRAM < 1 % of peak); "
-                    "achieved = bytes the kernel REQUESTS (32 B per lane-box test of the frustum traversal, 48 B per warp triangle test), most served by L1/L2 - see traffic and profiles/")
-        line = {
-            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "description": wl["desc"], "triangles": wl["triangles"], "width": W, "height": H, "spp": spp,
-                       "rays": "primary+shadow" if rays_shadow else "primary", "rays_primary": rays_primary, "rays_shadow": rays_shadow,
-                       "l2": "flushed between timed steps (256 MiB memset); warm-L2 figure in value_warm_l2",
-                       "tile_sharding": "16x8-px tiles in %d contiguous bands per rank, band c -> rank c %% %d" % (args.chunks or parallel.DEFAULT_CHUNKS_PER_RANK, world), "gather": gather, "leaf_max": args.leaf_max, "variant": args.variant},
-            "ms_per_step_spread": step_spread,
-            "primary_mrays_s": rays_primary / (ms * 1e-3) / 1e6,
-            "value_warm_l2": rays / (float(tw[:-1].mean()) * 1e-3) / 1e6,
-            "frame_kernel_ms_max_rank": float(tw[-1]), "gather_overhead_ms": ms - float(tw[-1]),
-            "bvh_nodes": int(info.num_nodes), "bvh_build_ms": float(info.build_ms), "bvh_build_first_call_ms": float(first.build_ms),
-            "scene_upload_ms": float(info.upload_ms),
-            "scene_upload_wall_s": upload_wall,
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": 1e3 * float(e2e_s.mean()),
-                    "h2d_bytes_per_step": int(C.sizeof(A.rt_frame) + 28 * len(frame.lights) + 8 * spp),
-                    "d2h_bytes_per_step": int(3 * W * H + 32), "spread": e2e_spread},
-            "gpu_launches": int(args.steps * launches_per_step),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                         "peak_kind": peak_kind + (" x %d GPUs" % world if world > 1 else ""), "bytes_per_ray": b_ray, "bytes_per_launch": bytes_launch,
-                         ("wide_entries_per_ray" if args.variant in (A.RT_VARIANT_DEFAULT, A.RT_VARIANT_FRUSTUM) and not brute else "nodes_per_ray"): nv_all / rays,
-                         "tris_per_ray": nt_all / rays, "node_lines_per_ray": nl_all / rays, "tri_blocks_per_ray": nb_all / rays,
-                         "note": note},
-            "clocks": clocks,
-        }
-        # SURVEY §8d's per-ray accounting (every ray pays for every node / triangle it takes part in: 64 B per node visit,
-        # 48 B per triangle test, 16 B of result), next to the per-request accounting above (a packet fetches a line once
-        # for its 32 rays).  Above 1 = served from cache, as §8d anticipates.
-        frustum = args.variant in (A.RT_VARIANT_DEFAULT, A.RT_VARIANT_FRUSTUM) and not brute
-        # frustum traversal: rays take no part in the inner-node tests (one lane = one box); the node term is the packet's
-        # 32-byte wide entries shared over its rays
-        b_ray_8d = (32.0 if frustum else 64.0) * nv_all / rays + 48.0 * nt_all / rays + 16.0
-        line["roofline"]["survey_8d_per_ray"] = {"bytes_per_ray": b_ray_8d, "achieved": rays * b_ray_8d / (ms * 1e-3) / 1e9,
-                                                 "frac": rays * b_ray_8d / (ms * 1e-3) / 1e9 / peak}
-        if winst and not brute:
-            # the bound the profile actually shows: warp-instruction issue (4 schedulers per SM, one warp instruction per cycle each)
-            mhz = (clocks or {}).get("sm_mhz") or 1965.0
-            pk = 148 * 4 * mhz * 1e6 / 1e9
-            line["issue_roofline"] = {"bound": "warp-instruction issue", "achieved": winst / (ms * 1e-3) / 1e9, "peak": pk, "unit": "G warp-instr/s",
-                                      "frac": winst / (ms * 1e-3) / 1e9 / pk, "warp_instructions_per_launch": winst, "source": traffic_src,
-                                      "peak_kind": "148 SMs x 4 schedulers x SM clock sampled during the run"}
-        if brute:   # 51 flop per ray-triangle test in the reference's unfused formulation (27 mul, 23 add/sub, 1 div)
-            tests_s = nt_all / (ms * 1e-3)
-            pk = 148 * 128 * 2 * 1.965e9 / 1e12 * world
-            line["fp32_issue"] = {"ray_triangle_tests_per_s": tests_s, "flop_per_test": 51, "achieved_tflops": tests_s * 51 / 1e12,
-                                  "peak_tflops": pk, "frac": tests_s * 51 / 1e12 / pk,
-                                  "note": "peak counts FMA as 2 flop; the exactly-rounded test cannot use FMA, so 0.5 is its ceiling"}
-        if world == 1 and not args.no_cpu_baseline and not args.profile:
-            ref = CpuReference(make_workload(args.workload))
-            stp = cpu_sample(ref, 12.0)
-            n, dt, passes = 0, 0.0, 0
-            while dt < 10.0 and passes < 64:                  # bounded sample: ~10 s of CPU work
-                a, b = ref.rays_in_rows(passes % stp, stp)
-                n += a; dt += b; passes += 1
-            ratio = rays_shadow / max(rays_primary, 1.0)
-            line["cpu_baseline"] = {"value": n * (1 + ratio) / dt / 1e6, "unit": "Mrays/s", "cores": ref.cores, "kind": ref.kind,
-                                    "sample": "%d pass(es) over every %d-th row of the %dx%d frame, %.1f s of CPU work; shadow rays = primary x %.4f (device count)" % (passes, stp, W, H, dt, ratio)}
+            extra = bench_workload(args, r, dist, rank, world, local_rank, "c5", max(3, min(args.steps, 10)), with_cpu=False)
+        except Exception as e:
+            extra = {"config": {"workload": "c5"}, "unavailable": "%s: %s" % (type(e).__name__, e)}
     r.close()
     if rank == 0:
+        rays, e2e_value = line.pop("_rays"), line.pop("_e2e_value")
+        if extra is not None:
+            extra.pop("_rays", None); extra.pop("_e2e_value", None)
+            line["configs"] = [extra]
         if world == 1 and not args.no_cpu_baseline and not args.profile:
             try:
                 rc = reference_cuda_leg(make_workload(args.workload), rays)
@@ -519,12 +612,17 @@ def run_ours(args, rank, world, local_rank):
                 rc = {"unavailable": "%s: %s" % (type(e).__name__, e)}
             if rc is not None:
                 if "value" in rc:
-                    rc["speedup_device"] = value / rc["value"]
+                    rc["speedup_device"] = line["value"] / rc["value"]
                     rc["speedup_e2e"] = e2e_value / rc["e2e_value"]
                 line["reference_cuda"] = rc
+        bad = line.get("gather_parity") and not all(v for k, v in line["gather_parity"].items() if k.endswith("_equal"))
         print(json.dumps(line))
+        if bad:
+            sys.stderr.write("bench.py: the gathered frame differs from the single-GPU frame\n")
     if dist is not None:
         dist.destroy_process_group()
+    if rank == 0 and line.get("gather_parity") and not all(v for k, v in line["gather_parity"].items() if k.endswith("_equal")):
+        sys.exit(3)
 
 
 def main():
@@ -537,11 +635,11 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--leaf-max", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="--gpus 8: skip the BASELINE config 5 record (configs[0] of the line)")
     ap.add_argument("--chunks", type=int, default=0, help="multi-GPU tile ownership bands per rank (0 = library default)")
     ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "peer"], help="multi-GPU tile delivery to rank 0")
     ap.add_argument("--no-shadows", action="store_true", help="primary rays only (diagnostic; not the headline workload)")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: honour --warmup < 3, skip the CPU baseline")
-    ap.add_argument("--shadow-ratio", type=float, default=-1.0, help="--impl reference: shadow rays per primary ray (default: the device count of the workload)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

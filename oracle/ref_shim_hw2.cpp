@@ -196,6 +196,56 @@ void ref_hw2_render_rows(void* h, const float* cpos, const float* look, const fl
     }
 }
 
+// Ray census of the same rows at depth 1 (untimed; bench.py's reference arm quotes rays/s): primary rays = pixels x spp;
+// shadow rays = IsInShadow calls that reach SearchBVH.  The reference has no counters and its shading functions are
+// inline, so the two conditions that gate the call are evaluated here with the reference's own primitives on the
+// reference's own hit record: `NdotL > 0` (shader.h:88-90) and `distToL > 0` (shader.h:52-54).
+void ref_hw2_count_rays_rows(void* h, const float* cpos, const float* look, const float* up, double focal_mm,
+                             double sensor_mm, int W, int H, int spp, const ref_lightc* lights, int num_lights,
+                             int row_begin, int row_step, int nthreads, uint64_t* primary_out, uint64_t* shadow_out)
+{
+    ref_world* w = (ref_world*)h;
+    Camera cam(make_vec3(cpos[0], cpos[1], cpos[2]), make_vec3(look[0], look[1], look[2]),
+               make_vec3(up[0], up[1], up[2]), focal_mm, sensor_mm, W, H);
+    const int triCount = (int)w->P;
+    if (nthreads < 1) nthreads = 1;
+    if (row_step < 1) row_step = 1;
+    std::vector<uint64_t> prim(nthreads, 0), shad(nthreads, 0);
+    auto body = [&](int tid) {
+        int kk = 0;
+        auto offsets = jittered_samples(spp, 42u);
+        for (int y = row_begin; y < H; y += row_step, ++kk) {
+            if (kk % nthreads != tid) continue;
+            for (int x = 0; x < W; ++x)
+                for (int si = 0; si < (int)offsets.size(); ++si) {
+                    const Ray ray = cam.get_ray(float(x) + offsets[si].first, float(y) + offsets[si].second);
+                    ++prim[tid];
+                    HitRecord rec;
+                    SearchBVH(triCount, ray, w->st.Nodes, w->st.AABBs, w->tris.data(), rec);
+                    if (!rec.hit) continue;
+                    const Vec3 N = unit_vector(rec.normal);
+                    for (int i = 0; i < num_lights; ++i) {
+                        const Light& light = ((const Light*)lights)[i];
+                        const Vec3 L = unit_vector(light.position - rec.p);
+                        if (fmaxf(dot(N, L), 0.0f) <= 0.0f) continue;
+                        if (length3(light.position - rec.p) <= 0.0f) continue;
+                        ++shad[tid];
+                    }
+                }
+        }
+    };
+    if (nthreads == 1) body(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; ++t) th.emplace_back(body, t);
+        for (auto& t : th) t.join();
+    }
+    uint64_t a = 0, b = 0;
+    for (int t = 0; t < nthreads; ++t) { a += prim[t]; b += shad[t]; }
+    if (primary_out) *primary_out = a;
+    if (shadow_out) *shadow_out = b;
+}
+
 // Single-triangle probe: intersectTriangle (query.h:72-132), tmin 1e-4, tmax FLT_MAX.
 int ref_hw2_ray_triangle(const float* orig, const float* dir, const float* v0, const float* v1,
                          const float* v2, float* t_out) {

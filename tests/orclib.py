@@ -119,3 +119,45 @@ def emul_render(handle, frame, want=("rgb", "rgb8", "tri_id", "t")):
     assert rc == 0
     out["stats"] = dict(rays_primary=stats[0], rays_shadow=stats[1], nodes=stats[2], tris=stats[3], max_stack=stats[4])
     return out
+
+
+def reference_render(scene, frame, row_begin=0, row_step=1, threads=None, want=("rgb", "tri_id", "t")):
+    """The frame through the REFERENCE ITSELF (oracle/_ref/libref_hw2.so: the unmodified GPUandCPU sources compiled in place,
+    Camera::get_ray + SearchBVH + TraceRayIterative per pixel over its own LBVH), threaded over rows; falls back to the
+    oracle's restatement of the same path (reference LBVH + SearchBVH) when the shim is not on this box.
+    Returns (planes dict, "reference" | "port").  HW2-BVH frames with a camera made by api.camera_init only."""
+    threads = threads or os.cpu_count() or 1
+    libs = ref_libs()
+    if "ref_hw2" not in libs:
+        out = oracle_render(scene, frame, bvh=oracle_bvh(scene), threads=threads, row_begin=row_begin, row_step=row_step,
+                            want=tuple(w for w in want if w != "rgb8") + (("rgb8",) if "rgb8" in want else ()))
+        return out, "port"
+    lib = libs["ref_hw2"]
+    lib.ref_hw2_world.restype = C.c_void_p
+    lib.ref_hw2_build.restype = C.c_double
+    f32p, u32p, i32p = A.f32p, A.u32p, A.i32p
+    nrm = scene.normals.ctypes.data_as(f32p) if scene.normals is not None else None
+    obj = scene.tri_obj_ids.ctypes.data_as(i32p) if scene.tri_obj_ids is not None else None
+    h = lib.ref_hw2_world(scene.positions.ctypes.data_as(f32p), nrm, C.c_uint64(scene.positions.shape[0]),
+                          scene.indices.ctypes.data_as(u32p), C.c_uint64(scene.indices.shape[0]), obj)
+    lib.ref_hw2_build(C.c_void_p(h))
+    W, H = frame.width, frame.height
+    cp = frame.cam.params
+    f3 = lambda v: np.array(v, np.float32)
+    cpos, look, up, ms = f3(cp["pos"]), f3(cp["look_at"]), f3(cp["up"]), f3(frame.miss_color)
+    out = {}
+    rgb = tid = tt = None
+    if "rgb" in want:
+        out["rgb"] = np.zeros((H, W, 3), np.float32); rgb = out["rgb"].ctypes.data_as(f32p)
+    if "tri_id" in want:
+        out["tri_id"] = np.full((H, W), -2, np.int32); tid = out["tri_id"].ctypes.data_as(i32p)
+    if "t" in want:
+        out["t"] = np.full((H, W), -2, np.float32); tt = out["t"].ctypes.data_as(f32p)
+    mats = scene.materials or []
+    marr = (A.rt_material * max(1, len(mats)))(*mats)
+    larr = (A.rt_light * max(1, len(frame.lights)))(*frame.lights)
+    lib.ref_hw2_render_rows(C.c_void_p(h), cpos.ctypes.data_as(f32p), look.ctypes.data_as(f32p), up.ctypes.data_as(f32p),
+                            C.c_double(cp["focal_mm"]), C.c_double(cp["sensor_mm"]), W, H, ms.ctypes.data_as(f32p), int(frame.max_depth), int(frame.spp),
+                            marr, len(mats), larr, len(frame.lights), int(frame.diffuse_bounce), row_begin, row_step, threads, rgb, tid, tt)
+    lib.ref_hw2_free(C.c_void_p(h))
+    return out, "reference"
