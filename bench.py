@@ -368,6 +368,9 @@ def bench_workload(args, r, dist, rank, world, local_rank, workload, steps, with
     gather = {A.RT_GATHER_NCCL: "nccl send/recv + unpack", A.RT_GATHER_PEER: "peer stores into rank 0's image over NVLink; band flags and the ready/done handshake inside the frame kernel"}[r.gather_mode()] if world > 1 else "none"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     pinned = torch.empty((H, W, 3), dtype=torch.uint8, pin_memory=True).numpy() if rank == 0 else None
+    # N > 1: the e2e frame goes to a host buffer shared by all ranks' processes (rt_host_image_create): every rank copies the bands
+    # it rendered over its own PCIe link; rank 0 reads the frame from its mapping
+    shared = r.host_image(3 * W * H)[:3 * W * H].reshape(H, W, 3) if world > 1 else None
 
     def barrier():
         if dist is not None:
@@ -450,9 +453,10 @@ def bench_workload(args, r, dist, rank, world, local_rank, workload, steps, with
     for i in range(-max(args.warmup, 3), steps):      # the warm-up calls pay rt_render_into's one-time stream / event / band set-up
         barrier()
         t0 = time.perf_counter()
-        e2e_out = r.render_into(frame, into={"rgb8": pinned} if rank == 0 else None)     # rt_render_into: the user-facing "frame to host memory" call
+        e2e_out = r.render_into(frame, into={"rgb8": shared} if world > 1 else {"rgb8": pinned})     # rt_render_into: the user-facing "frame to host memory" call
         if i >= 0:
             e2e_s.append(time.perf_counter() - t0)
+    e2e_kernel_ms = r.frame_times()[1]                 # the frame kernel inside the last end-to-end step (this rank)
     # PARITY OF WHAT WAS TIMED (world > 1): rank 0 renders the same frame alone and compares it with the gathered planes —
     # the 8-bit frame the e2e loop just delivered, and one extra untimed frame with ids and t
     gather_parity = None
@@ -472,7 +476,7 @@ def bench_workload(args, r, dist, rank, world, local_rank, workload, steps, with
             frame.outputs = keep
             solo.close()
             gather_parity = {"rgb8_equal": bool(np.array_equal(got["rgb8"], ref["rgb8"])), "tri_id_equal": bool(np.array_equal(got["tri_id"], ref["tri_id"])),
-                             "t_equal": bool(np.array_equal(got["t"], ref["t"])), "e2e_rgb8_equal": bool(np.array_equal(e2e_out["rgb8"], ref["rgb8"])),
+                             "t_equal": bool(np.array_equal(got["t"], ref["t"])), "e2e_rgb8_equal": bool(np.array_equal(shared, ref["rgb8"])),
                              "pixels": int(W * H), "against": "the same frame rendered by rank 0 alone (single-GPU context, same scene)"}
         barrier()
     t = torch.tensor([step_ms, e2e_s + [0.0] * (len(step_ms) - len(e2e_s))], dtype=torch.float64, device="cuda")
@@ -536,7 +540,8 @@ def bench_workload(args, r, dist, rank, world, local_rank, workload, steps, with
         "scene_upload_wall_s": upload_wall,
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": 1e3 * float(e2e_s.mean()),
                 "h2d_bytes_per_step": int(C.sizeof(A.rt_frame) + 28 * len(frame.lights) + 8 * spp),
-                "d2h_bytes_per_step": int(3 * W * H + 32), "spread": e2e_spread},
+                "d2h_bytes_per_step": int(3 * W * H + 32), "spread": e2e_spread, "frame_kernel_ms_rank0": float(e2e_kernel_ms),
+                "delivery": ("every rank copies its own bands into one shared page-locked host buffer (rt_host_image_create), %d PCIe links" % world) if world > 1 else "band-pipelined copy into pinned host memory"},
         "gpu_launches": int(steps * launches_per_step),
         "clocks": clocks,
     }

@@ -250,6 +250,15 @@ int  rt_download_image(rt_ctx* ctx, rt_image* img);
  * the following bands are still rendering (pinned host memory makes the copies asynchronous), which hides most of
  * the device->host transfer that the reference pays after its kernel (GPUandCPU/src/main.cu:370-378). */
 int  rt_render_into(rt_ctx* ctx, const rt_frame* frame, rt_image* img);
+/* Multi-GPU contexts: a host buffer shared by every rank's process (POSIX shared memory, page-locked on every rank).
+ * Collective; *ptr is this rank's mapping of the same `bytes` bytes.  When EVERY rank calls rt_render_into with plane
+ * pointers at the same offsets inside its mapping, each rank copies the bands it rendered straight into the buffer over
+ * its own PCIe link while later bands render — no gather to rank 0, no single D2H link (what the reference does after its
+ * kernel, GPUandCPU/src/main.cu:374, times the number of GPUs).  rt_render_into returns on rank 0 when every rank's bands
+ * have landed; the image is then valid in rank 0's mapping until rank 0 calls rt_render_into again.  After such a frame
+ * rt_download_image delivers ray counts and times only.  One image per context; creating another releases the first. */
+int  rt_host_image_create(rt_ctx* ctx, size_t bytes, void** ptr);
+int  rt_host_image_destroy(rt_ctx* ctx);
 /* Blocks until the last rt_render finished; returns its device time. */
 int  rt_sync(rt_ctx* ctx, float* gpu_ms);
 /* Device times of the last frame on this rank: the whole rt_render (frame kernel + tile delivery to rank 0)

@@ -99,6 +99,8 @@ EXPORTS = {
     "rt_render": (C.c_int, [C.c_void_p, C.POINTER(rt_frame)]),
     "rt_render_into": (C.c_int, [C.c_void_p, C.POINTER(rt_frame), C.POINTER(rt_image)]),
     "rt_download_image": (C.c_int, [C.c_void_p, C.POINTER(rt_image)]),
+    "rt_host_image_create": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "rt_host_image_destroy": (C.c_int, [C.c_void_p]),
     "rt_sync": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "rt_frame_stats": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_uint64)] * 4),
     "rt_camera_init": (C.c_int, [C.POINTER(rt_camera), f32p, f32p, f32p, C.c_double, C.c_double, C.c_int, C.c_int]),

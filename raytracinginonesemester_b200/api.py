@@ -304,12 +304,21 @@ class Renderer:
         self._check(self.lib.rt_stream_handle(self.ctx, C.byref(h)))
         return int(h.value or 0)
 
+    def host_image(self, nbytes):
+        """Collective (rt_host_image_create): a host buffer shared by every rank's process; returns this rank's mapping as
+        a uint8 numpy array.  Pass slices of it (the same on every rank) as `into` of render_into: every rank then copies
+        its own bands to the host over its own PCIe link."""
+        p = C.c_void_p()
+        self._check(self.lib.rt_host_image_create(self.ctx, int(nbytes), C.byref(p)))
+        self._shared = np.ctypeslib.as_array((C.c_uint8 * int(nbytes)).from_address(p.value))
+        return self._shared
+
     def _image(self, fr, into):
         W, H = fr.width, fr.height
         img = A.rt_image()
         out = {}
         into = into or {}
-        root = self.world == 1 or self.rank == 0
+        root = self.world == 1 or self.rank == 0 or bool(into)       # (ranks != 0 pass planes only for the shared host image)
 
         def buf(name, shape, dt):
             a = into.get(name)

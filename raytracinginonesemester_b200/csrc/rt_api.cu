@@ -10,6 +10,10 @@
 #include <cuda.h>           // driver API types only; cuStreamWaitValue32 is fetched with cudaGetDriverEntryPoint
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <nccl.h>   // types and prototypes only: the library is resolved at run time, see NcclApi below
 
 #include <chrono>
@@ -84,6 +88,7 @@ struct Plane {
 
 #define RT_BANDS 8
 #define RT_BAND_STREAMS 4
+#define RT_SHM_HEADER 4096            // shared host image: header with one 64-byte line per rank (done word), planes behind it
 #define RT_COUNTER_BYTES 64           // 8 x u64 ray / traversal counters, followed by the persistent kernel's PersistCtl
 
 struct rt_ctx {
@@ -122,6 +127,12 @@ struct rt_ctx {
     // rt_render_into: band-pipelined render + download (kernels of later bands overlap the D2H copy of earlier ones)
     cudaStream_t band_stream[RT_BAND_STREAMS] = {}; cudaStream_t copy_stream = nullptr, sig_stream = nullptr;
     cudaEvent_t band_ev[RT_BANDS] = {}; cudaEvent_t copy_done = nullptr;
+    // shared host image (rt_host_image_create): one POSIX shared-memory segment mapped and page-locked by every rank; each
+    // rank copies the bands IT rendered straight into it over its own PCIe link (rt_render_into), no gather to rank 0
+    char* shm_base = nullptr; size_t shm_bytes = 0;       // whole mapping: RT_SHM_HEADER bytes of per-rank done words, then the planes
+    unsigned* hflags = nullptr; unsigned* hflags_dev = nullptr;   // this rank's band flags in mapped pinned HOST memory (+ device alias): rt_render_into polls them
+    unsigned hseq = 0;                                   // frame sequence number of the shared-host protocol
+    bool last_host_direct = false;                       // the last frame went out through the shared host image
     unsigned long long peer_timeout_ns = 120ull * 1000000000ull;   // bound of every in-kernel / flag-kernel wait on another rank (rt_comm_set_timeout)
     int dbg_rank = 0, dbg_world = 0;              // rt_debug_set_shard: render one rank's share on a single GPU (timing only)
 };
@@ -267,6 +278,11 @@ void peer_teardown(rt_ctx* c, bool collective) {
     c->peer = false;
 }
 
+void shm_release(rt_ctx* c) {
+    if (c->shm_base) { cudaHostUnregister(c->shm_base); munmap(c->shm_base, c->shm_bytes); }
+    c->shm_base = nullptr; c->shm_bytes = 0;
+}
+
 int peer_timeout(rt_ctx* c, unsigned code) {
     cudaMemset(c->peer_err, 0, sizeof(unsigned));
     c->frame_valid = false;
@@ -395,6 +411,8 @@ int rt_destroy(rt_ctx* c) {
     // NOT a collective (ranks may destroy in any order, or after another rank died): mappings are closed, rank 0's
     // exported planes are left to process teardown because an importer may still have them mapped.
     peer_teardown(c, false);
+    shm_release(c);
+    if (c->hflags) cudaFreeHost(c->hflags);
     if (c->peer_err) cudaFree(c->peer_err);
     if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
     free_scene(c);
@@ -584,6 +602,52 @@ static int upload_local(rt_ctx* c, const rt_scene* sc) {
     return RT_OK;
 }
 
+int rt_host_image_create(rt_ctx* c, size_t bytes, void** out) {
+    if (!c || !out || bytes == 0) return fail(c, RT_ERR_ARG, "rt_host_image_create: bad arguments");
+    *out = nullptr;
+    CU(c, cudaSetDevice(c->device));
+    shm_release(c);
+    const size_t total = RT_SHM_HEADER + ((bytes + 4095) & ~(size_t)4095);
+    char name[64]; memset(name, 0, sizeof name);
+    int ok = 1, fd = -1;
+    if (c->rank == 0) {
+        static int serial = 0;
+        snprintf(name, sizeof name, "/rt_b200_%d_%d", (int)getpid(), ++serial);
+        fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+        if (fd < 0 || ftruncate(fd, (off_t)total) != 0) ok = 0;
+    }
+    if (c->world > 1) {                                         // collective: the name travels over the library's communicator
+        int rc = bcast_bytes(c, name, sizeof name);
+        if (rc != RT_OK) { if (fd >= 0) { close(fd); shm_unlink(name); } return rc; }
+        if (c->rank != 0) { fd = shm_open(name, O_RDWR, 0600); if (fd < 0) ok = 0; }
+    }
+    void* p = MAP_FAILED;
+    if (ok) p = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    if (fd >= 0) close(fd);
+    if (p == MAP_FAILED) ok = 0;
+    if (ok && c->rank == 0) memset(p, 0, RT_SHM_HEADER);
+    if (ok && cudaHostRegister(p, total, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) { cudaGetLastError(); munmap(p, total); p = MAP_FAILED; ok = 0; }
+    int all = ok;
+    if (c->world > 1) { int rc = all_min(c, ok, &all); if (rc != RT_OK) all = 0; }      // also the barrier before the name is unlinked
+    if (c->rank == 0 && name[0]) shm_unlink(name);              // the mappings keep the segment alive
+    if (!all) {
+        if (p != MAP_FAILED) { cudaHostUnregister(p); munmap(p, total); }
+        return fail(c, RT_ERR_NOMEM, "rt_host_image_create: cannot create / map / page-lock %zu bytes of shared host memory on every rank", total);
+    }
+    c->shm_base = (char*)p; c->shm_bytes = total; c->hseq = 0;
+    *out = c->shm_base + RT_SHM_HEADER;
+    return RT_OK;
+}
+
+int rt_host_image_destroy(rt_ctx* c) {
+    if (!c) return fail(nullptr, RT_ERR_ARG, "rt_host_image_destroy: NULL ctx");
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    shm_release(c);
+    return RT_OK;
+}
+
 int rt_upload_scene(rt_ctx* c, const rt_scene* sc) {
     if (!c) return fail(nullptr, RT_ERR_ARG, "rt_upload_scene: NULL ctx");
     CU(c, cudaSetDevice(c->device));
@@ -630,7 +694,37 @@ int ensure_flags(rt_ctx* c) {
     return RT_OK;
 }
 
+// Band flags the HOST polls (rt_render_into is a blocking call: its own thread waits for a band's word and issues the band's
+// copy — measured faster than stream-ordered cuStreamWaitValue32 waits on the copy stream).
+int ensure_host_flags(rt_ctx* c) {
+    if (c->hflags) return RT_OK;
+    CU(c, cudaHostAlloc((void**)&c->hflags, kFlagBytes, cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(c->hflags, 0, kFlagBytes);
+    CU(c, cudaHostGetDevicePointer((void**)&c->hflags_dev, c->hflags, 0));
+    return RT_OK;
+}
+
 struct HostOut { void* host; uint32_t bit; size_t bpp; const void* dev; const char* name; };
+
+// Bands of a rank's L local tile slots (completion flags of the persistent kernel).  Cuts at every ownership-chunk boundary
+// (chunks of `chunk` slots: a band must not straddle two chunks, their tiles are not contiguous in the frame) and, when
+// `refine`, at 1/2, 3/4, 7/8 ... of the LAST chunk: the copy of the last band is the only one that cannot overlap rendering,
+// so it should be short.  Returns the number of bands (<= RT_MAX_BANDS), band_end[] cumulative.
+int plan_bands(int L, int chunk, bool refine, int* band_end) {
+    int n = 0;
+    if (L <= 0) { band_end[0] = 0; return 1; }
+    if (chunk < 1) chunk = L;
+    int nchunks = (L + chunk - 1) / chunk;
+    if (nchunks > RT_MAX_BANDS) { band_end[0] = L; return 1; }        // (callers check; one band = the whole rank)
+    for (int k = 1; k < nchunks; ++k) band_end[n++] = k * chunk;
+    int lo = (nchunks - 1) * chunk;                                     // refine [lo, L): 1/2, 3/4, 7/8 (every band costs each block a
+    for (int k = 0; refine && k < 3 && n + 1 < RT_MAX_BANDS && L - lo >= 64; ++k) {   // barrier and a fence: measured +70 us per frame with 7 bands)
+        lo += (L - lo) / 2;
+        band_end[n++] = lo;
+    }
+    band_end[n++] = L;
+    return n;
+}
 
 // rt_render (into == NULL) and rt_render_into (into != NULL: finished bands of the frame are copied to the caller's host
 // buffers while later bands are still rendering).  One frame = ONE launch of the persistent kernel per rank: it
@@ -682,12 +776,29 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
     P.rank = c->rank; P.world = c->world;
     const bool dbg_shard = c->world == 1 && c->dbg_world > 1;
     if (dbg_shard) { P.rank = c->dbg_rank; P.world = c->dbg_world; }
-    if (c->world > 1 && c->peer) {                 // collective; may fall back to the NCCL gather
+    // rt_render_into with every plane inside the shared host image (rt_host_image_create): each rank renders into its own
+    // row-major planes and copies the bands it owns to the host itself; nothing is gathered on rank 0's device
+    bool host_direct = false;
+    if (c->world > 1 && into && c->shm_base) {
+        const int F0 = c->chunks_per_rank > 0 ? c->chunks_per_rank : RT_DEFAULT_CHUNKS_PER_RANK;
+        const size_t np = (size_t)fr->width * fr->height;
+        const void* pl[4] = {into->rgb, into->rgb8, into->tri_id, into->t};
+        const size_t bp[4] = {12, 3, 4, 4};
+        int n_in = 0, n_out = 0;
+        for (int i = 0; i < 4; ++i) {
+            if (!pl[i]) continue;
+            const char* a = (const char*)pl[i];
+            if (a >= c->shm_base + RT_SHM_HEADER && a + bp[i] * np <= c->shm_base + c->shm_bytes) ++n_in; else ++n_out;
+        }
+        if (n_in && n_out) return fail(c, RT_ERR_ARG, "rt_render_into: some planes are inside the shared host image and some are not");
+        host_direct = n_in > 0 && F0 <= RT_PEER_MAX_CHUNKS;
+    }
+    if (c->world > 1 && c->peer && !host_direct) {   // collective; may fall back to the NCCL gather
         int rc = peer_planes(c, outputs, (size_t)fr->width * fr->height);
         if (rc != RT_OK) return rc;
     }
-    const bool peer = c->world > 1 && c->peer;
-    P.packed = ((c->world > 1 && !peer) || dbg_shard) ? 1 : 0;
+    const bool peer = c->world > 1 && c->peer && !host_direct;
+    P.packed = ((c->world > 1 && !peer && !host_direct) || dbg_shard) ? 1 : 0;
     const int total_tiles = P.tiles_x * P.tiles_y;
     P.chunk_tiles = rt_chunk_tiles(total_tiles, P.world, c->chunks_per_rank);
     P.local_tiles = rt_tiles_of_rank(total_tiles, P.world, c->chunks_per_rank);
@@ -730,7 +841,7 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
         P.jitter = (const float*)c->jitter.p;
     }
     const size_t npix_full = (size_t)P.W * P.H;
-    const size_t npix_loc = P.world == 1 ? npix_full : (size_t)P.local_tiles * RT_BLOCK_THREADS;
+    const size_t npix_loc = (P.world == 1 || host_direct) ? npix_full : (size_t)P.local_tiles * RT_BLOCK_THREADS;
     if (peer) {                                    // every rank writes rank 0's row-major image in place
         const bool root = c->rank == 0;
         if (outputs & RT_OUT_RGB_F32) P.rgb = (float*)(root ? c->img_rgb.p : c->peer_img[0]);
@@ -762,18 +873,123 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
         return RT_OK;
     };
 
+    // copies the pixels of the row-major GLOBAL tiles [g0, g1) of every requested plane (row-major device planes) to the caller's
+    // buffers: a partial tile row, whole tile rows (one contiguous copy), a partial tile row
+    auto copy_tiles = [&](long long g0, long long g1) -> int {
+        if (g1 > total_tiles) g1 = total_tiles;
+        if (g0 >= g1) return RT_OK;
+        const int tx = P.tiles_x;
+        const int row0 = (int)(g0 / tx), col0 = (int)(g0 % tx), row1 = (int)((g1 - 1) / tx), col1 = (int)((g1 - 1) % tx) + 1;
+        struct Piece { int r0, r1, c0, c1; } pieces[3];
+        int np = 0;
+        if (row0 == row1) pieces[np++] = {row0, row0, col0, col1};
+        else {
+            int first_full = row0, last_full = row1;
+            if (col0 != 0) { pieces[np++] = {row0, row0, col0, tx}; first_full = row0 + 1; }
+            if (col1 != tx) { pieces[np++] = {row1, row1, 0, col1}; last_full = row1 - 1; }
+            if (first_full <= last_full) pieces[np++] = {first_full, last_full, 0, tx};
+        }
+        for (int q = 0; q < np; ++q) {
+            const size_t x0 = (size_t)pieces[q].c0 * RT_TILE_W, y0 = (size_t)pieces[q].r0 * RT_TILE_H;
+            size_t x1 = (size_t)pieces[q].c1 * RT_TILE_W, y1 = (size_t)(pieces[q].r1 + 1) * RT_TILE_H;
+            if (x1 > (size_t)P.W) x1 = (size_t)P.W;
+            if (y1 > (size_t)P.H) y1 = (size_t)P.H;
+            if (x0 >= x1 || y0 >= y1) continue;
+            if (x0 == 0 && x1 == (size_t)P.W) { int rc = copy_rows(y0, y1); if (rc != RT_OK) return rc; continue; }
+            for (const HostOut& o : outs) {
+                if (!o.host) continue;
+                const size_t pitch = (size_t)P.W * o.bpp, off = y0 * pitch + x0 * o.bpp;
+                CU(c, cudaMemcpy2DAsync((char*)o.host + off, pitch, (const char*)o.dev + off, pitch, (x1 - x0) * o.bpp, y1 - y0, cudaMemcpyDeviceToHost, c->copy_stream));
+            }
+        }
+        return RT_OK;
+    };
+    // the same for the rank-local slot range [s0, s1), which must lie inside one ownership chunk
+    auto copy_slots = [&](int s0, int s1) -> int {
+        if (s0 >= s1) return RT_OK;
+        if (P.world <= 1) return copy_tiles(s0, s1);
+        const int j = s0 / P.chunk_tiles;
+        const long long base = ((long long)j * P.world + P.rank) * P.chunk_tiles;
+        return copy_tiles(base + (s0 - j * P.chunk_tiles), base + (s1 - j * P.chunk_tiles));
+    };
+
+    // host-driven band pipeline: wait for band j's flag word (written by the frame kernel into mapped host memory), then enqueue
+    // the band's copies.  Bounded: a kernel that died never writes its flags.
+    auto pump_bands = [&](unsigned seq) -> int {
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int j = 0; j < P.num_chunks; ++j) {
+            volatile unsigned* f = c->hflags + RT_PEER_CHUNK_FLAG(0, j);
+            unsigned spins = 0;
+            while ((int)(*f - seq) < 0) {
+                if ((++spins & 0x3fffu) == 0u) {
+                    const cudaError_t q = cudaStreamQuery(c->stream);
+                    if (q != cudaErrorNotReady && (int)(*f - seq) < 0) {
+                        if (q != cudaSuccess) return fail(c, RT_ERR_CUDA, "rt_render_into: %s", cudaGetErrorString(q));
+                        return fail(c, RT_ERR_STATE, "rt_render_into: the frame kernel finished without publishing band %d", j);
+                    }
+                    if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e9 > (double)c->peer_timeout_ns)
+                        return fail(c, RT_ERR_STATE, "rt_render_into: band %d not finished after %llu s", j, c->peer_timeout_ns / 1000000000ull);
+                }
+            }
+            int rc = copy_slots(j ? P.band_end[j - 1] : 0, P.band_end[j]);
+            if (rc != RT_OK) return rc;
+        }
+        return RT_OK;
+    };
+
     CU(c, cudaEventRecord(c->ev0, c->stream));
     int launches = 0;
-    if (peer) {
+    c->last_host_direct = false;
+    if (host_direct) {
+        int rc = ensure_band_resources(c);
+        if (rc != RT_OK) return rc;
+        if (rc == RT_OK) rc = ensure_host_flags(c);
+        if (rc != RT_OK) return rc;
+        const unsigned seq = ++c->hseq;
+        volatile unsigned* hdr = (volatile unsigned*)c->shm_base;
+        // the caller of rank 0 is done with the previous frame's image once it is back in here: rank 0 says so, the others
+        // wait for it before anything of this frame can land in the shared buffer (host-side handshake through the header)
+        if (c->rank == 0) { __sync_synchronize(); hdr[0] = seq; }
+        else {
+            const auto t0 = std::chrono::steady_clock::now();
+            while ((int)(hdr[0] - seq) < 0) {
+                if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e9 > (double)c->peer_timeout_ns)
+                    return fail(c, RT_ERR_STATE, "rt_render_into: rank %d waited more than %llu s for rank 0 to enter the frame", c->rank, c->peer_timeout_ns / 1000000000ull);
+            }
+        }
+        P.num_chunks = plan_bands(P.local_tiles, P.chunk_tiles, true, P.band_end);
+        P.seq = seq;
+        P.flags = c->hflags_dev + RT_PEER_CHUNK_FLAG(0, 0);
+        int l = 0;
+        CU(c, cudaEventRecord(c->evk0, c->stream));
+        CU(c, rt_launch_render(P, fr->kernel_variant, c->stream, &l));
+        launches += l;
+        if (!persistent) { CU(c, rt_launch_flag_set(P.flags, RT_PEER_FLAG_STRIDE, P.num_chunks, seq, c->stream)); ++launches; }
+        CU(c, cudaEventRecord(c->evk1, c->stream));
+        CU(c, cudaStreamWaitEvent(c->copy_stream, c->evk0, 0));
+        rc = pump_bands(seq);
+        if (rc != RT_OK) return rc;
+        {   // this rank's bands are in the shared buffer: say so in the header (a store to mapped host memory, after the copies in stream order)
+            unsigned* dhdr = nullptr;
+            CU(c, cudaHostGetDevicePointer((void**)&dhdr, c->shm_base, 0));
+            CU(c, rt_launch_flag_set(dhdr + 16 * (1 + c->rank), 1, 1, seq, c->copy_stream));
+            ++launches;
+        }
+        CU(c, cudaEventRecord(c->copy_done, c->copy_stream));
+        CU(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));
+        if (pipelined) *pipelined = true;
+        c->last_host_direct = true;
+    } else if (peer) {
         // Frame k may overwrite rank 0's image only once rank 0 is done with frame k-1 (its downloads are stream-ordered
         // before this point): rank 0 publishes `ready = k`, the others wait for it — inside the persistent kernel.
         const unsigned seq = ++c->seq;
         const int F = c->chunks_per_rank > 0 ? c->chunks_per_rank : RT_DEFAULT_CHUNKS_PER_RANK;
         const bool banded = F <= RT_PEER_MAX_CHUNKS;            // one flag per ownership band, else one per rank
-        P.num_chunks = banded ? F : 1; P.band_tiles = banded ? P.chunk_tiles : P.local_tiles;
+        P.num_chunks = plan_bands(P.local_tiles, banded ? P.chunk_tiles : P.local_tiles, false, P.band_end);   // one flag per ownership band, else one per rank
         P.seq = seq;
         P.flags = c->flags + RT_PEER_CHUNK_FLAG(c->rank, 0);
         const bool root = c->rank == 0;
+        P.peer_stores = root ? 0 : 1;
         if (persistent) {
             if (root) { P.ready_out = c->flags; P.wait_ranks = c->world - 1; P.flags_base = c->flags; }
             else P.ready_in = c->flags;
@@ -825,30 +1041,21 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
             ++launches;
             CU(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));
         }
-    } else if (into && c->world == 1 && !dbg_shard && P.tiles_y >= 2 && persistent && stream_wait_value32()) {
-        // single GPU: one persistent launch; bands of whole tile rows, each published as it completes
+    } else if (into && c->world == 1 && !dbg_shard && P.tiles_y >= 2 && persistent) {
+        // single GPU: one persistent launch; each band is published by the kernel as it completes and copied out by this thread
         int rc = ensure_band_resources(c);
-        if (rc == RT_OK) rc = ensure_flags(c);
+        if (rc == RT_OK) rc = ensure_host_flags(c);
         if (rc != RT_OK) return rc;
-        const unsigned seq = ++c->seq;
-        const int rows_per_band = (P.tiles_y + RT_BANDS - 1) / RT_BANDS;
-        const int B = (P.tiles_y + rows_per_band - 1) / rows_per_band;
-        P.num_chunks = B; P.band_tiles = rows_per_band * P.tiles_x; P.seq = seq;
-        P.flags = c->flags + RT_PEER_CHUNK_FLAG(0, 0);
+        const unsigned seq = ++c->hseq;
+        P.num_chunks = plan_bands(P.local_tiles, (P.local_tiles + 1) / 2, true, P.band_end);     // halves, the second one halved three times: 1/2, 3/4, 7/8, 15/16, 1
+        P.seq = seq;
+        P.flags = c->hflags_dev + RT_PEER_CHUNK_FLAG(0, 0);
         CU(c, cudaEventRecord(c->evk0, c->stream));
         CU(c, rt_launch_render(P, fr->kernel_variant, c->stream, &launches));
         CU(c, cudaEventRecord(c->evk1, c->stream));
         CU(c, cudaStreamWaitEvent(c->copy_stream, c->evk0, 0));
-        StreamWaitValue32Fn wait32 = stream_wait_value32();
-        for (int k = 0; k < B; ++k) {
-            if (wait32((CUstream)c->copy_stream, (CUdeviceptr)(c->flags + RT_PEER_CHUNK_FLAG(0, k)), seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
-                return fail(c, RT_ERR_CUDA, "cuStreamWaitValue32 failed");
-            const size_t y0 = (size_t)k * rows_per_band * RT_TILE_H;
-            size_t y1 = (size_t)(k + 1) * rows_per_band * RT_TILE_H;
-            if (y1 > (size_t)P.H) y1 = (size_t)P.H;
-            rc = copy_rows(y0, y1);
-            if (rc != RT_OK) return rc;
-        }
+        rc = pump_bands(seq);
+        if (rc != RT_OK) return rc;
         CU(c, cudaEventRecord(c->copy_done, c->copy_stream));
         CU(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));
         if (pipelined) *pipelined = true;
@@ -931,7 +1138,7 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
         }
     }
     CU(c, cudaEventRecord(c->ev1, c->stream));
-    c->outputs = outputs;
+    c->outputs = host_direct ? 0u : outputs;          // shared-host frames leave nothing gathered on rank 0's device
     c->launches = launches;
     c->frame_valid = true;
     return RT_OK;
@@ -951,6 +1158,16 @@ int rt_render_into(rt_ctx* c, const rt_frame* fr, rt_image* img) {
     rt_image meta{};                                            // planes are already on their way: fetch counters and times only
     rc = rt_download_image(c, &meta);
     if (rc != RT_OK) return rc;
+    if (c->last_host_direct && c->rank == 0) {                  // shared host image: every rank's bands must have landed
+        volatile unsigned* hdr = (volatile unsigned*)c->shm_base;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int r = 0; r < c->world; ++r)
+            while ((int)(hdr[16 * (1 + r)] - c->hseq) < 0) {
+                if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e9 > (double)c->peer_timeout_ns)
+                    return fail(c, RT_ERR_STATE, "rt_render_into: rank 0 waited more than %llu s for rank %d's bands", c->peer_timeout_ns / 1000000000ull, r);
+            }
+        __sync_synchronize();
+    }
     img->width = meta.width; img->height = meta.height; img->rays_primary = meta.rays_primary; img->rays_shadow = meta.rays_shadow; img->gpu_ms = meta.gpu_ms;
     return RT_OK;
 }

@@ -35,7 +35,7 @@ cudaError_t rt_launch_unpack(const FrameParams& fp, int src_rank, const float* r
 // Completion flags of the peer-store gather (see k_flag_set / k_flag_wait in rt_trace.cu).
 #define RT_PEER_FLAG_STRIDE 16            // one 64-byte line per flag
 #define RT_PEER_MAX_RANKS 8
-#define RT_PEER_MAX_CHUNKS 16            // ownership chunks per rank that rt_render_into can pipeline
+#define RT_PEER_MAX_CHUNKS RT_MAX_BANDS   // bands per rank whose completion is published (rt_params.h)
 // flag block layout (uints, each flag on its own line): [0] ready (rank 0 -> everybody: the previous image has been read),
 // [16 + r*RT_PEER_MAX_CHUNKS + j] band j of rank r done
 #define RT_PEER_CHUNK_FLAG(r, j) ((size_t)(16 + (r) * RT_PEER_MAX_CHUNKS + (j)) * RT_PEER_FLAG_STRIDE)

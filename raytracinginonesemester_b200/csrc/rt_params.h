@@ -10,6 +10,7 @@
 #define RT_TILE_H 8
 #define RT_BLOCK_THREADS (RT_TILE_W * RT_TILE_H)
 #define RT_STACK_DEPTH 32
+#define RT_MAX_BANDS 16              // completion flags per rank and frame
 #define RT_CPU_MAX_DEPTH 16          // RT_MODE_HW2_CPU: deepest mirror recursion kept on the per-thread fold stack
 
 struct FrameParams {
@@ -41,7 +42,10 @@ struct FrameParams {
     int sample_group;               // packet kernel: samples of one pixel traced side by side (power of two dividing spp, <= 32)
     // persistent kernel (rt_trace.cu, k_render_persist): work queue + in-kernel completion protocol
     unsigned* queue;                // PersistCtl, zeroed by the host before the launch
-    int num_chunks, band_tiles;     // the rank's tile slots in num_chunks bands of band_tiles slots whose completion is published (0: none)
+    int num_chunks;                 // the rank's tile slots are cut into num_chunks bands whose completion is published (0: none);
+    int band_end[RT_MAX_BANDS];     // band j = slots [band_end[j-1], band_end[j]) (band_end[-1] = 0): big bands first, small ones last, so that
+                                    // the copy of the last band — the only one that cannot overlap rendering — is short
+    int peer_stores;                // 1: the output planes live in another GPU's memory (fused gather, ranks != 0)
     unsigned seq;                   // frame sequence number written into flag words
     unsigned* flags;                // this rank's band flags: band j -> flags[j * RT_PEER_FLAG_STRIDE] (own memory, or rank 0's over NVLink)
     const unsigned* flags_base;     // rank 0 of the fused gather: the whole flag block (all ranks' band flags), else unused

@@ -725,7 +725,7 @@ k_render_packet(const __grid_constant__ FrameParams P) {
 // pulls 16x8 tiles from the rank's tile queue (one atomicAdd per tile, issued one tile ahead) until it is empty; its
 // four warps take the tile's four 8x4 packets and meet at one barrier per tile.
 // Completion is published by the kernel itself — no flag kernels, no launch gaps: the rank's tile slots are cut into
-// P.num_chunks bands of P.band_tiles slots; a block counts the tiles it finished per band and, when it moves on to
+// P.num_chunks bands (P.band_end); a block counts the tiles it finished per band and, when it moves on to
 // another band (or runs dry), releases them: a block barrier, then one release-ordered atomicAdd on the band's counter
 // by thread 0; the block whose add completes a band writes the band's flag word P.flags[band] = P.seq — in this GPU's
 // memory or, in the fused multi-GPU gather, in rank 0's memory over NVLink, where the pixels went as well.
@@ -757,6 +757,7 @@ static_assert(sizeof(PersistCtl) <= RT_PERSIST_CTL_BYTES, "PersistCtl must fit t
 
 __device__ __forceinline__ unsigned long long rt_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ unsigned rt_atom_add_release_sys(unsigned* p, unsigned v) { unsigned o; asm volatile("atom.add.release.sys.global.u32 %0, [%1], %2;" : "=r"(o) : "l"(p), "r"(v) : "memory"); return o; }
+__device__ __forceinline__ unsigned rt_atom_add_release_gpu(unsigned* p, unsigned v) { unsigned o; asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(o) : "l"(p), "r"(v) : "memory"); return o; }
 __device__ __forceinline__ void rt_store_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 
 template <int MODE, bool STATS, bool FAST, int MINB, bool GROUPED, bool LAZY>
@@ -794,11 +795,11 @@ k_render_persist(const __grid_constant__ FrameParams P) {
     auto release_band = [&]() {
         __syncthreads();                              // every thread's pixel stores happen-before thread 0's release below
         if (threadIdx.x == 0 && s_band_cnt) {
-            const unsigned band = (unsigned)s_band, cnt = s_band_cnt, ntiles = (unsigned)P.local_tiles;
-            const unsigned first = band * (unsigned)P.band_tiles;
-            unsigned n = ntiles > first ? ntiles - first : 0u;
-            if (n > (unsigned)P.band_tiles) n = (unsigned)P.band_tiles;
-            const unsigned old = rt_atom_add_release_sys(&ctl->chunk_done[band], cnt);
+            const unsigned band = (unsigned)s_band, cnt = s_band_cnt;
+            const unsigned n = (unsigned)(P.band_end[band] - (band ? P.band_end[band - 1] : 0));
+            // pixels in this GPU's own memory: the per-block release only has to reach L2 (the completing block's st.release.sys below
+            // is cumulative); pixels stored into another GPU's memory over NVLink: every block releases at system scope
+            const unsigned old = P.peer_stores ? rt_atom_add_release_sys(&ctl->chunk_done[band], cnt) : rt_atom_add_release_gpu(&ctl->chunk_done[band], cnt);
             if (old + cnt == n) rt_store_release_sys(P.flags + (size_t)band * RT_PEER_FLAG_STRIDE, P.seq);
             s_band_cnt = 0u;
         }
@@ -810,7 +811,8 @@ k_render_persist(const __grid_constant__ FrameParams P) {
         if (tile >= (unsigned)P.local_tiles) break;
         if (threadIdx.x == 0) s_tile[(it + 1u) & 1u] = atomicAdd(&ctl->next_tile, 1u);      // one tile ahead: the atomic's latency is off the critical path
         if (P.num_chunks > 0) {
-            const int b = (int)(tile / (unsigned)P.band_tiles);
+            int b = 0;
+            while (b + 1 < P.num_chunks && tile >= (unsigned)P.band_end[b]) ++b;      // <= 16 uniform compares
             if (b != *(volatile int*)&s_band) {       // block-uniform
                 if (*(volatile int*)&s_band >= 0) release_band();
                 __syncthreads();

@@ -69,6 +69,35 @@ def main():
                     if k in ref and not np.array_equal(got[k], ref[k]):
                         print("MISMATCH render_into", gm, cpr, W, H, k, int((got[k] != ref[k]).sum()))
                         ok = False
+    # shared host image: every rank copies its own bands to one host buffer (rt_host_image_create + rt_render_into on every rank)
+    for cpr, (W, H), outs in ((0, (517, 301), ALL), (3, (640, 360), A.RT_OUT_RGB8), (16, (333, 201), ALL), (1, (40, 9), ALL), (0, (1920, 1080), A.RT_OUT_RGB8)):
+        r.set_sharding(cpr)
+        r.set_gather(A.RT_GATHER_AUTO)
+        fr = scenes.terrain_frame(W, H, outputs=outs)
+        n = W * H
+        buf = r.host_image(23 * n + 64)
+        into, off = {}, 0
+        for name, bit, bpp, dt, shape in (("rgb", A.RT_OUT_RGB_F32, 12, np.float32, (H, W, 3)), ("tri_id", A.RT_OUT_TRI_ID, 4, np.int32, (H, W)),
+                                          ("t", A.RT_OUT_T, 4, np.float32, (H, W)), ("rgb8", A.RT_OUT_RGB8, 3, np.uint8, (H, W, 3))):
+            if outs & bit:
+                into[name] = buf[off:off + bpp * n].view(dt).reshape(shape)
+                off += bpp * n
+        for rep in range(3):
+            if rank == 0:
+                for a in into.values():
+                    a[...] = 0
+            dist.barrier()
+            got = r.render_into(fr, into=into)
+        if rank == 0:
+            solo = api.Renderer(local_rank)
+            solo.upload_scene(sc)
+            ref = solo.render_into(fr)
+            solo.close()
+            for k in into:
+                if not np.array_equal(into[k], ref[k]):
+                    print("MISMATCH shared host image", cpr, W, H, k, int((into[k] != ref[k]).sum()))
+                    ok = False
+        dist.barrier()
     # back-to-back frames without a download in between (what bench.py's timed loop does), then one download
     r.set_sharding(0)
     r.set_gather(A.RT_GATHER_AUTO)

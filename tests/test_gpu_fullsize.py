@@ -34,7 +34,7 @@ def quantise(rgb, q):
     return np.fromiter((lib.orc_quantise(float(c), q) for c in flat), np.uint8, flat.size).reshape(rgb.shape)
 
 
-def bar(got, ref, rows, what, quant):
+def bar(got, ref, rows, what, quant, spp=1):
     """got: device planes (full frame); ref: reference planes (valid on `rows`)."""
     gid, rid = got["tri_id"][rows], ref["tri_id"][rows]
     gt, rt = got["t"][rows], ref["t"][rows]
@@ -56,7 +56,13 @@ def bar(got, ref, rows, what, quant):
         r8 = np.floor(np.clip(ref["rgb"][rows].astype(np.float64), 0.0, 1.0) * 255.0 + 0.5).astype(np.int32)
         d = np.abs(got["rgb8"][rows].astype(np.int32) - r8)
         ok = ~mism
-        assert d[ok].max() <= 1, "%s: 8-bit image differs by %d LSB" % (what, d[ok].max())
+        if spp == 1:
+            assert d[ok].max() <= 1, "%s: 8-bit image differs by %d LSB" % (what, d[ok].max())
+        else:
+            # the id plane describes sample 0 only; any of the spp samples of a pixel can be an epsilon tie (a different facet, a
+            # different colour for that sample).  The id budget of 1e-4 per sample therefore allows spp x 1e-4 of the pixels here.
+            far = (d > 1).any(-1) & ok
+            assert far.sum() <= spp * 1e-4 * n, "%s: %d pixels differ by more than 1 LSB" % (what, far.sum())
         return int(mism.sum()), int((rid < 0).sum()), float((d[ok] != 0).mean())
     return int(mism.sum()), int((rid < 0).sum()), None
 
@@ -94,7 +100,7 @@ def test_c5_real_frame_strided_rows_against_the_reference(renderer):
         assert np.array_equal(got[k], again[k]), k
     step, first = 270, 11                               # 16 rows x 7680 px x 16 spp = 2.0 M reference rays
     ref, kind = orclib.reference_render(sc, scenes.terrain_frame(W, H, spp=spp, outputs=ALL), row_begin=first, row_step=step)
-    mism, cracks, frac8 = bar(got, ref, slice(first, H, step), "c5 real frame vs %s" % kind, fr.quantiser)
+    mism, cracks, frac8 = bar(got, ref, slice(first, H, step), "c5 real frame vs %s" % kind, fr.quantiser, spp=spp)
     print("c5 8K x 16 spp, rows %d::%d vs %s: %d id mismatches, %d miss pixels, %.4f %% of channels off by 1 LSB" % (first, step, kind, mism, cracks, 100.0 * (frac8 or 0.0)))
 
 
