@@ -173,6 +173,17 @@ typedef struct rt_frame {
     int32_t         kernel_variant;/* 0 = default; >0 selects an experimental traversal kernel */
     int32_t         diffuse_bounce;/* max_depth > 1: settings.diffuse_bounce (query.h:193-209): 1 = pick a diffuse or
                                       a mirror bounce with the per-pixel hash RNG, 0 = mirror bounces only */
+    /* RT_MODE_HW2_CPU only — soft shadows of the CPUOnly renderer (CPUOnly/include/raytracer.h:37-46, 121-168): light i is a
+     * disk of radius light_radius[i] facing the shaded point, sampled light_shadow_samples[i] times per lit hit
+     * (random_in_unit_disk, make_basis); visibility = unoccluded / samples scales the light's contribution.  NULL arrays or a
+     * radius of 0 = point light, one shadow ray (the reference's own rule, :128-130).  The reference draws its samples from a
+     * process-wide std::mt19937 seeded by std::random_device, in pixel order on one thread, so no two of its runs agree; here the
+     * samples come from the reference's OTHER generator, the per-pixel hash RNG of GPUandCPU/include/query.h:32-48, seeded with
+     * (x, y, sample) and rng_seed: frames are reproducible and equal the oracle's bit for bit; against the reference the parity is
+     * statistical (tests: per-pixel mean and spread of 64 reference runs). */
+    const float*    light_radius;          /* [num_lights] or NULL */
+    const int32_t*  light_shadow_samples;  /* [num_lights] or NULL (= 1) */
+    uint32_t        rng_seed;
 } rt_frame;
 
 typedef struct rt_image {

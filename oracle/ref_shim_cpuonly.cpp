@@ -115,6 +115,55 @@ void ref_cpu_render_rows(const float* pos, const float* nrm, uint64_t nv, const 
         }
 }
 
+// Soft shadows (Light::radius / shadow_samples, raytracer.h:37-46,121-168): the same pixel loop run `runs` times with the
+// reference's own random_float() (std::mt19937 seeded by std::random_device, :12-16 — every run differs); per pixel and
+// channel the mean and the mean square of the `runs` colours.  Single-threaded: the generator is a function-local static.
+void ref_cpu_render_area_stats(const float* pos, const float* nrm, uint64_t nv, const uint32_t* idx, uint64_t nt, const int32_t* obj_ids,
+                               const void* materials52, int num_materials, const float* cpos, const float* look, const float* up,
+                               double focal_mm, double sensor_h_mm, double sensor_w_mm, int W, int H, const ref_cpu_light* lights_in,
+                               const float* radius, const int* shadow_samples, int num_lights, int max_bounces, int runs,
+                               double* mean, double* meansq)
+{
+    (void)nv;
+    const Vec3* P = (const Vec3*)pos; const Vec3* N = (const Vec3*)nrm;
+    const Material* mats = (const Material*)materials52;
+    std::vector<Triangle> tris;
+    tris.reserve(nt);
+    for (uint64_t k = 0; k < nt; ++k) {
+        Triangle tri;
+        const int o = obj_ids ? obj_ids[k] : 0;
+        tri.mat = (o >= 0 && o < num_materials) ? mats[o] : Material{};
+        tri.v0 = P[idx[3 * k]]; tri.v1 = P[idx[3 * k + 1]]; tri.v2 = P[idx[3 * k + 2]];
+        if (N) { tri.n0 = N[idx[3 * k]]; tri.n1 = N[idx[3 * k + 1]]; tri.n2 = N[idx[3 * k + 2]]; }
+        else { Vec3 faceN = unit_vector(cross(tri.v1 - tri.v0, tri.v2 - tri.v0)); tri.n0 = tri.n1 = tri.n2 = faceN; }
+        tris.push_back(tri);
+    }
+    std::vector<Light> lights;
+    for (int i = 0; i < num_lights; ++i) {
+        Light L;
+        L.position = make_vec3(lights_in[i].position[0], lights_in[i].position[1], lights_in[i].position[2]);
+        L.color = make_vec3(lights_in[i].color[0], lights_in[i].color[1], lights_in[i].color[2]);
+        L.intensity = lights_in[i].intensity; L.radius = radius[i]; L.shadow_samples = shadow_samples[i];
+        lights.push_back(L);
+    }
+    camera cam(make_vec3(cpos[0], cpos[1], cpos[2]), make_vec3(look[0], look[1], look[2]), make_vec3(up[0], up[1], up[2]),
+               focal_mm, sensor_h_mm, sensor_w_mm, W, H);
+    const Vec3 center = cam.get_center();
+    const int maxDepth = std::max(1, max_bounces);
+    for (size_t k = 0; k < (size_t)3 * W * H; ++k) { mean[k] = 0.0; meansq[k] = 0.0; }
+    for (int run = 0; run < runs; ++run)
+        for (int j = 0; j < H; ++j)
+            for (int i = 0; i < W; ++i) {
+                Vec3 target = cam.get_pixel_position(static_cast<double>(i) + 0.5, static_cast<double>(j) + 0.5);
+                Ray r(center, target - center);
+                const Vec3 c = make_vec3(0, 0, 0) + TraceRay(r, tris, lights, maxDepth, false);
+                const size_t pix = 3 * ((size_t)j * W + i);
+                mean[pix] += c.x; mean[pix + 1] += c.y; mean[pix + 2] += c.z;
+                meansq[pix] += (double)c.x * c.x; meansq[pix + 1] += (double)c.y * c.y; meansq[pix + 2] += (double)c.z * c.z;
+            }
+    for (size_t k = 0; k < (size_t)3 * W * H; ++k) { mean[k] /= runs; meansq[k] /= runs; }
+}
+
 // The 8-bit conversion of render.cpp:157-163: clamp to [0,1], (uchar)(255.99f*c).
 void ref_cpu_quantise(const float* rgb, uint64_t n, uint8_t* out) {
     for (uint64_t k = 0; k < n; ++k) {

@@ -62,7 +62,8 @@ class rt_frame(C.Structure):
                 ("cam", rt_camera), ("lights", C.POINTER(rt_light)), ("num_lights", C.c_int32),
                 ("miss_color", C.c_float * 3), ("spp", C.c_int32), ("jitter", f32p),
                 ("max_depth", C.c_int32), ("shadows", C.c_int32), ("outputs", C.c_uint32),
-                ("quantiser", C.c_int32), ("kernel_variant", C.c_int32), ("diffuse_bounce", C.c_int32)]
+                ("quantiser", C.c_int32), ("kernel_variant", C.c_int32), ("diffuse_bounce", C.c_int32),
+                ("light_radius", f32p), ("light_shadow_samples", i32p), ("rng_seed", C.c_uint32)]
 
 
 class rt_image(C.Structure):

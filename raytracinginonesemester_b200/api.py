@@ -189,8 +189,12 @@ class Frame:
 
     def __init__(self, cam, width, height, mode=A.RT_MODE_HW2_BVH, accel=A.RT_ACCEL_BVH, lights=(), miss_color=(0, 0, 0),
                  spp=1, jitter=None, max_depth=1, shadows=True, outputs=A.RT_OUT_RGB_F32, quantiser=A.RT_QUANT_PPM_LROUND,
-                 kernel_variant=0, diffuse_bounce=False):
+                 kernel_variant=0, diffuse_bounce=False, light_radius=None, light_shadow_samples=None, rng_seed=0):
         self.diffuse_bounce = bool(diffuse_bounce)
+        # RT_MODE_HW2_CPU soft shadows (CPUOnly/include/raytracer.h:37-46): per-light disk radius and shadow sample count
+        self.light_radius = _f32(light_radius) if light_radius is not None else None
+        self.light_shadow_samples = np.ascontiguousarray(light_shadow_samples, dtype=np.int32) if light_shadow_samples is not None else None
+        self.rng_seed = int(rng_seed)
         self.cam, self.width, self.height, self.mode, self.accel = cam, int(width), int(height), mode, accel
         self.lights = list(lights)
         self._light_arr = (A.rt_light * max(1, len(self.lights)))(*self.lights)
@@ -212,6 +216,9 @@ class Frame:
         f.max_depth, f.shadows, f.outputs, f.quantiser = self.max_depth, int(self.shadows), self.outputs, self.quantiser
         f.kernel_variant = self.kernel_variant
         f.diffuse_bounce = int(self.diffuse_bounce)
+        f.light_radius = _ptr(self.light_radius, A.f32p)
+        f.light_shadow_samples = _ptr(self.light_shadow_samples, A.i32p)
+        f.rng_seed = self.rng_seed & 0xFFFFFFFF
         return f
 
 

@@ -752,6 +752,14 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
     if (fr->num_lights < 0 || (fr->num_lights > 0 && !fr->lights)) return fail(c, RT_ERR_ARG, "rt_render: lights");
     if (fr->mode == RT_MODE_HW1 && fr->num_lights < 1) return fail(c, RT_ERR_ARG, "rt_render: HW1 mode needs one light");
     if (fr->quantiser < RT_QUANT_PPM_LROUND || fr->quantiser > RT_QUANT_CPU_TRUNC) return fail(c, RT_ERR_ARG, "rt_render: quantiser");
+    if (fr->light_radius) {
+        for (int i = 0; i < fr->num_lights; ++i) {
+            if (!(fr->light_radius[i] >= 0.0f)) return fail(c, RT_ERR_ARG, "rt_render: light_radius[%d] must be >= 0", i);
+            if (fr->light_radius[i] > 0.0f && fr->mode != RT_MODE_HW2_CPU)
+                return fail(c, RT_ERR_ARG, "rt_render: disk lights (light_radius > 0) belong to RT_MODE_HW2_CPU (the CPUOnly renderer's ShadowVisibility)");
+            if (fr->light_shadow_samples && fr->light_shadow_samples[i] > 4096) return fail(c, RT_ERR_ARG, "rt_render: light_shadow_samples[%d] > 4096", i);
+        }
+    }
     const uint32_t outputs = fr->outputs ? fr->outputs : RT_OUT_RGB_F32;
     if (into) {   // checked before any device work or collective step, so that an error leaves every rank in the same state
         const HostOut chk[4] = {{into->rgb, RT_OUT_RGB_F32, 12, nullptr, "rgb"}, {into->rgb8, RT_OUT_RGB8, 3, nullptr, "rgb8"},
@@ -831,9 +839,21 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
     }
 
     if (fr->num_lights) {
-        CU(c, c->lights.reserve(sizeof(rt_light) * (size_t)fr->num_lights));
-        CU(c, cudaMemcpyAsync(c->lights.p, fr->lights, sizeof(rt_light) * (size_t)fr->num_lights, cudaMemcpyHostToDevice, c->stream));
+        const size_t nl = (size_t)fr->num_lights, lbytes = (sizeof(rt_light) * nl + 15) & ~(size_t)15;
+        CU(c, c->lights.reserve(lbytes + 8 * nl));              // lights, then (soft shadows) radii and sample counts
+        CU(c, cudaMemcpyAsync(c->lights.p, fr->lights, sizeof(rt_light) * nl, cudaMemcpyHostToDevice, c->stream));
+        if (fr->light_radius && fr->mode == RT_MODE_HW2_CPU) {
+            float* d_rad = (float*)((char*)c->lights.p + lbytes);
+            CU(c, cudaMemcpyAsync(d_rad, fr->light_radius, 4 * nl, cudaMemcpyHostToDevice, c->stream));
+            P.light_radius = d_rad;
+            if (fr->light_shadow_samples) {
+                int* d_ns = (int*)(d_rad + nl);
+                CU(c, cudaMemcpyAsync(d_ns, fr->light_shadow_samples, 4 * nl, cudaMemcpyHostToDevice, c->stream));
+                P.light_samples = d_ns;
+            }
+        }
     }
+    P.rng_seed = fr->rng_seed;
     P.lights = (const rt_light*)c->lights.p;
     if (fr->jitter) {
         CU(c, c->jitter.reserve(sizeof(float) * 2 * (size_t)fr->spp));

@@ -26,6 +26,9 @@ struct FrameParams {
     const rt_material* materials;   // may be NULL
     const rt_light* lights;
     const float* jitter;            // [2*spp] or NULL
+    const float* light_radius;      // RT_MODE_HW2_CPU soft shadows: [num_lights] disk radii or NULL (point lights)
+    const int* light_samples;       // ... [num_lights] shadow samples per lit hit or NULL (1)
+    uint32_t rng_seed;              // ... mixed into the per-pixel hash RNG seed
     // tile sharding
     int tiles_x, tiles_y, rank, world;
     int local_tiles;                // tile slots of this rank (= grid size)

@@ -276,8 +276,18 @@ RT_HD bool rt_bounce_hw2(const FrameParams& P, const Surface& sf, Ray& ray, f3& 
 // (ShadeDirect :171-211, one shadow ray per lit hit, ShadowVisibility :121-168 with S == 1) plus perfect-mirror
 // recursion.  The recursion `Lo + kr * (tint * TraceRay(...))` is evaluated innermost-first like the reference: the
 // walk down records (Lo, kr, tint) per level, the fold runs back up.  Sky gradient on a miss (:224-230).
+// random_in_unit_disk, CPUOnly/include/raytracer.h:76-85, drawing from the hash RNG (see rt_frame.rng_seed)
+RT_HD void rt_random_in_unit_disk(uint32_t& state, float& dx, float& dy) {
+    for (;;) {
+        const float x = XSUB(XMUL(2.0f, rt_rng_next(state)), 1.0f);
+        const float y = XSUB(XMUL(2.0f, rt_rng_next(state)), 1.0f);
+        const float r2 = XADD(XMUL(x, x), XMUL(y, y));
+        if (r2 > 1e-10f && r2 <= 1.0f) { dx = x; dy = y; return; }
+    }
+}
+
 template <int STRIDE, bool STATS>
-RT_HD f3 rt_sample_cpuonly(const FrameParams& P, const Ray& primary, uint32_t* stk, Hit& first,
+RT_HD f3 rt_sample_cpuonly(const FrameParams& P, const Ray& primary, uint32_t rng, uint32_t* stk, Hit& first,
                            unsigned& nprim, unsigned& nshadow, TraceStats* st) {
     const float EPS = 1e-4f;                                           // RT_EPS, raytracer.h:49
     f3 lvl_Lo[RT_CPU_MAX_DEPTH], lvl_tint[RT_CPU_MAX_DEPTH];
@@ -318,19 +328,47 @@ RT_HD f3 rt_sample_cpuonly(const FrameParams& P, const Ray& primary, uint32_t* s
             const f3 L = xdivs(toL, dist);
             const float NdotL = fmaxf(xdot(N, L), 0.0f);
             if (NdotL <= 0.0f) continue;
+            float vis = 1.0f;
             if (P.shadows) {
-                Ray sray;
-                sray.o = xadd3(p, xmuls(N, EPS));
-                sray.d = xunit_c(L);                                   // the Ray constructor normalises again
-                // blocked iff some triangle has 1e-4 <= t and double(t) < double(dist) - double(1e-4f): as a float
-                // threshold, t < the smallest float >= that double
-                const float thr = RT_D2F_UP((double)dist - (double)EPS);
-                ++nshadow;
-                if (rt_trace_any<RT_MODE_HW2_CPU, STRIDE, STATS>(P, sray, thr, stk, st)) continue;
+                // ShadowVisibility, raytracer.h:121-168: S samples of a disk of `radius` at the light, facing the shaded point
+                // (radius 0: the light itself, once).  distC == dist > 0 here.
+                const float radius = P.light_radius ? P.light_radius[l] : 0.0f;
+                int S = (radius > 0.0f && P.light_samples) ? P.light_samples[l] : 1;
+                if (S < 1) S = 1;
+                const f3 lpos = ld3(light.position);
+                f3 T = mk3(0.f, 0.f, 0.f), B = T;
+                if (radius > 0.0f) {                                   // make_basis(W, T, B), :88-93
+                    const f3 Wd = xdivs(xsub3(p, lpos), dist);
+                    const f3 a = fabsf(Wd.x) > 0.9f ? mk3(0.f, 1.f, 0.f) : mk3(1.f, 0.f, 0.f);
+                    T = xunit_c(xcross(a, Wd));
+                    B = xcross(Wd, T);
+                }
+                float unoccluded = 0.0f;
+                for (int i = 0; i < S; ++i) {
+                    f3 lightPos = lpos;
+                    if (radius > 0.0f) {
+                        float dx, dy;
+                        rt_random_in_unit_disk(rng, dx, dy);
+                        lightPos = xadd3(xadd3(lpos, xmuls(T, XMUL(dx, radius))), xmuls(B, XMUL(dy, radius)));
+                    }
+                    const f3 toS = xsub3(lightPos, p);
+                    const float distToL = xlen3(toS);
+                    if (distToL <= 0.0f) { unoccluded = XADD(unoccluded, 1.0f); continue; }
+                    Ray sray;
+                    sray.o = xadd3(p, xmuls(N, EPS));
+                    sray.d = xunit_c(xdivs(toS, distToL));             // Ldir, and the Ray constructor normalises again
+                    // blocked iff some triangle has 1e-4 <= t and double(t) < double(dist) - double(1e-4f): as a float
+                    // threshold, t < the smallest float >= that double
+                    const float thr = RT_D2F_UP((double)distToL - (double)EPS);
+                    ++nshadow;
+                    if (!rt_trace_any<RT_MODE_HW2_CPU, STRIDE, STATS>(P, sray, thr, stk, st)) unoccluded = XADD(unoccluded, 1.0f);
+                }
+                vis = XDIV(unoccluded, (float)S);
             }
+            if (vis <= 0.0f) continue;
             const f3 f = rt_brdf_cpu(mat, N, V, L);
             const f3 radiance = xmuls(ld3(light.color), light.intensity_f);
-            Lo = xadd3(Lo, xmuls(xmulv(radiance, f), XMUL(NdotL, 1.0f)));
+            Lo = xadd3(Lo, xmuls(xmulv(radiance, f), XMUL(NdotL, vis)));
         }
         lvl_Lo[n] = Lo; lvl_kr[n] = 0.0f; lvl_tint[n] = mk3(0.f, 0.f, 0.f);
         const bool bounce = XADD(mat.kd, mat.kr) > 0.0f && mat.kr > 0.0f;
@@ -363,7 +401,7 @@ RT_HD f3 rt_sample_bvh(const FrameParams& P, int x, int y, int s, uint32_t* stk,
         rt_hit_reset(h);
         return mk3(0.f, 0.f, 0.f);
     }
-    if (MODE == RT_MODE_HW2_CPU) return rt_sample_cpuonly<STRIDE, STATS>(P, ray, stk, h, nprim, nshadow, st);
+    if (MODE == RT_MODE_HW2_CPU) return rt_sample_cpuonly<STRIDE, STATS>(P, ray, rt_rng_seed(x, y, s) ^ P.rng_seed, stk, h, nprim, nshadow, st);
     rt_trace_closest<MODE, STRIDE, STATS>(P, ray, stk, h, st);
     ++nprim;
     if (MODE == RT_MODE_HW1) return rt_shade_hw1(P, ray, h);

@@ -135,3 +135,18 @@ def cpuonly_case(g, name, width=None, height=None, outputs=A.RT_OUT_RGB_F32, acc
     fr = Frame(cam, W, H, mode=A.RT_MODE_HW2_CPU, accel=accel, lights=[make_light_f(li[0:3], li[3:6], li[6])], spp=1,
                jitter=np.array([[0.5, 0.5]], np.float32), max_depth=depth, shadows=True, outputs=outputs, quantiser=A.RT_QUANT_CPU_TRUNC)
     return sc, fr
+
+
+def cpuonly_area_case(g, outputs=A.RT_OUT_RGB_F32, rng_seed=0, accel=A.RT_ACCEL_BVH):
+    """Scene + frame of the soft-shadow fixture (tests/golden/cpuonly_area.npz, tools/make_golden_area.py): the reference's
+    config/sphere_area.json — one disk light (radius, shadow_samples), RT_MODE_HW2_CPU, one sample at the pixel centre."""
+    mats = [make_material(albedo=m[0:3], kd=m[3], specular_color=m[4:7], ks=m[7], shininess=m[8], kr=m[9], emission=m[10:13]) for m in g["materials"]]
+    nrm = g["normals"]
+    sc = Scene(g["positions"], g["indices"], normals=nrm if nrm.size else None, tri_obj_ids=g["tri_obj_ids"], materials=mats)
+    c, li = g["camera"], g["light"]
+    W, H, depth = (int(v) for v in g["frame"][:3])
+    cam = camera_init_cpuonly(c[0:3], c[3:6], c[6:9], c[9], c[10], c[11], W, H)
+    fr = Frame(cam, W, H, mode=A.RT_MODE_HW2_CPU, accel=accel, lights=[make_light_f(li[0:3], li[3:6], li[6])], spp=1,
+               jitter=np.array([[0.5, 0.5]], np.float32), max_depth=depth, shadows=True, outputs=outputs, quantiser=A.RT_QUANT_CPU_TRUNC,
+               light_radius=[li[7]], light_shadow_samples=[int(li[8])], rng_seed=rng_seed)
+    return sc, fr

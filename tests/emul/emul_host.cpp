@@ -195,6 +195,8 @@ int emu_render_rank(void* h, const rt_frame* fr, rt_image* img, uint64_t* stats,
     P.nodes = es->nodes.data(); P.geom = es->geom.data(); P.shade = es->shade.data(); P.num_tris = es->num_tris;
     P.materials = es->materials.empty() ? nullptr : es->materials.data();
     P.lights = fr->lights; P.jitter = fr->jitter;
+    if (fr->mode == RT_MODE_HW2_CPU) { P.light_radius = fr->light_radius; P.light_samples = fr->light_shadow_samples; }
+    P.rng_seed = fr->rng_seed;
     P.tiles_x = (P.W + RT_TILE_W - 1) / RT_TILE_W; P.tiles_y = (P.H + RT_TILE_H - 1) / RT_TILE_H;
     P.rank = rank; P.world = world; P.packed = world > 1 ? 1 : 0;
     P.chunk_tiles = rt_chunk_tiles(P.tiles_x * P.tiles_y, world, chunks_per_rank);
