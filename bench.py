@@ -32,7 +32,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = ("c4", "c5", "c3", "c3fill", "c2", "c4small")
+WORKLOADS = ("c4", "c5", "c3", "c3fill", "c2", "c4small", "c3bounce", "c3fillbounce", "n1sphere")
 FROG = os.path.join(ROOT, "tests", "golden", "frog_mesh.npz")
 
 
@@ -48,6 +48,12 @@ def make_workload(name, leaf_max=2, variant=0, shadows=True):
         frame = scenes.terrain_frame(W, H, spp=spp, outputs=A.RT_OUT_RGB8, kernel_variant=variant, shadows=shadows)
         return dict(name=name, scene=scene, frame=frame, triangles=nx * ny * 2, mode="hw2",
                     desc="synthetic terrain(%d,%d,seed 42), HW2 shading, primary + shadow rays, BVH" % (nx, ny))
+    if name == "n1sphere":     # CPUOnly/config/sphere.json as shipped (4 802 triangles, mirror spheres, max_bounces 4) at its own 360x240
+        g = np.load(os.path.join(ROOT, "tests", "golden", "cpuonly_scenes.npz"))
+        sc, fr = scenes.cpuonly_case(g, "sphere", width=360, height=240, outputs=A.RT_OUT_RGB8)
+        fr.kernel_variant = variant
+        return dict(name=name, scene=lambda: sc, frame=fr, triangles=int(sc.indices.shape[0]), mode="cpuonly", fixture=("sphere", g),
+                    desc="HW2/CPUOnly config/sphere.json (mirror recursion depth 4, hard shadows), 360x240, RT_MODE_HW2_CPU over the BVH")
     d = np.load(FROG)
 
     def frog(extra=0):
@@ -58,6 +64,11 @@ def make_workload(name, leaf_max=2, variant=0, shadows=True):
         frame = scenes.hw1_frame(1920, 1080, accel=A.RT_ACCEL_BRUTE, outputs=A.RT_OUT_RGB8)
         return dict(name=name, scene=lambda: frog(A.RT_BUILD_NO_BVH), frame=frame, triangles=ntri, mode="hw1",
                     desc="HW1 frog.obj (19 858 triangles), 1920x1080, brute-force ray-triangle, HW1 shade()")
+    if name in ("c3bounce", "c3fillbounce"):   # assets/json_files/frog.json AS SHIPPED: max_bounces 8, diffuse_bounce defaults to true (scene.h:18), 1920x1080
+        frame = scenes.frog_frame(1920, 1080, filling=name == "c3fillbounce", outputs=A.RT_OUT_RGB8, shadows=shadows, quantiser=A.RT_QUANT_PPM_LROUND)
+        frame.max_depth, frame.diffuse_bounce, frame.kernel_variant = 8, True, variant
+        return dict(name=name, scene=frog, frame=frame, triangles=ntri, mode="hw2",
+                    desc="HW2-BVH frog.json as shipped (max_bounces 8, hash-RNG diffuse bounces) at 1920x1080, %s" % ("frame-filling view" if name == "c3fillbounce" else "stock view"))
     filling = name == "c3fill"
     frame = scenes.frog_frame(3840, 2160, filling=filling, outputs=A.RT_OUT_RGB8, shadows=shadows, quantiser=A.RT_QUANT_PPM_LROUND)
     frame.kernel_variant = variant
@@ -156,6 +167,11 @@ def reference_lib():
     return None
 
 
+def cpuonly_lib():
+    p = os.path.join(ROOT, "oracle", "_ref", "libref_cpuonly.so")
+    return C.CDLL(p) if os.path.exists(p) else None
+
+
 def hw1_lib():
     p = os.path.join(ROOT, "oracle", "_ref", "libref_hw1.so")
     if os.path.exists(p):
@@ -176,11 +192,12 @@ class CpuReference:
         self.scene, self.frame = wl["scene"](), wl["frame"]
         self.cores = os.cpu_count() or 1
         self.hw1 = wl["mode"] == "hw1"
-        self.lib = hw1_lib() if self.hw1 else reference_lib()
+        self.cpuonly = wl["mode"] == "cpuonly"
+        self.lib = hw1_lib() if self.hw1 else cpuonly_lib() if self.cpuonly else reference_lib()
         self.kind = "reference" if self.lib else "port"
         scene = self.scene
         t0 = time.perf_counter()
-        if self.hw1:
+        if self.hw1 or self.cpuonly:
             self.h = None
         elif self.lib:
             f32p, u32p, i32p = A.f32p, A.u32p, A.i32p
@@ -193,13 +210,13 @@ class CpuReference:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import orclib
             self.orclib = orclib
-            self.h = None if self.hw1 else orclib.oracle_bvh(scene)
+            self.h = None if (self.hw1 or self.cpuonly) else orclib.oracle_bvh(scene)
         self.build_s = time.perf_counter() - t0
 
     def census(self, row_begin, row_step):
         """(primary, shadow) rays of a row-strided pass, counted by the reference shim itself (ref_hw2_count_rays_rows:
         the reference's SearchBVH + the two conditions that gate IsInShadow); None when only the port is available."""
-        if not self.lib or self.hw1:
+        if not self.lib or self.hw1 or self.cpuonly or self.frame.max_depth > 1:
             return None
         fr, A = self.frame, self.A
         cp = fr.cam.params
@@ -221,7 +238,29 @@ class CpuReference:
         f3 = lambda v: np.array(v, np.float32)
         cpos, look, up = f3(cp["pos"]), f3(cp["look_at"]), f3(cp["up"])
         t0 = time.perf_counter()
-        if self.lib and self.hw1:
+        if self.lib and self.cpuonly:
+            # the CPUOnly renderer's pixel loop (brute force over all triangles, as the reference runs it), rows interleaved over host threads
+            name, g = self.wl["fixture"]
+            c, li = g[name + "_camera"], g[name + "_light"]
+
+            class L(C.Structure):
+                _fields_ = [("position", C.c_float * 3), ("color", C.c_float * 3), ("intensity", C.c_float)]
+            l = L(); l.position[:] = [float(v) for v in li[0:3]]; l.color[:] = [float(v) for v in li[3:6]]; l.intensity = float(li[6])
+            marr = (A.rt_material * len(scene.materials))(*scene.materials)
+            rgb = np.zeros((H, W, 3), np.float32)
+            cposf, lookf, upf = f3(c[0:3]), f3(c[3:6]), f3(c[6:9])
+            rows_all = list(range(row_begin, H, row_step))
+
+            def work(t):
+                for y in rows_all[t::self.cores]:
+                    self.lib.ref_cpu_render_rows(scene.positions.ctypes.data_as(A.f32p), scene.normals.ctypes.data_as(A.f32p) if scene.normals is not None else None,
+                                                 C.c_uint64(scene.positions.shape[0]), scene.indices.ctypes.data_as(A.u32p), C.c_uint64(scene.indices.shape[0]),
+                                                 scene.tri_obj_ids.ctypes.data_as(A.i32p), marr, len(scene.materials), cposf.ctypes.data_as(A.f32p), lookf.ctypes.data_as(A.f32p),
+                                                 upf.ctypes.data_as(A.f32p), C.c_double(float(c[9])), C.c_double(float(c[10])), C.c_double(float(c[11])), W, H, C.byref(l), 1,
+                                                 int(fr.max_depth), y, H, rgb.ctypes.data_as(A.f32p), None, None)
+            th = [threading.Thread(target=work, args=(t,)) for t in range(self.cores)]
+            [t.start() for t in th]; [t.join() for t in th]
+        elif self.lib and self.hw1:
             l = fr.lights[0]
             lp, lc = f3(list(l.position)), f3(list(l.color))
             rgb8 = np.zeros((H, W, 3), np.uint8)
@@ -237,8 +276,8 @@ class CpuReference:
             marr = (A.rt_material * len(scene.materials))(*scene.materials)
             larr = (A.rt_light * len(fr.lights))(*fr.lights)
             self.lib.ref_hw2_render_rows(C.c_void_p(self.h), cpos.ctypes.data_as(A.f32p), look.ctypes.data_as(A.f32p), up.ctypes.data_as(A.f32p),
-                                         C.c_double(cp["focal_mm"]), C.c_double(cp["sensor_mm"]), W, H, ms.ctypes.data_as(A.f32p), 1, fr.spp,
-                                         marr, len(scene.materials), larr, len(fr.lights), 1, row_begin, row_step, self.cores,
+                                         C.c_double(cp["focal_mm"]), C.c_double(cp["sensor_mm"]), W, H, ms.ctypes.data_as(A.f32p), int(fr.max_depth), fr.spp,
+                                         marr, len(scene.materials), larr, len(fr.lights), int(fr.diffuse_bounce), row_begin, row_step, self.cores,
                                          rgb.ctypes.data_as(A.f32p), None, None)
         else:
             self.orclib.oracle_render(scene, fr, bvh=self.h, threads=self.cores, row_begin=row_begin, row_step=row_step, want=("rgb",))

@@ -945,6 +945,10 @@ static cudaError_t persist_grid(void (*kernel)(const FrameParams), int tiles, un
 // Which frames run on the persistent kernel (the host layer asks: it then leaves the completion protocol to the kernel).
 bool rt_render_is_persistent(const FrameParams& fp, int variant) {
     if (fp.accel != RT_ACCEL_BVH || !fp.wide || fp.mode == RT_MODE_HW2_CPU) return false;
+    // Bounce frames (max_depth > 1) run on the per-ray kernel.  Measured alternative (round 2): segment 0 as packets in this kernel, the
+    // rest of every path per lane with a private stack — bit-identical frames, but SLOWER than the per-ray kernel (frog.json as shipped,
+    // 1920x1080, depth 8, diffuse bounces: 1.09 vs 0.87 ms stock view, 2.66 vs 1.55 ms frame-filling view): the scalar continuation
+    // inherits the packet kernel's 56-register budget and spills ~100 words per thread where the per-ray kernel has 124 registers.
     if (fp.mode != RT_MODE_HW1 && fp.max_depth > 1) return false;
     return variant == RT_VARIANT_DEFAULT || variant == RT_VARIANT_STATS || variant == RT_VARIANT_PERSIST || variant == RT_VARIANT_PERSIST_EXACT_MT ||
            variant == RT_VARIANT_PERSIST_OCC8 || variant == RT_VARIANT_PERSIST_OCC10;

@@ -389,26 +389,13 @@ RT_HD f3 rt_sample_cpuonly(const FrameParams& P, const Ray& primary, uint32_t rn
     return v;
 }
 
-// One sample of one pixel through the BVH path: TraceRayIterative (query.h:156-220) — closest hit, shading,
-// shadow rays, then mirror / diffuse bounces up to P.max_depth.  h = the depth-0 hit.
+// The loop of TraceRayIterative (query.h:156-216) from the point where segment `depth` has found `cur`: miss colour or
+// surface + direct light (+ shadow rays), then the bounce and the next closest hit.  rt_sample_bvh enters it at depth 0; the
+// packet kernels trace depth 0 as packets and enter it at depth 1 with the first bounce ray's hit.
 template <int MODE, int STRIDE, bool STATS>
-RT_HD f3 rt_sample_bvh(const FrameParams& P, int x, int y, int s, uint32_t* stk, Hit& h,
-                       unsigned& nprim, unsigned& nshadow, TraceStats* st) {
-    const float jx = P.jitter ? RT_LDG(P.jitter + 2 * s) : 0.0f;
-    const float jy = P.jitter ? RT_LDG(P.jitter + 2 * s + 1) : 0.0f;
-    Ray ray = rt_make_ray(P.cam, MODE, x, y, jx, jy);
-    if (MODE == RT_MODE_HW2_BVH && P.max_depth <= 0) {   // TraceRayIterative: maxDepth <= 0 -> black
-        rt_hit_reset(h);
-        return mk3(0.f, 0.f, 0.f);
-    }
-    if (MODE == RT_MODE_HW2_CPU) return rt_sample_cpuonly<STRIDE, STATS>(P, ray, rt_rng_seed(x, y, s) ^ P.rng_seed, stk, h, nprim, nshadow, st);
-    rt_trace_closest<MODE, STRIDE, STATS>(P, ray, stk, h, st);
-    ++nprim;
-    if (MODE == RT_MODE_HW1) return rt_shade_hw1(P, ray, h);
-    f3 radiance = mk3(0.f, 0.f, 0.f), throughput = mk3(1.f, 1.f, 1.f);
-    uint32_t rng = rt_rng_seed(x, y, s);
-    Hit cur = h;
-    for (int depth = 0;;) {
+RT_HD void rt_path_continue(const FrameParams& P, Ray& ray, Hit cur, int depth, f3& radiance, f3& throughput, uint32_t& rng,
+                            uint32_t* stk, unsigned& nprim, unsigned& nshadow, TraceStats* st) {
+    for (;;) {
         if (cur.slot < 0) { radiance = xadd3(radiance, xmulv(throughput, ld3(P.miss))); break; }
         Surface sf;
         rt_surface_hw2(P, ray, cur, sf);
@@ -428,6 +415,27 @@ RT_HD f3 rt_sample_bvh(const FrameParams& P, int x, int y, int s, uint32_t* stk,
         rt_trace_closest<MODE, STRIDE, STATS>(P, ray, stk, cur, st);
         ++nprim;
     }
+}
+
+// One sample of one pixel through the BVH path: TraceRayIterative (query.h:156-220) — closest hit, shading,
+// shadow rays, then mirror / diffuse bounces up to P.max_depth.  h = the depth-0 hit.
+template <int MODE, int STRIDE, bool STATS>
+RT_HD f3 rt_sample_bvh(const FrameParams& P, int x, int y, int s, uint32_t* stk, Hit& h,
+                       unsigned& nprim, unsigned& nshadow, TraceStats* st) {
+    const float jx = P.jitter ? RT_LDG(P.jitter + 2 * s) : 0.0f;
+    const float jy = P.jitter ? RT_LDG(P.jitter + 2 * s + 1) : 0.0f;
+    Ray ray = rt_make_ray(P.cam, MODE, x, y, jx, jy);
+    if (MODE == RT_MODE_HW2_BVH && P.max_depth <= 0) {   // TraceRayIterative: maxDepth <= 0 -> black
+        rt_hit_reset(h);
+        return mk3(0.f, 0.f, 0.f);
+    }
+    if (MODE == RT_MODE_HW2_CPU) return rt_sample_cpuonly<STRIDE, STATS>(P, ray, rt_rng_seed(x, y, s) ^ P.rng_seed, stk, h, nprim, nshadow, st);
+    rt_trace_closest<MODE, STRIDE, STATS>(P, ray, stk, h, st);
+    ++nprim;
+    if (MODE == RT_MODE_HW1) return rt_shade_hw1(P, ray, h);
+    f3 radiance = mk3(0.f, 0.f, 0.f), throughput = mk3(1.f, 1.f, 1.f);
+    uint32_t rng = rt_rng_seed(x, y, s);
+    rt_path_continue<MODE, STRIDE, STATS>(P, ray, h, 0, radiance, throughput, rng, stk, nprim, nshadow, st);
     return rt_clamp01(radiance);
 }
 

@@ -127,6 +127,11 @@ def reference_render(scene, frame, row_begin=0, row_step=1, threads=None, want=(
     oracle's restatement of the same path (reference LBVH + SearchBVH) when the shim is not on this box.
     Returns (planes dict, "reference" | "port").  HW2-BVH frames with a camera made by api.camera_init only."""
     threads = threads or os.cpu_count() or 1
+    # the reference's pixel loop always jitters with jittered_samples(spp, 42u) (query.cu:142-148): the frame must do the same
+    want_j = np.zeros((frame.spp, 2), np.float32)
+    oracle().orc_jitter_table(want_j.ctypes.data_as(A.f32p), frame.spp, 42, 1)
+    assert frame.jitter is not None and np.array_equal(np.asarray(frame.jitter, np.float32).reshape(-1, 2), want_j), \
+        "reference_render: the frame must use the reference's jitter table (api.jitter_table(spp, 42, True))"
     libs = ref_libs()
     if "ref_hw2" not in libs:
         out = oracle_render(scene, frame, bvh=oracle_bvh(scene), threads=threads, row_begin=row_begin, row_step=row_step,

@@ -260,9 +260,8 @@ def test_axis_parallel_rays_and_flat_boxes(renderer):
     # (pixel rays pass exactly through grid lines of the mesh: exact-t ties between the triangles that share an edge or a vertex are
     # the rule here, so the id bar applies to non-tied pixels only — every id difference must be a t-tie, and hit/miss must agree)
     assert_reference_bar(got, ref["tri_id"], ref["t"], what="axis-parallel rays vs reference BVH", coplanar_overlaps=True)
-    live, kind = orclib.reference_render(sc, fr, want=("tri_id", "t"))
-    assert np.array_equal(got["tri_id"] >= 0, live["tri_id"] >= 0), kind
-    assert_reference_bar(got, live["tri_id"], live["t"], what="axis-parallel rays vs " + kind, coplanar_overlaps=True)
+    # (the reference compiled in place cannot render this frame: its pixel loop always applies jittered_samples(spp, 42),
+    # query.cu:142-148, and a jittered centre ray is no longer axis-parallel — the restated SearchBVH above is the check)
     # the same with the camera rays exactly parallel to x and y (flat boxes seen edge-on: every ray misses, in both)
     for pos_, up_ in (((3, 0, 0), (0, 0, 1)), ((0, 3, 0), (0, 0, 1))):
         fr2 = api.Frame(api.camera_init(pos_, (0, 0, 0), up_, 30.0, 24.0, 33, 33), 33, 33, lights=[api.make_light((0, 0, 5), (1, 1, 1), 2)], outputs=ALL)
