@@ -212,6 +212,14 @@ int  rt_api_version(void);
 /* Context bound to CUDA device `device` (replaces the cudaMalloc block of
  * GPUandCPU/src/main.cu:199-252). */
 int  rt_create(rt_ctx** out, int device);
+/* One context over n GPUs of one box driven by ONE host thread of ONE process — what an unmodified single-process
+ * main() (GPUandCPU/src/main.cu:98) can use: rt_upload_scene builds on devices[0] and copies the arena to the others
+ * over NVLink, rt_render launches every device's share of the frame (screen-space bands, see rt_comm_set_sharding) and
+ * the fused peer-store gather delivers it to devices[0], rt_download_image reads it there; rt_render_into makes every
+ * device copy its own bands straight into the caller's buffers.  Same kernels and the same in-kernel handshake as the
+ * process-per-GPU layout below (rt_comm_init), with peer pointers (cudaDeviceEnablePeerAccess) instead of CUDA IPC and
+ * no NCCL.  Needs peer access from every device to devices[0].  rt_image ray counts are totals over the devices. */
+int  rt_create_multi(rt_ctx** out, const int* devices, int n);
 int  rt_destroy(rt_ctx* ctx);
 /* Message of the last failing call on this thread (ctx may be NULL). */
 const char* rt_last_error(const rt_ctx* ctx);

@@ -84,6 +84,7 @@ assert C.sizeof(rt_material) == 52 and C.sizeof(rt_light) == 28 and C.sizeof(rt_
 EXPORTS = {
     "rt_api_version": (C.c_int, []),
     "rt_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "rt_create_multi": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int]),
     "rt_destroy": (C.c_int, [C.c_void_p]),
     "rt_last_error": (C.c_char_p, [C.c_void_p]),
     "rt_comm_unique_id": (C.c_int, [C.c_void_p]),

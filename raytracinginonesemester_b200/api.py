@@ -225,10 +225,14 @@ class Frame:
 class Renderer:
     """One context per GPU (one process per GPU; screen-space tiles are sharded across ranks)."""
 
-    def __init__(self, device=0, rank=0, world=1, nccl_id=None):
+    def __init__(self, device=0, rank=0, world=1, nccl_id=None, devices=None):
         self.lib = load_library()
         self.ctx = C.c_void_p()
-        rc = self.lib.rt_create(C.byref(self.ctx), int(device))
+        if devices is not None:          # rt_create_multi: one process, one thread, several GPUs (the caller sees one renderer)
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self.lib.rt_create_multi(C.byref(self.ctx), arr, len(devices))
+        else:
+            rc = self.lib.rt_create(C.byref(self.ctx), int(device))
         if rc != A.RT_OK:
             raise RtError(rc, (self.lib.rt_last_error(None) or b"").decode())
         self.rank, self.world = rank, world

@@ -72,6 +72,19 @@ StreamWaitValue32Fn stream_wait_value32() {
     return fn;
 }
 
+typedef CUresult (*StreamWriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamWriteValue32Fn stream_write_value32() {
+    static StreamWriteValue32Fn fn = []() -> StreamWriteValue32Fn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; }
+        return (StreamWriteValue32Fn)p;
+    }();
+    return fn;
+}
+
+struct HostOut { void* host; uint32_t bit; size_t bpp; const void* dev; const char* name; };
+
 struct Plane {
     void* p = nullptr; size_t cap = 0;
     cudaError_t reserve(size_t bytes) {
@@ -133,6 +146,12 @@ struct rt_ctx {
     unsigned* hflags = nullptr; unsigned* hflags_dev = nullptr;   // this rank's band flags in mapped pinned HOST memory (+ device alias): rt_render_into polls them
     unsigned hseq = 0;                                   // frame sequence number of the shared-host protocol
     bool last_host_direct = false;                       // the last frame went out through the shared host image
+    // rt_create_multi: one process, one host thread, several GPUs.  The context handed to the caller is rank 0 and owns the others;
+    // peers are reached through unified addressing (cudaDeviceEnablePeerAccess) instead of IPC mappings, nothing goes through NCCL.
+    std::vector<rt_ctx*> members;                        // ranks 1..n-1 (rank 0 of a group only)
+    bool inproc = false;                                 // this context is a rank of such a group
+    rt_ctx* group_root = nullptr;                        // ... and this is its rank 0
+    HostOut pump_outs[4] = {}; unsigned pump_seq = 0; int pump_next = 0; bool last_pumped = false;   // band copies of the rt_render_into in flight (band_pump)
     unsigned long long peer_timeout_ns = 120ull * 1000000000ull;   // bound of every in-kernel / flag-kernel wait on another rank (rt_comm_set_timeout)
     int dbg_rank = 0, dbg_world = 0;              // rt_debug_set_shard: render one rank's share on a single GPU (timing only)
 };
@@ -362,6 +381,26 @@ int peer_planes(rt_ctx* c, uint32_t outputs, size_t npix) {
     return RT_OK;
 }
 
+// In-process group (rt_create_multi): rank 0 (re)allocates the planes, the others use the same pointers.  Called on every
+// rank of the group with the same arguments, rank 0 first.
+int inproc_planes(rt_ctx* c, rt_ctx* root, uint32_t outputs, size_t npix) {
+    static const uint32_t bits[4] = {RT_OUT_RGB_F32, RT_OUT_RGB8, RT_OUT_TRI_ID, RT_OUT_T};
+    static const size_t bpp[4] = {12, 3, 4, 4};
+    Plane* planes[4] = {&root->img_rgb, &root->img_rgb8, &root->img_id, &root->img_t};
+    for (int i = 0; i < 4; ++i) {
+        if (!(outputs & bits[i])) continue;
+        if (c == root) {
+            if (bpp[i] * npix + 16 > planes[i]->cap) {
+                for (rt_ctx* m : root->members) { cudaSetDevice(m->device); cudaStreamSynchronize(m->stream); }   // nobody still writes the old plane
+                CU(c, cudaSetDevice(c->device));
+                CU(c, cudaStreamSynchronize(c->stream));
+                CU(c, planes[i]->reserve(bpp[i] * npix + 16));
+            }
+        } else c->peer_img[i] = planes[i]->p;
+    }
+    return RT_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -404,8 +443,63 @@ int rt_create(rt_ctx** out, int device) {
     return RT_OK;
 }
 
+int rt_create_multi(rt_ctx** out, const int* devices, int n) {
+    if (!out || !devices || n < 1 || n > RT_PEER_MAX_RANKS) return fail(nullptr, RT_ERR_ARG, "rt_create_multi: 1..%d devices", RT_PEER_MAX_RANKS);
+    *out = nullptr;
+    for (int i = 0; i < n; ++i) for (int j = 0; j < i; ++j)
+        if (devices[i] == devices[j]) return fail(nullptr, RT_ERR_ARG, "rt_create_multi: device %d listed twice", devices[i]);
+    rt_ctx* root = nullptr;
+    int rc = rt_create(&root, devices[0]);
+    if (rc != RT_OK || n == 1) { *out = root; return rc; }
+    auto bail = [&](int code) { rt_destroy(root); return code; };
+    root->rank = 0; root->world = n; root->inproc = true; root->group_root = root;
+    for (int i = 1; i < n; ++i) {
+        rt_ctx* m = nullptr;
+        rc = rt_create(&m, devices[i]);
+        if (rc != RT_OK) return bail(rc);
+        m->rank = i; m->world = n; m->inproc = true; m->group_root = root;
+        root->members.push_back(m);
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, devices[i], devices[0]) != cudaSuccess || !can)
+            return bail(fail(nullptr, RT_ERR_CUDA, "rt_create_multi: device %d cannot address device %d's memory (no NVLink / P2P path)", devices[i], devices[0]));
+        cudaSetDevice(devices[i]);
+        cudaError_t e = cudaDeviceEnablePeerAccess(devices[0], 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return bail(fail(nullptr, RT_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)));
+        cudaGetLastError();
+        cudaSetDevice(devices[0]);
+        e = cudaDeviceEnablePeerAccess(devices[i], 0);           // rank 0 -> rank i: the scene copy
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return bail(fail(nullptr, RT_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)));
+        cudaGetLastError();
+    }
+    // the fused gather's flag block lives on rank 0; every rank addresses it directly
+    cudaSetDevice(devices[0]);
+    if (cudaMalloc(&root->flags, kFlagBytes) != cudaSuccess || cudaMemset(root->flags, 0, kFlagBytes) != cudaSuccess)
+        return bail(fail(nullptr, RT_ERR_CUDA, "rt_create_multi: flag block"));
+    std::vector<rt_ctx*> all{root};
+    all.insert(all.end(), root->members.begin(), root->members.end());
+    for (rt_ctx* m : all) {
+        cudaSetDevice(m->device);
+        if (cudaMalloc(&m->peer_err, sizeof(unsigned)) != cudaSuccess || cudaMemset(m->peer_err, 0, sizeof(unsigned)) != cudaSuccess)
+            return bail(fail(nullptr, RT_ERR_CUDA, "rt_create_multi: error word"));
+        m->flags = root->flags; m->peer = true; m->seq = 0;
+    }
+    cudaSetDevice(devices[0]);
+    *out = root;
+    return RT_OK;
+}
+
 int rt_destroy(rt_ctx* c) {
     if (!c) return RT_OK;
+    if (c->inproc && c->group_root == c) {                       // a group: the other ranks first (they address rank 0's memory)
+        for (rt_ctx* m : c->members) { cudaSetDevice(m->device); if (m->stream) cudaStreamSynchronize(m->stream); }
+        for (rt_ctx* m : c->members) { m->flags = nullptr; for (void*& p : m->peer_img) p = nullptr; m->peer = false; m->inproc = false; rt_destroy(m); }
+        c->members.clear();
+        cudaSetDevice(c->device);
+        if (c->stream) cudaStreamSynchronize(c->stream);
+        if (c->flags) cudaFree(c->flags);
+        c->flags = nullptr; c->peer = false; c->inproc = false; c->world = 1;
+        for (size_t& g : c->gather_cap) g = 0;
+    }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     // NOT a collective (ranks may destroy in any order, or after another rank died): mappings are closed, rank 0's
@@ -445,6 +539,7 @@ int rt_comm_unique_id(void* id128) {
 
 int rt_comm_init(rt_ctx* c, int rank, int world, const void* id128) {
     if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(c, RT_ERR_ARG, "rt_comm_init: bad arguments");
+    if (c->inproc) return fail(c, RT_ERR_STATE, "rt_comm_init: this context is a single-process group (rt_create_multi)");
     CU(c, cudaSetDevice(c->device));
     if (world > 8) return fail(c, RT_ERR_ARG, "rt_comm_init: at most 8 ranks (one box)");
     peer_teardown(c, true);
@@ -465,6 +560,7 @@ int rt_comm_set_gather(rt_ctx* c, int mode) {
     CU(c, cudaSetDevice(c->device));
     c->frame_valid = false;
     if (c->world <= 1) return RT_OK;
+    if (c->inproc) return mode == RT_GATHER_NCCL ? fail(c, RT_ERR_ARG, "rt_comm_set_gather: a single-process group gathers with peer stores only") : RT_OK;
     if (mode == RT_GATHER_NCCL) { peer_teardown(c, true); return RT_OK; }
     if (!c->peer) { int rc = peer_setup(c); if (rc != RT_OK) return rc; }
     if (mode == RT_GATHER_PEER && !c->peer) return fail(c, RT_ERR_CUDA, "rt_comm_set_gather: CUDA IPC peer mapping of rank 0's memory is not available on every rank");
@@ -475,6 +571,7 @@ int rt_comm_set_sharding(rt_ctx* c, int chunks_per_rank) {
     if (!c || chunks_per_rank < 0 || chunks_per_rank > 4096) return fail(c, RT_ERR_ARG, "rt_comm_set_sharding: bad arguments");
     c->chunks_per_rank = chunks_per_rank;
     c->frame_valid = false;
+    for (rt_ctx* m : c->members) { m->chunks_per_rank = chunks_per_rank; m->frame_valid = false; }
     return RT_OK;
 }
 
@@ -655,6 +752,34 @@ int rt_upload_scene(rt_ctx* c, const rt_scene* sc) {
     if (c->world > 1 && c->rank != 0) return broadcast_scene(c, RT_OK);   // collective: rank 0's scene (and status) arrives here
     int rc = sc ? upload_local(c, sc)
                 : fail(c, RT_ERR_ARG, "rt_upload_scene: scene is NULL (only ranks != 0 of a multi-GPU context may receive)");
+    if (c->inproc) {                                            // single-process group: peer copies of the arena, rank by rank
+        if (rc != RT_OK) return rc;
+        rc = build_wide_nodes(c);
+        for (rt_ctx* m : c->members) {
+            if (rc != RT_OK) break;
+            CU(c, cudaSetDevice(m->device));
+            m->frame_valid = false;
+            free_scene(m);
+            m->num_tris = c->num_tris; m->num_nodes = c->num_nodes; m->num_materials = c->num_materials;
+            m->has_bvh = c->has_bvh; m->has_normals = c->has_normals; m->info = c->info;
+            if (m->num_nodes) CU(c, cudaMalloc(&m->nodes, sizeof(BvhNode) * (size_t)m->num_nodes));
+            CU(c, cudaMalloc(&m->geom, sizeof(TriBlock) * (size_t)m->num_tris));
+            CU(c, cudaMalloc(&m->shade, sizeof(TriBlock) * (size_t)m->num_tris));
+            if (m->num_materials) CU(c, cudaMalloc(&m->materials, sizeof(rt_material) * (size_t)m->num_materials));
+            if (m->num_nodes) CU(c, cudaMemcpyPeerAsync(m->nodes, m->device, c->nodes, c->device, sizeof(BvhNode) * (size_t)m->num_nodes, m->stream));
+            CU(c, cudaMemcpyPeerAsync(m->geom, m->device, c->geom, c->device, sizeof(TriBlock) * (size_t)m->num_tris, m->stream));
+            CU(c, cudaMemcpyPeerAsync(m->shade, m->device, c->shade, c->device, sizeof(TriBlock) * (size_t)m->num_tris, m->stream));
+            if (m->num_materials) CU(c, cudaMemcpyPeerAsync(m->materials, m->device, c->materials, c->device, sizeof(rt_material) * (size_t)m->num_materials, m->stream));
+            CU(c, cudaStreamSynchronize(m->stream));
+            m->has_scene = true;
+            m->info.arena_bytes = sizeof(BvhNode) * (uint64_t)m->num_nodes + 2 * sizeof(TriBlock) * (uint64_t)m->num_tris + sizeof(rt_material) * (uint64_t)m->num_materials;
+            m->info.build_ms = 0.f;
+            rc = build_wide_nodes(m);
+            if (rc != RT_OK) fail(c, rc, "rt_upload_scene: rank %d: %s", m->rank, m->err.c_str());
+        }
+        cudaSetDevice(c->device);
+        return rc;
+    }
     if (c->world > 1) return broadcast_scene(c, rc);           // also on failure: the other ranks are waiting in the broadcast
     if (rc != RT_OK) return rc;
     return build_wide_nodes(c);
@@ -704,7 +829,6 @@ int ensure_host_flags(rt_ctx* c) {
     return RT_OK;
 }
 
-struct HostOut { void* host; uint32_t bit; size_t bpp; const void* dev; const char* name; };
 
 // Bands of a rank's L local tile slots (completion flags of the persistent kernel).  Cuts at every ownership-chunk boundary
 // (chunks of `chunk` slots: a band must not straddle two chunks, their tiles are not contiguous in the frame) and, when
@@ -724,6 +848,92 @@ int plan_bands(int L, int chunk, bool refine, int* band_end) {
     }
     band_end[n++] = L;
     return n;
+}
+
+// ---- band copies of rt_render_into (the frame's parameters are c->fp, the destinations c->pump_outs) ----
+// rows [y0, y1) of every requested plane
+int band_copy_rows(rt_ctx* c, size_t y0, size_t y1) {
+    const FrameParams& P = c->fp;
+    for (const HostOut& o : c->pump_outs) {
+        if (!o.host) continue;
+        const size_t off = y0 * (size_t)P.W * o.bpp, bytes = (y1 - y0) * (size_t)P.W * o.bpp;
+        CU(c, cudaMemcpyAsync((char*)o.host + off, (const char*)o.dev + off, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    return RT_OK;
+}
+// the pixels of the row-major GLOBAL tiles [g0, g1) (row-major device planes): a partial tile row, whole tile rows (one contiguous
+// copy), a partial tile row
+int band_copy_tiles(rt_ctx* c, long long g0, long long g1) {
+    const FrameParams& P = c->fp;
+    const long long total_tiles = (long long)P.tiles_x * P.tiles_y;
+    if (g1 > total_tiles) g1 = total_tiles;
+    if (g0 >= g1) return RT_OK;
+    const int tx = P.tiles_x;
+    const int row0 = (int)(g0 / tx), col0 = (int)(g0 % tx), row1 = (int)((g1 - 1) / tx), col1 = (int)((g1 - 1) % tx) + 1;
+    struct Piece { int r0, r1, c0, c1; } pieces[3];
+    int np = 0;
+    if (row0 == row1) pieces[np++] = {row0, row0, col0, col1};
+    else {
+        int first_full = row0, last_full = row1;
+        if (col0 != 0) { pieces[np++] = {row0, row0, col0, tx}; first_full = row0 + 1; }
+        if (col1 != tx) { pieces[np++] = {row1, row1, 0, col1}; last_full = row1 - 1; }
+        if (first_full <= last_full) pieces[np++] = {first_full, last_full, 0, tx};
+    }
+    for (int q = 0; q < np; ++q) {
+        const size_t x0 = (size_t)pieces[q].c0 * RT_TILE_W, y0 = (size_t)pieces[q].r0 * RT_TILE_H;
+        size_t x1 = (size_t)pieces[q].c1 * RT_TILE_W, y1 = (size_t)(pieces[q].r1 + 1) * RT_TILE_H;
+        if (x1 > (size_t)P.W) x1 = (size_t)P.W;
+        if (y1 > (size_t)P.H) y1 = (size_t)P.H;
+        if (x0 >= x1 || y0 >= y1) continue;
+        if (x0 == 0 && x1 == (size_t)P.W) { int rc = band_copy_rows(c, y0, y1); if (rc != RT_OK) return rc; continue; }
+        for (const HostOut& o : c->pump_outs) {
+            if (!o.host) continue;
+            const size_t pitch = (size_t)P.W * o.bpp, off = y0 * pitch + x0 * o.bpp;
+            CU(c, cudaMemcpy2DAsync((char*)o.host + off, pitch, (const char*)o.dev + off, pitch, (x1 - x0) * o.bpp, y1 - y0, cudaMemcpyDeviceToHost, c->copy_stream));
+        }
+    }
+    return RT_OK;
+}
+// the same for the rank-local slot range [s0, s1), which must lie inside one ownership chunk
+int band_copy_slots(rt_ctx* c, int s0, int s1) {
+    const FrameParams& P = c->fp;
+    if (s0 >= s1) return RT_OK;
+    if (P.world <= 1) return band_copy_tiles(c, s0, s1);
+    const int j = s0 / P.chunk_tiles;
+    const long long base = ((long long)j * P.world + P.rank) * P.chunk_tiles;
+    return band_copy_tiles(c, base + (s0 - j * P.chunk_tiles), base + (s1 - j * P.chunk_tiles));
+}
+// Host-driven band pipeline: wait for the next band's flag word (written by the frame kernel into mapped host memory), then
+// enqueue the band's copies.  wait == false: only the bands that are already published (used to pump several ranks from one
+// thread); returns RT_OK with c->pump_next == num_chunks when the rank is done.  Bounded: a kernel that died never writes its flags.
+int band_pump(rt_ctx* c, bool wait) {
+    const FrameParams& P = c->fp;
+    const unsigned seq = c->pump_seq;
+    const auto t0 = std::chrono::steady_clock::now();
+    static const bool timing = getenv("RT_TIMING") != nullptr;
+    CU(c, cudaSetDevice(c->device));
+    while (c->pump_next < P.num_chunks) {
+        const int j = c->pump_next;
+        volatile unsigned* f = c->hflags + RT_PEER_CHUNK_FLAG(0, j);
+        unsigned spins = 0;
+        while ((int)(*f - seq) < 0) {
+            if (!wait) return RT_OK;
+            if ((++spins & 0x3fffu) == 0u) {
+                const cudaError_t q = cudaStreamQuery(c->stream);
+                if (q != cudaErrorNotReady && (int)(*f - seq) < 0) {
+                    if (q != cudaSuccess) return fail(c, RT_ERR_CUDA, "rt_render_into: %s", cudaGetErrorString(q));
+                    return fail(c, RT_ERR_STATE, "rt_render_into: the frame kernel finished without publishing band %d", j);
+                }
+                if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e9 > (double)c->peer_timeout_ns)
+                    return fail(c, RT_ERR_STATE, "rt_render_into: band %d not finished after %llu s", j, c->peer_timeout_ns / 1000000000ull);
+            }
+        }
+        if (timing) fprintf(stderr, "[band_pump r%d] band %d of %d published %8.1f us after the pump started\n", c->rank, j, P.num_chunks, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+        int rc = band_copy_slots(c, j ? P.band_end[j - 1] : 0, P.band_end[j]);
+        if (rc != RT_OK) return rc;
+        ++c->pump_next;
+    }
+    return RT_OK;
 }
 
 // rt_render (into == NULL) and rt_render_into (into != NULL: finished bands of the frame are copied to the caller's host
@@ -801,8 +1011,10 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
         if (n_in && n_out) return fail(c, RT_ERR_ARG, "rt_render_into: some planes are inside the shared host image and some are not");
         host_direct = n_in > 0 && F0 <= RT_PEER_MAX_CHUNKS;
     }
-    if (c->world > 1 && c->peer && !host_direct) {   // collective; may fall back to the NCCL gather
-        int rc = peer_planes(c, outputs, (size_t)fr->width * fr->height);
+    if (c->inproc && into && (into->rgb || into->rgb8 || into->tri_id || into->t)) host_direct = true;   // one process: every rank can write the caller's buffers
+    if (c->world > 1 && c->peer && !host_direct) {
+        int rc = c->inproc ? inproc_planes(c, c->group_root, outputs, (size_t)fr->width * fr->height)
+                           : peer_planes(c, outputs, (size_t)fr->width * fr->height);   // collective; may fall back to the NCCL gather
         if (rc != RT_OK) return rc;
     }
     const bool peer = c->world > 1 && c->peer && !host_direct;
@@ -883,83 +1095,20 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
     const bool persistent = rt_render_is_persistent(P, fr->kernel_variant);
     const HostOut outs[4] = {{into ? into->rgb : nullptr, RT_OUT_RGB_F32, 12, P.rgb, "rgb"}, {into ? into->rgb8 : nullptr, RT_OUT_RGB8, 3, P.rgb8, "rgb8"},
                              {into ? into->tri_id : nullptr, RT_OUT_TRI_ID, 4, P.tri_id, "tri_id"}, {into ? into->t : nullptr, RT_OUT_T, 4, P.t, "t"}};
-    // copies rows [y0, y1) of every requested plane to the caller's buffers
-    auto copy_rows = [&](size_t y0, size_t y1) -> int {
-        for (const HostOut& o : outs) {
-            if (!o.host) continue;
-            const size_t off = y0 * (size_t)P.W * o.bpp, bytes = (y1 - y0) * (size_t)P.W * o.bpp;
-            CU(c, cudaMemcpyAsync((char*)o.host + off, (const char*)o.dev + off, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
-        }
-        return RT_OK;
-    };
-
-    // copies the pixels of the row-major GLOBAL tiles [g0, g1) of every requested plane (row-major device planes) to the caller's
-    // buffers: a partial tile row, whole tile rows (one contiguous copy), a partial tile row
-    auto copy_tiles = [&](long long g0, long long g1) -> int {
-        if (g1 > total_tiles) g1 = total_tiles;
-        if (g0 >= g1) return RT_OK;
-        const int tx = P.tiles_x;
-        const int row0 = (int)(g0 / tx), col0 = (int)(g0 % tx), row1 = (int)((g1 - 1) / tx), col1 = (int)((g1 - 1) % tx) + 1;
-        struct Piece { int r0, r1, c0, c1; } pieces[3];
-        int np = 0;
-        if (row0 == row1) pieces[np++] = {row0, row0, col0, col1};
-        else {
-            int first_full = row0, last_full = row1;
-            if (col0 != 0) { pieces[np++] = {row0, row0, col0, tx}; first_full = row0 + 1; }
-            if (col1 != tx) { pieces[np++] = {row1, row1, 0, col1}; last_full = row1 - 1; }
-            if (first_full <= last_full) pieces[np++] = {first_full, last_full, 0, tx};
-        }
-        for (int q = 0; q < np; ++q) {
-            const size_t x0 = (size_t)pieces[q].c0 * RT_TILE_W, y0 = (size_t)pieces[q].r0 * RT_TILE_H;
-            size_t x1 = (size_t)pieces[q].c1 * RT_TILE_W, y1 = (size_t)(pieces[q].r1 + 1) * RT_TILE_H;
-            if (x1 > (size_t)P.W) x1 = (size_t)P.W;
-            if (y1 > (size_t)P.H) y1 = (size_t)P.H;
-            if (x0 >= x1 || y0 >= y1) continue;
-            if (x0 == 0 && x1 == (size_t)P.W) { int rc = copy_rows(y0, y1); if (rc != RT_OK) return rc; continue; }
-            for (const HostOut& o : outs) {
-                if (!o.host) continue;
-                const size_t pitch = (size_t)P.W * o.bpp, off = y0 * pitch + x0 * o.bpp;
-                CU(c, cudaMemcpy2DAsync((char*)o.host + off, pitch, (const char*)o.dev + off, pitch, (x1 - x0) * o.bpp, y1 - y0, cudaMemcpyDeviceToHost, c->copy_stream));
-            }
-        }
-        return RT_OK;
-    };
-    // the same for the rank-local slot range [s0, s1), which must lie inside one ownership chunk
-    auto copy_slots = [&](int s0, int s1) -> int {
-        if (s0 >= s1) return RT_OK;
-        if (P.world <= 1) return copy_tiles(s0, s1);
-        const int j = s0 / P.chunk_tiles;
-        const long long base = ((long long)j * P.world + P.rank) * P.chunk_tiles;
-        return copy_tiles(base + (s0 - j * P.chunk_tiles), base + (s1 - j * P.chunk_tiles));
-    };
-
-    // host-driven band pipeline: wait for band j's flag word (written by the frame kernel into mapped host memory), then enqueue
-    // the band's copies.  Bounded: a kernel that died never writes its flags.
+    c->pump_outs[0] = outs[0]; c->pump_outs[1] = outs[1]; c->pump_outs[2] = outs[2]; c->pump_outs[3] = outs[3];
+    auto copy_rows = [&](size_t y0, size_t y1) -> int { return band_copy_rows(c, y0, y1); };
+    auto copy_slots = [&](int s0, int s1) -> int { return band_copy_slots(c, s0, s1); };
     auto pump_bands = [&](unsigned seq) -> int {
-        const auto t0 = std::chrono::steady_clock::now();
-        for (int j = 0; j < P.num_chunks; ++j) {
-            volatile unsigned* f = c->hflags + RT_PEER_CHUNK_FLAG(0, j);
-            unsigned spins = 0;
-            while ((int)(*f - seq) < 0) {
-                if ((++spins & 0x3fffu) == 0u) {
-                    const cudaError_t q = cudaStreamQuery(c->stream);
-                    if (q != cudaErrorNotReady && (int)(*f - seq) < 0) {
-                        if (q != cudaSuccess) return fail(c, RT_ERR_CUDA, "rt_render_into: %s", cudaGetErrorString(q));
-                        return fail(c, RT_ERR_STATE, "rt_render_into: the frame kernel finished without publishing band %d", j);
-                    }
-                    if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e9 > (double)c->peer_timeout_ns)
-                        return fail(c, RT_ERR_STATE, "rt_render_into: band %d not finished after %llu s", j, c->peer_timeout_ns / 1000000000ull);
-                }
-            }
-            int rc = copy_slots(j ? P.band_end[j - 1] : 0, P.band_end[j]);
-            if (rc != RT_OK) return rc;
-        }
-        return RT_OK;
+        c->pump_seq = seq; c->pump_next = 0; c->last_pumped = true;
+        if (c->inproc) return RT_OK;                 // single-process group: the caller pumps every rank's bands together (rt_render_into)
+        return band_pump(c, true);
     };
+    (void)copy_rows; (void)copy_slots;
 
     CU(c, cudaEventRecord(c->ev0, c->stream));
     int launches = 0;
     c->last_host_direct = false;
+    c->last_pumped = false;
     if (host_direct) {
         int rc = ensure_band_resources(c);
         if (rc != RT_OK) return rc;
@@ -969,7 +1118,8 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
         volatile unsigned* hdr = (volatile unsigned*)c->shm_base;
         // the caller of rank 0 is done with the previous frame's image once it is back in here: rank 0 says so, the others
         // wait for it before anything of this frame can land in the shared buffer (host-side handshake through the header)
-        if (c->rank == 0) { __sync_synchronize(); hdr[0] = seq; }
+        if (c->inproc) { /* one thread drives every rank: nothing to wait for */ }
+        else if (c->rank == 0) { __sync_synchronize(); hdr[0] = seq; }
         else {
             const auto t0 = std::chrono::steady_clock::now();
             while ((int)(hdr[0] - seq) < 0) {
@@ -989,22 +1139,28 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
         CU(c, cudaStreamWaitEvent(c->copy_stream, c->evk0, 0));
         rc = pump_bands(seq);
         if (rc != RT_OK) return rc;
-        {   // this rank's bands are in the shared buffer: say so in the header (a store to mapped host memory, after the copies in stream order)
+        if (!c->inproc) {   // this rank's bands are in the shared buffer: say so in the header (a store to mapped host memory, after the copies in stream order)
             unsigned* dhdr = nullptr;
             CU(c, cudaHostGetDevicePointer((void**)&dhdr, c->shm_base, 0));
-            CU(c, rt_launch_flag_set(dhdr + 16 * (1 + c->rank), 1, 1, seq, c->copy_stream));
-            ++launches;
+            StreamWriteValue32Fn write32 = stream_write_value32();          // a stream memory operation: no kernel launch, no SM
+            if (!write32 || write32((CUstream)c->copy_stream, (CUdeviceptr)(dhdr + 16 * (1 + c->rank)), seq, 0) != CUDA_SUCCESS) {
+                CU(c, rt_launch_flag_set(dhdr + 16 * (1 + c->rank), 1, 1, seq, c->copy_stream));
+                ++launches;
+            }
         }
         CU(c, cudaEventRecord(c->copy_done, c->copy_stream));
         CU(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));
         if (pipelined) *pipelined = true;
-        c->last_host_direct = true;
+        c->last_host_direct = !c->inproc;
     } else if (peer) {
         // Frame k may overwrite rank 0's image only once rank 0 is done with frame k-1 (its downloads are stream-ordered
         // before this point): rank 0 publishes `ready = k`, the others wait for it — inside the persistent kernel.
         const unsigned seq = ++c->seq;
         const int F = c->chunks_per_rank > 0 ? c->chunks_per_rank : RT_DEFAULT_CHUNKS_PER_RANK;
-        const bool banded = F <= RT_PEER_MAX_CHUNKS;            // one flag per ownership band, else one per rank
+        // one flag per ownership band when rank 0 pipelines its copies behind them (rt_render_into), else one per rank: every band
+        // costs every block a barrier and a system-scope fence over NVLink (measured at 8 GPUs: 0.35 ms per-rank kernel with 4
+        // bands, where the round-1 kernel without them took 0.30 ms)
+        const bool banded = into != nullptr && F <= RT_PEER_MAX_CHUNKS;
         P.num_chunks = plan_bands(P.local_tiles, banded ? P.chunk_tiles : P.local_tiles, false, P.band_end);   // one flag per ownership band, else one per rank
         P.seq = seq;
         P.flags = c->flags + RT_PEER_CHUNK_FLAG(c->rank, 0);
@@ -1167,16 +1323,82 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
 
 extern "C" {
 
-int rt_render(rt_ctx* c, const rt_frame* fr) { return render_impl(c, fr, nullptr, nullptr); }
+int rt_render(rt_ctx* c, const rt_frame* fr) {
+    int rc = render_impl(c, fr, nullptr, nullptr);
+    if (c && c->inproc && c->group_root == c)                   // single-process group: the same frame on every rank, from this thread
+        for (rt_ctx* m : c->members) {
+            if (rc != RT_OK) break;
+            rc = render_impl(m, fr, nullptr, nullptr);
+            if (rc != RT_OK) fail(c, rc, "rt_render: rank %d: %s", m->rank, m->err.c_str());
+        }
+    if (c) cudaSetDevice(c->device);
+    return rc;
+}
 
 int rt_render_into(rt_ctx* c, const rt_frame* fr, rt_image* img) {
     if (!img) return fail(c, RT_ERR_ARG, "rt_render_into: NULL image");
     bool pipelined = false;
+    static const bool timing = getenv("RT_TIMING") != nullptr;        // host-side phase times on stderr (diagnostic)
+    const auto tp0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (timing && c) fprintf(stderr, "[rt_render_into r%d] %-28s %8.1f us\n", c->rank, what, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tp0).count());
+    };
+    if (c && c->inproc && c->group_root == c) {
+        // single-process group: every rank renders its bands and copies them straight into the caller's buffers (one host thread
+        // enqueues all ranks' frames first, then pumps each rank's band copies); no gather on rank 0's device
+        std::vector<rt_ctx*> all{c};
+        all.insert(all.end(), c->members.begin(), c->members.end());
+        int rc = RT_OK;
+        uint64_t prim = 0, shad = 0;
+        for (rt_ctx* m : all) {
+            rc = render_impl(m, fr, img, &pipelined);
+            if (rc != RT_OK) { if (m != c) fail(c, rc, "rt_render_into: rank %d: %s", m->rank, m->err.c_str()); break; }
+        }
+        // pump every rank's band copies from this thread until all bands of all ranks are on their way
+        const auto t0 = std::chrono::steady_clock::now();
+        for (unsigned spins = 0; rc == RT_OK; ++spins) {
+            bool pending = false;
+            for (rt_ctx* m : all) {
+                if (!m->last_pumped || m->pump_next >= m->fp.num_chunks) continue;
+                rc = band_pump(m, false);
+                if (rc != RT_OK) { if (m != c) fail(c, rc, "rt_render_into: rank %d: %s", m->rank, m->err.c_str()); break; }
+                pending = pending || m->pump_next < m->fp.num_chunks;
+            }
+            if (!pending || rc != RT_OK) break;
+            if ((spins & 0xfffu) == 0xfffu) {
+                for (rt_ctx* m : all) {
+                    cudaSetDevice(m->device);
+                    const cudaError_t q = cudaStreamQuery(m->stream);
+                    if (q != cudaSuccess && q != cudaErrorNotReady) { rc = fail(c, RT_ERR_CUDA, "rt_render_into: rank %d: %s", m->rank, cudaGetErrorString(q)); break; }
+                }
+                if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e9 > (double)c->peer_timeout_ns)
+                    rc = fail(c, RT_ERR_STATE, "rt_render_into: bands not finished after %llu s", c->peer_timeout_ns / 1000000000ull);
+            }
+        }
+        for (rt_ctx* m : all) {
+            if (rc != RT_OK || !m->last_pumped) continue;
+            cudaSetDevice(m->device);
+            if (cudaStreamSynchronize(m->copy_stream) != cudaSuccess) rc = fail(c, RT_ERR_CUDA, "rt_render_into: rank %d: copy stream", m->rank);
+        }
+        for (rt_ctx* m : all) {
+            if (rc != RT_OK) break;
+            rt_image meta{};
+            rc = rt_download_image(m, &meta);
+            if (rc != RT_OK) { if (m != c) fail(c, rc, "rt_render_into: rank %d: %s", m->rank, m->err.c_str()); break; }
+            prim += meta.rays_primary; shad += meta.rays_shadow;
+            if (m == c) { img->width = meta.width; img->height = meta.height; img->gpu_ms = meta.gpu_ms; }
+        }
+        img->rays_primary = prim; img->rays_shadow = shad;
+        cudaSetDevice(c->device);
+        return rc;
+    }
     int rc = render_impl(c, fr, img, &pipelined);
+    lap("frame + copies enqueued");
     if (rc != RT_OK) return rc;
     if (!pipelined) return rt_download_image(c, img);           // multi-GPU contexts: gather first, then one copy
     rt_image meta{};                                            // planes are already on their way: fetch counters and times only
     rc = rt_download_image(c, &meta);
+    lap("stream drained, counters read");
     if (rc != RT_OK) return rc;
     if (c->last_host_direct && c->rank == 0) {                  // shared host image: every rank's bands must have landed
         volatile unsigned* hdr = (volatile unsigned*)c->shm_base;
@@ -1187,6 +1409,7 @@ int rt_render_into(rt_ctx* c, const rt_frame* fr, rt_image* img) {
                     return fail(c, RT_ERR_STATE, "rt_render_into: rank 0 waited more than %llu s for rank %d's bands", c->peer_timeout_ns / 1000000000ull, r);
             }
         __sync_synchronize();
+        lap("every rank's bands landed");
     }
     img->width = meta.width; img->height = meta.height; img->rays_primary = meta.rays_primary; img->rays_shadow = meta.rays_shadow; img->gpu_ms = meta.gpu_ms;
     return RT_OK;
@@ -1262,6 +1485,16 @@ int rt_download_image(rt_ctx* c, rt_image* img) {
     float ms = 0.f;
     CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     img->gpu_ms = ms;
+    if (c->inproc && c->group_root == c && (img->rgb || img->rgb8 || img->tri_id || img->t || !c->last_pumped)) {
+        // single-process group, called by the user on the group: ray counts of every rank (rank 0's kernel ends after the others')
+        for (rt_ctx* m : c->members) {
+            rt_image meta{};
+            int rc = rt_download_image(m, &meta);
+            if (rc != RT_OK) return fail(c, rc, "rt_download_image: rank %d: %s", m->rank, m->err.c_str());
+            img->rays_primary += meta.rays_primary; img->rays_shadow += meta.rays_shadow;
+        }
+        cudaSetDevice(c->device);
+    }
     return RT_OK;
 }
 
