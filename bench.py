@@ -467,7 +467,8 @@ def bench_workload(args, r, dist, rank, world, local_rank, workload, steps, with
     rays_primary, rays_shadow, nv_all, nt_all, nl_all, nb_all, n_node_1, n_tri_1 = [float(x) for x in cnt.cpu()]
     rays = rays_primary + rays_shadow
 
-    persistent = (not brute) and args.variant in (A.RT_VARIANT_DEFAULT, A.RT_VARIANT_PERSIST, A.RT_VARIANT_PERSIST_EXACT_MT, A.RT_VARIANT_PERSIST_OCC8, A.RT_VARIANT_PERSIST_OCC10)
+    # rt_render (the device-timed steps): RT_VARIANT_DEFAULT is the block-per-tile launch; the persistent kernel when asked for by name
+    persistent = (not brute) and args.variant in (A.RT_VARIANT_PERSIST, A.RT_VARIANT_PERSIST_EXACT_MT, A.RT_VARIANT_PERSIST_OCC8, A.RT_VARIANT_PERSIST_OCC10)
     if world == 1:
         launches_per_step = 1
     elif r.gather_mode() == A.RT_GATHER_PEER:
@@ -518,6 +519,10 @@ def bench_workload(args, r, dist, rank, world, local_rank, workload, steps, with
                              "t_equal": bool(np.array_equal(got["t"], ref["t"])), "e2e_rgb8_equal": bool(np.array_equal(shared, ref["rgb8"])),
                              "pixels": int(W * H), "against": "the same frame rendered by rank 0 alone (single-GPU context, same scene)"}
         barrier()
+    per_rank = torch.zeros(world, dtype=torch.float64, device="cuda")
+    per_rank[rank] = kern_ms
+    if dist is not None:
+        dist.all_reduce(per_rank)
     t = torch.tensor([step_ms, e2e_s + [0.0] * (len(step_ms) - len(e2e_s))], dtype=torch.float64, device="cuda")
     tw = torch.tensor(warm_ms + [kern_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -574,6 +579,7 @@ def bench_workload(args, r, dist, rank, world, local_rank, workload, steps, with
         "primary_mrays_s": rays_primary / (ms * 1e-3) / 1e6,
         "value_warm_l2": rays / (float(tw[:-1].mean()) * 1e-3) / 1e6,
         "frame_kernel_ms_max_rank": float(tw[-1]), "gather_overhead_ms": ms - float(tw[-1]),
+        "frame_kernel_ms_per_rank": [round(float(x), 4) for x in per_rank.cpu()],
         "bvh_nodes": int(info.num_nodes), "bvh_build_ms": float(info.build_ms), "bvh_build_first_call_ms": float(first.build_ms),
         "scene_upload_ms": float(info.upload_ms),
         "scene_upload_wall_s": upload_wall,

@@ -70,16 +70,17 @@ extern "C" {
 #define RT_QUANT_CPU_TRUNC    4  /* CPUOnly/src/render.cpp:157-163 clamp to [0,1], (uchar)(255.99f*c) */
 
 /* rt_frame.kernel_variant */
-#define RT_VARIANT_DEFAULT          0  /* persistent packet kernel: warps pull 8x4 packets from a tile queue; frustum-culled wide traversal;
-                                          division-free front end of the triangle test (= RT_VARIANT_PERSIST) */
+#define RT_VARIANT_DEFAULT          0  /* packet kernel (one warp = one 8x4 packet), frustum-culled wide traversal, division-free front end of the
+                                          triangle test.  rt_render_into: the PERSISTENT launch (blocks pull tiles from a queue and publish finished
+                                          bands themselves, = RT_VARIANT_PERSIST); rt_render: one block per tile (= RT_VARIANT_FRUSTUM) */
 #define RT_VARIANT_PACKET_OCC6      1  /* retired round-1 experiments 1, 2, 4: accepted, run RT_VARIANT_PACKET */
 #define RT_VARIANT_PACKET_OCC10     2
 #define RT_VARIANT_PACKET_EXACT_SLAB 3 /* per-lane packet traversal with the unfused (b-o)*inv slab test */
 #define RT_VARIANT_PACKET_PREFETCH  4
 #define RT_VARIANT_PACKET_PIXEL_MAJOR 5 /* one sample of 32 pixels per packet even when spp > 1 (per-lane traversal) */
-#define RT_VARIANT_FRUSTUM          6  /* round-1 default: one block per 16x8 tile, frustum-culled wide traversal (one lane = one box, 32 boxes per round) */
+#define RT_VARIANT_FRUSTUM          6  /* one block per 16x8 tile, frustum-culled wide traversal (one lane = one box, 32 boxes per round) */
 #define RT_VARIANT_PACKET           7  /* one block per tile, per-lane traversal (every lane slab-tests both children of a node) */
-#define RT_VARIANT_PERSIST          8  /* the default, by name */
+#define RT_VARIANT_PERSIST          8  /* the persistent launch also for rt_render */
 #define RT_VARIANT_PERSIST_EXACT_MT 9  /* persistent kernel with the reference-order triangle test (IEEE divide first): A/B of the lazy front end */
 #define RT_VARIANT_PERSIST_OCC8    11  /* persistent kernel compiled for >= 8 resident blocks per SM (64 registers) */
 #define RT_VARIANT_PERSIST_OCC10   12  /* ... >= 10 resident blocks per SM (48 registers) */

@@ -151,6 +151,11 @@ struct rt_ctx {
     std::vector<rt_ctx*> members;                        // ranks 1..n-1 (rank 0 of a group only)
     bool inproc = false;                                 // this context is a rank of such a group
     rt_ctx* group_root = nullptr;                        // ... and this is its rank 0
+    unsigned long long* pin_dev = nullptr;               // device alias of pin; pin[8..10]: ray counters + sequence number written by the persistent kernel's last block,
+                                                         // pin[12]: 'copies done' word written by a stream memory operation (host-polled end of rt_render_into)
+    unsigned long long* pin = nullptr;                   // 128 bytes of page-locked host memory: small device->host reads (ray counters, error word)
+                                                         // land here — into pageable memory each of them is a staged, synchronous copy of tens of microseconds
+    bool fast_finish = false;                            // the rt_render_into in flight ends with host-polled words (no stream synchronisation)
     HostOut pump_outs[4] = {}; unsigned pump_seq = 0; int pump_next = 0; bool last_pumped = false;   // band copies of the rt_render_into in flight (band_pump)
     unsigned long long peer_timeout_ns = 120ull * 1000000000ull;   // bound of every in-kernel / flag-kernel wait on another rank (rt_comm_set_timeout)
     int dbg_rank = 0, dbg_world = 0;              // rt_debug_set_shard: render one rank's share on a single GPU (timing only)
@@ -438,6 +443,8 @@ int rt_create(rt_ctx** out, int device) {
     if (e == cudaSuccess) e = cudaEventCreate(&c->evk0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->evk1);
     if (e == cudaSuccess) e = c->counters.reserve(RT_COUNTER_BYTES + RT_PERSIST_CTL_BYTES);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&c->pin, 128, cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e == cudaSuccess) { memset(c->pin, 0, 128); e = cudaHostGetDevicePointer((void**)&c->pin_dev, c->pin, 0); }
     if (e != cudaSuccess) { int r = fail(nullptr, RT_ERR_CUDA, "rt_create: %s", cudaGetErrorString(e)); delete c; return r; }
     *out = c;
     return RT_OK;
@@ -507,6 +514,7 @@ int rt_destroy(rt_ctx* c) {
     peer_teardown(c, false);
     shm_release(c);
     if (c->hflags) cudaFreeHost(c->hflags);
+    if (c->pin) cudaFreeHost(c->pin);
     if (c->peer_err) cudaFree(c->peer_err);
     if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
     free_scene(c);
@@ -1092,7 +1100,8 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
     CU(c, cudaMemsetAsync(c->counters.p, 0, RT_COUNTER_BYTES + RT_PERSIST_CTL_BYTES, c->stream));
     P.peer_timeout_ns = c->peer_timeout_ns;
     P.peer_err = c->peer_err;
-    const bool persistent = rt_render_is_persistent(P, fr->kernel_variant);
+    const bool persistent = rt_render_is_persistent(P, fr->kernel_variant, into != nullptr);
+    P.persist = persistent ? 1 : 0;
     const HostOut outs[4] = {{into ? into->rgb : nullptr, RT_OUT_RGB_F32, 12, P.rgb, "rgb"}, {into ? into->rgb8 : nullptr, RT_OUT_RGB8, 3, P.rgb8, "rgb8"},
                              {into ? into->tri_id : nullptr, RT_OUT_TRI_ID, 4, P.tri_id, "tri_id"}, {into ? into->t : nullptr, RT_OUT_T, 4, P.t, "t"}};
     c->pump_outs[0] = outs[0]; c->pump_outs[1] = outs[1]; c->pump_outs[2] = outs[2]; c->pump_outs[3] = outs[3];
@@ -1109,6 +1118,7 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
     int launches = 0;
     c->last_host_direct = false;
     c->last_pumped = false;
+    c->fast_finish = false;
     if (host_direct) {
         int rc = ensure_band_resources(c);
         if (rc != RT_OK) return rc;
@@ -1130,6 +1140,7 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
         P.num_chunks = plan_bands(P.local_tiles, P.chunk_tiles, true, P.band_end);
         P.seq = seq;
         P.flags = c->hflags_dev + RT_PEER_CHUNK_FLAG(0, 0);
+        if (persistent) P.host_counters = c->pin_dev + 8;
         int l = 0;
         CU(c, cudaEventRecord(c->evk0, c->stream));
         CU(c, rt_launch_render(P, fr->kernel_variant, c->stream, &l));
@@ -1148,8 +1159,16 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
                 ++launches;
             }
         }
+        // end of the frame without a stream synchronisation: a stream memory operation writes "copies done" into page-locked host
+        // memory behind the last copy; rt_render_into polls that word and takes the ray counts from the words the kernel's last
+        // block wrote (measured: the event + small device->host reads + cudaStreamSynchronize it replaces cost 70-170 us per frame)
+        c->fast_finish = false;
+        if (persistent && !c->inproc) {
+            StreamWriteValue32Fn w32 = stream_write_value32();
+            if (w32 && w32((CUstream)c->copy_stream, (CUdeviceptr)(c->pin_dev + 12), seq, 0) == CUDA_SUCCESS) c->fast_finish = true;
+        }
         CU(c, cudaEventRecord(c->copy_done, c->copy_stream));
-        CU(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));
+        if (!c->fast_finish) CU(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));
         if (pipelined) *pipelined = true;
         c->last_host_direct = !c->inproc;
     } else if (peer) {
@@ -1226,14 +1245,23 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
         P.num_chunks = plan_bands(P.local_tiles, (P.local_tiles + 1) / 2, true, P.band_end);     // halves, the second one halved three times: 1/2, 3/4, 7/8, 15/16, 1
         P.seq = seq;
         P.flags = c->hflags_dev + RT_PEER_CHUNK_FLAG(0, 0);
+        P.host_counters = c->pin_dev + 8;
         CU(c, cudaEventRecord(c->evk0, c->stream));
         CU(c, rt_launch_render(P, fr->kernel_variant, c->stream, &launches));
         CU(c, cudaEventRecord(c->evk1, c->stream));
         CU(c, cudaStreamWaitEvent(c->copy_stream, c->evk0, 0));
         rc = pump_bands(seq);
         if (rc != RT_OK) return rc;
+        // end of the frame without a stream synchronisation: a stream memory operation writes "copies done" into page-locked host
+        // memory behind the last copy; rt_render_into polls that word and takes the ray counts from the words the kernel's last
+        // block wrote (measured: the event + small device->host reads + cudaStreamSynchronize it replaces cost 70-170 us per frame)
+        c->fast_finish = false;
+        if (persistent && !c->inproc) {
+            StreamWriteValue32Fn w32 = stream_write_value32();
+            if (w32 && w32((CUstream)c->copy_stream, (CUdeviceptr)(c->pin_dev + 12), seq, 0) == CUDA_SUCCESS) c->fast_finish = true;
+        }
         CU(c, cudaEventRecord(c->copy_done, c->copy_stream));
-        CU(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));
+        if (!c->fast_finish) CU(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));
         if (pipelined) *pipelined = true;
     } else if (into && c->world == 1 && !dbg_shard && P.tiles_y >= 2) {
         // kernels without in-kernel completion flags: one launch per band on a few streams, copies chained with events
@@ -1270,7 +1298,7 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
         CU(c, cudaEventRecord(c->evk1, c->stream));
     }
 
-    if (c->world > 1 && !peer) {
+    if (c->world > 1 && !peer && !host_direct) {
         // Tile gather to rank 0: one grouped send/recv per requested plane, then an unpack kernel per source rank.
         const size_t other_pix = (size_t)(c->world - 1) * npix_loc;   // every rank has the same number of tile slots
         if (c->rank == 0) {
@@ -1397,7 +1425,26 @@ int rt_render_into(rt_ctx* c, const rt_frame* fr, rt_image* img) {
     if (rc != RT_OK) return rc;
     if (!pipelined) return rt_download_image(c, img);           // multi-GPU contexts: gather first, then one copy
     rt_image meta{};                                            // planes are already on their way: fetch counters and times only
-    rc = rt_download_image(c, &meta);
+    if (c->fast_finish) {
+        const unsigned seq = c->pump_seq;
+        volatile unsigned long long* pin = c->pin;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (unsigned spins = 0; (unsigned)pin[12] != seq || (unsigned)pin[10] != seq; ++spins) {
+            if ((spins & 0x3fffu) == 0x3fffu) {
+                const cudaError_t q = cudaStreamQuery(c->copy_stream);
+                if (q != cudaSuccess && q != cudaErrorNotReady) return fail(c, RT_ERR_CUDA, "rt_render_into: %s", cudaGetErrorString(q));
+                if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e9 > (double)c->peer_timeout_ns)
+                    return fail(c, RT_ERR_STATE, "rt_render_into: copies not finished after %llu s", c->peer_timeout_ns / 1000000000ull);
+            }
+        }
+        __sync_synchronize();
+        meta.width = c->fp.W; meta.height = c->fp.H; meta.rays_primary = pin[8]; meta.rays_shadow = pin[9];
+        float ms = 0.f;
+        CU(c, cudaEventSynchronize(c->ev1));                    // (recorded behind the kernel, which ended before its last band's copy)
+        CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        meta.gpu_ms = ms;
+        rc = RT_OK;
+    } else rc = rt_download_image(c, &meta);
     lap("stream drained, counters read");
     if (rc != RT_OK) return rc;
     if (c->last_host_direct && c->rank == 0) {                  // shared host image: every rank's bands must have landed
@@ -1419,9 +1466,10 @@ int rt_sync(rt_ctx* c, float* gpu_ms) {
     if (!c) return fail(nullptr, RT_ERR_ARG, "rt_sync: NULL ctx");
     CU(c, cudaSetDevice(c->device));
     if (!c->frame_valid) return fail(c, RT_ERR_STATE, "rt_sync: no frame rendered");
-    unsigned perr = 0;
-    if (c->peer && c->peer_err) CU(c, cudaMemcpyAsync(&perr, c->peer_err, sizeof perr, cudaMemcpyDeviceToHost, c->stream));
+    c->pin[4] = 0ull;
+    if (c->peer && c->peer_err) CU(c, cudaMemcpyAsync(&c->pin[4], c->peer_err, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    const unsigned perr = (unsigned)c->pin[4];
     if (perr) return peer_timeout(c, perr);
     if (gpu_ms) CU(c, cudaEventElapsedTime(gpu_ms, c->ev0, c->ev1));
     return RT_OK;
@@ -1474,11 +1522,12 @@ int rt_download_image(rt_ctx* c, rt_image* img) {
             CU(c, cudaMemcpyAsync(o.host, src->p, o.bpp * npix, cudaMemcpyDeviceToHost, c->stream));
         }
     }
-    unsigned long long cnt[2] = {0, 0};
-    unsigned perr = 0;
-    CU(c, cudaMemcpyAsync(cnt, c->counters.p, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
-    if (c->peer && c->peer_err) CU(c, cudaMemcpyAsync(&perr, c->peer_err, sizeof perr, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long* cnt = c->pin;                          // page-locked: truly asynchronous small reads
+    c->pin[4] = 0ull;
+    CU(c, cudaMemcpyAsync(cnt, c->counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    if (c->peer && c->peer_err) CU(c, cudaMemcpyAsync(&c->pin[4], c->peer_err, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    const unsigned perr = (unsigned)c->pin[4];
     if (perr) return peer_timeout(c, perr);
     img->width = P.W; img->height = P.H;
     img->rays_primary = cnt[0]; img->rays_shadow = cnt[1];

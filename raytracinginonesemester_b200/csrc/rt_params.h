@@ -43,6 +43,7 @@ struct FrameParams {
     float scene_c[3], scene_r2;     // scene bounding sphere (centre, padded squared radius): packets that miss it skip the traversal set-up
     float frustum_eps;              // frustum traversal: absolute slack of the plane tests = 1.6e-5 x largest coordinate in play (host)
     int sample_group;               // packet kernel: samples of one pixel traced side by side (power of two dividing spp, <= 32)
+    int persist;                    // 1: this frame runs on the persistent kernel (host decides: rt_render_is_persistent)
     // persistent kernel (rt_trace.cu, k_render_persist): work queue + in-kernel completion protocol
     unsigned* queue;                // PersistCtl, zeroed by the host before the launch
     int num_chunks;                 // the rank's tile slots are cut into num_chunks bands whose completion is published (0: none);
@@ -55,6 +56,8 @@ struct FrameParams {
     int wait_ranks;                 // rank 0 of the fused gather: ranks 1..wait_ranks are awaited by the last warp; else 0
     const unsigned* ready_in;       // ranks != 0 of the fused gather: rank 0's `ready` word, awaited before the first store; else NULL
     unsigned* ready_out;            // rank 0 of the fused gather: where `ready = seq` is published at kernel start; else NULL
+    unsigned long long* host_counters; // persistent kernel: when set, the last block out copies counters[0..1] (primary / shadow rays of the frame)
+                                    // here — mapped page-locked host memory — so that rt_render_into needs no device->host read afterwards
     unsigned long long peer_timeout_ns;
     unsigned* peer_err;             // set when a wait above timed out
 };

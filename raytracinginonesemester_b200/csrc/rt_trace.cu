@@ -698,6 +698,9 @@ __device__ __forceinline__ void flush_warp_counters(const FrameParams& P, const 
     }
 }
 
+#ifndef RT_X_TILE_LAZY
+#define RT_X_TILE_LAZY 1
+#endif
 // Block-per-tile launch (one 128-thread block = one 16x8 tile, grid = the rank's tile slots): kept as the comparison
 // point of the persistent kernel below and for the experimental traversal variants.
 template <int MODE, bool STATS, bool FAST, int MINB, bool PF = false, bool GROUPED = false, bool FRUSTUM = false>
@@ -714,7 +717,7 @@ k_render_packet(const __grid_constant__ FrameParams P) {
     if ((threadIdx.x & 31) == 0) { ws->tile = blockIdx.x + (unsigned)P.tile_offset; ws->sub = threadIdx.x >> 5; ws->nprim = 0u; ws->nshadow = 0u; }
     __syncwarp();
     TraceStats st{0, 0, 0, 0, 0};
-    render_packet<MODE, STATS, FAST, PF, GROUPED, FRUSTUM, false, TAG>(P, ws, s_stash + threadIdx.x, wstack, wfr, STATS ? &st : nullptr);
+    render_packet<MODE, STATS, FAST, PF, GROUPED, FRUSTUM, RT_X_TILE_LAZY != 0, TAG>(P, ws, s_stash + threadIdx.x, wstack, wfr, STATS ? &st : nullptr);
     __syncwarp();
     flush_warp_counters(P, ws);
     if (STATS) flush_stats(P, st, FRUSTUM);
@@ -722,7 +725,7 @@ k_render_packet(const __grid_constant__ FrameParams P) {
 
 // --------------------------------------------------------------- persistent frame kernel ----
 // The default frame kernel.  The grid is sized to the machine (SMs x resident blocks), not to the frame: every block
-// pulls 16x8 tiles from the rank's tile queue (one atomicAdd per tile, issued one tile ahead) until it is empty; its
+// pulls 16x8 tiles from the rank's tile queue (one atomicAdd per tile, issued by the first warp that finishes the current one) until it is empty; its
 // four warps take the tile's four 8x4 packets and meet at one barrier per tile.
 // Completion is published by the kernel itself — no flag kernels, no launch gaps: the rank's tile slots are cut into
 // P.num_chunks bands (P.band_end); a block counts the tiles it finished per band and, when it moves on to
@@ -768,6 +771,7 @@ k_render_persist(const __grid_constant__ FrameParams P) {
     __shared__ float s_stash[RT_STASH_WORDS * RT_BLOCK_THREADS];
     __shared__ WarpSlot s_ws[RT_BLOCK_THREADS / 32];
     __shared__ unsigned s_tile[2];                    // double-buffered: one barrier per tile
+    __shared__ unsigned s_claim;                      // iteration whose successor tile has been pulled from the queue
     __shared__ int s_go, s_band;
     __shared__ unsigned s_band_cnt, s_last;
     int* const wstack = s_wstack + (threadIdx.x >> 5) * RT_FSTACK;
@@ -778,6 +782,7 @@ k_render_persist(const __grid_constant__ FrameParams P) {
     if ((threadIdx.x & 31) == 0) { ws->sub = threadIdx.x >> 5; ws->nprim = 0u; ws->nshadow = 0u; }
     if (threadIdx.x == 0) {
         s_tile[0] = atomicAdd(&ctl->next_tile, 1u);
+        s_claim = 0u;
         s_band = -1; s_band_cnt = 0u;
         int go = 1;
         if (P.ready_out && blockIdx.x == 0) { *(volatile unsigned*)P.ready_out = P.seq; }
@@ -809,7 +814,6 @@ k_render_persist(const __grid_constant__ FrameParams P) {
         // broadcast with a warp reduction: the result is warp-uniform FOR THE COMPILER (uniform datapath for the tile arithmetic)
         const unsigned tile = __reduce_max_sync(FULLMASK, *(volatile unsigned*)&s_tile[it & 1u]);
         if (tile >= (unsigned)P.local_tiles) break;
-        if (threadIdx.x == 0) s_tile[(it + 1u) & 1u] = atomicAdd(&ctl->next_tile, 1u);      // one tile ahead: the atomic's latency is off the critical path
         if (P.num_chunks > 0) {
             int b = 0;
             while (b + 1 < P.num_chunks && tile >= (unsigned)P.band_end[b]) ++b;      // <= 16 uniform compares
@@ -824,17 +828,31 @@ k_render_persist(const __grid_constant__ FrameParams P) {
         __syncwarp();
         if (*(volatile int*)&s_go)
             render_packet<MODE, STATS, FAST, false, GROUPED, true, LAZY, TAG>(P, ws, s_stash + threadIdx.x, wstack, wfr, STATS ? &st : nullptr);
+        // The FIRST warp to finish its packet pulls the block's next tile: the atomic's round trip (~1 us) overlaps its wait for the
+        // siblings at the barrier, and the tile is claimed as late as possible (tiles claimed early and held while another block idles
+        // lengthen the tail).  (Pulled by thread 0 at the top of the iteration, the store of the result stalled warp 0 for the round
+        // trip before its packet: +2.5 % on the whole frame.)
+        if ((threadIdx.x & 31) == 0 && atomicCAS(&s_claim, it, it + 1u) == it) s_tile[(it + 1u) & 1u] = atomicAdd(&ctl->next_tile, 1u);
     }
     if (P.num_chunks > 0 && *(volatile int*)&s_band >= 0) release_band();
     __syncwarp();
     flush_warp_counters(P, ws);
     if (STATS) flush_stats(P, st, true);
-    if (P.wait_ranks > 0) {
+    if (P.wait_ranks > 0 || P.host_counters) {
+        __syncthreads();                              // this block's counter atomics happen-before thread 0's acq_rel add
+        if (threadIdx.x == 0) {
+            unsigned old;
+            asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(&ctl->blocks_done) : "memory");
+            s_last = old + 1u == gridDim.x ? 1u : 0u;
+            if (s_last && P.host_counters && P.counters) {      // every block's rays are in: hand the totals to the host
+                const unsigned long long a = *(volatile unsigned long long*)&P.counters[0], b = *(volatile unsigned long long*)&P.counters[1];
+                P.host_counters[0] = a; P.host_counters[1] = b;
+                asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(&P.host_counters[2]), "l"((unsigned long long)P.seq) : "memory");
+            }
+        }
+        __syncthreads();
         // rank 0 of the fused gather: the last block out waits for the other ranks' band flags (they live in this GPU's memory)
-        __syncthreads();
-        if (threadIdx.x == 0) s_last = atomicAdd(&ctl->blocks_done, 1u) + 1u == gridDim.x ? 1u : 0u;
-        __syncthreads();
-        if (s_last) {
+        if (s_last && P.wait_ranks > 0) {
             const int nflags = P.wait_ranks * P.num_chunks;
             const unsigned long long t0 = rt_globaltimer();
             for (int i = (int)threadIdx.x; i < nflags; i += RT_BLOCK_THREADS) {
@@ -942,16 +960,16 @@ static cudaError_t persist_grid(void (*kernel)(const FrameParams), int tiles, un
 #define RT_LAUNCH_PERSIST(...) do { unsigned g_ = 1; cudaError_t e_ = persist_grid(k_render_persist<__VA_ARGS__>, fp.local_tiles, &g_); if (e_ != cudaSuccess) return e_; \
                                     k_render_persist<__VA_ARGS__><<<g_, block, 0, stream>>>(fp); } while (0)
 
-// Which frames run on the persistent kernel (the host layer asks: it then leaves the completion protocol to the kernel).
-bool rt_render_is_persistent(const FrameParams& fp, int variant) {
+// Which frames run on the persistent kernel (see rt_kernels.h).
+bool rt_render_is_persistent(const FrameParams& fp, int variant, bool banded) {
     if (fp.accel != RT_ACCEL_BVH || !fp.wide || fp.mode == RT_MODE_HW2_CPU) return false;
     // Bounce frames (max_depth > 1) run on the per-ray kernel.  Measured alternative (round 2): segment 0 as packets in this kernel, the
     // rest of every path per lane with a private stack — bit-identical frames, but SLOWER than the per-ray kernel (frog.json as shipped,
     // 1920x1080, depth 8, diffuse bounces: 1.09 vs 0.87 ms stock view, 2.66 vs 1.55 ms frame-filling view): the scalar continuation
     // inherits the packet kernel's 56-register budget and spills ~100 words per thread where the per-ray kernel has 124 registers.
     if (fp.mode != RT_MODE_HW1 && fp.max_depth > 1) return false;
-    return variant == RT_VARIANT_DEFAULT || variant == RT_VARIANT_STATS || variant == RT_VARIANT_PERSIST || variant == RT_VARIANT_PERSIST_EXACT_MT ||
-           variant == RT_VARIANT_PERSIST_OCC8 || variant == RT_VARIANT_PERSIST_OCC10;
+    if (variant == RT_VARIANT_DEFAULT || variant == RT_VARIANT_STATS) return banded;
+    return variant == RT_VARIANT_PERSIST || variant == RT_VARIANT_PERSIST_EXACT_MT || variant == RT_VARIANT_PERSIST_OCC8 || variant == RT_VARIANT_PERSIST_OCC10;
 }
 
 template <int MODE>
@@ -959,7 +977,7 @@ static cudaError_t launch_mode(const FrameParams& fp, int variant, cudaStream_t 
     dim3 grid((unsigned)fp.local_tiles), block(RT_BLOCK_THREADS);
     if (fp.accel == RT_ACCEL_BRUTE) { k_render_brute<MODE><<<grid, block, 0, stream>>>(fp); return cudaGetLastError(); }
     const bool fast = fp.fast_slab != 0;
-    if (rt_render_is_persistent(fp, variant)) {
+    if (fp.persist) {
         const bool grouped = fp.sample_group > 1;
         switch (variant) {
         case RT_VARIANT_STATS:
@@ -979,10 +997,10 @@ static cudaError_t launch_mode(const FrameParams& fp, int variant, cudaStream_t 
     // carries TraceRayIterative's full loop; the packet kernels implement depth 1.
     if (MODE != RT_MODE_HW1 && fp.max_depth > 1)
         variant = (variant == RT_VARIANT_STATS || variant == RT_VARIANT_PER_RAY_STATS || variant == RT_VARIANT_FRUSTUM_STATS || variant == RT_VARIANT_PACKET_STATS) ? RT_VARIANT_PER_RAY_STATS : RT_VARIANT_PER_RAY;
-    // no 8-wide view (it could not be allocated): per-lane packet traversal
+    // default: the frustum traversal, one block per tile; no 8-wide view (it could not be allocated): per-lane packet traversal
     if (variant == RT_VARIANT_DEFAULT || variant == RT_VARIANT_PERSIST || variant == RT_VARIANT_PERSIST_EXACT_MT || variant == RT_VARIANT_PERSIST_OCC8 || variant == RT_VARIANT_PERSIST_OCC10)
-        variant = RT_VARIANT_PACKET;
-    if (variant == RT_VARIANT_STATS) variant = RT_VARIANT_PACKET_STATS;
+        variant = fp.wide ? RT_VARIANT_FRUSTUM : RT_VARIANT_PACKET;
+    if (variant == RT_VARIANT_STATS) variant = fp.wide ? RT_VARIANT_FRUSTUM_STATS : RT_VARIANT_PACKET_STATS;
     if ((variant == RT_VARIANT_FRUSTUM || variant == RT_VARIANT_FRUSTUM_STATS) && !fp.wide) return cudaErrorInvalidValue;
     switch (variant) {
     case RT_VARIANT_PACKET_OCC6: case RT_VARIANT_PACKET_OCC10: case RT_VARIANT_PACKET_PREFETCH:   // retired round-1 experiments: the plain per-lane kernel
