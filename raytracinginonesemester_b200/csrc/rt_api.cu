@@ -1289,8 +1289,17 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
             rc = copy_rows(y0, y1);
             if (rc != RT_OK) return rc;
         }
+        {   // end of the frame without a stream synchronisation (see rt_render_into): ray counters into page-locked memory and a
+            // "copies done" word behind the last copy, both on the copy stream, which has waited for every band kernel by now
+            StreamWriteValue32Fn w32 = stream_write_value32();
+            const unsigned seq = ++c->hseq;
+            if (w32) {
+                CU(c, cudaMemcpyAsync(c->pin + 8, c->counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->copy_stream));
+                if (w32((CUstream)c->copy_stream, (CUdeviceptr)(c->pin_dev + 12), seq, 0) == CUDA_SUCCESS) { c->fast_finish = true; c->pump_seq = seq; c->pin[10] = seq; }
+            }
+        }
         CU(c, cudaEventRecord(c->copy_done, c->copy_stream));
-        CU(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));
+        if (!c->fast_finish) CU(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));
         if (pipelined) *pipelined = true;
     } else {
         CU(c, cudaEventRecord(c->evk0, c->stream));

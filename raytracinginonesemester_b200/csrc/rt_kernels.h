@@ -26,9 +26,11 @@ cudaError_t rt_launch_render(const FrameParams& fp, int kernel_variant, cudaStre
 // Which frames run on the persistent kernel, which publishes band-completion flags and runs the multi-GPU handshake itself
 // (FrameParams.queue / flags / ready_* / wait_ranks); other kernels need the flag kernels below around them.  `banded`: the
 // caller wants bands published while the frame renders (rt_render_into).  RT_VARIANT_DEFAULT picks the persistent kernel for
-// banded frames and the block-per-tile launch of the same traversal otherwise (measured, B200, C4: 1.911 vs 1.954 ms on one
-// GPU, 0.336 vs 0.374 ms per frame on eight — the hardware's block scheduler does the same job with ~2 % fewer instructions
-// when nothing has to be published mid-frame).  The host stores the answer in FrameParams.persist.
+// banded frames of multi-GPU contexts (every rank's copy engine follows its own kernel's band flags) and the block-per-tile
+// launch of the same traversal otherwise — measured, B200, C4: device time 1.847 vs 1.954 ms on one GPU, 0.336 vs 0.374 ms per
+// frame on eight; end to end on one GPU (one launch per band + event-chained copies vs one persistent launch + band flags) 1.96
+// vs 2.03 ms: the hardware's block scheduler does the same job without a barrier per tile (11 % of the persistent kernel's stall
+// samples) and tolerates one more resident block per SM.  The host stores the answer in FrameParams.persist.
 bool rt_render_is_persistent(const FrameParams& fp, int kernel_variant, bool banded);
 #define RT_PERSIST_CTL_BYTES 128          // device bytes behind FrameParams.queue
 // Scatter tile-packed planes of rank `src_rank` into the row-major image (rank 0, world > 1).

@@ -312,7 +312,12 @@ __device__ __noinline__ TraceResult packet_trace(const BvhNode* __restrict__ nod
 // and every plane offset by feps = 1.6e-5 x the largest coordinate in play (host: scene bounds, camera) — an
 // order of magnitude more than the error of the 6-term FMA sums.
 // 9 resident blocks (36 warps, 56 registers) measured best for the frustum kernel on C4: 6 -> 2.21 ms, 8 -> 2.07, 9 -> 2.01, 10 -> 2.05, 12 -> 2.04
-#define RT_FRUSTUM_MINB 9
+#ifndef RT_FRUSTUM_MINB
+#define RT_FRUSTUM_MINB 9               // persistent kernel
+#endif
+#ifndef RT_TILE_MINB
+#define RT_TILE_MINB 10                 // block-per-tile launch of the frustum traversal: r2, with the shared-memory stash, 10 blocks (48 registers): 9 -> 1.883 ms, 10 -> 1.848 ms
+#endif
 
 // sm_100a: float min/max reductions are one instruction (CREDUX.MIN/MAX.F32, result in a uniform register)
 __device__ __forceinline__ float warp_fmin(float v) { float r; asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v)); return r; }
@@ -968,7 +973,7 @@ bool rt_render_is_persistent(const FrameParams& fp, int variant, bool banded) {
     // 1920x1080, depth 8, diffuse bounces: 1.09 vs 0.87 ms stock view, 2.66 vs 1.55 ms frame-filling view): the scalar continuation
     // inherits the packet kernel's 56-register budget and spills ~100 words per thread where the per-ray kernel has 124 registers.
     if (fp.mode != RT_MODE_HW1 && fp.max_depth > 1) return false;
-    if (variant == RT_VARIANT_DEFAULT || variant == RT_VARIANT_STATS) return banded;
+    if (variant == RT_VARIANT_DEFAULT || variant == RT_VARIANT_STATS) return banded && fp.world > 1;
     return variant == RT_VARIANT_PERSIST || variant == RT_VARIANT_PERSIST_EXACT_MT || variant == RT_VARIANT_PERSIST_OCC8 || variant == RT_VARIANT_PERSIST_OCC10;
 }
 
@@ -1026,20 +1031,20 @@ static cudaError_t launch_mode(const FrameParams& fp, int variant, cudaStream_t 
     case RT_VARIANT_PACKET_EXACT_SLAB: k_render_packet<MODE, false, false, 8><<<grid, block, 0, stream>>>(fp); break;
     case RT_VARIANT_FRUSTUM:            // round-1 default: block-per-tile launch of the frustum traversal
         if (fp.sample_group > 1) {
-            if (fast) k_render_packet<MODE, false, true, RT_FRUSTUM_MINB, false, true, true><<<grid, block, 0, stream>>>(fp);
-            else k_render_packet<MODE, false, false, RT_FRUSTUM_MINB, false, true, true><<<grid, block, 0, stream>>>(fp);
+            if (fast) k_render_packet<MODE, false, true, RT_TILE_MINB, false, true, true><<<grid, block, 0, stream>>>(fp);
+            else k_render_packet<MODE, false, false, RT_TILE_MINB, false, true, true><<<grid, block, 0, stream>>>(fp);
         } else {
-            if (fast) k_render_packet<MODE, false, true, RT_FRUSTUM_MINB, false, false, true><<<grid, block, 0, stream>>>(fp);
-            else k_render_packet<MODE, false, false, RT_FRUSTUM_MINB, false, false, true><<<grid, block, 0, stream>>>(fp);
+            if (fast) k_render_packet<MODE, false, true, RT_TILE_MINB, false, false, true><<<grid, block, 0, stream>>>(fp);
+            else k_render_packet<MODE, false, false, RT_TILE_MINB, false, false, true><<<grid, block, 0, stream>>>(fp);
         }
         break;
     case RT_VARIANT_FRUSTUM_STATS:
         if (fp.sample_group > 1) {
-            if (fast) k_render_packet<MODE, true, true, RT_FRUSTUM_MINB, false, true, true><<<grid, block, 0, stream>>>(fp);
-            else k_render_packet<MODE, true, false, RT_FRUSTUM_MINB, false, true, true><<<grid, block, 0, stream>>>(fp);
+            if (fast) k_render_packet<MODE, true, true, RT_TILE_MINB, false, true, true><<<grid, block, 0, stream>>>(fp);
+            else k_render_packet<MODE, true, false, RT_TILE_MINB, false, true, true><<<grid, block, 0, stream>>>(fp);
         } else {
-            if (fast) k_render_packet<MODE, true, true, RT_FRUSTUM_MINB, false, false, true><<<grid, block, 0, stream>>>(fp);
-            else k_render_packet<MODE, true, false, RT_FRUSTUM_MINB, false, false, true><<<grid, block, 0, stream>>>(fp);
+            if (fast) k_render_packet<MODE, true, true, RT_TILE_MINB, false, false, true><<<grid, block, 0, stream>>>(fp);
+            else k_render_packet<MODE, true, false, RT_TILE_MINB, false, false, true><<<grid, block, 0, stream>>>(fp);
         }
         break;
     case RT_VARIANT_PER_RAY:       k_render_bvh<MODE, false><<<grid, block, 0, stream>>>(fp); break;
