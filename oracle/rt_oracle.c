@@ -4,11 +4,16 @@
  * include/) may link, import or call this file; only tests/, __graft_entry__.smoke()
  * and bench.py's cpu_baseline / --impl reference legs do, and only as the checker.
  *
- * Parity status: PINNED.  tests/test_oracle.py checks this file against
- *   - the reference's own code compiled in place (oracle/ref_shim.cpp -> oracle/_ref/),
- *   - the reference's committed golden image HW1/frog_output.png and the
- *     ray/triangle unit vectors of HW1/test_ray_tri_inter_STANDALONE,
- *   - golden fixtures under tests/golden/ generated by tools/make_golden.py.
+ * Parity status: PINNED.  tests/test_oracle_golden.py (and tests/test_soft_shadows.py for the
+ * disk lights) check this file against
+ *   - the reference's own code compiled in place (oracle/ref_shim_hw1.cpp, ref_shim_hw2.cpp,
+ *     ref_shim_cpuonly.cpp, ref_shim_ppm.cpp -> oracle/_ref/*.so, built by oracle/build.py),
+ *   - the reference's committed golden images HW1/frog_output.png and
+ *     CPUOnly/output/sphere_point_output.png, and the ray/triangle unit vectors of
+ *     HW1/test_ray_tri_inter_STANDALONE,
+ *   - golden fixtures under tests/golden/ generated from those shims by tools/make_golden*.py
+ *     (make_golden.py, make_golden_bounce.py, make_golden_cpuonly.py, make_golden_area.py,
+ *     make_golden_e2e.py).
  *
  * Build: gcc -O2 -ffp-contract=off -fPIC -shared -pthread (no -march=native, no
  * -ffast-math): the x86-64 reference build has no FMA contraction and the hit
