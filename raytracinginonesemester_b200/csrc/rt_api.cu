@@ -185,26 +185,39 @@ void free_scene(rt_ctx* c) {
 }
 
 
+// Device bytes of the scene arrays (the 8-wide view adds its own in build_wide_nodes).  The per-vertex-normal blocks exist
+// only when the mesh has normals.
+static uint64_t scene_arena_bytes(const rt_ctx* c) {
+    return sizeof(BvhNode) * (uint64_t)c->num_nodes + (c->has_normals ? 2u : 1u) * sizeof(TriBlock) * (uint64_t)c->num_tris +
+           sizeof(rt_material) * (uint64_t)c->num_materials;
+}
+
 // 8-wide view of the BVH2 for the frustum traversal: derived data, rebuilt by every rank from its copy of the nodes.
 int build_wide_nodes(rt_ctx* c) {
     if (c->wide) { cudaFree(c->wide); c->wide = nullptr; }
     if (!c->has_bvh || !c->num_nodes) return RT_OK;
-    if (cudaMalloc(&c->wide, sizeof(WideNode) * (size_t)c->num_nodes) != cudaSuccess) {
-        (void)cudaGetLastError();          // not enough memory for the 8-wide view: frames use the per-lane traversal
-        c->wide = nullptr;
-        return RT_OK;
-    }
     cudaEvent_t e0, e1;
     CU(c, cudaEventCreate(&e0)); CU(c, cudaEventCreate(&e1));
     CU(c, cudaEventRecord(e0, c->stream));
-    CU(c, rt_build_wide(c->nodes, c->num_nodes, c->wide, c->stream));
+    uint32_t count = 0;
+    // Phase 0 (wide nodes at depth 0, 3, 6, ...): on the LBVHs measured the three thirds are the same size to 2 % and the
+    // full first hop renders 1.5 % faster (tools/wide_probe.py).  RT_B200_WIDE_PHASE = 1, 2 or -1 (smallest) is a measurement knob.
+    const char* ph = getenv("RT_B200_WIDE_PHASE");
+    const cudaError_t we = rt_build_wide(c->nodes, c->num_nodes, ph && *ph ? atoi(ph) : 0, &c->wide, &count, c->stream);
+    if (we == cudaErrorMemoryAllocation) {
+        (void)cudaGetLastError();          // not enough memory for the 8-wide view: frames use the per-lane traversal
+        c->wide = nullptr;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        return RT_OK;
+    }
+    CU(c, we);
     CU(c, cudaEventRecord(e1, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     c->info.build_ms += ms;
-    c->info.arena_bytes += sizeof(WideNode) * (uint64_t)c->num_nodes;
+    c->info.arena_bytes += sizeof(WideNode) * (uint64_t)count;
     return RT_OK;
 }
 
@@ -237,7 +250,7 @@ int broadcast_scene(rt_ctx* c, int root_status) {
         c->num_tris = h.num_tris; c->num_nodes = h.num_nodes; c->num_materials = (int)h.num_materials; c->has_bvh = h.has_bvh != 0; c->has_normals = h.has_normals != 0;
         if (c->num_nodes) CU(c, cudaMalloc(&c->nodes, sizeof(BvhNode) * (size_t)c->num_nodes));
         CU(c, cudaMalloc(&c->geom, sizeof(TriBlock) * (size_t)c->num_tris));
-        CU(c, cudaMalloc(&c->shade, sizeof(TriBlock) * (size_t)c->num_tris));
+        if (c->has_normals) CU(c, cudaMalloc(&c->shade, sizeof(TriBlock) * (size_t)c->num_tris));
         if (c->num_materials) CU(c, cudaMalloc(&c->materials, sizeof(rt_material) * (size_t)c->num_materials));
         memset(&c->info, 0, sizeof c->info);
         c->info.num_triangles = h.num_tris; c->info.num_nodes = h.num_nodes; c->info.num_leaves = h.num_leaves;
@@ -246,13 +259,12 @@ int broadcast_scene(rt_ctx* c, int root_status) {
     NC(c, GroupStart());
     if (c->num_nodes) NC(c, Broadcast(c->nodes, c->nodes, sizeof(BvhNode) * (size_t)c->num_nodes, ncclUint8, 0, c->comm, c->stream));
     NC(c, Broadcast(c->geom, c->geom, sizeof(TriBlock) * (size_t)c->num_tris, ncclUint8, 0, c->comm, c->stream));
-    NC(c, Broadcast(c->shade, c->shade, sizeof(TriBlock) * (size_t)c->num_tris, ncclUint8, 0, c->comm, c->stream));
+    if (c->has_normals) NC(c, Broadcast(c->shade, c->shade, sizeof(TriBlock) * (size_t)c->num_tris, ncclUint8, 0, c->comm, c->stream));
     if (c->num_materials) NC(c, Broadcast(c->materials, c->materials, sizeof(rt_material) * (size_t)c->num_materials, ncclUint8, 0, c->comm, c->stream));
     NC(c, GroupEnd());
     CU(c, cudaStreamSynchronize(c->stream));
     c->has_scene = true;
-    c->info.arena_bytes = sizeof(BvhNode) * (uint64_t)c->num_nodes + 2 * sizeof(TriBlock) * (uint64_t)c->num_tris +
-                          sizeof(rt_material) * (uint64_t)c->num_materials;
+    c->info.arena_bytes = scene_arena_bytes(c);
     return build_wide_nodes(c);
 }
 
@@ -639,7 +651,7 @@ static int upload_local(rt_ctx* c, const rt_scene* sc) {
     if (sc->normals) CUS(cudaMalloc(&d_nrm, sizeof(float) * 3 * nv));
     if (sc->tri_obj_ids) CUS(cudaMalloc(&d_obj, sizeof(int32_t) * nt));
     CUS(cudaMalloc(&c->geom, sizeof(TriBlock) * nt));
-    CUS(cudaMalloc(&c->shade, sizeof(TriBlock) * nt));
+    if (sc->normals) CUS(cudaMalloc(&c->shade, sizeof(TriBlock) * nt));      // normals blocks: only for meshes that have normals
     if (sc->num_materials) CUS(cudaMalloc(&c->materials, sizeof(rt_material) * (size_t)sc->num_materials));
     lap("cudaMalloc");
     CUS(cudaEventRecord(e0, c->stream));
@@ -702,8 +714,7 @@ static int upload_local(rt_ctx* c, const rt_scene* sc) {
 #undef CUS
     c->num_tris = (uint32_t)nt; c->num_materials = sc->num_materials; c->has_scene = true; c->has_normals = sc->normals != nullptr;
     c->info.num_triangles = nt; c->info.num_nodes = c->num_nodes; c->info.build_ms = b_ms; c->info.upload_ms = up_ms;
-    c->info.arena_bytes = sizeof(BvhNode) * (uint64_t)c->num_nodes + 2 * sizeof(TriBlock) * (uint64_t)nt +
-                          sizeof(rt_material) * (uint64_t)sc->num_materials;
+    c->info.arena_bytes = scene_arena_bytes(c);
     return RT_OK;
 }
 
@@ -772,15 +783,15 @@ int rt_upload_scene(rt_ctx* c, const rt_scene* sc) {
             m->has_bvh = c->has_bvh; m->has_normals = c->has_normals; m->info = c->info;
             if (m->num_nodes) CU(c, cudaMalloc(&m->nodes, sizeof(BvhNode) * (size_t)m->num_nodes));
             CU(c, cudaMalloc(&m->geom, sizeof(TriBlock) * (size_t)m->num_tris));
-            CU(c, cudaMalloc(&m->shade, sizeof(TriBlock) * (size_t)m->num_tris));
+            if (m->has_normals) CU(c, cudaMalloc(&m->shade, sizeof(TriBlock) * (size_t)m->num_tris));
             if (m->num_materials) CU(c, cudaMalloc(&m->materials, sizeof(rt_material) * (size_t)m->num_materials));
             if (m->num_nodes) CU(c, cudaMemcpyPeerAsync(m->nodes, m->device, c->nodes, c->device, sizeof(BvhNode) * (size_t)m->num_nodes, m->stream));
             CU(c, cudaMemcpyPeerAsync(m->geom, m->device, c->geom, c->device, sizeof(TriBlock) * (size_t)m->num_tris, m->stream));
-            CU(c, cudaMemcpyPeerAsync(m->shade, m->device, c->shade, c->device, sizeof(TriBlock) * (size_t)m->num_tris, m->stream));
+            if (m->has_normals) CU(c, cudaMemcpyPeerAsync(m->shade, m->device, c->shade, c->device, sizeof(TriBlock) * (size_t)m->num_tris, m->stream));
             if (m->num_materials) CU(c, cudaMemcpyPeerAsync(m->materials, m->device, c->materials, c->device, sizeof(rt_material) * (size_t)m->num_materials, m->stream));
             CU(c, cudaStreamSynchronize(m->stream));
             m->has_scene = true;
-            m->info.arena_bytes = sizeof(BvhNode) * (uint64_t)m->num_nodes + 2 * sizeof(TriBlock) * (uint64_t)m->num_tris + sizeof(rt_material) * (uint64_t)m->num_materials;
+            m->info.arena_bytes = scene_arena_bytes(m);
             m->info.build_ms = 0.f;
             rc = build_wide_nodes(m);
             if (rc != RT_OK) fail(c, rc, "rt_upload_scene: rank %d: %s", m->rank, m->err.c_str());

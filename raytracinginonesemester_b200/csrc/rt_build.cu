@@ -123,14 +123,15 @@ __global__ void k_keep_flags(const Topo* __restrict__ topo, int n, uint32_t leaf
 }
 
 __global__ void k_emit_nodes(const Topo* __restrict__ topo, int n, const uint32_t* __restrict__ keep,
-                             const uint32_t* __restrict__ newidx, const float4* __restrict__ blo,
-                             const float4* __restrict__ bhi, BvhNode* nodes) {
+                             const uint32_t* __restrict__ newidx, const uint32_t* __restrict__ parent,
+                             const float4* __restrict__ blo, const float4* __restrict__ bhi, BvhNode* nodes) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1 || !keep[i]) return;
     const Topo tp = topo[i];
     const BvhNode nd = rt_make_node(blo[tp.left], bhi[tp.left], blo[tp.right], bhi[tp.right],
                                     rt_child_ref(tp.left, n, topo, keep, newidx), rt_child_ref(tp.right, n, topo, keep, newidx),
-                                    tp.first, (RT_TOPO_LAST(tp) - tp.first + 1u) | RT_NODE_AXIS_BITS(RT_TOPO_AXIS(tp)));
+                                    tp.first | RT_NODE_DEPTH3_BITS(rt_node_depth(parent, (uint32_t)i)),
+                                    (RT_TOPO_LAST(tp) - tp.first + 1u) | RT_NODE_AXIS_BITS(RT_TOPO_AXIS(tp)));
     float4* dst = reinterpret_cast<float4*>(nodes + newidx[i]);
     const float4* src = reinterpret_cast<const float4*>(&nd);
     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
@@ -153,7 +154,7 @@ __global__ void k_emit_single(int n, const float4* __restrict__ blo, const float
 __global__ void k_pack_tris(BuildParams bp, const uint32_t* __restrict__ vals, TriBlock* geom, TriBlock* shade) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= bp.num_tris) return;
-    rt_pack_tri(bp, vals ? vals[k] : k, geom + k, shade + k);
+    rt_pack_tri(bp, vals ? vals[k] : k, geom + k, shade ? shade + k : nullptr);
 }
 
 inline unsigned blocks_for(size_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
@@ -196,17 +197,74 @@ cudaError_t rt_bake_transform(float* pos, float* nrm, size_t first, size_t count
     return cudaGetLastError();
 }
 
-// One thread per BVH2 node: expand three levels into the node's eight wide entries (rt_wide_node, rt_build_core.h).
-__global__ void k_build_wide(const BvhNode* __restrict__ nodes, uint32_t num_nodes, WideNode* __restrict__ wide) {
+// ---- 8-wide view, compact ----
+// The frustum traversal hops three BVH2 levels at a time, so only the BVH2 nodes at every third depth ever serve as wide nodes
+// (a leaf met early ends its path).  Only those get a WideNode, and their references to each other are indices into the compact
+// array (round 1 built one WideNode per BVH2 node: 139 of 270 MB on C4, 1.39 GB on C5, most of it never read).  Which third is
+// free to choose: with phase f the root hops f levels (3 when f = 0) and every later wide node sits at depth = f (mod 3).  A
+// complete tree would make the three choices differ 4:2:1; on a real LBVH the leaf depths spread over many levels and the
+// thirds come out equal to 2 % (C4: 33.5 / 32.8 / 33.7 % of the nodes), so the caller normally asks for phase 0.  Derived data,
+// rebuilt by every rank from its copy of the nodes: each node carries its depth modulo 3 (RT_NODE_DEPTH3, k_emit_nodes).
+__global__ void k_depth_census(const BvhNode* __restrict__ nodes, uint32_t num_nodes, unsigned* __restrict__ census) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= num_nodes) return;
-    wide[i] = rt_wide_node(nodes, i);
+    const unsigned cls = i < num_nodes ? RT_NODE_DEPTH3(nodes[i].first_slot) : 3u;
+    for (unsigned c = 0; c < 3; ++c) {
+        const unsigned n = __popc(__ballot_sync(0xffffffffu, cls == c));
+        if ((threadIdx.x & 31) == 0 && n) atomicAdd(&census[c], n);
+    }
+}
+__global__ void k_wide_flags(const BvhNode* __restrict__ nodes, uint32_t num_nodes, unsigned phase, uint32_t* __restrict__ need) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < num_nodes) need[i] = (i == 0 || RT_NODE_DEPTH3(nodes[i].first_slot) == phase) ? 1u : 0u;
+}
+// One thread per needed BVH2 node: expand three levels (the root: `root_levels`) into the node's eight wide entries
+// (rt_wide_node, rt_build_core.h) and translate the inner references into compact indices.
+__global__ void k_build_wide(const BvhNode* __restrict__ nodes, uint32_t num_nodes, const uint32_t* __restrict__ need,
+                             const uint32_t* __restrict__ widx, int root_levels, WideNode* __restrict__ wide) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num_nodes || !need[i]) return;
+    WideNode w = rt_wide_node(nodes, i, i == 0 ? root_levels : 3);
+    for (int k = 0; k < 8; ++k) if (w.e[k].ref >= 0) w.e[k].ref = (int32_t)widx[w.e[k].ref];
+    wide[widx[i]] = w;
 }
 
-cudaError_t rt_build_wide(const BvhNode* nodes, uint32_t num_nodes, WideNode* wide, cudaStream_t stream) {
+// `phase`: 0, 1 or 2 forces that third; anything else picks the smallest.
+cudaError_t rt_build_wide(const BvhNode* nodes, uint32_t num_nodes, int phase, WideNode** wide_out, uint32_t* count_out, cudaStream_t stream) {
+    *wide_out = nullptr; *count_out = 0;
     if (num_nodes == 0) return cudaSuccess;
-    k_build_wide<<<blocks_for(num_nodes, 128), 128, 0, stream>>>(nodes, num_nodes, wide);
-    return cudaGetLastError();
+    uint32_t *d_need = nullptr, *d_widx = nullptr; unsigned* d_census = nullptr; void* d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cudaError_t err = cudaSuccess;
+    WideNode* wide = nullptr;
+    unsigned census[3] = {0, 0, 0};
+#define CKW(x) do { err = (x); if (err != cudaSuccess) goto done; } while (0)
+    CKW(cudaMallocAsync(&d_need, sizeof(uint32_t) * (size_t)num_nodes, stream));
+    CKW(cudaMallocAsync(&d_widx, sizeof(uint32_t) * (size_t)num_nodes, stream));
+    CKW(cudaMallocAsync(&d_census, sizeof census, stream));
+    CKW(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_need, d_widx, (int)num_nodes, stream));
+    CKW(cudaMallocAsync(&d_tmp, tmp_bytes ? tmp_bytes : 16, stream));
+    CKW(cudaMemsetAsync(d_census, 0, sizeof census, stream));
+    k_depth_census<<<blocks_for(num_nodes, 256), 256, 0, stream>>>(nodes, num_nodes, d_census);
+    CKW(cudaMemcpyAsync(census, d_census, sizeof census, cudaMemcpyDeviceToHost, stream));
+    CKW(cudaStreamSynchronize(stream));
+    {
+        // wide nodes per phase: the class itself, plus the root when it is not in the class
+        const unsigned size[3] = {census[0], census[1] + 1u, census[2] + 1u};
+        if (phase < 0 || phase > 2) { phase = 0; for (int f = 1; f < 3; ++f) if (size[f] < size[phase]) phase = f; }
+        const uint32_t count = size[phase];
+        k_wide_flags<<<blocks_for(num_nodes, 256), 256, 0, stream>>>(nodes, num_nodes, (unsigned)phase, d_need);
+        CKW(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_need, d_widx, (int)num_nodes, stream));
+        CKW(cudaMalloc(&wide, sizeof(WideNode) * (size_t)count));
+        k_build_wide<<<blocks_for(num_nodes, 128), 128, 0, stream>>>(nodes, num_nodes, d_need, d_widx, phase == 0 ? 3 : phase, wide);
+        CKW(cudaGetLastError());
+        *wide_out = wide; *count_out = count;
+        wide = nullptr;
+    }
+done:
+#undef CKW
+    if (wide) cudaFree(wide);
+    cudaFreeAsync(d_need, stream); cudaFreeAsync(d_widx, stream); cudaFreeAsync(d_census, stream); cudaFreeAsync(d_tmp, stream);
+    return err;
 }
 
 cudaError_t rt_pack_triangles(const BuildParams& bp, TriBlock* geom, TriBlock* shade, cudaStream_t stream) {
@@ -271,7 +329,7 @@ cudaError_t rt_build_bvh(const BuildParams& bp, BvhNode** nodes_out, TriBlock* g
         CKG(cudaStreamSynchronize(stream));
         num_nodes = last_idx;
         CKG(cudaMalloc(&nodes, sizeof(BvhNode) * (size_t)num_nodes));
-        k_emit_nodes<<<blocks_for(n - 1, T), T, 0, stream>>>(d_topo, n, d_keep, d_newidx, d_blo, d_bhi, nodes);
+        k_emit_nodes<<<blocks_for(n - 1, T), T, 0, stream>>>(d_topo, n, d_keep, d_newidx, d_parent, d_blo, d_bhi, nodes);
     } else {
         num_nodes = 1;
         CKG(cudaMalloc(&nodes, sizeof(BvhNode)));

@@ -12,6 +12,10 @@ struct Topo { uint32_t left, right, first, last; };   // last: bits 0..29 = inde
 // Node word slot_count: bits 0..28 = triangle slots of the subtree, bits 29..31 = one-hot split axis (29 z, 30 y, 31 x;
 // none set = no spatial split), so the packet kernel's descent order is one AND with its direction-sign mask.
 #define RT_NODE_AXIS_BITS(axis) ((axis) < 3u ? (1u << (29u + (axis))) : 0u)
+// Node word first_slot: bits 0..27 = first triangle slot of the subtree (slots < 2^28, rt_leaf_ref), bits 28..29 = the node's
+// depth modulo 3, which the compact 8-wide view is derived from (rt_build_wide).
+#define RT_NODE_DEPTH3_BITS(depth) ((uint32_t)((depth) % 3u) << 28)
+#define RT_NODE_DEPTH3(first_slot) (((first_slot) >> 28) & 3u)
 
 RT_HD void rt_tri_verts(const BuildParams& bp, uint32_t i, f3& a, f3& b, f3& c, uint32_t& ia, uint32_t& ib, uint32_t& ic) {
     ia = RT_LDG(bp.indices + 3 * (size_t)i); ib = RT_LDG(bp.indices + 3 * (size_t)i + 1); ic = RT_LDG(bp.indices + 3 * (size_t)i + 2);
@@ -115,6 +119,14 @@ RT_HD void rt_box_to_ch(float lo, float hi, float& c, float& h) {
     const float e = fmaxf(hi - c, c - lo);
     h = e * 1.000001f + 1e-30f + fabsf(c) * 1.2e-7f;
 }
+// Depth of Karras internal node i (root = 0) by its parent links; a kept node's ancestors are all kept, so this is also its
+// depth in the emitted tree.
+RT_HD uint32_t rt_node_depth(const uint32_t* __restrict__ parent, uint32_t i) {
+    uint32_t d = 0;
+    for (uint32_t p = parent[i]; p != 0xFFFFFFFFu; p = parent[p]) ++d;
+    return d;
+}
+
 RT_HD BvhNode rt_make_node(float4 l0, float4 h0, float4 l1, float4 h1, int32_t r0, int32_t r1, uint32_t first, uint32_t count) {
     BvhNode nd;
     rt_box_to_ch(l0.x, h0.x, nd.q[0], nd.q[3]); rt_box_to_ch(l0.y, h0.y, nd.q[1], nd.q[4]); rt_box_to_ch(l0.z, h0.z, nd.q[2], nd.q[5]);
@@ -125,18 +137,19 @@ RT_HD BvhNode rt_make_node(float4 l0, float4 h0, float4 l1, float4 h1, int32_t r
 
 // 8-wide view of BVH2 node i (WideNode, rt_core.h): entry k = the box reached by the left/right steps k2 k1 k0; a leaf met
 // early sits in the entry whose remaining path bits are zero; everything else below it, and absent children, are "absent"
-// entries (negative half extents, ref -1).
-RT_HD WideNode rt_wide_node(const BvhNode* __restrict__ nodes, uint32_t i) {
+// entries (negative half extents, ref -1).  `levels` < 3 stops the expansion early (the root of a phased view, rt_build.cu):
+// an inner box reached at that level is placed like an early leaf and keeps its (non-negative) node reference.
+RT_HD WideNode rt_wide_node(const BvhNode* __restrict__ nodes, uint32_t i, int levels = 3) {
     WideNode out;
     for (int k = 0; k < 8; ++k) {
         bool valid = true;
         uint32_t par = i;
         int pb = (k >> 2) & 1;
         int ref = pb ? nodes[par].ref1 : nodes[par].ref0;
-        if (ref < 0) valid = (k & 3) == 0;
+        if (ref < 0 || levels == 1) valid = (k & 3) == 0;
         else {
             par = (uint32_t)ref; pb = (k >> 1) & 1; ref = pb ? nodes[par].ref1 : nodes[par].ref0;
-            if (ref < 0) valid = (k & 1) == 0;
+            if (ref < 0 || levels == 2) valid = (k & 1) == 0;
             else { par = (uint32_t)ref; pb = k & 1; ref = pb ? nodes[par].ref1 : nodes[par].ref0; }
         }
         const float* q = nodes[par].q + 6 * pb;
@@ -149,20 +162,22 @@ RT_HD WideNode rt_wide_node(const BvhNode* __restrict__ nodes, uint32_t i) {
 }
 
 // Triangle blocks of slot k (triangle `tri`).  e1/e2 are the same rounded differences the
-// reference forms inside every test (query.h:80-81, HW1 ray.h:72-73).
+// reference forms inside every test (query.h:80-81, HW1 ray.h:72-73).  The geometry block also carries the object id
+// (g[1].w); the normals block exists only for meshes with per-vertex normals (shade_k == nullptr otherwise).
 RT_HD void rt_pack_tri(const BuildParams& bp, uint32_t tri, TriBlock* geom_k, TriBlock* shade_k) {
     f3 a, b, c; uint32_t ia, ib, ic;
     rt_tri_verts(bp, tri, a, b, c, ia, ib, ic);
     const f3 e1 = xsub3(b, a), e2 = xsub3(c, a);
+    const int obj = bp.obj_ids ? bp.obj_ids[tri] : -1;
     float4* g = reinterpret_cast<float4*>(geom_k);
     g[0] = make_float4(a.x, a.y, a.z, RT_I2F((int)tri));
-    g[1] = make_float4(e1.x, e1.y, e1.z, 0.f);
+    g[1] = make_float4(e1.x, e1.y, e1.z, RT_I2F(obj));
     g[2] = make_float4(e2.x, e2.y, e2.z, 0.f);
+    if (shade_k == nullptr) return;
     f3 n0 = mk3(0.f, 0.f, 0.f), n1 = n0, n2 = n0;
     if (bp.normals) {
         n0 = ld3(bp.normals + 3 * (size_t)ia); n1 = ld3(bp.normals + 3 * (size_t)ib); n2 = ld3(bp.normals + 3 * (size_t)ic);
     }
-    const int obj = bp.obj_ids ? bp.obj_ids[tri] : -1;
     float4* s = reinterpret_cast<float4*>(shade_k);
     s[0] = make_float4(n0.x, n0.y, n0.z, RT_I2F(obj));
     s[1] = make_float4(n1.x, n1.y, n1.z, 0.f);

@@ -16,8 +16,9 @@ cudaError_t rt_validate_indices(const uint32_t* idx, size_t n, uint32_t num_vert
 // Bakes an object's transform into its vertex range in place (device arrays), before the build.
 struct BakeXform;
 cudaError_t rt_bake_transform(float* pos, float* nrm, size_t first, size_t count, const BakeXform& T, cudaStream_t stream);
-// 8-wide view of a finished BVH2 (one WideNode per BVH2 node), for the frustum traversal.
-cudaError_t rt_build_wide(const BvhNode* nodes, uint32_t num_nodes, WideNode* wide, cudaStream_t stream);
+// 8-wide view of a finished BVH2 for the frustum traversal: one WideNode per BVH2 node at depth 0, 3, 6, ... (compact array,
+// allocated here with cudaMalloc; *count_out nodes; references between wide nodes are indices into it; the root is wide[0]).
+cudaError_t rt_build_wide(const BvhNode* nodes, uint32_t num_nodes, int phase, WideNode** wide_out, uint32_t* count_out, cudaStream_t stream);
 // Pack triangles in input order without a BVH (brute-force-only scenes).
 cudaError_t rt_pack_triangles(const BuildParams& bp, TriBlock* geom, TriBlock* shade, cudaStream_t stream);
 

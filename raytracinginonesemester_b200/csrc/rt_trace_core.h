@@ -152,7 +152,15 @@ struct Surface {       // hit-point state shared by the per-light steps
     rt_material mat;
 };
 
+// Per-vertex normals + object id of a slot.  A mesh without normals has no normals blocks (P.shade == nullptr, uniform over
+// the launch): the normals read as zero, which is what the reference's loaders leave there, and the id comes from the
+// geometry block.
 RT_HD void rt_load_normals(const FrameParams& P, int slot, f3& n0, f3& n1, f3& n2, int& obj) {
+    if (P.shade == nullptr) {
+        n0 = n1 = n2 = mk3(0.f, 0.f, 0.f);
+        obj = RT_F2I(RT_LDG(reinterpret_cast<const float4*>(P.geom + slot) + 1).w);
+        return;
+    }
     const float4* p = reinterpret_cast<const float4*>(P.shade + slot);
     const float4 a = RT_LDG(p), b = RT_LDG(p + 1), c = RT_LDG(p + 2);
     n0 = mk3(a.x, a.y, a.z); obj = RT_F2I(a.w);

@@ -98,7 +98,8 @@ void* emu_build(const rt_scene* sc, uint32_t leaf_max) {
             es->nodes[newidx[i]] = rt_make_node(blo[tp.left], bhi[tp.left], blo[tp.right], bhi[tp.right],
                                                 rt_child_ref(tp.left, n, topo.data(), keep.data(), newidx.data()),
                                                 rt_child_ref(tp.right, n, topo.data(), keep.data(), newidx.data()),
-                                                tp.first, (RT_TOPO_LAST(tp) - tp.first + 1u) | RT_NODE_AXIS_BITS(RT_TOPO_AXIS(tp)));
+                                                tp.first | RT_NODE_DEPTH3_BITS(rt_node_depth(parent.data(), (uint32_t)i)),
+                                                (RT_TOPO_LAST(tp) - tp.first + 1u) | RT_NODE_AXIS_BITS(RT_TOPO_AXIS(tp)));
         }
     } else {
         float4 lo = make_float4(INFINITY, INFINITY, INFINITY, 0.f), hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
@@ -116,6 +117,7 @@ void* emu_build(const rt_scene* sc, uint32_t leaf_max) {
 void* emu_adopt(const void* nodes64, uint32_t num_nodes, const void* geom48, uint32_t num_tris, const rt_scene* sc) {
     EmuScene* es = new EmuScene;
     es->num_tris = num_tris;
+    es->has_normals = sc->normals != nullptr;
     es->nodes.resize(num_nodes); es->geom.resize(num_tris); es->shade.resize(num_tris);
     memcpy(es->nodes.data(), nodes64, sizeof(BvhNode) * (size_t)num_nodes);
     memcpy(es->geom.data(), geom48, sizeof(TriBlock) * (size_t)num_tris);
@@ -144,6 +146,30 @@ void emu_wide(void* h, void* wide256) {
     EmuScene* es = (EmuScene*)h;
     WideNode* w = (WideNode*)wide256;
     for (size_t i = 0; i < es->nodes.size(); ++i) w[i] = rt_wide_node(es->nodes.data(), (uint32_t)i);
+}
+
+// The compact, phased view (rt_build_wide, rt_build.cu) step by step on the host: census of the depth classes, phase choice,
+// flags, exclusive scan, expansion with translated references.  Returns the number of wide nodes; *phase_io < 0 = smallest.
+uint32_t emu_wide_compact(void* h, int* phase_io, void* wide256) {
+    EmuScene* es = (EmuScene*)h;
+    const uint32_t nn = (uint32_t)es->nodes.size();
+    unsigned census[3] = {0, 0, 0};
+    for (uint32_t i = 0; i < nn; ++i) census[RT_NODE_DEPTH3(es->nodes[i].first_slot)]++;
+    const unsigned size[3] = {census[0], census[1] + 1u, census[2] + 1u};
+    int phase = *phase_io;
+    if (phase < 0 || phase > 2) { phase = 0; for (int f = 1; f < 3; ++f) if (size[f] < size[phase]) phase = f; }
+    *phase_io = phase;
+    std::vector<uint32_t> need(nn), widx(nn);
+    uint32_t run = 0;
+    for (uint32_t i = 0; i < nn; ++i) { need[i] = (i == 0 || RT_NODE_DEPTH3(es->nodes[i].first_slot) == (unsigned)phase) ? 1u : 0u; widx[i] = run; run += need[i]; }
+    WideNode* out = (WideNode*)wide256;
+    for (uint32_t i = 0; i < nn; ++i) {
+        if (!need[i]) continue;
+        WideNode w = rt_wide_node(es->nodes.data(), i, i == 0 ? (phase == 0 ? 3 : phase) : 3);
+        for (int k = 0; k < 8; ++k) if (w.e[k].ref >= 0) w.e[k].ref = (int32_t)widx[w.e[k].ref];
+        out[widx[i]] = w;
+    }
+    return run == size[phase] ? run : 0xFFFFFFFFu;
 }
 
 // Structural check of a flattened BVH: every slot reachable exactly once, child boxes contain
@@ -192,7 +218,7 @@ int emu_render_rank(void* h, const rt_frame* fr, rt_image* img, uint64_t* stats,
     P.max_depth = fr->max_depth; P.diffuse_bounce = fr->diffuse_bounce ? 1 : 0; P.shadows = fr->shadows; P.quantiser = fr->quantiser; P.num_lights = fr->num_lights;
     P.num_materials = (int)es->materials.size(); P.has_normals = es->has_normals ? 1 : 0;
     memcpy(P.miss, fr->miss_color, sizeof P.miss);
-    P.nodes = es->nodes.data(); P.geom = es->geom.data(); P.shade = es->shade.data(); P.num_tris = es->num_tris;
+    P.nodes = es->nodes.data(); P.geom = es->geom.data(); P.shade = es->has_normals ? es->shade.data() : nullptr; P.num_tris = es->num_tris;
     P.materials = es->materials.empty() ? nullptr : es->materials.data();
     P.lights = fr->lights; P.jitter = fr->jitter;
     if (fr->mode == RT_MODE_HW2_CPU) { P.light_radius = fr->light_radius; P.light_samples = fr->light_shadow_samples; }

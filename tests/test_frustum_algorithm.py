@@ -111,3 +111,73 @@ def test_wide_view_of_the_bvh(nx, ny, leaf_max):
                 first, cnt = ps.leaf_range(r)
                 seen[first:first + cnt] += 1
     assert (seen == 1).all()
+
+
+@pytest.mark.parametrize("nx,ny,leaf_max", [(60, 30, 2), (17, 9, 1), (8, 4, 4), (1, 1, 2)])
+def test_compact_wide_view_in_every_phase(nx, ny, leaf_max):
+    """The view the product keeps (rt_build_wide): wide nodes only for the BVH2 nodes at every third depth, the root hopping
+    `phase` levels.  Each node's depth-mod-3 tag is its real depth; in every phase the walk from wide node 0 stays inside the
+    compact array, reaches every triangle slot exactly once and finds the same leaf boxes as the BVH2; the automatic choice
+    is the smallest of the three."""
+    import ctypes as C
+    import orclib
+    import packet_sim as ps
+    from raytracinginonesemester_b200 import scenes
+    sc = scenes.terrain_scene(nx, ny)
+    h = orclib.emul_build(sc, leaf_max)
+    lib = orclib.emul()
+    lib.emu_num_nodes.restype = C.c_uint32
+    lib.emu_wide_compact.restype = C.c_uint32
+    nn = lib.emu_num_nodes(C.c_void_p(h))
+    nodes = np.zeros((nn, 16), np.uint32)
+    lib.emu_export(C.c_void_p(h), nodes.ctypes.data_as(C.c_void_p), None)
+    q = nodes[:, :12].view(np.float32)
+    refs = nodes[:, 12:14].view(np.int32)
+    tag = (nodes[:, 14] >> 28) & 3
+    depth = np.full(nn, -1)
+    depth[0] = 0
+    leaves = {}
+    stack = [0]
+    while stack:
+        n = stack.pop()
+        for k in range(2):
+            if q[n, 6 * k + 3] < 0:
+                continue
+            r = int(refs[n, k])
+            if r >= 0:
+                depth[r] = depth[n] + 1
+                stack.append(r)
+            else:
+                leaves[r] = q[n, 6 * k:6 * k + 6].copy()
+    assert (depth >= 0).all() and np.array_equal(tag, depth % 3)
+    sizes = []
+    for phase in (0, 1, 2, -1):
+        wide = np.zeros((nn, 8, 8), np.uint32)
+        ph = C.c_int(phase)
+        cnt = lib.emu_wide_compact(C.c_void_p(h), C.byref(ph), wide.ctypes.data_as(C.c_void_p))
+        assert cnt != 0xFFFFFFFF and cnt <= nn
+        if phase >= 0:
+            sizes.append(cnt)
+            assert cnt == int((depth % 3 == phase).sum()) + (phase != 0)
+        else:
+            assert cnt == min(sizes) and sizes[ph.value] == cnt
+        wf, wref = wide[..., :6].view(np.float32), wide[..., 6].view(np.int32)
+        seen = np.zeros(sc.indices.shape[0], int)
+        visited = np.zeros(cnt, int)
+        stack = [0]
+        while stack:
+            n = stack.pop()
+            visited[n] += 1
+            for k in range(8):
+                if wf[n, k, 3] < 0:
+                    assert wref[n, k] == -1
+                    continue
+                r = int(wref[n, k])
+                if r >= 0:
+                    assert r < cnt
+                    stack.append(r)
+                else:
+                    first, c = ps.leaf_range(r)
+                    seen[first:first + c] += 1
+                    assert np.array_equal(wf[n, k], leaves[r])
+        assert (seen == 1).all() and (visited == 1).all()

@@ -71,6 +71,8 @@ def test_c4_whole_frame_against_the_reference_itself(renderer):
     sc = scenes.terrain_scene(1000, 500)
     info = renderer.upload_scene(sc)
     assert info.num_triangles == 1000000 and info.num_leaves == info.num_nodes + 1
+    # compact 8-wide view (one WideNode per BVH2 node at depth 0, 3, 6, ...): nodes 64 B + 2 x 48 B per triangle + ~1/7 x 256 B per node
+    assert info.arena_bytes <= 175e6, info.arena_bytes
     W, H = 3840, 2160
     fr = scenes.terrain_frame(W, H, outputs=A.RT_OUT_RGB8 | A.RT_OUT_TRI_ID | A.RT_OUT_T)
     got = run(renderer, fr)

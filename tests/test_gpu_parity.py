@@ -635,3 +635,26 @@ def test_ppm_bytes_match_reference_writer(renderer, frog_scene, tmp_path):
         head = b"P6\n160 90\n255\n"
         assert data[:len(head)] == head
         assert data[len(head):] == got["rgb8"].tobytes()
+
+
+def test_compact_wide_view_phases_render_the_same_image(frog_scene, monkeypatch):
+    """rt_build_wide keeps WideNodes only for every third BVH2 depth; forcing each phase (RT_B200_WIDE_PHASE; -1 = the
+    smallest) changes the arena size and the traversal order, never the image."""
+    from raytracinginonesemester_b200 import Renderer
+    fr = scenes.frog_frame(320, 180, filling=True, outputs=ALL)
+    base, sizes = None, {}
+    for phase in ("", "0", "1", "2", "-1"):
+        monkeypatch.setenv("RT_B200_WIDE_PHASE", phase)
+        r = Renderer(0)
+        try:
+            info = r.upload_scene(frog_scene)
+            sizes[phase] = int(info.arena_bytes)
+            got = run(r, fr)
+        finally:
+            r.close()
+        if base is None:
+            base = got
+        for k in ("tri_id", "t", "rgb", "rgb8"):
+            assert np.array_equal(base[k], got[k]), (phase, k)
+    assert sizes[""] == sizes["0"] and sizes["-1"] == min(sizes[p] for p in "012")
+    assert sizes[""] < 64 * info.num_nodes + 96 * info.num_triangles + 256 * info.num_nodes // 2      # well under one WideNode per node
