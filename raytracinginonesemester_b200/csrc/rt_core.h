@@ -27,11 +27,12 @@ struct alignas(64) BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be one 64-byte line");
 
-// 8-wide view of the same tree for the frustum traversal (rt_trace.cu, frustum_trace): wide[i] holds the boxes and
-// references reached from BVH2 node i by three left/right steps (entry k = path bits k2 k1 k0; a leaf met early sits in
+// 8-wide view of the same tree for the frustum traversal (rt_trace.cu, frustum_trace): a wide node holds the boxes and
+// references reached from one BVH2 node by three left/right steps (entry k = path bits k2 k1 k0; a leaf met early sits in
 // the entry whose remaining path bits are zero, the other entries of that subtree are absent).  32 bytes per entry:
-// (c.x, c.y, c.z, h.x) (h.y, h.z, bits(ref), 0); absent: h = -1.  References are BVH2 node indices / leaf references
-// exactly as in BvhNode, so wide[ref] is the next wide node.  Built on the device from the finished BVH2 (k_build_wide).
+// (c.x, c.y, c.z, h.x) (h.y, h.z, bits(ref), 0); absent: h = -1.  Leaf references are those of BvhNode; an inner reference
+// is the index of the next WIDE node: only the BVH2 nodes at every third depth get one, in a compact array
+// (rt_build_wide, rt_build.cu; rt_wide_node below leaves BVH2 indices, the build translates them).
 struct alignas(32) WideEntry { float cx, cy, cz, hx, hy, hz; int32_t ref; int32_t pad; };
 struct alignas(256) WideNode { WideEntry e[8]; };
 static_assert(sizeof(WideNode) == 256, "WideNode must be 256 bytes");
