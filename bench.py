@@ -545,8 +545,12 @@ def bench_workload(args, r, dist, rank, world, local_rank, workload, steps, with
     traffic, traffic_src, winst, tkern = None, None, None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload)
-        if tj and world == 1 and args.variant == 0:
-            traffic, traffic_src, tkern = float(tj["dram_bytes_per_launch"]), tj["source"], tj.get("kernel")
+        if tj and args.variant == 0:
+            # The instruction count of a frame does not depend on which rank renders which tile (same packets, same kernel code:
+            # the persistent launch of the multi-GPU path executed 1.704e9 against 1.700e9), so the single-GPU capture also
+            # gives the N-rank issue roofline; the DRAM bytes are per launch of ONE GPU and are only reported at N = 1.
+            traffic_src, tkern = tj["source"], tj.get("kernel")
+            traffic = float(tj["dram_bytes_per_launch"]) if world == 1 else None
             winst = float(tj.get("warp_instructions_per_launch", 0)) or None
     except Exception:
         pass
@@ -607,7 +611,8 @@ def bench_workload(args, r, dist, rank, world, local_rank, workload, steps, with
             line["roofline"] = {"bound": "issue", "achieved": winst / (ms * 1e-3) / 1e9, "peak": pk, "unit": "G warp-instr/s", "frac": winst / (ms * 1e-3) / 1e9 / pk,
                                 "traffic": traffic, "warp_instructions_per_launch": winst, "source": traffic_src, "kernel": tkern,
                                 "peak_kind": "148 SMs x 4 schedulers x SM clock sampled during the run",
-                                "note": "issue-slot roofline: smsp__inst_executed.sum of the ncu capture named in `source` / this run's kernel time; traffic = dram bytes of the same capture",
+                                "note": "issue-slot roofline: smsp__inst_executed.sum of the ncu capture named in `source` / this run's kernel time; traffic = dram bytes of the same capture" +
+                                        ("" if world == 1 else "; N ranks: the whole frame's instruction count (single-GPU capture; it does not depend on the sharding) over the max-over-ranks time, peak = N GPUs; no per-rank DRAM capture (never ncu a multi-rank run)"),
                                 "hbm": hbm}
         else:   # no capture for this workload / variant / rank count: only the byte roofline can be formed from this run
             line["roofline"] = dict(hbm, traffic=traffic, issue_peak_g_warp_instr_s=pk,
