@@ -175,17 +175,9 @@ k_render_brute(const __grid_constant__ FrameParams P) {
 // single ray's while SIMD efficiency goes from ~44 % (per-ray, ncu r1_v1) to ~100 %.
 #define FULLMASK 0xffffffffu
 #define RT_PACKET_STACK 64
-#ifndef RT_X_PAIRS
-#define RT_X_PAIRS 0                              // (ray, leaf) pair queue in frustum_trace, see there
-#endif
 #ifndef RT_FSTACK
-#define RT_FSTACK (RT_X_PAIRS ? 64 : 128)         // frontier stack of the frustum traversal, entries per warp
+#define RT_FSTACK 128                             // frontier stack of the frustum traversal, entries per warp
 #endif
-// Per-warp shared-memory region behind `wstack`, in 32-bit words: the frontier stack, and with RT_X_PAIRS the pair queue
-// (64 words) and one 64-bit (t, id) key per ray (64 words).
-#define RT_WQ_OFF RT_FSTACK
-#define RT_WKEY_OFF (RT_FSTACK + 64)
-#define RT_WSTRIDE (RT_X_PAIRS ? RT_FSTACK + 128 : RT_FSTACK)
 #define RT_SLOT_DEAD (-2)                         // Hit.slot of a lane that traced nothing (outside the frame, depth 0)
 
 struct TraceResult { Hit hit; bool blocked; };
@@ -332,14 +324,10 @@ __device__ __forceinline__ float warp_fmin(float v) { float r; asm volatile("red
 __device__ __forceinline__ float warp_fmax(float v) { float r; asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v)); return r; }
 __device__ __forceinline__ float warp_bcast(float v, int src, int lane) { return __int_as_float((int)__reduce_or_sync(FULLMASK, lane == src ? (unsigned)__float_as_int(v) : 0u)); }
 
-// words of the per-thread shared-memory stash (render_packet below)
-enum { ST_DX = 0, ST_DY, ST_DZ, ST_HT, ST_HU, ST_HV, ST_HSLOT, ST_LOX, ST_LOY, ST_LOZ, ST_DIX, ST_DIY, ST_DIZ, ST_ACX, ST_ACY, ST_ACZ, RT_STASH_WORDS };
-
 template <int MODE, bool STATS, bool FAST, int TAG, bool LAZY = false>
 __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ nodes, const WideNode* __restrict__ wide, const TriBlock* __restrict__ geom, const uint32_t num_tris,
                                                   const Ray ray, bool live, const bool any, const bool same_origin, float tlimit, TraceStats* st,
-                                                  int* __restrict__ wstack, float4* __restrict__ wfr, const float feps, const f3 sc, const float sr2,
-                                                  volatile float* const stash = nullptr) {
+                                                  int* __restrict__ wstack, float4* __restrict__ wfr, const float feps, const f3 sc, const float sr2) {
     Hit best; rt_hit_reset(best);
     if (!live) best.slot = RT_SLOT_DEAD;          // lets the caller tell "traced nothing" from "missed" without keeping `live` across the call
     bool blocked = false;
@@ -420,170 +408,6 @@ __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ no
     bool overflow = false;
     __syncwarp();
     int sp = 1;
-#if RT_X_PAIRS
-    // (ray, leaf) PAIR QUEUE.  In the loop further down a leaf that survives is tested by the whole warp although only a
-    // quarter of the lanes' rays enter its box (stats on C4: 7.5 of 25.8 executing lanes per warp-level triangle test, 6.84 M
-    // such tests per frame, a third of all instructions).  Here the lanes whose ray enters the box only QUEUE the pair
-    // (own lane, leaf) in shared memory; whenever 32 pairs are waiting (and once more when the traversal has finished) they are
-    // dealt out one pair per lane: the lane fetches that ray by shuffle, runs the leaf's triangle tests, and the results
-    // return to the owning lanes through a 64-bit shared-memory atomicMin on (t bits, id) per ray — which is the canonical
-    // rule (min t, then min id) — with u, v, slot written by the winner into the owner's stash column; any-hit rays need one
-    // warp OR-reduction of "ray r is blocked" bits.  t limits, the far plane and the any-hit exit are refreshed after every
-    // deal instead of after every leaf: a lane can only see a later limit, i.e. test a superset.
-    {
-        unsigned* const wq = reinterpret_cast<unsigned*>(wstack) + RT_WQ_OFF;
-        unsigned long long* const wkey = reinterpret_cast<unsigned long long*>(wstack + RT_WKEY_OFF);
-        const unsigned long long KEY0 = ((unsigned long long)__float_as_uint(FLT_MAX) << 32) | 0x7fffffffull;
-        if (!any) wkey[lane] = KEY0;                  // the owner's best (t, id); ordered before the first deal by the round's __syncwarp
-        int qh = 0, qn = 0;
-        const unsigned lt = (1u << lane) - 1u;
-        for (;;) {
-            unsigned mleaf = 0u;
-            int par = 0;
-            if (sp > 0) {
-            // ---- one round: up to four wide nodes, one box per lane (same as the loop further down)
-            const int npop = sp < 4 ? sp : 4;
-            const bool valid = (lane >> 3) < npop;
-            par = valid ? wstack[sp - 1 - (lane >> 3)] : 0;
-            sp -= npop;
-            __syncwarp();
-            float cx, cy, cz, hx, hy, hz;
-            int ref;
-            {
-                const float* ep = reinterpret_cast<const float*>(wide + par) + 8 * (lane & 7);
-                float fr, fp;
-                asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                             : "=f"(cx), "=f"(cy), "=f"(cz), "=f"(hx), "=f"(hy), "=f"(hz), "=f"(fr), "=f"(fp) : "l"(ep));
-                ref = __float_as_int(fr);
-            }
-            if (STATS) {
-                int tot = valid ? 1 : 0;
-                for (int q = 16; q > 0; q >>= 1) tot += __shfl_xor_sync(FULLMASK, tot, q);
-                if (lane == 0) { st->wnodes += (uint32_t)tot; st->nodes += (uint32_t)tot; }
-            }
-            bool hit = valid && hx >= 0.f;
-            {
-                const float4 p0 = wfr[0], p1 = wfr[1], p2 = wfr[2], p3 = wfr[3], pw = wfr[4];
-                const float s0 = fmaf(hx, fabsf(p0.x), fmaf(hy, fabsf(p0.y), fmaf(hz, fabsf(p0.z), fmaf(cx, p0.x, fmaf(cy, p0.y, cz * p0.z)))));
-                const float s1 = fmaf(hx, fabsf(p1.x), fmaf(hy, fabsf(p1.y), fmaf(hz, fabsf(p1.z), fmaf(cx, p1.x, fmaf(cy, p1.y, cz * p1.z)))));
-                const float s2 = fmaf(hx, fabsf(p2.x), fmaf(hy, fabsf(p2.y), fmaf(hz, fabsf(p2.z), fmaf(cx, p2.x, fmaf(cy, p2.y, cz * p2.z)))));
-                const float s3 = fmaf(hx, fabsf(p3.x), fmaf(hy, fabsf(p3.y), fmaf(hz, fabsf(p3.z), fmaf(cx, p3.x, fmaf(cy, p3.y, cz * p3.z)))));
-                const float dep = fmaf(cx, pw.x, fmaf(cy, pw.y, cz * pw.z)), dh = fmaf(hx, fabsf(pw.x), fmaf(hy, fabsf(pw.y), hz * fabsf(pw.z)));
-                hit = hit && s0 >= p0.w && s1 >= p1.w && s2 >= p2.w && s3 >= p3.w && dep + dh >= pw.w && dep - dh <= farD;
-            }
-            const unsigned minner = __ballot_sync(FULLMASK, hit && ref >= 0);
-            mleaf = __ballot_sync(FULLMASK, hit && ref < 0);
-            const int ninner = __popc(minner);
-            if (sp + ninner > RT_FSTACK) { overflow = true; break; }
-            if (hit && ref >= 0) wstack[sp + __popc(minner & lt)] = ref;
-            sp += ninner;
-            __syncwarp();
-            } else if (qn == 0) break;
-            // the round's leaf candidates; a deal whenever 32 pairs wait, and for the rest once the frontier is empty
-            // (ONE copy of the deal in the binary: the kernel is instruction-cache sensitive)
-            while (mleaf || qn >= 32 || (sp == 0 && qn > 0)) {
-                if (qn >= 32 || mleaf == 0u) {
-                    const int n = qn < 32 ? qn : 32;
-                    const bool has = lane < n;
-                    const unsigned pr = wq[(qh + lane) & 63];
-                    qh = (qh + n) & 63; qn -= n;
-                    const int rl = has ? (int)(pr & 31u) : lane;
-                    Ray r2;
-                    r2.o.x = __shfl_sync(FULLMASK, ray.o.x, rl); r2.o.y = __shfl_sync(FULLMASK, ray.o.y, rl); r2.o.z = __shfl_sync(FULLMASK, ray.o.z, rl);
-                    r2.d.x = __shfl_sync(FULLMASK, ray.d.x, rl); r2.d.y = __shfl_sync(FULLMASK, ray.d.y, rl); r2.d.z = __shfl_sync(FULLMASK, ray.d.z, rl);
-                    const float tl = __shfl_sync(FULLMASK, tlimit, rl);
-                    Hit lb; lb.t = tl; lb.u = 0.f; lb.v = 0.f; lb.slot = -1; lb.id = 0x7fffffff;
-                    bool got = false;
-                    if (has) {
-                        const uint32_t first = pr >> 8, cnt = ((pr >> 5) & 7u) + 1u;
-                        if (STATS) st->tris += cnt;
-        #pragma unroll 1
-                        for (uint32_t s = first; s < first + cnt; ++s) {
-                            Tri tr;
-                            const float4* tp = reinterpret_cast<const float4*>(geom + s);
-                            float idf, p0, p1;
-                            asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(tr.v0.x), "=f"(tr.v0.y), "=f"(tr.v0.z), "=f"(idf) : "l"(tp));
-                            asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(tr.e1.x), "=f"(tr.e1.y), "=f"(tr.e1.z), "=f"(p0) : "l"(tp + 1));
-                            asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(tr.e2.x), "=f"(tr.e2.y), "=f"(tr.e2.z), "=f"(p1) : "l"(tp + 2));
-                            tr.id = __float_as_int(idf);
-                            float t, uu, vv;
-                            if (LAZY ? rt_moller_trumbore_lazy(r2, tr.v0, tr.e1, tr.e2, det_eps, tmin, any ? FLT_MAX : lb.t, t, uu, vv)
-                                     : rt_moller_trumbore(r2, tr.v0, tr.e1, tr.e2, det_eps, tmin, any ? FLT_MAX : lb.t, t, uu, vv)) {
-                                if (any) { if (t < tl) got = true; }
-                                else if (t < lb.t || tr.id < lb.id) { lb.t = t; lb.u = uu; lb.v = vv; lb.slot = (int)s; lb.id = tr.id; got = true; }
-                            }
-                        }
-                    }
-                    if (STATS && lane == 0) st->wtris += 2u;
-                    if (any) {
-                        const unsigned mb = __reduce_or_sync(FULLMASK, got ? (1u << rl) : 0u);
-                        if ((mb >> lane) & 1u) { blocked = true; live = false; }
-                    } else {
-                        // (t + 0: a hit at -0.0 must not sort above every positive t)
-                        const unsigned long long mykey = ((unsigned long long)__float_as_uint(lb.t + 0.0f) << 32) | (unsigned)lb.id;
-                        if (got) atomicMin(&wkey[rl], mykey);
-                        __syncwarp();
-                        if (got && wkey[rl] == mykey) {
-                            volatile float* const rec = stash + (rl - lane);
-                            rec[ST_HT * RT_BLOCK_THREADS] = lb.t; rec[ST_HU * RT_BLOCK_THREADS] = lb.u; rec[ST_HV * RT_BLOCK_THREADS] = lb.v;
-                            rec[ST_HSLOT * RT_BLOCK_THREADS] = __int_as_float(lb.slot);
-                        }
-                        const float nt = __uint_as_float((unsigned)(wkey[lane] >> 32));
-                        const bool improved = nt < tlimit;
-                        tlimit = nt;
-                        if (__any_sync(FULLMASK, improved)) {        // pull the far plane in to the farthest current hit
-                            const float4 pw = wfr[4];
-                            const float hx_ = fmaf(tlimit, ray.d.x, ray.o.x), hy_ = fmaf(tlimit, ray.d.y, ray.o.y), hz_ = fmaf(tlimit, ray.d.z, ray.o.z);
-                            farD = warp_fmax(live ? fmaf(hx_, pw.x, fmaf(hy_, pw.y, hz_ * pw.z)) : -BIG);
-                            farD += fabsf(farD) * 4e-6f + feps;
-                        }
-                        __syncwarp();
-                    }
-                    if (any && !__any_sync(FULLMASK, live)) return TraceResult{best, blocked};
-                    continue;
-                }
-                // ---- one leaf candidate: its entry again by every lane, per-lane slab test, queue the lanes that enter it
-                const int src = __ffs(mleaf) - 1;
-                mleaf &= mleaf - 1u;
-                const int eidx = __shfl_sync(FULLMASK, par * 8 + (lane & 7), src);
-                float lcx, lcy, lcz, lhx, lhy, lhz, lfr, lfp;
-                asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                             : "=f"(lcx), "=f"(lcy), "=f"(lcz), "=f"(lhx), "=f"(lhy), "=f"(lhz), "=f"(lfr), "=f"(lfp)
-                             : "l"(reinterpret_cast<const float*>(wide) + 8 * (size_t)eidx));
-                if (STATS && lane == 0) { st->wnodes++; st->nodes++; }
-                bool lh; float tn;
-                if (FAST) lh = rt_slab_fma_tight(kf, lcx, lcy, lcz, lhx, lhy, lhz, tmin, tlimit);
-                else lh = rt_slab(k, lcx, lcy, lcz, lhx, lhy, lhz, tmin, tlimit, tn);
-                lh = lh && live;
-                const unsigned mh = __ballot_sync(FULLMASK, lh);
-                if (!mh) continue;
-                // pair word: (first slot, count - 1, lane) = (~ref) << 5 | lane; the host uses this kernel below 2^24 triangles
-                if (lh) wq[(qh + qn + __popc(mh & lt)) & 63] = ((unsigned)~__float_as_int(lfr) << 5) | (unsigned)lane;
-                qn += __popc(mh);
-                __syncwarp();
-            }
-        }
-        if (!overflow) {
-            if (!any) {
-                const unsigned long long kfin = wkey[lane];
-                if (kfin != KEY0) {
-                    best.t = stash[ST_HT * RT_BLOCK_THREADS]; best.u = stash[ST_HU * RT_BLOCK_THREADS]; best.v = stash[ST_HV * RT_BLOCK_THREADS];
-                    best.slot = __float_as_int(stash[ST_HSLOT * RT_BLOCK_THREADS]); best.id = (int)(unsigned)kfin;
-                }
-            }
-        } else if (!any) {
-            // (the brute-force pass below re-tests every triangle, the queued ones included, against the hits found so far)
-            const unsigned long long kfin = wkey[lane];
-            if (kfin != KEY0) {
-                best.t = stash[ST_HT * RT_BLOCK_THREADS]; best.u = stash[ST_HU * RT_BLOCK_THREADS]; best.v = stash[ST_HV * RT_BLOCK_THREADS];
-                best.slot = __float_as_int(stash[ST_HSLOT * RT_BLOCK_THREADS]); best.id = (int)(unsigned)kfin;
-                tlimit = best.t;
-            }
-        }
-    }
-    // (overflow: the brute-force pass below covers every queued pair as well)
-    if (!RT_X_PAIRS)
-#endif
     while (sp > 0) {
         const int npop = sp < 4 ? sp : 4;
         bool valid = (lane >> 3) < npop;
@@ -672,13 +496,7 @@ __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ no
                     tr.id = __float_as_int(idf);
                 }
                 if (STATS && lane == 0) st->wtris++;
-#ifndef RT_X_LANE_CULL
-#define RT_X_LANE_CULL 0
-#endif
-                // Only the lanes whose own ray enters the leaf box run the test: the others cannot hit (the vote above already
-                // relies on that), and leaving them out lets the warp drop out of the staged test as soon as the lanes that
-                // matter have failed.
-                if (RT_X_LANE_CULL ? (live && lh) : live) {
+                if (live) {
                     if (STATS) st->tris++;
                     float t, uu, vv;
                     // LAZY: division-free front end, exact test for the survivors (rt_core.h, rt_moller_trumbore_lazy)
@@ -726,6 +544,7 @@ __device__ __noinline__ TraceResult frustum_trace(const BvhNode* __restrict__ no
 // registers or hoisted), and everything else is recomputed from them.  Side effect: the ray is generated once per
 // sample instead of three times, and the surface code exists once — the kernel is instruction-cache bound outside the
 // traversal loop, so code that is not there is the cheapest code.
+enum { ST_DX = 0, ST_DY, ST_DZ, ST_HT, ST_HU, ST_HV, ST_HSLOT, ST_LOX, ST_LOY, ST_LOZ, ST_DIX, ST_DIY, ST_DIZ, ST_ACX, ST_ACY, ST_ACZ, RT_STASH_WORDS };
 #define STASH(k) stash[(k) * RT_BLOCK_THREADS]
 struct WarpSlot { unsigned tile, sub, nprim, nshadow; };       // per warp, shared memory: the packet in flight + ray counters
 
@@ -762,7 +581,7 @@ __device__ __forceinline__ void render_packet(const FrameParams& P, volatile War
             const unsigned nlive = (unsigned)__popc(__ballot_sync(FULLMASK, live));
             if (lane == 0) ws->nprim += nlive;
             Hit h;
-            if (FRUSTUM) h = frustum_trace<MODE, STATS, FAST, TAG, LAZY>(P.nodes, P.wide, P.geom, P.num_tris, ray, live, false, true, 0.f, st, wstack, wfr, P.frustum_eps, ld3(P.scene_c), P.scene_r2, stash).hit;
+            if (FRUSTUM) h = frustum_trace<MODE, STATS, FAST, TAG, LAZY>(P.nodes, P.wide, P.geom, P.num_tris, ray, live, false, true, 0.f, st, wstack, wfr, P.frustum_eps, ld3(P.scene_c), P.scene_r2).hit;
             else h = packet_trace<MODE, STATS, FAST, PF, TAG>(P.nodes, P.geom, P.num_tris, ray, live, false, 0.f, st).hit;
             // (a lane that traced nothing comes back with slot == RT_SLOT_DEAD)
             STASH(ST_HT) = h.t; STASH(ST_HU) = h.u; STASH(ST_HV) = h.v; STASH(ST_HSLOT) = __int_as_float(h.slot);
@@ -811,7 +630,7 @@ __device__ __forceinline__ void render_packet(const FrameParams& P, volatile War
                     const unsigned nneed = (unsigned)__popc(__ballot_sync(FULLMASK, need));
                     if (lane == 0) ws->nshadow += nneed;
                     bool blocked;
-                    if (FRUSTUM) blocked = frustum_trace<MODE, STATS, FAST, TAG, LAZY>(P.nodes, P.wide, P.geom, P.num_tris, sray, need, true, false, dist, st, wstack, wfr, P.frustum_eps, ld3(P.scene_c), P.scene_r2, stash).blocked;
+                    if (FRUSTUM) blocked = frustum_trace<MODE, STATS, FAST, TAG, LAZY>(P.nodes, P.wide, P.geom, P.num_tris, sray, need, true, false, dist, st, wstack, wfr, P.frustum_eps, ld3(P.scene_c), P.scene_r2).blocked;
                     else blocked = packet_trace<MODE, STATS, FAST, PF, TAG>(P.nodes, P.geom, P.num_tris, sray, need, true, dist, st).blocked;
                     // an unlit light left a zero contribution: Lo + 0 == Lo bit for bit (no -0 can arise: Lo >= +0)
                     if (!blocked) {
@@ -892,8 +711,8 @@ __device__ __forceinline__ void flush_warp_counters(const FrameParams& P, const 
 template <int MODE, bool STATS, bool FAST, int MINB, bool PF = false, bool GROUPED = false, bool FRUSTUM = false>
 __global__ void __launch_bounds__(RT_BLOCK_THREADS, MINB)
 k_render_packet(const __grid_constant__ FrameParams P) {
-    __shared__ __align__(16) int s_wstack[FRUSTUM ? (RT_BLOCK_THREADS / 32) * RT_WSTRIDE : 1];
-    int* const wstack = s_wstack + (FRUSTUM ? (threadIdx.x >> 5) * RT_WSTRIDE : 0);
+    __shared__ int s_wstack[FRUSTUM ? (RT_BLOCK_THREADS / 32) * RT_FSTACK : 1];
+    int* const wstack = s_wstack + (FRUSTUM ? (threadIdx.x >> 5) * RT_FSTACK : 0);
     __shared__ float4 s_wfr[FRUSTUM ? (RT_BLOCK_THREADS / 32) * 5 : 1];
     float4* const wfr = s_wfr + (FRUSTUM ? (threadIdx.x >> 5) * 5 : 0);
     __shared__ float s_stash[RT_STASH_WORDS * RT_BLOCK_THREADS];
@@ -952,7 +771,7 @@ __device__ __forceinline__ void rt_store_release_sys(unsigned* p, unsigned v) { 
 template <int MODE, bool STATS, bool FAST, int MINB, bool GROUPED, bool LAZY>
 __global__ void __launch_bounds__(RT_BLOCK_THREADS, MINB)
 k_render_persist(const __grid_constant__ FrameParams P) {
-    __shared__ __align__(16) int s_wstack[(RT_BLOCK_THREADS / 32) * RT_WSTRIDE];
+    __shared__ int s_wstack[(RT_BLOCK_THREADS / 32) * RT_FSTACK];
     __shared__ float4 s_wfr[(RT_BLOCK_THREADS / 32) * 5];
     __shared__ float s_stash[RT_STASH_WORDS * RT_BLOCK_THREADS];
     __shared__ WarpSlot s_ws[RT_BLOCK_THREADS / 32];
@@ -960,7 +779,7 @@ k_render_persist(const __grid_constant__ FrameParams P) {
     __shared__ unsigned s_claim;                      // iteration whose successor tile has been pulled from the queue
     __shared__ int s_go, s_band;
     __shared__ unsigned s_band_cnt, s_last;
-    int* const wstack = s_wstack + (threadIdx.x >> 5) * RT_WSTRIDE;
+    int* const wstack = s_wstack + (threadIdx.x >> 5) * RT_FSTACK;
     float4* const wfr = s_wfr + (threadIdx.x >> 5) * 5;
     volatile WarpSlot* const ws = s_ws + (threadIdx.x >> 5);
     constexpr int TAG = 1000 + MINB * 8 + (GROUPED ? 1 : 0) + (LAZY ? 2 : 0) + (STATS ? 4 : 0);
