@@ -40,6 +40,7 @@ extern "C" {
 #define RT_ERR_STATE    -3   /* call order: render before upload, etc.           */
 #define RT_ERR_NCCL     -4   /* NCCL failure                                      */
 #define RT_ERR_NOMEM    -5
+#define RT_ERR_UNSUPPORTED -6 /* input outside what the device OBJ parser handles (see rt_dmesh_parse_obj) */
 
 /* rt_frame.mode — which reference renderer's contract the frame follows
  * (SURVEY §8a "mode parameters"). */
@@ -288,6 +289,7 @@ int  rt_frame_times(rt_ctx* ctx, float* total_ms, float* kernel_ms);
  * against rt_render / rt_download_image.  The reference serialises everything on the default stream
  * (CHECK_CUDA, GPUandCPU/include/imports.h:40-47). */
 int  rt_stream_handle(const rt_ctx* ctx, void** cuda_stream);
+int  rt_device_of(const rt_ctx* ctx, int* device);       /* CUDA device ordinal of the context (rank 0's for rt_create_multi) */
 
 /* Traversal work of the last frame rendered with a *_STATS variant, summed over primary and shadow
  * queries of this rank: per-ray BVH node visits and triangle tests, and the memory requests behind
@@ -325,6 +327,27 @@ int  rt_mesh_copy(const rt_mesh* mesh, float* positions, float* normals, uint32_
 int  rt_mesh_transform(rt_mesh* mesh, const float position[3], const float rotation_deg[3], const float scale[3]);
 int  rt_mesh_append(rt_mesh* dst, const rt_mesh* src);
 const char* rt_mesh_last_error(void);
+
+/* -- OBJ ingest on the device ------------------------------------ */
+/* The same loader contract as rt_mesh_load_obj (LoadOBJ_ToMesh, GPUandCPU/include/MeshOBJ.h:260-427), executed on the GPU:
+ * `text` (host memory, `nbytes` bytes: the file as it is on disk) is copied to the context's device and parsed there;
+ * positions / normals / indices / per-triangle object ids come out as DEVICE arrays.  rt_upload_scene accepts device pointers
+ * in rt_scene (cudaMemcpyDefault), so rt_dmesh_arrays feeds it directly, transforms included (rt_scene.transforms are
+ * baked on the device) — the mesh never exists in host memory.  Identical, bit for bit, to what rt_mesh_load_obj returns
+ * for the same bytes (tests/test_gpu_ingest.py); numbers follow strtof (the few literals fp64 cannot decide are converted by
+ * the host's own strtof, rt_dmesh_stats counts them).  Refused with RT_ERR_UNSUPPORTED: inf / nan / hexadecimal literals,
+ * lines of 1024 bytes or more (the reference's fgets buffer would split them), files of 2 GiB or more.
+ * *next_object_id: in = id of the file's first object, out = first unused id (NULL = start at 0). */
+typedef struct rt_dmesh rt_dmesh;
+int  rt_dmesh_parse_obj(rt_ctx* ctx, const char* text, uint64_t nbytes, int32_t* next_object_id, rt_dmesh** out);
+int  rt_dmesh_create(rt_dmesh** out);               /* empty mesh, target of rt_dmesh_append */
+void rt_dmesh_free(rt_dmesh* mesh);
+int  rt_dmesh_counts(const rt_dmesh* mesh, uint64_t* num_vertices, uint64_t* num_normals, uint64_t* num_triangles);
+int  rt_dmesh_arrays(const rt_dmesh* mesh, const float** positions, const float** normals, const uint32_t** indices, const int32_t** tri_obj_ids);
+int  rt_dmesh_copy(const rt_dmesh* mesh, float* positions, float* normals, uint32_t* indices, int32_t* tri_obj_ids);   /* to host memory */
+int  rt_dmesh_append(rt_dmesh* dst, const rt_dmesh* src);                     /* AppendMesh (MeshOBJ.h:429-466) on the device */
+int  rt_dmesh_stats(const rt_dmesh* mesh, float* parse_ms, uint64_t* lines, uint64_t* host_converted_numbers);
+const char* rt_dmesh_last_error(void);
 
 /* -- introspection for tests / profiling ---------------------------------- */
 /* Copies the flattened BVH back to the host (nodes: 64 B each; tri blocks: 48 B

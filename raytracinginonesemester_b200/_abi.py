@@ -2,7 +2,7 @@
 import ctypes as C
 
 RT_API_VERSION = 4          # include/rt_api.h
-RT_OK, RT_ERR_ARG, RT_ERR_CUDA, RT_ERR_STATE, RT_ERR_NCCL, RT_ERR_NOMEM = 0, -1, -2, -3, -4, -5
+RT_OK, RT_ERR_ARG, RT_ERR_CUDA, RT_ERR_STATE, RT_ERR_NCCL, RT_ERR_NOMEM, RT_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 RT_MODE_HW1, RT_MODE_HW2_BVH, RT_MODE_HW2_CPU = 0, 1, 2
 RT_ACCEL_BRUTE, RT_ACCEL_BVH = 0, 1
 RT_OUT_RGB_F32, RT_OUT_RGB8, RT_OUT_TRI_ID, RT_OUT_T = 1, 2, 4, 8
@@ -116,6 +116,16 @@ EXPORTS = {
     "rt_mesh_transform": (C.c_int, [C.c_void_p, f32p, f32p, f32p]),
     "rt_mesh_append": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rt_mesh_last_error": (C.c_char_p, []),
+    "rt_device_of": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "rt_dmesh_parse_obj": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, i32p, C.POINTER(C.c_void_p)]),
+    "rt_dmesh_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "rt_dmesh_free": (None, [C.c_void_p]),
+    "rt_dmesh_counts": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_uint64)] * 3),
+    "rt_dmesh_arrays": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "rt_dmesh_copy": (C.c_int, [C.c_void_p, f32p, f32p, u32p, i32p]),
+    "rt_dmesh_append": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rt_dmesh_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "rt_dmesh_last_error": (C.c_char_p, []),
     "rt_debug_set_shard": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "rt_debug_download_bvh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, i32p]),
 }

@@ -184,6 +184,89 @@ class Scene:
         return s
 
 
+class DeviceMesh:
+    """A mesh that exists only in device memory: OBJ text parsed on the GPU (rt_dmesh_parse_obj), same arrays as load_obj."""
+
+    def __init__(self, renderer, handle=None):
+        self.lib = renderer.lib
+        self.h = handle if handle is not None else C.c_void_p()
+        if handle is None:
+            rc = self.lib.rt_dmesh_create(C.byref(self.h))
+            if rc != A.RT_OK:
+                raise RtError(rc, "rt_dmesh_create")
+
+    @classmethod
+    def parse_obj(cls, renderer, text, next_object_id=0):
+        """text: the OBJ file's bytes.  Returns (DeviceMesh, next_object_id)."""
+        data = bytes(text)
+        h = C.c_void_p()
+        nid = C.c_int32(next_object_id)
+        rc = renderer.lib.rt_dmesh_parse_obj(renderer.ctx, data, len(data), C.byref(nid), C.byref(h))
+        if rc != A.RT_OK:
+            raise RtError(rc, (renderer.lib.rt_dmesh_last_error() or b"").decode())
+        return cls(renderer, h), int(nid.value)
+
+    def counts(self):
+        nv, nn, nt = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.lib.rt_dmesh_counts(self.h, C.byref(nv), C.byref(nn), C.byref(nt))
+        return int(nv.value), int(nn.value), int(nt.value)
+
+    def stats(self):
+        """(device ms of the whole parse incl. the H2D copy of the text, lines, numbers converted by the host's strtof)"""
+        ms, ln, hard = C.c_float(), C.c_uint64(), C.c_uint64()
+        self.lib.rt_dmesh_stats(self.h, C.byref(ms), C.byref(ln), C.byref(hard))
+        return float(ms.value), int(ln.value), int(hard.value)
+
+    def append(self, other):
+        rc = self.lib.rt_dmesh_append(self.h, other.h)
+        if rc != A.RT_OK:
+            raise RtError(rc, (self.lib.rt_dmesh_last_error() or b"").decode())
+
+    def download(self):
+        """(positions, normals | None, indices, tri_obj_ids) copied to the host — for tests."""
+        nv, nn, nt = self.counts()
+        pos = np.zeros((nv, 3), np.float32)
+        nrm = np.zeros((nn, 3), np.float32)
+        idx = np.zeros((nt, 3), np.uint32)
+        obj = np.zeros(nt, np.int32)
+        rc = self.lib.rt_dmesh_copy(self.h, _ptr(pos, A.f32p), _ptr(nrm, A.f32p) if nn else A.f32p(), _ptr(idx, A.u32p), _ptr(obj, A.i32p))
+        if rc != A.RT_OK:
+            raise RtError(rc, (self.lib.rt_dmesh_last_error() or b"").decode())
+        return pos, (nrm if nn else None), idx, obj
+
+    def close(self):
+        if self.h:
+            self.lib.rt_dmesh_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceScene(Scene):
+    """rt_scene over a DeviceMesh: the pointers are device pointers, which rt_upload_scene accepts as they are."""
+
+    def __init__(self, dmesh, materials=None, build_flags=0, transforms=None):
+        self.dmesh = dmesh
+        nv, nn, nt = dmesh.counts()
+        self._counts = (nv, nn, nt)
+        super().__init__(np.zeros((1, 3), np.float32), np.zeros((1, 3), np.uint32), materials=materials, build_flags=build_flags, transforms=transforms)
+
+    def c_struct(self):
+        s = super().c_struct()
+        p, n, i, o = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self.dmesh.lib.rt_dmesh_arrays(self.dmesh.h, C.byref(p), C.byref(n), C.byref(i), C.byref(o))
+        s.positions = C.cast(p, A.f32p)
+        s.normals = C.cast(n, A.f32p) if n.value else A.f32p()
+        s.indices = C.cast(i, A.u32p)
+        s.tri_obj_ids = C.cast(o, A.i32p)
+        s.num_vertices, s.num_triangles = self._counts[0], self._counts[2]
+        return s
+
+
 class Frame:
     """Per-frame arguments of render() (query.h:13-29): camera, lights, miss colour, spp, depth."""
 

@@ -655,10 +655,10 @@ static int upload_local(rt_ctx* c, const rt_scene* sc) {
     if (sc->num_materials) CUS(cudaMalloc(&c->materials, sizeof(rt_material) * (size_t)sc->num_materials));
     lap("cudaMalloc");
     CUS(cudaEventRecord(e0, c->stream));
-    CUS(cudaMemcpyAsync(d_pos, sc->positions, sizeof(float) * 3 * nv, cudaMemcpyHostToDevice, c->stream));
-    CUS(cudaMemcpyAsync(d_idx, sc->indices, sizeof(uint32_t) * 3 * nt, cudaMemcpyHostToDevice, c->stream));
-    if (d_nrm) CUS(cudaMemcpyAsync(d_nrm, sc->normals, sizeof(float) * 3 * nv, cudaMemcpyHostToDevice, c->stream));
-    if (d_obj) CUS(cudaMemcpyAsync(d_obj, sc->tri_obj_ids, sizeof(int32_t) * nt, cudaMemcpyHostToDevice, c->stream));
+    CUS(cudaMemcpyAsync(d_pos, sc->positions, sizeof(float) * 3 * nv, cudaMemcpyDefault, c->stream));
+    CUS(cudaMemcpyAsync(d_idx, sc->indices, sizeof(uint32_t) * 3 * nt, cudaMemcpyDefault, c->stream));
+    if (d_nrm) CUS(cudaMemcpyAsync(d_nrm, sc->normals, sizeof(float) * 3 * nv, cudaMemcpyDefault, c->stream));
+    if (d_obj) CUS(cudaMemcpyAsync(d_obj, sc->tri_obj_ids, sizeof(int32_t) * nt, cudaMemcpyDefault, c->stream));
     if (sc->num_materials) CUS(cudaMemcpyAsync(c->materials, sc->materials, sizeof(rt_material) * (size_t)sc->num_materials, cudaMemcpyHostToDevice, c->stream));
     for (int k = 0; k < sc->num_transforms; ++k) {             // applyObjectTransform on the device (main.cu:75-96)
         const rt_object_transform& o = sc->transforms[k];
@@ -1499,6 +1499,12 @@ int rt_frame_times(rt_ctx* c, float* total_ms, float* kernel_ms) {
     int rc = rt_sync(c, total_ms);
     if (rc != RT_OK) return rc;
     if (kernel_ms) CU(c, cudaEventElapsedTime(kernel_ms, c->evk0, c->evk1));
+    return RT_OK;
+}
+
+int rt_device_of(const rt_ctx* c, int* device) {
+    if (!c || !device) return RT_ERR_ARG;
+    *device = c->device;
     return RT_OK;
 }
 
