@@ -341,15 +341,16 @@ __global__ void k_rebase(uint32_t* __restrict__ idx, uint64_t n, uint32_t base) 
 
 inline unsigned blocks_for(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
 
-struct Scratch {          // everything freed on every exit path
+struct Scratch {          // stream-ordered scratch, everything freed on every exit path
+    cudaStream_t stream = nullptr;
     std::vector<void*> ptrs;
     template <typename T> cudaError_t alloc(T** p, size_t count) {
         *p = nullptr;
-        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), (count ? count : 1) * sizeof(T));
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(p), (count ? count : 1) * sizeof(T), stream);
         if (e == cudaSuccess) ptrs.push_back(*p);
         return e;
     }
-    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+    ~Scratch() { for (void* p : ptrs) cudaFreeAsync(p, stream); }
 };
 
 int fail(int code, const std::string& why) { g_err = why; return code; }
@@ -382,6 +383,7 @@ int rt_dmesh_parse_obj(rt_ctx* ctx, const char* text, uint64_t nbytes, int32_t* 
     const uint32_t n = (uint32_t)nbytes;
     const unsigned T = 256;
     Scratch sc;
+    sc.stream = stream;
     cudaError_t ce = cudaSuccess;
 #define CK(x) do { ce = (x); if (ce != cudaSuccess) return fail(RT_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(ce)); } while (0)
     CK(cudaSetDevice(device));
@@ -425,7 +427,8 @@ int rt_dmesh_parse_obj(rt_ctx* ctx, const char* text, uint64_t nbytes, int32_t* 
     uint32_t tris_before_first_tag = 0;
     if (g1.first_tag_line != 0xffffffffu) {
         LineCounts p{};
-        CK(cudaMemcpy(&p, d_pref + g1.first_tag_line, sizeof p, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpyAsync(&p, d_pref + g1.first_tag_line, sizeof p, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
         tris_before_first_tag = p.tri;
     }
 
@@ -450,12 +453,14 @@ int rt_dmesh_parse_obj(rt_ctx* ctx, const char* text, uint64_t nbytes, int32_t* 
     if (g1.num_hard > hard_cap) return fail(RT_ERR_UNSUPPORTED, "rt_dmesh_parse_obj: more than 65536 numbers need the host's strtof");
     if (g1.num_hard) {               // the literals fp64 cannot decide: the host's strtof on the caller's own buffer
         std::vector<HardToken> hard(g1.num_hard);
-        CK(cudaMemcpy(hard.data(), po.hard, sizeof(HardToken) * g1.num_hard, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpyAsync(hard.data(), po.hard, sizeof(HardToken) * g1.num_hard, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
         for (const HardToken& h : hard) {
             if (h.array > 1u) continue;
             const std::string tok(text + h.start, text + h.start + h.len);
             const float v = strtof(tok.c_str(), nullptr);
-            CK(cudaMemcpy((h.array == 0u ? po.rp : po.rn) + h.index, &v, sizeof v, cudaMemcpyHostToDevice));
+            CK(cudaMemcpyAsync((h.array == 0u ? po.rp : po.rn) + h.index, &v, sizeof v, cudaMemcpyHostToDevice, stream));
+            CK(cudaStreamSynchronize(stream));
         }
     }
     // streams the loader keeps aligned with the vertices: a stream that appears after the first vertex was created is an error

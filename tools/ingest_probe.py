@@ -23,18 +23,17 @@ gen_s = time.time() - t0
 path = os.path.join(tempfile.mkdtemp(), "terrain.obj")
 open(path, "wb").write(text)
 r = Renderer(0)
-DeviceMesh.parse_obj(r, text[:4096] + b"\n")[0].close() if False else None
 ms = []
-for _ in range(4):
+for rep in range(4):
     t0 = time.perf_counter()
-    dm, _ = DeviceMesh.parse_obj(r, text)
+    dm, nid = DeviceMesh.parse_obj(r, text)
     wall = time.perf_counter() - t0
     ms.append((dm.stats()[0], wall * 1e3))
     st = dm.stats()
-    if _ < 3:
+    if rep < 3:
         dm.close()
 t0 = time.perf_counter()
-hp, hn, hi, ho, _ = api.load_obj(path)
+hp, hn, hi, ho, hid = api.load_obj(path)
 host_s = time.perf_counter() - t0
 dp, dn, di, do = dm.download()
 same = bool(np.array_equal(hp.view(np.uint32), dp.view(np.uint32)) and np.array_equal(hi, di) and np.array_equal(ho, do))
