@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RT_API_VERSION 4
+#define RT_API_VERSION 5
 
 /* status codes */
 #define RT_OK            0

@@ -1,7 +1,7 @@
 """ctypes mirror of include/rt_api.h (struct layouts and constants)."""
 import ctypes as C
 
-RT_API_VERSION = 4          # include/rt_api.h
+RT_API_VERSION = 5          # include/rt_api.h
 RT_OK, RT_ERR_ARG, RT_ERR_CUDA, RT_ERR_STATE, RT_ERR_NCCL, RT_ERR_NOMEM, RT_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 RT_MODE_HW1, RT_MODE_HW2_BVH, RT_MODE_HW2_CPU = 0, 1, 2
 RT_ACCEL_BRUTE, RT_ACCEL_BVH = 0, 1

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "librt_b200.so does not export " + n
     assert set(names) == set(A.EXPORTS), set(names) ^ set(A.EXPORTS)
-    assert lib.rt_api_version() == A.RT_API_VERSION == 4
+    assert lib.rt_api_version() == A.RT_API_VERSION == 5
 
 
 def test_struct_layouts_match_the_reference():
