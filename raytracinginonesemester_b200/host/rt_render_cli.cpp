@@ -67,7 +67,7 @@ bool write_ppm(const std::string& path, int W, int H, const std::vector<float>& 
 } // namespace
 
 int main(int argc, char** argv) {
-    bool hw1 = false, gamma2 = false, brute = false, host_transform = false;
+    bool hw1 = false, gamma2 = false, brute = false, host_transform = false, device_ingest = false;
     int device = 0, width = 0, height = 0, spp_override = 0, depth_override = 0;
     std::string out_path;
     std::vector<std::string> inputs;
@@ -77,6 +77,7 @@ int main(int argc, char** argv) {
         else if (a == "--gamma2") gamma2 = true;
         else if (a == "--brute") brute = true;
         else if (a == "--host-transform") host_transform = true;     // bake object transforms on the host instead of the device
+        else if (a == "--device-ingest") device_ingest = true;       // parse the OBJ files on the GPU (rt_dmesh_parse_obj): no host copy of the mesh
         else if (a == "--device" && i + 1 < argc) device = std::atoi(argv[++i]);
         else if (a == "--width" && i + 1 < argc) width = std::atoi(argv[++i]);
         else if (a == "--height" && i + 1 < argc) height = std::atoi(argv[++i]);
@@ -84,7 +85,7 @@ int main(int argc, char** argv) {
         else if (a == "--depth" && i + 1 < argc) depth_override = std::atoi(argv[++i]);
         else if ((a == "-o" || a == "--out") && i + 1 < argc) out_path = argv[++i];
         else if (a == "-h" || a == "--help") {
-            std::printf("usage: rt_render_cli [--hw1] [--brute] [--host-transform] [--width W --height H] [--spp N] [--depth D] [--gamma2] [--device D] [-o out.ppm] [scene.json | mesh.obj ...]\n");
+            std::printf("usage: rt_render_cli [--hw1] [--brute] [--host-transform | --device-ingest] [--width W --height H] [--spp N] [--depth D] [--gamma2] [--device D] [-o out.ppm] [scene.json | mesh.obj ...]\n");
             return 0;
         } else inputs.push_back(a);
     }
@@ -111,7 +112,12 @@ int main(int argc, char** argv) {
         for (auto& p : inputs) { SceneObjectDesc o; o.path = p; o.material = default_material(); objects.push_back(o); }
     }
 
+    rt_ctx* ctx = nullptr;
+    if (rt_create(&ctx, device) != RT_OK) return die(nullptr, "rt_create");
     HostMesh mesh;
+    rt_dmesh* dmesh = nullptr;                                // --device-ingest: the mesh lives here instead
+    uint64_t dnv = 0, dnt = 0;
+    if (device_ingest && rt_dmesh_create(&dmesh) != RT_OK) return die(ctx, "rt_dmesh_create");
     std::vector<rt_material> materials;
     std::vector<rt_object_transform> transforms;             // applyObjectTransform runs on the device at upload
     int next_id = 0;
@@ -120,6 +126,36 @@ int main(int argc, char** argv) {
         HostMesh part;
         const int first = next_id;
         std::string err;
+        if (device_ingest) {
+            std::string bytes;
+            if (FILE* f = std::fopen(o.path.c_str(), "rb")) {
+                char buf[1 << 16];
+                size_t k;
+                while ((k = std::fread(buf, 1, sizeof buf, f)) > 0) bytes.append(buf, k);
+                std::fclose(f);
+            } else { std::fprintf(stderr, "Failed to load OBJ: %s (cannot open)\n", o.path.c_str()); continue; }
+            rt_dmesh* part_d = nullptr;
+            int32_t nid = next_id;
+            if (rt_dmesh_parse_obj(ctx, bytes.data(), bytes.size(), &nid, &part_d) != RT_OK) {
+                std::fprintf(stderr, "Failed to load OBJ: %s (%s)\n", o.path.c_str(), rt_dmesh_last_error());
+                continue;
+            }
+            next_id = nid;
+            uint64_t pv = 0, pn = 0, pt = 0;
+            rt_dmesh_counts(part_d, &pv, &pn, &pt);
+            rt_object_transform t{};
+            t.first_vertex = dnv; t.num_vertices = pv;
+            std::memcpy(t.position, o.position, sizeof t.position); std::memcpy(t.rotation_deg, o.rotation, sizeof t.rotation_deg);
+            std::memcpy(t.scale, o.scale, sizeof t.scale);
+            transforms.push_back(t);
+            if (rt_dmesh_append(dmesh, part_d) != RT_OK) { std::fprintf(stderr, "rt_dmesh_append: %s\n", rt_dmesh_last_error()); return 1; }
+            rt_dmesh_free(part_d);
+            dnv += pv; dnt += pt;
+            materials.resize((size_t)next_id, default_material());
+            for (int id = first; id < next_id; ++id) materials[(size_t)id] = o.material;
+            std::printf("  -> Loaded %llu triangles.\n", (unsigned long long)pt);
+            continue;
+        }
         if (!load_obj(o.path, part, next_id, &err)) { std::fprintf(stderr, "Failed to load OBJ: %s (%s)\n", o.path.c_str(), err.c_str()); continue; }
         if (host_transform) transform_mesh(part, o.position, o.rotation, o.scale);
         else {
@@ -134,18 +170,23 @@ int main(int argc, char** argv) {
         std::printf("  -> Loaded %zu triangles.\n", part.num_triangles());
         append_mesh(mesh, part);
     }
-    if (mesh.positions.empty()) { std::fprintf(stderr, "No valid geometry loaded.\n"); return 1; }
-    if (hw1 && mesh.normals.empty()) mesh.normals.assign(mesh.positions.size(), 0.f);
+    if (device_ingest ? dnt == 0 : mesh.positions.empty()) { std::fprintf(stderr, "No valid geometry loaded.\n"); return 1; }
+    if (hw1 && !device_ingest && mesh.normals.empty()) mesh.normals.assign(mesh.positions.size(), 0.f);
 
-    rt_ctx* ctx = nullptr;
-    if (rt_create(&ctx, device) != RT_OK) return die(nullptr, "rt_create");
     rt_scene sc{};
-    sc.positions = mesh.positions.data(); sc.normals = mesh.normals.empty() ? nullptr : mesh.normals.data();
-    sc.num_vertices = mesh.num_vertices(); sc.indices = mesh.indices.data(); sc.num_triangles = mesh.num_triangles();
-    sc.tri_obj_ids = mesh.tri_obj_ids.data(); sc.materials = materials.data(); sc.num_materials = (int)materials.size();
+    if (device_ingest) {                                       // device pointers: rt_upload_scene copies device to device
+        rt_dmesh_arrays(dmesh, &sc.positions, &sc.normals, &sc.indices, &sc.tri_obj_ids);
+        sc.num_vertices = dnv; sc.num_triangles = dnt;
+    } else {
+        sc.positions = mesh.positions.data(); sc.normals = mesh.normals.empty() ? nullptr : mesh.normals.data();
+        sc.num_vertices = mesh.num_vertices(); sc.indices = mesh.indices.data(); sc.num_triangles = mesh.num_triangles();
+        sc.tri_obj_ids = mesh.tri_obj_ids.data();
+    }
+    sc.materials = materials.data(); sc.num_materials = (int)materials.size();
     sc.build_flags = (hw1 && brute) ? RT_BUILD_NO_BVH : RT_BUILD_DEFAULT;
     sc.transforms = transforms.empty() ? nullptr : transforms.data(); sc.num_transforms = (int)transforms.size();
     if (rt_upload_scene(ctx, &sc) != RT_OK) return die(ctx, "rt_upload_scene");
+    if (dmesh) rt_dmesh_free(dmesh);
     rt_build_info bi{};
     rt_build_info_get(ctx, &bi);
     std::printf("GPU LBVH Build Time: %.3f ms (%llu triangles, %llu nodes)\n", bi.build_ms, (unsigned long long)bi.num_triangles, (unsigned long long)bi.num_nodes);

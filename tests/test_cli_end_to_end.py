@@ -1,7 +1,7 @@
 """Drop-in check of the C++ host driver: rt_render_cli (built here with g++ against the in-tree librt_b200.so) is
 run on the very scene JSON + OBJ files the reference's whole bvh_viz program was run on (fixture
 tests/golden/e2e_scene.npz, tools/make_golden_e2e.py), and its PPM is compared with the reference's 8-bit image.
-Covers the JSON dialect, OBJ ingest, transforms (baked on the device by default, on the host with --host-transform), per-object materials, two lights, 2 spp jitter, mirror and
+Covers the JSON dialect, OBJ ingest (on the host, and on the device with --device-ingest), transforms (baked on the device by default, on the host with --host-transform), per-object materials, two lights, 2 spp jitter, mirror and
 hash-RNG diffuse bounces (max_bounces 3) and the P6 writer."""
 import os
 import subprocess
@@ -44,7 +44,7 @@ def cli(tmp_path_factory):
     return exe
 
 
-@pytest.mark.parametrize("name,extra", [("mirror", []), ("diffuse", []), ("mirror", ["--host-transform"])])
+@pytest.mark.parametrize("name,extra", [("mirror", []), ("diffuse", []), ("mirror", ["--host-transform"]), ("mirror", ["--device-ingest"]), ("diffuse", ["--device-ingest"])])
 def test_cli_matches_reference_program(cli, golden, tmp_path, name, extra):
     g = golden("e2e_scene.npz")
     open(tmp_path / "ball.obj", "w").write(str(g["ball_obj"]))
