@@ -1111,7 +1111,10 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
     CU(c, cudaMemsetAsync(c->counters.p, 0, RT_COUNTER_BYTES + RT_PERSIST_CTL_BYTES, c->stream));
     P.peer_timeout_ns = c->peer_timeout_ns;
     P.peer_err = c->peer_err;
-    const bool persistent = rt_render_is_persistent(P, fr->kernel_variant, into != nullptr);
+    // RT_VARIANT_DEFAULT: the persistent kernel where the completion protocol has to live inside the kernel (banded peer-store
+    // gather); frames that go out through the shared host image / the caller's buffers use the faster block-per-tile kernel, one
+    // launch per band (below), like single-GPU rt_render_into.
+    const bool persistent = rt_render_is_persistent(P, fr->kernel_variant, into != nullptr && !host_direct);
     P.persist = persistent ? 1 : 0;
     const HostOut outs[4] = {{into ? into->rgb : nullptr, RT_OUT_RGB_F32, 12, P.rgb, "rgb"}, {into ? into->rgb8 : nullptr, RT_OUT_RGB8, 3, P.rgb8, "rgb8"},
                              {into ? into->tri_id : nullptr, RT_OUT_TRI_ID, 4, P.tri_id, "tri_id"}, {into ? into->t : nullptr, RT_OUT_T, 4, P.t, "t"}};
@@ -1154,9 +1157,35 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
         if (persistent) P.host_counters = c->pin_dev + 8;
         int l = 0;
         CU(c, cudaEventRecord(c->evk0, c->stream));
-        CU(c, rt_launch_render(P, fr->kernel_variant, c->stream, &l));
-        launches += l;
-        if (!persistent) { CU(c, rt_launch_flag_set(P.flags, RT_PEER_FLAG_STRIDE, P.num_chunks, seq, c->stream)); ++launches; }
+        StreamWriteValue32Fn band_w32 = stream_write_value32();
+        const bool band_launches = !persistent && P.num_chunks <= RT_BANDS && P.accel == RT_ACCEL_BVH;
+        if (band_launches) {
+            // Block-per-tile kernel (the faster one): one launch per band on a few streams, so that the hardware scheduler
+            // fills the tail of one band with the blocks of the next; the band's flag word is written into mapped host memory by a
+            // stream memory operation behind its kernel (no flag kernel, no SM), and this thread's pump copies the band out.
+            int start = 0;
+            for (int k = 0; k < P.num_chunks; ++k) {
+                FrameParams Q = P;
+                Q.tile_offset = P.tile_offset + start; Q.local_tiles = P.band_end[k] - start;
+                start = P.band_end[k];
+                cudaStream_t s = c->band_stream[k % RT_BAND_STREAMS];
+                CU(c, cudaStreamWaitEvent(s, c->evk0, 0));
+                int lk = 0;
+                if (Q.local_tiles > 0) CU(c, rt_launch_render(Q, fr->kernel_variant, s, &lk));
+                launches += lk;
+                unsigned* flag = P.flags + (size_t)k * RT_PEER_FLAG_STRIDE;
+                if (!band_w32 || band_w32((CUstream)s, (CUdeviceptr)flag, seq, 0) != CUDA_SUCCESS) {
+                    CU(c, rt_launch_flag_set(flag, RT_PEER_FLAG_STRIDE, 1, seq, s));
+                    ++launches;
+                }
+                CU(c, cudaEventRecord(c->band_ev[k], s));
+                CU(c, cudaStreamWaitEvent(c->stream, c->band_ev[k], 0));
+            }
+        } else {
+            CU(c, rt_launch_render(P, fr->kernel_variant, c->stream, &l));
+            launches += l;
+            if (!persistent) { CU(c, rt_launch_flag_set(P.flags, RT_PEER_FLAG_STRIDE, P.num_chunks, seq, c->stream)); ++launches; }
+        }
         CU(c, cudaEventRecord(c->evk1, c->stream));
         CU(c, cudaStreamWaitEvent(c->copy_stream, c->evk0, 0));
         rc = pump_bands(seq);
@@ -1177,6 +1206,13 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
         if (persistent && !c->inproc) {
             StreamWriteValue32Fn w32 = stream_write_value32();
             if (w32 && w32((CUstream)c->copy_stream, (CUdeviceptr)(c->pin_dev + 12), seq, 0) == CUDA_SUCCESS) c->fast_finish = true;
+        } else if (band_launches && !c->inproc) {
+            // (the pump has seen every band's flag, i.e. every band kernel has finished: the ray counters are final)
+            StreamWriteValue32Fn w32 = stream_write_value32();
+            if (w32) {
+                CU(c, cudaMemcpyAsync(c->pin + 8, c->counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->copy_stream));
+                if (w32((CUstream)c->copy_stream, (CUdeviceptr)(c->pin_dev + 12), seq, 0) == CUDA_SUCCESS) { c->fast_finish = true; c->pin[10] = seq; }
+            }
         }
         CU(c, cudaEventRecord(c->copy_done, c->copy_stream));
         if (!c->fast_finish) CU(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));
