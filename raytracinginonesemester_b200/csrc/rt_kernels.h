@@ -26,9 +26,10 @@ cudaError_t rt_pack_triangles(const BuildParams& bp, TriBlock* geom, TriBlock* s
 cudaError_t rt_launch_render(const FrameParams& fp, int kernel_variant, cudaStream_t stream, int* launches);
 // Which frames run on the persistent kernel, which publishes band-completion flags and runs the multi-GPU handshake itself
 // (FrameParams.queue / flags / ready_* / wait_ranks); other kernels need the flag kernels below around them.  `banded`: the
-// caller wants bands published while the frame renders (rt_render_into).  RT_VARIANT_DEFAULT picks the persistent kernel for
-// banded frames of multi-GPU contexts (every rank's copy engine follows its own kernel's band flags) and the block-per-tile
-// launch of the same traversal otherwise — measured, B200, C4: device time 1.847 vs 1.954 ms on one GPU, 0.336 vs 0.374 ms per
+// caller wants bands published while the frame renders AND cannot launch them one by one (rt_render_into of a multi-GPU context
+// into rank 0's own buffer: the banded peer-store gather).  RT_VARIANT_DEFAULT picks the persistent kernel for those frames and the
+// block-per-tile launch of the same traversal otherwise (single GPU and shared-host-image frames: one launch per band) — measured,
+// B200, C4: device time 1.847 vs 1.954 ms on one GPU, 0.336 vs 0.374 ms per
 // frame on eight; end to end on one GPU (one launch per band + event-chained copies vs one persistent launch + band flags) 1.96
 // vs 2.03 ms: the hardware's block scheduler does the same job without a barrier per tile (11 % of the persistent kernel's stall
 // samples) and tolerates one more resident block per SM.  The host stores the answer in FrameParams.persist.
