@@ -11,7 +11,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "librt_b200.so")
 SOURCES = ["rt_api.cu", "rt_build.cu", "rt_trace.cu", "rt_obj_device.cu", "rt_host.cpp", "rt_mesh_api.cpp", os.path.join("..", "host", "mesh_ingest.cpp")]
-HEADERS = ["rt_math.h", "rt_core.h", "rt_kernels.h", "rt_params.h", "rt_trace_core.h", "rt_build_core.h",
+HEADERS = ["rt_math.h", "rt_core.h", "rt_kernels.h", "rt_params.h", "rt_trace_core.h", "rt_build_core.h", "rt_obj_core.h",
            os.path.join("..", "host", "mesh_ingest.hpp"), os.path.join("..", "..", "include", "rt_api.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

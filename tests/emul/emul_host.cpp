@@ -12,6 +12,9 @@
 
 #include "../../raytracinginonesemester_b200/csrc/rt_build_core.h"
 #include "../../raytracinginonesemester_b200/csrc/rt_trace_core.h"
+#include "../../raytracinginonesemester_b200/csrc/rt_obj_core.h"
+#include <cstdlib>
+#include <string>
 
 struct EmuScene {
     std::vector<BvhNode> nodes;
@@ -351,6 +354,51 @@ uint64_t emu_mt_lazy_sweep(uint64_t n, uint64_t seed, uint64_t* stats) {
     }
     if (stats) { stats[0] = acc; stats[1] = early; stats[2] = late; }
     return bad;
+}
+
+
+// ---- device OBJ parser, per-line functions (rt_obj_core.h) on the host ----
+// parse_real over every '\n'-separated literal of `buf` against glibc's strtof on the same characters.
+// out[0] = literals converted on the "device" and equal to strtof bit for bit, out[1] = handed to the host ("hard"),
+// out[2] = refused forms (inf / nan / hex), out[3] = no conversion on both sides, out[4] = VALUE mismatches,
+// out[5] = end-of-token mismatches (incl. conversion on one side only), out[6] = index of the first mismatch (or -1).
+void emu_obj_real_sweep(const char* buf, uint64_t n, long long* out) {
+    for (int k = 0; k < 7; ++k) out[k] = 0;
+    out[6] = -1;
+    uint64_t s = 0; long long idx = 0;
+    while (s < n) {
+        uint64_t e = s;
+        while (e < n && buf[e] != '\n') ++e;
+        const uint64_t end = e < n ? e + 1 : e;                 // the line keeps its newline, like fgets
+        std::string line(buf + s, buf + end);
+        char* ep = nullptr;
+        const float want = strtof(line.c_str(), &ep);
+        const uint32_t want_end = (uint32_t)(ep - line.c_str());
+        DCur c{buf + s, 0u, (uint32_t)(end - s)};
+        float got = 0.f; uint32_t tok0 = 0;
+        const int r = parse_real(c, got, tok0);
+        bool bad_end = false, bad_val = false;
+        if (r == 0) { if (want_end != 0) bad_end = true; else out[3]++; }
+        else if (r == 3) out[2]++;
+        else {
+            if (c.i != want_end) bad_end = true;
+            if (r == 2) out[1]++;
+            else if (memcmp(&got, &want, 4) != 0) bad_val = true;
+            else out[0]++;
+        }
+        if (bad_val) out[4]++;
+        if (bad_end) out[5]++;
+        if ((bad_val || bad_end) && out[6] < 0) out[6] = idx;
+        s = end; ++idx;
+    }
+}
+// parse_face on one line (after the 'f'); corners: 12 ints (v, t, n) x 4.  Returns the corner count.
+int emu_obj_face(const char* line, uint32_t n, uint32_t nv, uint32_t nt, uint32_t nn, int* corners) {
+    DCur c{line, 0u, n};
+    Corner k[4];
+    const int nc = parse_face(c, k, nv, nt, nn);
+    for (int j = 0; j < nc; ++j) { corners[3 * j] = k[j].v; corners[3 * j + 1] = k[j].t; corners[3 * j + 2] = k[j].n; }
+    return nc;
 }
 
 } // extern "C"
