@@ -67,3 +67,23 @@ def test_documented_binding_runs_and_matches_the_ctypes_path(tmp_path):
     ref = rr.download()["rgb"]
     rr.close()
     assert np.array_equal(got, ref)
+
+
+def test_device_ingest_binding_compiles_and_links(tmp_path):
+    """The second binding of INTEGRATION.md §1 (LoadOBJ_ToMesh replaced by the device parser) as C, verbatim, against the header
+    and the library."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    sec = doc[doc.index("## 1. What replaces what"):doc.index("## 2. HW2/GPUandCPU")]
+    block = re.search(r"```c\n(.*?)```", sec, re.S).group(1)
+    assert "rt_dmesh_parse_obj" in block and "rt_dmesh_arrays" in block and "rt_upload_scene" in block
+    src = tmp_path / "device_ingest_snippet.c"
+    src.write_text('#include <stdio.h>\n#include <stdlib.h>\n#include "rt_api.h"\n'
+                   "static void die(const char* why) { fprintf(stderr, \"%s\\n\", why); exit(1); }\n"
+                   "int bind(rt_ctx* ctx, const char* buf, uint64_t nbytes, int32_t first_id, const rt_material* mats, int32_t nmats, rt_object_transform xf) {\n"
+                   + block + "  return 0;\n}\n"
+                   "int main(void) { return 0; }\n")
+    lib = os.path.join(ROOT, "raytracinginonesemester_b200", "librt_b200.so")
+    api.load_library()
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), lib, "-Wl,-rpath," + os.path.dirname(lib),
+                        "-o", str(tmp_path / "device_ingest_snippet")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
