@@ -1315,22 +1315,30 @@ int render_impl(rt_ctx* c, const rt_frame* fr, rt_image* into, bool* pipelined) 
         int rc = ensure_band_resources(c);
         if (rc != RT_OK) return rc;
         const int B = P.tiles_y < RT_BANDS ? P.tiles_y : RT_BANDS;
+        // Band boundaries in tile rows.  Only the LAST band's copy cannot overlap the rendering, so the bands shrink towards the end
+        // of the frame (the last one is 2 % of it: 0.5 MB of a 4K 8-bit frame instead of 3.1 MB with equal bands).
+        auto band_row = [&](int k) -> int {
+            static const int kCut[RT_BANDS + 1] = {0, 18, 36, 54, 70, 83, 92, 98, 100};     // per cent of the frame
+            if (B != RT_BANDS) return (int)((long long)P.tiles_y * k / B);
+            return (int)((long long)P.tiles_y * kCut[k] / 100);
+        };
         CU(c, cudaEventRecord(c->evk0, c->stream));
         for (int k = 0; k < B; ++k) {                 // all band kernels first: a pageable destination makes the copies host-synchronous
-            const int row_a = (int)((long long)P.tiles_y * k / B), row_b = (int)((long long)P.tiles_y * (k + 1) / B);
+            const int row_a = band_row(k), row_b = band_row(k + 1);
             FrameParams Q = P;
             Q.tile_offset = row_a * P.tiles_x; Q.local_tiles = (row_b - row_a) * P.tiles_x;
             cudaStream_t s = c->band_stream[k % RT_BAND_STREAMS];
             CU(c, cudaStreamWaitEvent(s, c->evk0, 0));
             int l = 0;
-            CU(c, rt_launch_render(Q, fr->kernel_variant, s, &l));
+            if (row_b > row_a) CU(c, rt_launch_render(Q, fr->kernel_variant, s, &l));
             launches += l;
             CU(c, cudaEventRecord(c->band_ev[k], s));
             CU(c, cudaStreamWaitEvent(c->stream, c->band_ev[k], 0));
         }
         CU(c, cudaEventRecord(c->evk1, c->stream));    // every band kernel has finished
         for (int k = 0; k < B; ++k) {
-            const int row_a = (int)((long long)P.tiles_y * k / B), row_b = (int)((long long)P.tiles_y * (k + 1) / B);
+            const int row_a = band_row(k), row_b = band_row(k + 1);
+            if (row_b <= row_a) continue;
             const size_t y0 = (size_t)row_a * RT_TILE_H, y1 = (size_t)row_b * RT_TILE_H < (size_t)P.H ? (size_t)row_b * RT_TILE_H : (size_t)P.H;
             CU(c, cudaStreamWaitEvent(c->copy_stream, c->band_ev[k], 0));
             rc = copy_rows(y0, y1);
