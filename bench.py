@@ -489,13 +489,33 @@ def bench_workload(args, r, dist, rank, world, local_rank, workload, steps, with
     clocks = sampler.stop() if sampler else None      # clocks were sampled during the device-timed steps
     # end to end through the C ABI with host buffers (render + copy into pinned host memory), wall clock per rank; the
     # ranks are aligned before every step (outside the timed region) and the step's time is the max over ranks
-    e2e_s = []
-    for i in range(-max(args.warmup, 3), steps):      # the warm-up calls pay rt_render_into's one-time stream / event / band set-up
+    e2e_s, start_late = [], []
+
+    def aligned_start():
+        """Ranks leave a collective tens of microseconds apart, and on a 0.4 ms frame that skew would be counted twice (the other
+        ranks wait for rank 0 to enter the frame, rank 0 waits for the last rank's copies).  So the ranks agree on a start TIME:
+        rank 0 proposes one 400 us ahead on the host's monotonic clock (one clock for all processes of the node) and everybody
+        spins until it.  Returns how late this rank was (0 when it made it)."""
         barrier()
+        if dist is None:
+            return 0.0
+        tt = torch.zeros(1, dtype=torch.float64, device="cuda")
+        if rank == 0:
+            tt[0] = time.perf_counter() + 400e-6
+        dist.broadcast(tt, 0)
+        target = float(tt.item())
+        late = time.perf_counter() - target
+        while time.perf_counter() < target:
+            pass
+        return max(late, 0.0)
+
+    for i in range(-max(args.warmup, 3), steps):      # the warm-up calls pay rt_render_into's one-time stream / event / band set-up
+        late = aligned_start()
         t0 = time.perf_counter()
         e2e_out = r.render_into(frame, into={"rgb8": shared} if world > 1 else {"rgb8": pinned})     # rt_render_into: the user-facing "frame to host memory" call
         if i >= 0:
             e2e_s.append(time.perf_counter() - t0)
+            start_late.append(late)
     e2e_kernel_ms = r.frame_times()[1]                 # the frame kernel inside the last end-to-end step (this rank)
     # PARITY OF WHAT WAS TIMED (world > 1): rank 0 renders the same frame alone and compares it with the gathered planes —
     # the 8-bit frame the e2e loop just delivered, and one extra untimed frame with ids and t
@@ -523,13 +543,14 @@ def bench_workload(args, r, dist, rank, world, local_rank, workload, steps, with
     per_rank[rank] = kern_ms
     if dist is not None:
         dist.all_reduce(per_rank)
-    t = torch.tensor([step_ms, e2e_s + [0.0] * (len(step_ms) - len(e2e_s))], dtype=torch.float64, device="cuda")
+    t = torch.tensor([step_ms, e2e_s + [0.0] * (len(step_ms) - len(e2e_s)), start_late + [0.0] * (len(step_ms) - len(start_late))], dtype=torch.float64, device="cuda")
     tw = torch.tensor(warm_ms + [kern_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tw, op=dist.ReduceOp.MAX)
     step_ms = t[0].cpu().numpy()
     e2e_s = t[1].cpu().numpy()
+    start_late_us = 1e6 * float(t[2].max())            # worst lateness of any rank at any timed step's agreed start (0 = all on time)
     ms = float(step_ms.mean())
     step_spread = {"median_ms": float(np.median(step_ms)), "min_ms": float(step_ms.min()), "max_ms": float(step_ms.max())}
     value = rays / (ms * 1e-3) / 1e6
@@ -589,7 +610,7 @@ def bench_workload(args, r, dist, rank, world, local_rank, workload, steps, with
         "scene_upload_wall_s": upload_wall,
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": 1e3 * float(e2e_s.mean()),
                 "h2d_bytes_per_step": int(C.sizeof(A.rt_frame) + 28 * len(frame.lights) + 8 * spp),
-                "d2h_bytes_per_step": int(3 * W * H + 32), "spread": e2e_spread, "frame_kernel_ms_rank0": float(e2e_kernel_ms),
+                "d2h_bytes_per_step": int(3 * W * H + 32), "spread": e2e_spread, "frame_kernel_ms_rank0": float(e2e_kernel_ms), "start_late_us_max": start_late_us,
                 "delivery": ("every rank copies its own bands into one shared page-locked host buffer (rt_host_image_create), %d PCIe links" % world) if world > 1 else "band-pipelined copy into pinned host memory"},
         "gpu_launches": int(steps * launches_per_step),
         "clocks": clocks,
